@@ -1,0 +1,123 @@
+/*
+ * b200mvs.h -- C ABI of the B200-native MultiViewStereoNet depth-inference hot path.
+ *
+ * The reference (robustrobotics/multi_view_stereonet) is pure Python over torch.nn and has no
+ * FFI of its own; the drop-in boundary is the call `stereo_network(left_image_pyr, K_pyr,
+ * T_right_in_left, right_image_pyr, num_idepth_samples, cost_volume_filter, refiners)` made at
+ * multi_view_stereonet/multi_view_stereonet_utils.py:647-654 (signature at
+ * multi_view_stereonet/multi_view_stereonet.py:538-545).  The entry points below are what a
+ * binding for that call needs: plain pointers and sizes, no torch types.  INTEGRATION.md shows
+ * the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - all tensors are contiguous float32 unless stated; images are NCHW (planar) exactly as the
+ *     reference holds them; masks are one byte per element (0 / 1), True(1) = invalid, as in the
+ *     reference (image_predictor.py:513-516).
+ *   - every function returns 0 on success or a negative B200MVS_E* code; b200mvs_last_error()
+ *     returns a thread-local message for the last failure on the calling thread.
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, never synchronised, unless
+ *     the function name ends in _host.
+ *   - a handle is bound to one CUDA device; one handle per device per process (one process per
+ *     GPU).  A handle must not be used from two threads at once.
+ */
+#ifndef B200MVS_H_
+#define B200MVS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define B200MVS_API __attribute__((visibility("default")))
+#else
+#define B200MVS_API
+#endif
+
+#define B200MVS_OK 0
+#define B200MVS_EINVAL (-1)   /* bad argument (the reference's `assert`s, e.g. multi_view_stereonet.py:548-549) */
+#define B200MVS_ECUDA (-2)    /* CUDA runtime error */
+#define B200MVS_EWEIGHTS (-3) /* state dict is missing a tensor or a tensor has the wrong size */
+#define B200MVS_ENOMEM (-4)
+
+#define B200MVS_NUM_LEVELS 5  /* multi_view_stereonet.py:504 */
+
+typedef struct b200mvs_net b200mvs_net;
+
+B200MVS_API const char* b200mvs_last_error(void);
+B200MVS_API const char* b200mvs_version(void);
+
+/* Builds a network on `device` from the reference's state dict (the 226 tensors named as in
+ * multi_view_stereonet.py:506-532, e.g. "left_feature_extractor.conv0.weight"); replaces
+ * `MultiViewStereoNet().load_state_dict(...)` + `.to(device)` (test.py:311-313).  `data[i]` are HOST
+ * pointers in the reference's (O, I, k...) layout; the library repacks and uploads them. */
+B200MVS_API int b200mvs_create(int device, int num_tensors, const char* const* names, const float* const* data,
+                   const int64_t* numels, b200mvs_net** out);
+B200MVS_API void b200mvs_destroy(b200mvs_net* net);
+
+/* Shape of one call.  rows/cols are the level-0 image size; level l+1 is ((h+1)/2, (w+1)/2)
+ * (utils/image_utils.py:111-128). */
+typedef struct b200mvs_shape {
+  int32_t batch;  /* B image groups */
+  int32_t views;  /* V comparison views per group, len(T_right_in_lefts) */
+  int32_t rows, cols;
+  int32_t num_idepth_samples; /* D */
+  int32_t do_cost_volume_filter;
+  int32_t do_refiners[B200MVS_NUM_LEVELS];
+} b200mvs_shape;
+
+/* MultiViewStereoNet.forward (multi_view_stereonet.py:538-695) on DEVICE pointers.
+ *   left_image_pyr[l]      (B,3,H_l,W_l)
+ *   K_pyr[l]               (B,4,4)
+ *   T_right_in_lefts[v]    (B,4,4)
+ *   right_image_l0[v]      (B,3,H_0,W_0)   = right_image_pyrs[v][0]
+ *   right_image_l4[v]      (B,3,H_4,W_4)   = right_image_pyrs[v][4]   (the only two levels the
+ *                                            reference reads, multi_view_stereonet.py:255-257,275)
+ * outputs, each level 0..4 (any pointer may be NULL to skip that output):
+ *   out_idepth[l]          (B,1,H_l,W_l)   "left_idepthmap_pyr"
+ *   out_idepth_raw[l]      (B,1,H_l,W_l)   "left_idepthmap_raw_pyr"
+ *   out_mask[l]            (B,D,H_l,W_l) uint8  "left_idepthmap_mask_pyr"
+ * Inputs are not modified. */
+B200MVS_API int b200mvs_forward(b200mvs_net* net, const b200mvs_shape* shape, const float* const* left_image_pyr,
+                    const float* const* K_pyr, const float* const* T_right_in_lefts,
+                    const float* const* right_image_l0, const float* const* right_image_l4,
+                    float* const* out_idepth, float* const* out_idepth_raw, uint8_t* const* out_mask,
+                    void* stream);
+
+/* Same call on HOST pointers (pinned or pageable): uploads the inputs, runs the path, downloads the
+ * requested outputs and synchronises.  This is the end-to-end entry bench.py's `e2e` figure times.
+ * `h2d_bytes` / `d2h_bytes` (may be NULL) receive the bytes copied in each direction. */
+B200MVS_API int b200mvs_forward_host(b200mvs_net* net, const b200mvs_shape* shape, const float* const* left_image_pyr,
+                         const float* const* K_pyr, const float* const* T_right_in_lefts,
+                         const float* const* right_image_l0, const float* const* right_image_l4,
+                         float* const* out_idepth, float* const* out_idepth_raw, uint8_t* const* out_mask,
+                         int64_t* h2d_bytes, int64_t* d2h_bytes);
+
+/* Number of kernels the last b200mvs_forward on this handle launched. */
+B200MVS_API int64_t b200mvs_last_launch_count(const b200mvs_net* net);
+
+/* Stage access for parity tests: copies an internal buffer of the LAST forward into `dst` (DEVICE
+ * pointer, `capacity` bytes) on `stream`; `*nbytes` receives its size.  Names:
+ *   "idepth_samples" (B*V,D)  "baseline" (B*V)  "H0" (B*V,3,3)  "H" (B*V,D,3,3)  "H_inc" (B*V,D,3,3)
+ *   "right_image0_warped" (B*V,3,H0,W0)   "l0_mask" (B*V,H0,W0) u8   "l4_mask" (B*V,D,h4,w4) u8
+ *   "left_feature1".."left_feature4" (B,H_l,W_l,32 channels-last)
+ *   "right_feature_volume" (B*V,D,h4,w4,32 channels-last, unmasked; only valid if kept, see
+ *    b200mvs_set_debug)      "cost_filtered" (B*V,D,h4,w4)    "idepth4_raw_views" (B*V,h4,w4)
+ * Image index n = b*V + v. */
+B200MVS_API int b200mvs_get_stage(b200mvs_net* net, const char* name, void* dst, int64_t capacity, int64_t* nbytes,
+                      void* stream);
+/* keep_stages != 0 makes the forward preserve buffers it would otherwise overwrite in place. */
+B200MVS_API int b200mvs_set_debug(b200mvs_net* net, int keep_stages);
+
+/* HomographyImagePredictor.forward (stereo/image_predictor.py:470-523) on DEVICE pointers:
+ * H (N,3,3), image (N,C,rows,cols) -> pred (N,C,rows,cols), mask (N,rows,cols) uint8.
+ * Needs no handle; `zero_invalid` != 0 additionally zeroes masked pixels as PlaneSweepWarper does
+ * (multi_view_stereonet.py:230-233). */
+B200MVS_API int b200mvs_homography_warp(const float* H, const float* image, int32_t n, int32_t channels, int32_t rows,
+                            int32_t cols, int32_t zero_invalid, float* pred, uint8_t* mask, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MVS_H_ */

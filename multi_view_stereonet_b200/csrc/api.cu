@@ -1,0 +1,951 @@
+// C ABI (include/b200mvs.h): handle, weight packing, workspace and the forward orchestration.
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/b200mvs.h"
+#include "conv.cuh"
+#include "kernels.cuh"
+
+namespace b200mvs {
+
+static thread_local std::string g_error;
+static thread_local int64_t g_launches = 0;
+void set_error(const std::string& msg) { g_error = msg; }
+void note_launch() { ++g_launches; }
+
+namespace {
+
+struct ConvW {
+  float* w = nullptr;
+  float* bias = nullptr;
+};
+struct GnW {
+  float* gamma = nullptr;
+  float* beta = nullptr;
+};
+
+struct Refiner {
+  ConvW conv0, res[6], fin;
+  GnW gn0, gn[6];
+};
+
+// Bump allocator over one device allocation; sizes are computed from the call shape.
+struct Arena {
+  char* base = nullptr;
+  size_t capacity = 0, used = 0;
+  bool dry = false;
+  template <class T>
+  T* take(size_t count) {
+    const size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+    T* p = dry ? nullptr : reinterpret_cast<T*>(base + used);
+    used += bytes;
+    return p;
+  }
+};
+
+struct Workspace {
+  // geometry
+  GeomOut geo{};
+  // level-0 warp
+  float* warped0 = nullptr;
+  uint8_t* l0mask = nullptr;
+  // feature network ((1+V)*B images; left images first)
+  float *f1 = nullptr, *f2 = nullptr, *f3 = nullptr, *feat4 = nullptr;
+  float *l4x[2] = {nullptr, nullptr}, *l4y[2] = {nullptr, nullptr};
+  // recurrence
+  float *vol = nullptr, *wf = nullptr, *wimg = nullptr, *sy0 = nullptr, *sx0 = nullptr, *sy1 = nullptr;
+  // cost volume
+  float *cost = nullptr, *cvfA = nullptr, *cost1 = nullptr;
+  uint8_t* mask_views = nullptr;
+  float *raw_views = nullptr, *refined_views = nullptr;
+  // refiners (shared by all levels)
+  float *rx[2] = {nullptr, nullptr}, *ry[2] = {nullptr, nullptr};
+  // output scratch
+  float* idepth[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  float* prior[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint8_t* mask[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  // GroupNorm statistics arena
+  double* stats = nullptr;
+  size_t stats_count = 0;
+};
+
+}  // namespace
+}  // namespace b200mvs
+
+using namespace b200mvs;
+
+struct b200mvs_net {
+  int device = 0;
+  std::vector<void*> allocs;  // weight allocations
+  // FeatureNetwork (multi_view_stereonet.py:78-129)
+  ConvW feat_conv[4];
+  ConvW feat_res[6];
+  GnW feat_gn[6];
+  ConvW feat_final;
+  // FeatureRefiner (multi_view_stereonet.py:398-440)
+  ConvW fr_conv0, fr_res0, fr_final;
+  GnW fr_gn0, fr_gn1;
+  // CostVolumeFilter (multi_view_stereonet.py:302-353)
+  ConvW cvf[5];
+  GnW cvf_gn[4];
+  // IDepthmapRefiner x5 (multi_view_stereonet.py:442-484)
+  Refiner refiner[5];
+
+  Arena arena;
+  Workspace ws;
+  b200mvs_shape ws_shape{};
+  bool ws_valid = false;
+  bool keep_stages = false;
+  b200mvs_shape last_shape{};
+  bool have_last = false;
+  int64_t last_launches = 0;
+};
+
+namespace {
+
+struct StateDict {
+  std::map<std::string, std::pair<const float*, int64_t>> t;
+  const float* get(const std::string& name, int64_t numel) const {
+    auto it = t.find(name);
+    if (it == t.end()) {
+      set_error("state dict has no tensor '" + name + "'");
+      return nullptr;
+    }
+    if (it->second.second != numel) {
+      set_error("tensor '" + name + "' has " + std::to_string(it->second.second) + " elements, expected " +
+                std::to_string(numel));
+      return nullptr;
+    }
+    return it->second.first;
+  }
+};
+
+int upload(b200mvs_net* net, const std::vector<float>& host, float** dev) {
+  B200MVS_CUDA_OK(cudaMalloc(dev, host.size() * sizeof(float)));
+  net->allocs.push_back(*dev);
+  B200MVS_CUDA_OK(cudaMemcpy(*dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// Packs a reference conv weight (O, I, taps) into [chunk][tap][8][O]: four chunks for the 32
+// feature channels (reference input index feat_off + c) if has_feat, then one zero-padded chunk for
+// the planar "extra" channels (reference indices extra_idx[0..n_extra)).
+int pack_conv(b200mvs_net* net, const StateDict& sd, const std::string& name, int cout, int cin, int taps,
+              bool has_feat, int feat_off, const std::vector<int>& extra_idx, bool has_bias, ConvW* out) {
+  const float* w = sd.get(name + ".weight", (int64_t)cout * cin * taps);
+  if (w == nullptr) return B200MVS_EWEIGHTS;
+  const int chunks = (has_feat ? 4 : 0) + (extra_idx.empty() ? 0 : 1);
+  std::vector<float> packed((size_t)chunks * taps * 8 * cout, 0.f);
+  for (int chunk = 0; chunk < chunks; ++chunk)
+    for (int tap = 0; tap < taps; ++tap)
+      for (int k = 0; k < 8; ++k) {
+        int ci;
+        if (has_feat && chunk < 4) {
+          ci = feat_off + chunk * 8 + k;
+        } else {
+          if (k >= (int)extra_idx.size()) continue;
+          ci = extra_idx[k];
+        }
+        for (int o = 0; o < cout; ++o)
+          packed[(((size_t)chunk * taps + tap) * 8 + k) * cout + o] = w[((size_t)o * cin + ci) * taps + tap];
+      }
+  int rc = upload(net, packed, &out->w);
+  if (rc) return rc;
+  if (has_bias) {
+    const float* b = sd.get(name + ".bias", cout);
+    if (b == nullptr) return B200MVS_EWEIGHTS;
+    std::vector<float> hb(b, b + cout);
+    rc = upload(net, hb, &out->bias);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int pack_gn(b200mvs_net* net, const StateDict& sd, const std::string& name, GnW* out) {
+  const float* g = sd.get(name + ".weight", kC);
+  const float* b = sd.get(name + ".bias", kC);
+  if (g == nullptr || b == nullptr) return B200MVS_EWEIGHTS;
+  int rc = upload(net, std::vector<float>(g, g + kC), &out->gamma);
+  if (rc) return rc;
+  return upload(net, std::vector<float>(b, b + kC), &out->beta);
+}
+
+#define RC(expr)            \
+  do {                      \
+    int _rc = (expr);       \
+    if (_rc != 0) return _rc; \
+  } while (0)
+
+int build_weights(b200mvs_net* net, const StateDict& sd) {
+  const std::string fe = "left_feature_extractor";
+  RC(pack_conv(net, sd, fe + ".conv0", 32, 3, 25, false, 0, {0, 1, 2}, false, &net->feat_conv[0]));
+  for (int i = 1; i < 4; ++i)
+    RC(pack_conv(net, sd, fe + ".conv" + std::to_string(i), 32, 32, 25, true, 0, {}, false, &net->feat_conv[i]));
+  for (int i = 0; i < 6; ++i) {
+    const std::string r = fe + ".res" + std::to_string(i);
+    RC(pack_conv(net, sd, r + ".conv1", 32, 32, 9, true, 0, {}, false, &net->feat_res[i]));
+    RC(pack_gn(net, sd, r + ".bn1", &net->feat_gn[i]));
+  }
+  RC(pack_conv(net, sd, fe + ".conv_final", 32, 32, 9, true, 0, {}, true, &net->feat_final));
+
+  const std::string fr = "right_feature_extractor.refiner";
+  // input = cat([image(3), features(32)])  (multi_view_stereonet.py:425)
+  RC(pack_conv(net, sd, fr + ".conv0", 32, 35, 9, true, 3, {0, 1, 2}, true, &net->fr_conv0));
+  RC(pack_gn(net, sd, fr + ".bn0", &net->fr_gn0));
+  RC(pack_conv(net, sd, fr + ".res0.conv1", 32, 32, 9, true, 0, {}, true, &net->fr_res0));
+  RC(pack_gn(net, sd, fr + ".res0.bn1", &net->fr_gn1));
+  RC(pack_conv(net, sd, fr + ".conv_final", 32, 32, 9, true, 0, {}, true, &net->fr_final));
+
+  for (int i = 0; i < 4; ++i) {
+    RC(pack_conv(net, sd, "volume_filter4.conv" + std::to_string(i), 32, 32, 27, true, 0, {}, true, &net->cvf[i]));
+    RC(pack_gn(net, sd, "volume_filter4.bn" + std::to_string(i), &net->cvf_gn[i]));
+  }
+  RC(pack_conv(net, sd, "volume_filter4.conv4", 1, 32, 27, true, 0, {}, true, &net->cvf[4]));
+
+  for (int lvl = 0; lvl < 5; ++lvl) {
+    const std::string r = "refiner" + std::to_string(lvl);
+    Refiner& R = net->refiner[lvl];
+    // input = cat([image(3), features(32), idepth(1)]) for levels 1..4, cat([image(3), idepth(1)]) at
+    // level 0 (multi_view_stereonet.py:469, 610, 679).
+    if (lvl > 0)
+      RC(pack_conv(net, sd, r + ".conv0", 32, 36, 9, true, 3, {0, 1, 2, 35}, true, &R.conv0));
+    else
+      RC(pack_conv(net, sd, r + ".conv0", 32, 4, 9, false, 0, {0, 1, 2, 3}, true, &R.conv0));
+    RC(pack_gn(net, sd, r + ".bn0", &R.gn0));
+    for (int i = 0; i < 6; ++i) {
+      RC(pack_conv(net, sd, r + ".res" + std::to_string(i) + ".conv1", 32, 32, 9, true, 0, {}, true, &R.res[i]));
+      RC(pack_gn(net, sd, r + ".res" + std::to_string(i) + ".bn1", &R.gn[i]));
+    }
+    RC(pack_conv(net, sd, r + ".conv_final", 1, 32, 9, true, 0, {}, true, &R.fin));
+  }
+  return 0;
+}
+
+struct Levels {
+  int h[5], w[5];
+  size_t px[5];
+};
+Levels levels_of(const b200mvs_shape& s) {
+  Levels L;
+  L.h[0] = s.rows;
+  L.w[0] = s.cols;
+  for (int l = 1; l < 5; ++l) {
+    L.h[l] = (L.h[l - 1] + 1) / 2;
+    L.w[l] = (L.w[l - 1] + 1) / 2;
+  }
+  for (int l = 0; l < 5; ++l) L.px[l] = (size_t)L.h[l] * L.w[l];
+  return L;
+}
+
+// Lays the workspace out in the arena (dry run computes the size).
+void layout(b200mvs_net* net, const b200mvs_shape& s, bool dry) {
+  Arena& A = net->arena;
+  Workspace& W = net->ws;
+  A.used = 0;
+  A.dry = dry;
+  const Levels L = levels_of(s);
+  const size_t B = s.batch, V = s.views, D = s.num_idepth_samples;
+  const size_t n = B * V, NI = B + n;
+  W.geo.baseline = A.take<float>(n);
+  W.geo.samples = A.take<float>(n * D);
+  W.geo.H0 = A.take<float>(n * 9);
+  W.geo.H = A.take<float>(n * D * 9);
+  W.geo.Hinc = A.take<float>(n * D * 9);
+  W.warped0 = A.take<float>(n * 3 * L.px[0]);
+  W.l0mask = A.take<uint8_t>(n * L.px[0]);
+  W.f1 = A.take<float>(NI * L.px[1] * kC);
+  W.f2 = A.take<float>(NI * L.px[2] * kC);
+  W.f3 = A.take<float>(NI * L.px[3] * kC);
+  W.feat4 = A.take<float>(NI * L.px[4] * kC);
+  for (int i = 0; i < 2; ++i) {
+    W.l4x[i] = A.take<float>(NI * L.px[4] * kC);
+    W.l4y[i] = A.take<float>(NI * L.px[4] * kC);
+  }
+  W.vol = A.take<float>(n * D * L.px[4] * kC);
+  W.wf = A.take<float>(n * L.px[4] * kC);
+  W.wimg = A.take<float>(n * 3 * L.px[4]);
+  W.sy0 = A.take<float>(n * L.px[4] * kC);
+  W.sx0 = A.take<float>(n * L.px[4] * kC);
+  W.sy1 = A.take<float>(n * L.px[4] * kC);
+  W.cost = net->keep_stages ? A.take<float>(n * D * L.px[4] * kC) : nullptr;
+  W.cvfA = A.take<float>(n * D * L.px[4] * kC);
+  W.cost1 = A.take<float>(n * D * L.px[4]);
+  W.mask_views = A.take<uint8_t>(n * D * L.px[4]);
+  W.raw_views = A.take<float>(n * L.px[4]);
+  W.refined_views = A.take<float>(n * L.px[4]);
+  // refiner ping-pong buffers: B images at level 0 or B*V images at level 4, whichever is larger
+  const size_t rmax = (B * L.px[0] > n * L.px[4]) ? B * L.px[0] : n * L.px[4];
+  for (int i = 0; i < 2; ++i) {
+    W.rx[i] = A.take<float>(rmax * kC);
+    W.ry[i] = A.take<float>(rmax * kC);
+  }
+  for (int l = 0; l < 5; ++l) {
+    W.idepth[l] = A.take<float>(B * L.px[l]);
+    W.prior[l] = A.take<float>(B * L.px[l]);
+    W.mask[l] = (l == 0) ? nullptr : A.take<uint8_t>(B * D * L.px[l]);
+  }
+  // statistics: featnet 6 layers x NI, recurrence 2 x (D-1) x n, cvf 4 x n, refiners 7 x (n + 4B)
+  W.stats_count = (6 * NI + 2 * (D > 0 ? D - 1 : 0) * n + 4 * n + 7 * (n + 4 * B)) * 2 * kGroups;
+  W.stats = A.take<double>(W.stats_count);
+}
+
+bool same_shape(const b200mvs_shape& a, const b200mvs_shape& b) {
+  return a.batch == b.batch && a.views == b.views && a.rows == b.rows && a.cols == b.cols &&
+         a.num_idepth_samples == b.num_idepth_samples;
+}
+
+int ensure_workspace(b200mvs_net* net, const b200mvs_shape& s) {
+  if (net->ws_valid && same_shape(net->ws_shape, s)) return 0;
+  layout(net, s, true);
+  const size_t need = net->arena.used;
+  if (need > net->arena.capacity) {
+    if (net->arena.base != nullptr) {
+      B200MVS_CUDA_OK(cudaDeviceSynchronize());
+      B200MVS_CUDA_OK(cudaFree(net->arena.base));
+      net->arena.base = nullptr;
+      net->arena.capacity = 0;
+    }
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&net->arena.base), need);
+    if (e != cudaSuccess) {
+      set_error("workspace allocation of " + std::to_string(need) + " bytes failed: " + cudaGetErrorString(e));
+      return B200MVS_ENOMEM;
+    }
+    net->arena.capacity = need;
+  }
+  layout(net, s, false);
+  net->ws_shape = s;
+  net->ws_valid = true;
+  return 0;
+}
+
+struct StatsCursor {
+  double* base;
+  size_t used = 0, cap;
+  double* take(size_t imgs) {
+    double* p = base + used;
+    used += imgs * 2 * kGroups;
+    return p;
+  }
+};
+
+// One IDepthmapRefiner (multi_view_stereonet.py:468-484) with the caller-side fx scaling
+// (:607-611) folded into the first loader and the last epilogue.
+int run_refiner(b200mvs_net* net, const Refiner& R, StatsCursor& sc, int m, int H, int W, const float* guide_feat,
+                int guide_div, const float* image, int image_div, const float* prior, const float* Kl, int k_div,
+                float* out, cudaStream_t stream) {
+  Workspace& ws = net->ws;
+  const size_t P = (size_t)H * W;
+  const double inv_count = 1.0 / (8.0 * (double)P);
+  double* st_prev = nullptr;
+
+  ConvParams p;
+  p.n_img = m;
+  p.Hi = p.Ho = H;
+  p.Wi = p.Wo = W;
+  // conv0
+  if (guide_feat != nullptr) {
+    p.feat.ptr = guide_feat;
+    p.feat.mode = FEAT_RAW;
+    p.feat.img_div = guide_div;
+  }
+  p.extra.n = 4;
+  for (int e = 0; e < 3; ++e) {
+    p.extra.ptr[e] = image + e * P;
+    p.extra.img_stride[e] = 3 * (long long)P;
+    p.extra.img_div[e] = image_div;
+  }
+  p.extra.ptr[3] = prior;
+  p.extra.img_stride[3] = (long long)P;
+  p.extra.img_div[3] = 1;
+  p.extra.scale[3] = Kl;  // fx = K[b][0][0]
+  p.extra.scale_div[3] = k_div;
+  p.extra.scale_stride[3] = 16;
+  p.w = R.conv0.w;
+  p.bias = R.conv0.bias;
+  p.dil = 1;
+  p.out = ws.ry[0];
+  p.out_stats = st_prev = sc.take(m);
+  RC(launch_conv(CONV_3x3, 32, p, stream));
+
+  static const int dilations[6] = {1, 2, 4, 8, 1, 1};  // multi_view_stereonet.py:457
+  const GnW* gn_prev = &R.gn0;
+  int ycur = 0;      // ry[ycur] holds the raw output of the previous conv
+  int xres = -1;     // rx[xres] holds the previous block's input (the residual), -1 = none
+  for (int i = 0; i < 6; ++i) {
+    ConvParams q;
+    q.n_img = m;
+    q.Hi = q.Ho = H;
+    q.Wi = q.Wo = W;
+    q.feat.ptr = ws.ry[ycur];
+    q.feat.mode = (xres < 0) ? FEAT_GN : FEAT_GN_RES;
+    q.feat.stats = st_prev;
+    q.feat.gamma = gn_prev->gamma;
+    q.feat.beta = gn_prev->beta;
+    q.feat.inv_count = inv_count;
+    q.feat.resid = (xres < 0) ? nullptr : ws.rx[xres];
+    const int xnew = (xres < 0) ? 0 : 1 - xres;
+    q.feat.x_out = ws.rx[xnew];
+    q.w = R.res[i].w;
+    q.bias = R.res[i].bias;
+    q.dil = dilations[i];
+    q.out = ws.ry[1 - ycur];
+    q.out_stats = sc.take(m);
+    RC(launch_conv(CONV_3x3, 32, q, stream));
+    st_prev = q.out_stats;
+    gn_prev = &R.gn[i];
+    ycur = 1 - ycur;
+    xres = xnew;
+  }
+  // conv_final 32 -> 1 on x6 = lrelu(gn(y)) + x5, then relu(prior * fx + delta) / fx
+  ConvParams f;
+  f.n_img = m;
+  f.Hi = f.Ho = H;
+  f.Wi = f.Wo = W;
+  f.feat.ptr = ws.ry[ycur];
+  f.feat.mode = FEAT_GN_RES;
+  f.feat.stats = st_prev;
+  f.feat.gamma = gn_prev->gamma;
+  f.feat.beta = gn_prev->beta;
+  f.feat.inv_count = inv_count;
+  f.feat.resid = ws.rx[xres];
+  f.w = R.fin.w;
+  f.bias = R.fin.bias;
+  f.dil = 1;
+  f.out = out;
+  f.epi1_mode = 1;
+  f.prior = prior;
+  f.fx = Kl;
+  f.fx_div = k_div;
+  f.fx_stride = 16;
+  RC(launch_conv(CONV_3x3, 1, f, stream));
+  return 0;
+}
+
+int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* left_pyr, const float* const* K_pyr,
+                 const float* const* Ts, const float* const* right_l0, const float* const* right_l4,
+                 float* const* out_idepth, float* const* out_raw, uint8_t* const* out_mask, cudaStream_t stream) {
+  if (s.batch < 1 || s.views < 1 || s.views > kMaxViews || s.rows < 16 || s.cols < 16 ||
+      s.num_idepth_samples < 2 || s.num_idepth_samples > 4096) {
+    set_error("b200mvs_forward: bad shape (need batch>=1, 1<=views<=16, rows,cols>=16, 2<=D<=4096)");
+    return B200MVS_EINVAL;
+  }
+  for (int l = 0; l < 5; ++l)
+    if (left_pyr[l] == nullptr || K_pyr[l] == nullptr) {
+      // the reference asserts len(K_pyr) == len(left_image_pyr) == 5 (multi_view_stereonet.py:548-549)
+      set_error("b200mvs_forward: left_image_pyr and K_pyr need 5 levels");
+      return B200MVS_EINVAL;
+    }
+  for (int v = 0; v < s.views; ++v)
+    if (Ts[v] == nullptr || right_l0[v] == nullptr || right_l4[v] == nullptr) {
+      set_error("b200mvs_forward: missing per-view input");
+      return B200MVS_EINVAL;
+    }
+  B200MVS_CUDA_OK(cudaSetDevice(net->device));
+  RC(ensure_workspace(net, s));
+  Workspace& ws = net->ws;
+  const Levels L = levels_of(s);
+  const int B = s.batch, V = s.views, D = s.num_idepth_samples;
+  const int n = B * V, NI = B + n;
+  const int h4 = L.h[4], w4 = L.w[4];
+  const size_t P4 = L.px[4];
+  g_launches = 0;
+
+  B200MVS_CUDA_OK(cudaMemsetAsync(ws.stats, 0, ws.stats_count * sizeof(double), stream));
+  StatsCursor sc{ws.stats, 0, ws.stats_count};
+
+  ViewPtrs Tv{}, R0{}, R4{};
+  Tv.views = R0.views = R4.views = V;
+  for (int v = 0; v < V; ++v) {
+    Tv.p[v] = Ts[v];
+    R0.p[v] = right_l0[v];
+    R4.p[v] = right_l4[v];
+  }
+
+  // 1. geometry
+  RC(launch_geometry(Tv, K_pyr[0], K_pyr[4], B, D, h4, w4, ws.geo, stream));
+
+  // 2. full-resolution warp of every comparison image by the idepth-0 homography
+  //    (multi_view_stereonet.py:254-258)
+  RC(launch_warp_planar(ws.geo.H0, 9, R0, n, 3, L.h[0], L.w[0], true, ws.warped0, ws.l0mask, stream));
+
+  // 3. FeatureNetwork on the B left images and the B*V warped right images (shared weights, :507)
+  {
+    ConvParams p;
+    p.Hi = L.h[0];
+    p.Wi = L.w[0];
+    p.Ho = L.h[1];
+    p.Wo = L.w[1];
+    p.extra.n = 3;
+    p.w = net->feat_conv[0].w;
+    for (int e = 0; e < 3; ++e) {
+      p.extra.ptr[e] = left_pyr[0] + e * L.px[0];
+      p.extra.img_stride[e] = 3 * (long long)L.px[0];
+    }
+    p.n_img = B;
+    p.out = ws.f1;
+    RC(launch_conv(CONV_5x5_S2, 32, p, stream));
+    for (int e = 0; e < 3; ++e) p.extra.ptr[e] = ws.warped0 + e * L.px[0];
+    p.n_img = n;
+    p.out = ws.f1 + (size_t)B * L.px[1] * kC;
+    RC(launch_conv(CONV_5x5_S2, 32, p, stream));
+  }
+  {
+    const float* src[3] = {ws.f1, ws.f2, ws.f3};
+    float* dst[3] = {ws.f2, ws.f3, ws.l4x[0]};
+    for (int i = 0; i < 3; ++i) {
+      ConvParams p;
+      p.n_img = NI;
+      p.Hi = L.h[i + 1];
+      p.Wi = L.w[i + 1];
+      p.Ho = L.h[i + 2];
+      p.Wo = L.w[i + 2];
+      p.feat.ptr = src[i];
+      p.feat.mode = FEAT_RAW;
+      p.w = net->feat_conv[i + 1].w;
+      p.out = dst[i];
+      RC(launch_conv(CONV_5x5_S2, 32, p, stream));
+    }
+  }
+  {
+    // six residual blocks + conv_final at level 4 (multi_view_stereonet.py:119-127)
+    const double inv_count = 1.0 / (8.0 * (double)P4);
+    double* st_prev = nullptr;
+    int xcur = 0, ycur = 0;
+    for (int i = 0; i <= 6; ++i) {
+      ConvParams p;
+      p.n_img = NI;
+      p.Hi = p.Ho = h4;
+      p.Wi = p.Wo = w4;
+      if (i == 0) {
+        p.feat.ptr = ws.l4x[0];
+        p.feat.mode = FEAT_RAW;
+      } else {
+        p.feat.ptr = ws.l4y[ycur];
+        p.feat.mode = FEAT_GN_RES;
+        p.feat.stats = st_prev;
+        p.feat.gamma = net->feat_gn[i - 1].gamma;
+        p.feat.beta = net->feat_gn[i - 1].beta;
+        p.feat.inv_count = inv_count;
+        p.feat.resid = ws.l4x[xcur];
+        if (i < 6) p.feat.x_out = ws.l4x[1 - xcur];
+      }
+      if (i < 6) {
+        p.w = net->feat_res[i].w;
+        p.out = ws.l4y[i == 0 ? 0 : 1 - ycur];
+        p.out_stats = sc.take(NI);
+      } else {
+        p.w = net->feat_final.w;
+        p.bias = net->feat_final.bias;
+        p.out = ws.feat4;
+      }
+      RC(launch_conv(CONV_3x3, 32, p, stream));
+      if (i > 0) {
+        ycur = 1 - ycur;
+        if (i < 6) xcur = 1 - xcur;
+      }
+      st_prev = p.out_stats;
+    }
+  }
+
+  // 4. hypothesis 0 of every view's feature volume = features of the warped image (:261, 278)
+  B200MVS_CUDA_OK(cudaMemcpy2DAsync(ws.vol, (size_t)D * P4 * kC * sizeof(float), ws.feat4 + (size_t)B * P4 * kC,
+                                    P4 * kC * sizeof(float), P4 * kC * sizeof(float), n, cudaMemcpyDeviceToDevice,
+                                    stream));
+
+  // 5. the depth-sweep recurrence (multi_view_stereonet.py:279-290)
+  {
+    const double inv_count = 1.0 / (8.0 * (double)P4);
+    for (int step = 1; step < D; ++step) {
+      RC(launch_step_warp(ws.vol, ws.geo, R4, n, D, step, h4, w4, ws.wf, ws.wimg, stream));
+      ConvParams a;  // conv0 on cat([warped image, warped features])
+      a.n_img = n;
+      a.Hi = a.Ho = h4;
+      a.Wi = a.Wo = w4;
+      a.feat.ptr = ws.wf;
+      a.feat.mode = FEAT_RAW;
+      a.extra.n = 3;
+      for (int e = 0; e < 3; ++e) {
+        a.extra.ptr[e] = ws.wimg + e * P4;
+        a.extra.img_stride[e] = 3 * (long long)P4;
+      }
+      a.w = net->fr_conv0.w;
+      a.bias = net->fr_conv0.bias;
+      a.out = ws.sy0;
+      a.out_stats = sc.take(n);
+      RC(launch_conv(CONV_3x3, 32, a, stream));
+
+      ConvParams b;  // res0.conv1 on x0 = lrelu(gn0(y0))
+      b.n_img = n;
+      b.Hi = b.Ho = h4;
+      b.Wi = b.Wo = w4;
+      b.feat.ptr = ws.sy0;
+      b.feat.mode = FEAT_GN;
+      b.feat.stats = a.out_stats;
+      b.feat.gamma = net->fr_gn0.gamma;
+      b.feat.beta = net->fr_gn0.beta;
+      b.feat.inv_count = inv_count;
+      b.feat.x_out = ws.sx0;
+      b.w = net->fr_res0.w;
+      b.bias = net->fr_res0.bias;
+      b.out = ws.sy1;
+      b.out_stats = sc.take(n);
+      RC(launch_conv(CONV_3x3, 32, b, stream));
+
+      ConvParams c;  // conv_final on x1 = lrelu(gn1(y1)) + x0 ; features_d = warped + delta
+      c.n_img = n;
+      c.Hi = c.Ho = h4;
+      c.Wi = c.Wo = w4;
+      c.feat.ptr = ws.sy1;
+      c.feat.mode = FEAT_GN_RES;
+      c.feat.stats = b.out_stats;
+      c.feat.gamma = net->fr_gn1.gamma;
+      c.feat.beta = net->fr_gn1.beta;
+      c.feat.inv_count = inv_count;
+      c.feat.resid = ws.sx0;
+      c.w = net->fr_final.w;
+      c.bias = net->fr_final.bias;
+      c.add_src = ws.wf;
+      // hypothesis `step` of image i lives at vol + (i * D + step) * P4 * 32
+      c.out = ws.vol + (size_t)step * P4 * kC;
+      c.out_img_stride = (long long)D * P4 * kC;
+      RC(launch_conv(CONV_3x3, 32, c, stream));
+    }
+  }
+
+  // 6. cost volume |L - R| with invalid voxels zeroed (multi_view_stereonet.py:586-592)
+  float* cost = net->keep_stages ? ws.cost : ws.vol;
+  RC(launch_cost(ws.feat4, ws.vol, ws.geo.H, n, V, D, h4, w4, cost, ws.mask_views, stream));
+
+  // 7. CostVolumeFilter (five Conv3d, :341-353) or the channel norm (:598)
+  if (s.do_cost_volume_filter) {
+    const double inv_count = 1.0 / (8.0 * (double)D * (double)P4);
+    float* bufs[2] = {ws.cvfA, cost};
+    const float* src = cost;
+    double* st_prev = nullptr;
+    for (int i = 0; i < 5; ++i) {
+      ConvParams p;
+      p.n_img = n;
+      p.Di = p.Do = D;
+      p.Hi = p.Ho = h4;
+      p.Wi = p.Wo = w4;
+      p.feat.ptr = src;
+      if (i == 0) {
+        p.feat.mode = FEAT_RAW;
+      } else {
+        p.feat.mode = FEAT_GN;
+        p.feat.stats = st_prev;
+        p.feat.gamma = net->cvf_gn[i - 1].gamma;
+        p.feat.beta = net->cvf_gn[i - 1].beta;
+        p.feat.inv_count = inv_count;
+      }
+      p.w = net->cvf[i].w;
+      p.bias = net->cvf[i].bias;
+      if (i < 4) {
+        p.out = bufs[i & 1];
+        p.out_stats = sc.take(n);
+        RC(launch_conv(CONV_3x3x3, 32, p, stream));
+        src = p.out;
+        st_prev = p.out_stats;
+      } else {
+        p.out = ws.cost1;
+        RC(launch_conv(CONV_3x3x3, 1, p, stream));
+      }
+    }
+  } else {
+    RC(launch_cost_norm(cost, (long long)n * D * P4, ws.cost1, stream));
+  }
+
+  // 8. soft-argmin (:602)
+  RC(launch_softargmin(ws.cost1, ws.geo.samples, n, D, (int)P4, ws.raw_views, stream));
+
+  // 9. level-4 refiner per view (:605-613)
+  if (s.do_refiners[4]) {
+    RC(run_refiner(net, net->refiner[4], sc, n, h4, w4, ws.feat4, V, left_pyr[4], V, ws.raw_views, K_pyr[4], V,
+                   ws.refined_views, stream));
+  }
+
+  // 10. baseline un-normalisation, mean over views, mask vote (:616-627)
+  float* idepth_l[5];
+  float* prior_l[5];
+  uint8_t* mask_l[5];
+  int lowest_mask = 5;
+  for (int l = 0; l < 5; ++l) {
+    idepth_l[l] = out_idepth != nullptr && out_idepth[l] != nullptr ? out_idepth[l] : ws.idepth[l];
+    prior_l[l] = out_raw != nullptr && out_raw[l] != nullptr ? out_raw[l] : ws.prior[l];
+    mask_l[l] = out_mask != nullptr && out_mask[l] != nullptr ? out_mask[l] : ws.mask[l];
+    if (out_mask != nullptr && out_mask[l] != nullptr && l < lowest_mask) lowest_mask = l;
+  }
+  RC(launch_view_reduce(ws.raw_views, ws.refined_views, ws.mask_views, ws.geo.baseline, B, V, D, (int)P4,
+                        !s.do_refiners[4], prior_l[4], idepth_l[4], mask_l[4], stream));
+
+  // 11. coarse-to-fine: bilinear prior, mask upsample, guided refinement (:629-682)
+  for (int l = 3; l >= 0; --l) {
+    RC(launch_upsample_f32(idepth_l[l + 1], B, L.h[l + 1], L.w[l + 1], L.h[l], L.w[l], prior_l[l], stream));
+    if (l >= lowest_mask)
+      RC(launch_upsample_mask(mask_l[l + 1], (long long)B * D, L.h[l + 1], L.w[l + 1], L.h[l], L.w[l], mask_l[l],
+                              stream));
+    if (s.do_refiners[l]) {
+      const float* guide = (l == 0) ? nullptr : (l == 1 ? ws.f1 : (l == 2 ? ws.f2 : ws.f3));
+      RC(run_refiner(net, net->refiner[l], sc, B, L.h[l], L.w[l], guide, 1, left_pyr[l], 1, prior_l[l], K_pyr[l], 1,
+                     idepth_l[l], stream));
+    } else {
+      B200MVS_CUDA_OK(cudaMemcpyAsync(idepth_l[l], prior_l[l], (size_t)B * L.px[l] * sizeof(float),
+                                      cudaMemcpyDeviceToDevice, stream));
+    }
+  }
+  if (sc.used > sc.cap) {
+    set_error("internal: GroupNorm statistics arena overflow");
+    return B200MVS_EINVAL;
+  }
+  net->last_shape = s;
+  net->have_last = true;
+  net->last_launches = g_launches;
+  return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+B200MVS_API const char* b200mvs_last_error(void) { return g_error.c_str(); }
+B200MVS_API const char* b200mvs_version(void) { return "b200mvs 0.1 (sm_100a)"; }
+
+B200MVS_API int b200mvs_create(int device, int num_tensors, const char* const* names, const float* const* data,
+                   const int64_t* numels, b200mvs_net** out) {
+  if (out == nullptr || names == nullptr || data == nullptr || numels == nullptr) {
+    set_error("b200mvs_create: null argument");
+    return B200MVS_EINVAL;
+  }
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    set_error("b200mvs_create: no CUDA device visible; this library has no CPU path");
+    return B200MVS_ECUDA;
+  }
+  B200MVS_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  B200MVS_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error(std::string("b200mvs_create: built for sm_100a, device is sm_") + std::to_string(prop.major) +
+              std::to_string(prop.minor));
+    return B200MVS_ECUDA;
+  }
+  StateDict sd;
+  for (int i = 0; i < num_tensors; ++i) sd.t[names[i]] = {data[i], numels[i]};
+  b200mvs_net* net = new b200mvs_net();
+  net->device = device;
+  int rc = build_weights(net, sd);
+  if (rc != 0) {
+    b200mvs_destroy(net);
+    return rc;
+  }
+  *out = net;
+  return 0;
+}
+
+B200MVS_API void b200mvs_destroy(b200mvs_net* net) {
+  if (net == nullptr) return;
+  cudaSetDevice(net->device);
+  for (void* p : net->allocs) cudaFree(p);
+  if (net->arena.base != nullptr) cudaFree(net->arena.base);
+  delete net;
+}
+
+B200MVS_API int b200mvs_set_debug(b200mvs_net* net, int keep_stages) {
+  if (net == nullptr) return B200MVS_EINVAL;
+  if (net->keep_stages != (keep_stages != 0)) {
+    net->keep_stages = keep_stages != 0;
+    net->ws_valid = false;  // layout changes
+  }
+  return 0;
+}
+
+B200MVS_API int64_t b200mvs_last_launch_count(const b200mvs_net* net) { return net == nullptr ? 0 : net->last_launches; }
+
+B200MVS_API int b200mvs_forward(b200mvs_net* net, const b200mvs_shape* shape, const float* const* left_image_pyr,
+                    const float* const* K_pyr, const float* const* T_right_in_lefts,
+                    const float* const* right_image_l0, const float* const* right_image_l4,
+                    float* const* out_idepth, float* const* out_idepth_raw, uint8_t* const* out_mask,
+                    void* stream) {
+  if (net == nullptr || shape == nullptr || left_image_pyr == nullptr || K_pyr == nullptr ||
+      T_right_in_lefts == nullptr || right_image_l0 == nullptr || right_image_l4 == nullptr) {
+    set_error("b200mvs_forward: null argument");
+    return B200MVS_EINVAL;
+  }
+  return forward_impl(net, *shape, left_image_pyr, K_pyr, T_right_in_lefts, right_image_l0, right_image_l4,
+                      out_idepth, out_idepth_raw, out_mask, static_cast<cudaStream_t>(stream));
+}
+
+B200MVS_API int b200mvs_forward_host(b200mvs_net* net, const b200mvs_shape* shape, const float* const* left_image_pyr,
+                         const float* const* K_pyr, const float* const* T_right_in_lefts,
+                         const float* const* right_image_l0, const float* const* right_image_l4,
+                         float* const* out_idepth, float* const* out_idepth_raw, uint8_t* const* out_mask,
+                         int64_t* h2d_bytes, int64_t* d2h_bytes) {
+  if (net == nullptr || shape == nullptr) {
+    set_error("b200mvs_forward_host: null argument");
+    return B200MVS_EINVAL;
+  }
+  const b200mvs_shape& s = *shape;
+  if (s.batch < 1 || s.views < 1 || s.views > kMaxViews) {
+    set_error("b200mvs_forward_host: bad shape");
+    return B200MVS_EINVAL;
+  }
+  B200MVS_CUDA_OK(cudaSetDevice(net->device));
+  const Levels L = levels_of(s);
+  const size_t B = s.batch, V = s.views, D = s.num_idepth_samples;
+  // Staging buffers for one call.
+  size_t in_floats = 0;
+  for (int l = 0; l < 5; ++l) in_floats += B * 3 * L.px[l] + B * 16;
+  in_floats += V * (B * 16 + B * 3 * L.px[0] + B * 3 * L.px[4]);
+  size_t out_f = 0, out_m = 0;
+  for (int l = 0; l < 5; ++l) {
+    out_f += 2 * B * L.px[l];
+    out_m += B * D * L.px[l];
+  }
+  float* din = nullptr;
+  float* dof = nullptr;
+  uint8_t* dom = nullptr;
+  B200MVS_CUDA_OK(cudaMalloc(&din, in_floats * sizeof(float)));
+  B200MVS_CUDA_OK(cudaMalloc(&dof, out_f * sizeof(float)));
+  B200MVS_CUDA_OK(cudaMalloc(&dom, out_m));
+  cudaStream_t stream = nullptr;
+  int64_t h2d = 0, d2h = 0;
+  int rc = 0;
+  auto up = [&](const float* src, size_t count, float*& cursor) -> const float* {
+    float* dst = cursor;
+    cursor += count;
+    if (cudaMemcpyAsync(dst, src, count * sizeof(float), cudaMemcpyHostToDevice, stream) != cudaSuccess) rc = -2;
+    h2d += (int64_t)(count * sizeof(float));
+    return dst;
+  };
+  float* cur = din;
+  const float* dl[5];
+  const float* dk[5];
+  const float *dT[kMaxViews], *dr0[kMaxViews], *dr4[kMaxViews];
+  for (int l = 0; l < 5; ++l) {
+    dl[l] = up(left_image_pyr[l], B * 3 * L.px[l], cur);
+    dk[l] = up(K_pyr[l], B * 16, cur);
+  }
+  for (size_t v = 0; v < V; ++v) {
+    dT[v] = up(T_right_in_lefts[v], B * 16, cur);
+    dr0[v] = up(right_image_l0[v], B * 3 * L.px[0], cur);
+    dr4[v] = up(right_image_l4[v], B * 3 * L.px[4], cur);
+  }
+  float *oi[5], *orw[5];
+  uint8_t* om[5];
+  {
+    float* c = dof;
+    uint8_t* m = dom;
+    for (int l = 0; l < 5; ++l) {
+      oi[l] = c;
+      c += B * L.px[l];
+      orw[l] = c;
+      c += B * L.px[l];
+      om[l] = (out_mask != nullptr && out_mask[l] != nullptr) ? m : nullptr;
+      m += B * D * L.px[l];
+    }
+  }
+  if (rc == 0) rc = forward_impl(net, s, dl, dk, dT, dr0, dr4, oi, orw, om, stream);
+  if (rc == 0) {
+    for (int l = 0; l < 5; ++l) {
+      if (out_idepth != nullptr && out_idepth[l] != nullptr) {
+        cudaMemcpyAsync(out_idepth[l], oi[l], B * L.px[l] * sizeof(float), cudaMemcpyDeviceToHost, stream);
+        d2h += (int64_t)(B * L.px[l] * sizeof(float));
+      }
+      if (out_idepth_raw != nullptr && out_idepth_raw[l] != nullptr) {
+        cudaMemcpyAsync(out_idepth_raw[l], orw[l], B * L.px[l] * sizeof(float), cudaMemcpyDeviceToHost, stream);
+        d2h += (int64_t)(B * L.px[l] * sizeof(float));
+      }
+      if (om[l] != nullptr) {
+        cudaMemcpyAsync(out_mask[l], om[l], B * D * L.px[l], cudaMemcpyDeviceToHost, stream);
+        d2h += (int64_t)(B * D * L.px[l]);
+      }
+    }
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) {
+      set_error(std::string("b200mvs_forward_host: ") + cudaGetErrorString(e));
+      rc = B200MVS_ECUDA;
+    }
+  } else {
+    cudaStreamSynchronize(stream);
+    if (rc == -2 && g_error.empty()) set_error("b200mvs_forward_host: upload failed");
+  }
+  cudaFree(din);
+  cudaFree(dof);
+  cudaFree(dom);
+  if (h2d_bytes != nullptr) *h2d_bytes = h2d;
+  if (d2h_bytes != nullptr) *d2h_bytes = d2h;
+  return rc;
+}
+
+B200MVS_API int b200mvs_get_stage(b200mvs_net* net, const char* name, void* dst, int64_t capacity, int64_t* nbytes,
+                      void* stream) {
+  if (net == nullptr || name == nullptr || !net->have_last) {
+    set_error("b200mvs_get_stage: no forward has run on this handle");
+    return B200MVS_EINVAL;
+  }
+  const b200mvs_shape& s = net->last_shape;
+  const Levels L = levels_of(s);
+  const Workspace& ws = net->ws;
+  const size_t B = s.batch, V = s.views, D = s.num_idepth_samples, n = B * V;
+  const std::string k(name);
+  const void* src = nullptr;
+  size_t bytes = 0;
+  if (k == "idepth_samples") { src = ws.geo.samples; bytes = n * D * 4; }
+  else if (k == "baseline") { src = ws.geo.baseline; bytes = n * 4; }
+  else if (k == "H0") { src = ws.geo.H0; bytes = n * 9 * 4; }
+  else if (k == "H") { src = ws.geo.H; bytes = n * D * 9 * 4; }
+  else if (k == "H_inc") { src = ws.geo.Hinc; bytes = n * D * 9 * 4; }
+  else if (k == "right_image0_warped") { src = ws.warped0; bytes = n * 3 * L.px[0] * 4; }
+  else if (k == "l0_mask") { src = ws.l0mask; bytes = n * L.px[0]; }
+  else if (k == "l4_mask") { src = ws.mask_views; bytes = n * D * L.px[4]; }
+  else if (k == "left_feature1") { src = ws.f1; bytes = B * L.px[1] * kC * 4; }
+  else if (k == "left_feature2") { src = ws.f2; bytes = B * L.px[2] * kC * 4; }
+  else if (k == "left_feature3") { src = ws.f3; bytes = B * L.px[3] * kC * 4; }
+  else if (k == "left_feature4") { src = ws.feat4; bytes = B * L.px[4] * kC * 4; }
+  else if (k == "right_feature_volume") {
+    if (!net->keep_stages) {
+      set_error("b200mvs_get_stage: right_feature_volume needs b200mvs_set_debug(net, 1) before the forward");
+      return B200MVS_EINVAL;
+    }
+    src = ws.vol; bytes = n * D * L.px[4] * kC * 4;
+  }
+  else if (k == "cost_filtered") { src = ws.cost1; bytes = n * D * L.px[4] * 4; }
+  else if (k == "idepth4_raw_views") { src = ws.raw_views; bytes = n * L.px[4] * 4; }
+  else {
+    set_error("b200mvs_get_stage: unknown stage '" + k + "'");
+    return B200MVS_EINVAL;
+  }
+  if (nbytes != nullptr) *nbytes = (int64_t)bytes;
+  if (dst == nullptr) return 0;  // size query
+  if ((int64_t)bytes > capacity) {
+    set_error("b200mvs_get_stage: destination too small");
+    return B200MVS_EINVAL;
+  }
+  B200MVS_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+B200MVS_API int b200mvs_homography_warp(const float* H, const float* image, int32_t n, int32_t channels, int32_t rows,
+                            int32_t cols, int32_t zero_invalid, float* pred, uint8_t* mask, void* stream) {
+  if (H == nullptr || image == nullptr || pred == nullptr || n < 0 || channels < 1 || rows < 1 || cols < 1) {
+    set_error("b200mvs_homography_warp: bad argument");
+    return B200MVS_EINVAL;
+  }
+  if (n > 65535) {
+    set_error("b200mvs_homography_warp: at most 65535 images per call");
+    return B200MVS_EINVAL;
+  }
+  ViewPtrs src{};
+  src.views = 1;
+  src.p[0] = image;
+  return launch_warp_planar(H, 9, src, n, channels, rows, cols, zero_invalid != 0, pred, mask,
+                            static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

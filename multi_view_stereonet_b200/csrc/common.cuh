@@ -1,0 +1,98 @@
+// Shared definitions for the b200mvs kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace b200mvs {
+
+constexpr int kC = 32;            // feature channels everywhere (multi_view_stereonet.py:87)
+constexpr int kGroups = 4;        // GroupNorm(32 // 8, 32)  (multi_view_stereonet.py:25-31)
+constexpr float kGnEps = 1e-5f;
+constexpr float kLreluSlope = 0.2f;  // multi_view_stereonet.py:64
+
+void set_error(const std::string& msg);
+// Counts kernel launches of the current forward (api.cu).
+void note_launch();
+
+#define B200MVS_CUDA_OK(expr)                                                              \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      ::b200mvs::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));            \
+      return -2;                                                                           \
+    }                                                                                      \
+  } while (0)
+
+#define B200MVS_LAUNCH_OK(what)                                                            \
+  do {                                                                                     \
+    ::b200mvs::note_launch();                                                              \
+    cudaError_t _e = cudaPeekAtLastError();                                                \
+    if (_e != cudaSuccess) {                                                               \
+      ::b200mvs::set_error(std::string(what) + ": " + cudaGetErrorString(_e));             \
+      return -2;                                                                           \
+    }                                                                                      \
+  } while (0)
+
+__host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------------
+// Homography pixel transfer with the reference's float32 operation order.
+//
+// stereo/image_predictor.py:493-516 computes  p = H @ (x, y, 1)  with a float32 GEMM (each output
+// is the FMA chain  fma(h2, 1, fma(h1, y, h0 * x)) -- verified bit-exact against torch.matmul on
+// the CPU), divides by p.z with no epsilon, maps to grid_sample's normalised coordinate
+// u = ((px + 0.5) * 2) / size - 1  and masks where |u| > 1.  The mask is a hard threshold, so the
+// same roundings are reproduced here with explicit non-contracted intrinsics; out-of-image
+// decisions then agree with the reference wherever they are not decided by the last bit of H.
+// ---------------------------------------------------------------------------------------------
+struct WarpCoord {
+  float ix, iy;   // source coordinates in pixels, border-clamped to [0, size-1]
+  bool invalid;   // True = outside the image (reference mask convention)
+};
+
+__device__ __forceinline__ WarpCoord homography_coord(const float* __restrict__ H, float x, float y,
+                                                      int rows, int cols) {
+  const float X = __fadd_rn(__fmaf_rn(H[1], y, __fmul_rn(H[0], x)), H[2]);
+  const float Y = __fadd_rn(__fmaf_rn(H[4], y, __fmul_rn(H[3], x)), H[5]);
+  const float Z = __fadd_rn(__fmaf_rn(H[7], y, __fmul_rn(H[6], x)), H[8]);
+  const float px = __fdiv_rn(X, Z);
+  const float py = __fdiv_rn(Y, Z);
+  const float u = __fsub_rn(__fdiv_rn(__fmul_rn(__fadd_rn(px, 0.5f), 2.0f), (float)cols), 1.0f);
+  const float v = __fsub_rn(__fdiv_rn(__fmul_rn(__fadd_rn(py, 0.5f), 2.0f), (float)rows), 1.0f);
+  WarpCoord r;
+  r.invalid = (fabsf(u) > 1.0f) || (fabsf(v) > 1.0f);
+  // grid_sample(align_corners=False) un-normalisation as ATen's CPU kernel does it:
+  // (u + 1) * (size / 2) - 0.5, then border clipping to [0, size - 1].
+  float ix = __fsub_rn(__fmul_rn(__fadd_rn(u, 1.0f), 0.5f * (float)cols), 0.5f);
+  float iy = __fsub_rn(__fmul_rn(__fadd_rn(v, 1.0f), 0.5f * (float)rows), 0.5f);
+  r.ix = fminf(fmaxf(ix, 0.0f), (float)(cols - 1));
+  r.iy = fminf(fmaxf(iy, 0.0f), (float)(rows - 1));
+  return r;
+}
+
+struct Bilinear {
+  int x0, y0, x1, y1;
+  float w00, w01, w10, w11;  // (y0,x0) (y0,x1) (y1,x0) (y1,x1)
+};
+
+__device__ __forceinline__ Bilinear bilinear_setup(const WarpCoord& c, int rows, int cols) {
+  Bilinear b;
+  const float fx0 = floorf(c.ix), fy0 = floorf(c.iy);
+  const float we = c.ix - fx0, ws = c.iy - fy0;   // weight of the east / south neighbour
+  const float ww = 1.0f - we, wn = 1.0f - ws;
+  b.x0 = (int)fx0;
+  b.y0 = (int)fy0;
+  b.x1 = min(b.x0 + 1, cols - 1);   // the out-of-range neighbour always carries weight 0
+  b.y1 = min(b.y0 + 1, rows - 1);
+  b.w00 = wn * ww;
+  b.w01 = wn * we;
+  b.w10 = ws * ww;
+  b.w11 = ws * we;
+  return b;
+}
+
+__device__ __forceinline__ float lrelu(float v) { return v > 0.0f ? v : kLreluSlope * v; }
+
+}  // namespace b200mvs

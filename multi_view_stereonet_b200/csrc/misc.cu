@@ -1,0 +1,327 @@
+// Warps, cost build, soft-argmin, view reduction and upsampling kernels.
+#include "kernels.cuh"
+
+namespace b200mvs {
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// HomographyImagePredictor.forward on planar (NCHW) images; stereo/image_predictor.py:470-523.
+// One thread per output pixel, looping over channels; writes are coalesced along x.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) warp_planar_kernel(const float* __restrict__ H, int h_stride, ViewPtrs src,
+                                                          int channels, int rows, int cols, int zero_invalid,
+                                                          float* __restrict__ pred, uint8_t* __restrict__ mask) {
+  const int n = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= rows * cols) return;
+  const int x = p % cols, y = p / cols;
+  const float* Hn = H + (size_t)n * h_stride;
+  const WarpCoord c = homography_coord(Hn, (float)x, (float)y, rows, cols);
+  const Bilinear bl = bilinear_setup(c, rows, cols);
+  const size_t plane = (size_t)rows * cols;
+  const float* img = src.p[n % src.views] + (size_t)(n / src.views) * channels * plane;
+  if (mask != nullptr) mask[(size_t)n * plane + p] = c.invalid ? 1 : 0;
+  const bool zero = zero_invalid && c.invalid;
+  for (int ch = 0; ch < channels; ++ch) {
+    const float* pl = img + ch * plane;
+    float v = 0.f;
+    if (!zero) {
+      v = __ldg(pl + (size_t)bl.y0 * cols + bl.x0) * bl.w00 + __ldg(pl + (size_t)bl.y0 * cols + bl.x1) * bl.w01 +
+          __ldg(pl + (size_t)bl.y1 * cols + bl.x0) * bl.w10 + __ldg(pl + (size_t)bl.y1 * cols + bl.x1) * bl.w11;
+    }
+    pred[((size_t)n * channels + ch) * plane + p] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One recurrence step's warps (multi_view_stereonet.py:275, 285).  8 lanes per pixel, one float4
+// of the 32 feature channels each; lanes 0..2 additionally warp one plane of the 1/16 right image.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) step_warp_kernel(const float* __restrict__ vol, GeomOut geo, ViewPtrs right_l4,
+                                                        int D, int step, int rows, int cols,
+                                                        float* __restrict__ wf, float* __restrict__ wimg) {
+  const int n = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pixels = rows * cols;
+  const int p = i >> 3, q = i & 7;
+  if (p >= pixels) return;
+  const int x = p % cols, y = p / cols;
+  {
+    const float* Hinc = geo.Hinc + ((size_t)n * D + step) * 9;
+    const WarpCoord c = homography_coord(Hinc, (float)x, (float)y, rows, cols);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!c.invalid) {
+      const Bilinear bl = bilinear_setup(c, rows, cols);
+      const float* prev = vol + ((size_t)n * D + (step - 1)) * pixels * kC + 4 * q;
+      const float4 a = __ldg(reinterpret_cast<const float4*>(prev + ((size_t)bl.y0 * cols + bl.x0) * kC));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(prev + ((size_t)bl.y0 * cols + bl.x1) * kC));
+      const float4 cc = __ldg(reinterpret_cast<const float4*>(prev + ((size_t)bl.y1 * cols + bl.x0) * kC));
+      const float4 d = __ldg(reinterpret_cast<const float4*>(prev + ((size_t)bl.y1 * cols + bl.x1) * kC));
+      v.x = a.x * bl.w00 + b.x * bl.w01 + cc.x * bl.w10 + d.x * bl.w11;
+      v.y = a.y * bl.w00 + b.y * bl.w01 + cc.y * bl.w10 + d.y * bl.w11;
+      v.z = a.z * bl.w00 + b.z * bl.w01 + cc.z * bl.w10 + d.z * bl.w11;
+      v.w = a.w * bl.w00 + b.w * bl.w01 + cc.w * bl.w10 + d.w * bl.w11;
+    }
+    *reinterpret_cast<float4*>(wf + ((size_t)n * pixels + p) * kC + 4 * q) = v;
+  }
+  if (q < 3) {
+    const float* Hd = geo.H + ((size_t)n * D + step) * 9;
+    const WarpCoord c = homography_coord(Hd, (float)x, (float)y, rows, cols);
+    float v = 0.f;
+    if (!c.invalid) {
+      const Bilinear bl = bilinear_setup(c, rows, cols);
+      const float* pl = right_l4.p[n % right_l4.views] + ((size_t)(n / right_l4.views) * 3 + q) * pixels;
+      v = __ldg(pl + bl.y0 * cols + bl.x0) * bl.w00 + __ldg(pl + bl.y0 * cols + bl.x1) * bl.w01 +
+          __ldg(pl + bl.y1 * cols + bl.x0) * bl.w10 + __ldg(pl + bl.y1 * cols + bl.x1) * bl.w11;
+    }
+    wimg[((size_t)n * 3 + q) * pixels + p] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// cost = valid ? |L - R| : 0   and the mask volume  (multi_view_stereonet.py:293-298, 586-592).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cost_kernel(const float* __restrict__ left, const float* vol,
+                                                   const float* __restrict__ H, int views, int D, int rows, int cols,
+                                                   float* cost, uint8_t* __restrict__ mask) {
+  const int n = blockIdx.z, d = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pixels = rows * cols;
+  const int p = i >> 3, q = i & 7;
+  if (p >= pixels) return;
+  const WarpCoord c = homography_coord(H + ((size_t)n * D + d) * 9, (float)(p % cols), (float)(p / cols), rows, cols);
+  const size_t o = (((size_t)n * D + d) * pixels + p) * kC + 4 * q;
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!c.invalid) {
+    const float4 l = __ldg(reinterpret_cast<const float4*>(left + ((size_t)(n / views) * pixels + p) * kC + 4 * q));
+    const float4 v = *reinterpret_cast<const float4*>(vol + o);
+    r.x = fabsf(l.x - v.x);
+    r.y = fabsf(l.y - v.y);
+    r.z = fabsf(l.z - v.z);
+    r.w = fabsf(l.w - v.w);
+  }
+  *reinterpret_cast<float4*>(cost + o) = r;
+  if (q == 0) mask[((size_t)n * D + d) * pixels + p] = c.invalid ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) cost_norm_kernel(const float* __restrict__ cost, long long voxels,
+                                                        float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= voxels) return;
+  const float4* c = reinterpret_cast<const float4*>(cost + i * kC);
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < kC / 4; ++k) {
+    const float4 v = __ldg(c + k);
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  out[i] = sqrtf(s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Soft-argmin over the hypothesis axis (multi_view_stereonet.py:486-492).  One thread per pixel;
+// consecutive threads read consecutive pixels of each hypothesis plane.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) softargmin_kernel(const float* __restrict__ cost,
+                                                         const float* __restrict__ samples, int D, int pixels,
+                                                         float* __restrict__ raw) {
+  const int n = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= pixels) return;
+  const float* c = cost + (size_t)n * D * pixels + p;
+  float m = -INFINITY;
+  for (int d = 0; d < D; ++d) m = fmaxf(m, -__ldg(c + (size_t)d * pixels));
+  float den = 0.f;
+  for (int d = 0; d < D; ++d) den += expf(-__ldg(c + (size_t)d * pixels) - m);
+  float acc = 0.f;
+  for (int d = 0; d < D; ++d) {
+    const float pr = expf(-__ldg(c + (size_t)d * pixels) - m) / den;
+    acc += pr * __ldg(samples + (size_t)n * D + d);
+  }
+  raw[(size_t)n * pixels + p] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Baseline un-normalisation per view, mean over views, mask vote (multi_view_stereonet.py:616-627).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) view_reduce_kernel(const float* __restrict__ raw_views,
+                                                          const float* __restrict__ refined_views,
+                                                          const uint8_t* __restrict__ mask_views,
+                                                          const float* __restrict__ baseline, int views, int D,
+                                                          int pixels, int alias, float* __restrict__ raw4,
+                                                          float* __restrict__ idepth4, uint8_t* __restrict__ mask4) {
+  const int b = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= pixels) return;
+  float rs = 0.f, is = 0.f;
+  for (int v = 0; v < views; ++v) {
+    const int n = b * views + v;
+    const float bl = __ldg(baseline + n);
+    float r = __ldg(raw_views + (size_t)n * pixels + p);
+    float f;
+    if (alias) {
+      // do_refiners[4] == False: the reference's two in-place divisions hit the same tensor
+      // (multi_view_stereonet.py:613-619).
+      r = __fdiv_rn(__fdiv_rn(r, bl), bl);
+      f = r;
+    } else {
+      r = __fdiv_rn(r, bl);
+      f = __fdiv_rn(__ldg(refined_views + (size_t)n * pixels + p), bl);
+    }
+    rs += r;
+    is += f;
+  }
+  const float nv = (float)views;
+  if (raw4 != nullptr) raw4[(size_t)b * pixels + p] = __fdiv_rn(rs, nv);
+  idepth4[(size_t)b * pixels + p] = __fdiv_rn(is, nv);
+  for (int d = 0; d < D; ++d) {
+    float ms = 0.f;
+    for (int v = 0; v < views; ++v) ms += (float)__ldg(mask_views + ((size_t)(b * views + v) * D + d) * pixels + p);
+    mask4[((size_t)b * D + d) * pixels + p] = (__fdiv_rn(ms, nv) > 0.5f) ? 1 : 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bilinear resize, align_corners=False (ATen upsample_bilinear2d): src = scale*(dst+0.5)-0.5
+// clamped at 0, i1 = i0 + (i0 < in-1), l1 = src - i0.
+// ---------------------------------------------------------------------------------------------
+struct Lerp {
+  int i0, i1;
+  float l0, l1;
+};
+__device__ __forceinline__ Lerp lerp_setup(int dst, float scale, int in_size) {
+  float src = __fsub_rn(__fmul_rn(scale, __fadd_rn((float)dst, 0.5f)), 0.5f);
+  src = src < 0.f ? 0.f : src;
+  Lerp r;
+  r.i0 = (int)src;
+  if (r.i0 > in_size - 1) r.i0 = in_size - 1;
+  r.i1 = r.i0 + (r.i0 < in_size - 1 ? 1 : 0);
+  r.l1 = __fsub_rn(src, (float)r.i0);
+  r.l0 = __fsub_rn(1.0f, r.l1);
+  return r;
+}
+
+__global__ void __launch_bounds__(256) upsample_f32_kernel(const float* __restrict__ in, int h, int w, int H, int W,
+                                                           float* __restrict__ out) {
+  const int plane = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= H * W) return;
+  const int x = p % W, y = p / W;
+  const Lerp ly = lerp_setup(y, (float)h / (float)H, h);
+  const Lerp lx = lerp_setup(x, (float)w / (float)W, w);
+  const float* src = in + (size_t)plane * h * w;
+  const float v00 = __ldg(src + ly.i0 * w + lx.i0), v01 = __ldg(src + ly.i0 * w + lx.i1);
+  const float v10 = __ldg(src + ly.i1 * w + lx.i0), v11 = __ldg(src + ly.i1 * w + lx.i1);
+  out[(size_t)plane * H * W + p] = ly.l0 * (lx.l0 * v00 + lx.l1 * v01) + ly.l1 * (lx.l0 * v10 + lx.l1 * v11);
+}
+
+// Mask volume upsampling: float(mask) -> bilinear -> > 0.5 (multi_view_stereonet.py:389-396).
+// Each thread produces 4 horizontally adjacent outputs (one 32-bit store) when W % 4 == 0.
+template <int VEC>
+__global__ void __launch_bounds__(256) upsample_mask_kernel(const uint8_t* __restrict__ in, int h, int w, int H, int W,
+                                                            uint8_t* __restrict__ out) {
+  const long long plane = blockIdx.y;
+  const int wv = W / VEC;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * wv) return;
+  const int xv = i % wv, y = i / wv;
+  const Lerp ly = lerp_setup(y, (float)h / (float)H, h);
+  const uint8_t* r0 = in + (size_t)plane * h * w + (size_t)ly.i0 * w;
+  const uint8_t* r1 = in + (size_t)plane * h * w + (size_t)ly.i1 * w;
+  uint32_t packed = 0;
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    const Lerp lx = lerp_setup(xv * VEC + k, (float)w / (float)W, w);
+    const float v00 = (float)__ldg(r0 + lx.i0), v01 = (float)__ldg(r0 + lx.i1);
+    const float v10 = (float)__ldg(r1 + lx.i0), v11 = (float)__ldg(r1 + lx.i1);
+    const float v = ly.l0 * (lx.l0 * v00 + lx.l1 * v01) + ly.l1 * (lx.l0 * v10 + lx.l1 * v11);
+    packed |= (v > 0.5f ? 1u : 0u) << (8 * k);
+  }
+  uint8_t* dst = out + (size_t)plane * H * W + (size_t)y * W + xv * VEC;
+  if (VEC == 4) {
+    *reinterpret_cast<uint32_t*>(dst) = packed;
+  } else {
+    dst[0] = (uint8_t)packed;
+  }
+}
+
+}  // namespace
+
+int launch_warp_planar(const float* H, int h_stride, const ViewPtrs& src, int n, int channels, int rows, int cols,
+                       bool zero_invalid, float* pred, uint8_t* mask, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  dim3 grid(cdiv(rows * cols, 256), n);
+  warp_planar_kernel<<<grid, 256, 0, stream>>>(H, h_stride, src, channels, rows, cols, zero_invalid ? 1 : 0, pred,
+                                               mask);
+  B200MVS_LAUNCH_OK("warp_planar_kernel");
+  return 0;
+}
+
+int launch_step_warp(const float* vol, const GeomOut& geo, const ViewPtrs& right_l4, int n, int D, int step,
+                     int rows, int cols, float* wf, float* wimg, cudaStream_t stream) {
+  dim3 grid(cdiv(rows * cols * 8, 256), n);
+  step_warp_kernel<<<grid, 256, 0, stream>>>(vol, geo, right_l4, D, step, rows, cols, wf, wimg);
+  B200MVS_LAUNCH_OK("step_warp_kernel");
+  return 0;
+}
+
+int launch_cost(const float* left_feat4, const float* vol, const float* H, int n, int views, int D, int rows,
+                int cols, float* cost, uint8_t* mask, cudaStream_t stream) {
+  dim3 grid(cdiv(rows * cols * 8, 256), D, n);
+  cost_kernel<<<grid, 256, 0, stream>>>(left_feat4, vol, H, views, D, rows, cols, cost, mask);
+  B200MVS_LAUNCH_OK("cost_kernel");
+  return 0;
+}
+
+int launch_cost_norm(const float* cost, long long voxels, float* out, cudaStream_t stream) {
+  cost_norm_kernel<<<(unsigned)((voxels + 255) / 256), 256, 0, stream>>>(cost, voxels, out);
+  B200MVS_LAUNCH_OK("cost_norm_kernel");
+  return 0;
+}
+
+int launch_softargmin(const float* cost, const float* samples, int n, int D, int pixels, float* raw,
+                      cudaStream_t stream) {
+  dim3 grid(cdiv(pixels, 128), n);
+  softargmin_kernel<<<grid, 128, 0, stream>>>(cost, samples, D, pixels, raw);
+  B200MVS_LAUNCH_OK("softargmin_kernel");
+  return 0;
+}
+
+int launch_view_reduce(const float* raw_views, const float* refined_views, const uint8_t* mask_views,
+                       const float* baseline, int batch, int views, int D, int pixels, bool refined_is_alias,
+                       float* raw4, float* idepth4, uint8_t* mask4, cudaStream_t stream) {
+  dim3 grid(cdiv(pixels, 128), batch);
+  view_reduce_kernel<<<grid, 128, 0, stream>>>(raw_views, refined_views, mask_views, baseline, views, D, pixels,
+                                               refined_is_alias ? 1 : 0, raw4, idepth4, mask4);
+  B200MVS_LAUNCH_OK("view_reduce_kernel");
+  return 0;
+}
+
+int launch_upsample_f32(const float* in, int n_planes, int h, int w, int H, int W, float* out, cudaStream_t stream) {
+  dim3 grid(cdiv(H * W, 256), n_planes);
+  upsample_f32_kernel<<<grid, 256, 0, stream>>>(in, h, w, H, W, out);
+  B200MVS_LAUNCH_OK("upsample_f32_kernel");
+  return 0;
+}
+
+int launch_upsample_mask(const uint8_t* in, long long n_planes, int h, int w, int H, int W, uint8_t* out,
+                         cudaStream_t stream) {
+  // gridDim.y is limited to 65535 planes per launch.
+  const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 3) == 0) && (((long long)H * W) % 4 == 0);
+  for (long long p0 = 0; p0 < n_planes; p0 += 65535) {
+    const int np = (int)((n_planes - p0) < 65535 ? (n_planes - p0) : 65535);
+    const uint8_t* src = in + (size_t)p0 * h * w;
+    uint8_t* dst = out + (size_t)p0 * H * W;
+    if (vec) {
+      dim3 grid(cdiv(H * (W / 4), 256), np);
+      upsample_mask_kernel<4><<<grid, 256, 0, stream>>>(src, h, w, H, W, dst);
+    } else {
+      dim3 grid(cdiv(H * W, 256), np);
+      upsample_mask_kernel<1><<<grid, 256, 0, stream>>>(src, h, w, H, W, dst);
+    }
+    B200MVS_LAUNCH_OK("upsample_mask_kernel");
+  }
+  return 0;
+}
+
+}  // namespace b200mvs
