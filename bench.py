@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Benchmark of the MultiViewStereoNet depth-inference hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch-per-gpu B]
+
+Metric (BASELINE.json): depthmaps/sec at 512x640, 2-view (1 comparison view), 64 idepth
+hypotheses.  One "step" is one MultiViewStereoNet.forward over one batch of synthetic image groups
+(BASELINE cfg2: batch 1 per GPU).  For N > 1 the driver launches this file under torchrun; every
+rank runs the same per-GPU workload on its own seeded items (weak scaling, no data-path collective)
+and rank 0 prints ONE JSON line.
+
+--impl reference times the reference's CPU implementation of the path: the reference is pure
+PyTorch and cannot travel to the GPU box, so this is the oracle port (oracle/mvsnet_oracle.py, pinned
+to the reference's outputs by tests/test_oracle.py) on all host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+import torch  # noqa: E402
+
+ROWS, COLS, VIEWS, HYPS = 512, 640, 1, 64       # BASELINE cfg2 / cfg4 per-item shape
+METRIC = "depthmaps/sec at 512x640, 2-view, 64 hyp"
+UNIT = "depthmaps/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def load_state():
+    """Pretrained GTA-SfM weights if the fixture is present, else seeded random weights of the same
+    architecture (timing does not depend on the values)."""
+    from multi_view_stereonet_b200 import weights
+    path = os.path.join(REPO, "tests", "golden", "gta_sfm_150epochs_state.npz")
+    if os.path.exists(path):
+        sd = weights.load_state_npz(path)
+        fe = "left_feature_extractor."
+        for k in [k for k in sd if k.startswith(fe)]:
+            sd["right_feature_extractor.feature_extractor." + k[len(fe):]] = sd[k]
+        return sd, "pretrained gta_sfm_150epochs (reference fixture)"
+    return weights.seeded_random_state(0), "seeded random"
+
+
+def algorithmic_work(rows, cols, views, hyps):
+    """MACs and layerwise-compulsory fp32 bytes per depthmap."""
+    h, w = [rows], [cols]
+    for _ in range(4):
+        h.append((h[-1] + 1) // 2)
+        w.append((w[-1] + 1) // 2)
+    P = [a * b for a, b in zip(h, w)]
+    V, D = views, hyps
+    mac = (1 + V) * (P[1] * 3 * 32 * 25 + (P[2] + P[3] + P[4]) * 32 * 32 * 25 + 7 * P[4] * 32 * 32 * 9)
+    mac += V * (D - 1) * P[4] * (35 * 32 * 9 + 2 * 32 * 32 * 9)
+    mac += V * D * P[4] * (4 * 32 * 32 * 27 + 32 * 27)
+    byt = (1 + V) * 4 * ((3 * P[0] + 32 * P[1]) + 32 * (P[1] + P[2]) + 32 * (P[2] + P[3]) + 32 * (P[3] + P[4]) + 7 * 64 * P[4])
+    byt += V * 4 * (6 * P[0] + 3 * P[4] + 3 * D * P[4])
+    byt += V * (D - 1) * 4 * P[4] * (64 + 67 + 64 + 64)
+    byt += V * 4 * (32 * P[4] + 64 * D * P[4])
+    byt += V * 4 * D * P[4] * (4 * 64 + 33)
+    byt += V * 4 * (D * P[4] + P[4])
+    for lvl in range(5):
+        cin = 4 if lvl == 0 else 36
+        mult = V if lvl == 4 else 1
+        mac += mult * P[lvl] * (cin * 32 * 9 + 6 * 32 * 32 * 9 + 32 * 9)
+        byt += mult * 4 * P[lvl] * ((cin + 32) + 6 * 64 + 33)
+    return mac, byt, P
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons with nvidia-smi while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag.is_set():
+                    break
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag.set()
+        if self.proc is not None:
+            self.proc.terminate()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, s[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_throughput(state, steps, warmup, budget_s=25.0):
+    """The oracle port on all host cores; returns (depthmaps/s, ms per depthmap, cores, runs)."""
+    from oracle import mvsnet_oracle as oracle
+    from multi_view_stereonet_b200 import synthetic
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    inputs = synthetic.make_inputs(ROWS, COLS, VIEWS, 1)
+    times = []
+    with torch.no_grad():
+        for _ in range(warmup):
+            oracle.forward(state, *inputs, HYPS, True, (True,) * 5)
+        t_begin = time.perf_counter()
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            oracle.forward(state, *inputs, HYPS, True, (True,) * 5)
+            times.append(time.perf_counter() - t0)
+            if time.perf_counter() - t_begin > budget_s:
+                break
+    ms = 1e3 * sum(times) / len(times)
+    return 1e3 / ms, ms, cores, len(times)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    state, wsrc = load_state()
+    dmps, ms, cores, runs = cpu_oracle_throughput(state, args.steps, max(1, min(args.warmup, 2)), budget_s=150.0)
+    sample = f"{runs} full forwards of one 512x640 / 1 comparison view / 64 hypotheses image group (batch 1)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": dmps, "unit": UNIT, "n_gpus": args.gpus, "steps": runs,
+        "warmup": max(1, min(args.warmup, 2)), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2: 512x640, 1 comparison view, 64 idepth hypotheses, batch 1", "weights": wsrc,
+                   "device": "host CPU (torch %s, %d threads)" % (torch.__version__, cores)},
+        "cpu_baseline": {"value": dmps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": dmps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from multi_view_stereonet_b200 import MultiViewStereoNet, synthetic
+
+    assert torch.cuda.is_available(), "bench.py --impl ours needs a CUDA device (there is no CPU path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    state, wsrc = load_state()
+    net = MultiViewStereoNet()
+    net.load_state_dict(state, strict=True)
+    net = net.to(dev).eval()
+
+    B = args.batch_per_gpu
+    cpu_inputs = synthetic.make_inputs(ROWS, COLS, VIEWS, B, first_item=rank * B)
+    inputs = synthetic.to_device(cpu_inputs, dev)
+    flags = (HYPS, True, [True] * 5)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput ("value") ----
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            net(*inputs, *flags)
+        launches_per_step = net.last_launch_count()
+        net.probe_select("refine_conv32_l0")
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        time.sleep(0.3)
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        barrier()
+        wall0 = time.perf_counter()
+        for i in range(args.steps):
+            flush.zero_()                      # evict L2 between timed iterations (outside the event pair)
+            starts[i].record()
+            out = net(*inputs, *flags)
+            ends[i].record()
+        barrier()
+        wall = time.perf_counter() - wall0
+        step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+        probe_ms, probe_launches = net.probe_read()
+        net.probe_select("none")
+        time.sleep(0.2)
+        sampler.stop()
+    total_ms = sum(step_ms)
+
+    # ---- end to end through the host entry: pinned inputs -> H2D -> forward -> D2H ----
+    pin = lambda t: t.pin_memory()
+    host_inputs = ([pin(t) for t in cpu_inputs[0]], [pin(t) for t in cpu_inputs[1]], [pin(t) for t in cpu_inputs[2]],
+                   [[pin(t) for t in p] for p in cpu_inputs[3]])
+    host_out = {"left_idepthmap_pyr": [torch.empty((B, 1) + tuple(t.shape[-2:]), dtype=torch.float32).pin_memory()
+                                       for t in cpu_inputs[0]]}
+    net.set_host_outputs(host_out)
+    e2e_steps = args.steps
+    with torch.no_grad():
+        for _ in range(3):
+            net(*host_inputs, *flags)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            net(*host_inputs, *flags)          # synchronous: returns after the D2H copy
+        torch.cuda.synchronize(dev)
+        e2e_s = time.perf_counter() - t0
+    net.set_host_outputs(None)
+    h2d, d2h = net.last_h2d_bytes, net.last_d2h_bytes
+
+    # ---- max over ranks ----
+    mine = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        gathered = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)          # the path's only collective: per-rank timings
+        allt = torch.stack(gathered).cpu()
+    else:
+        allt = mine.cpu().unsqueeze(0)
+    worst_ms = float(allt[:, 0].max())
+    worst_e2e_ms = float(allt[:, 1].max())
+
+    if rank == 0:
+        mac, byt, P = algorithmic_work(ROWS, COLS, VIEWS, HYPS)
+        peaks = {}
+        ppath = os.path.join(REPO, "MEASURED_PEAKS.json")
+        peak_src = "fallback (B200_PROFILING.md)"
+        hbm_peak = 6650.0
+        if os.path.exists(ppath):
+            peaks = json.load(open(ppath))
+            hbm_peak = float(peaks.get("hbm_gbs", hbm_peak))
+            peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+        # dominant kernel: the 3x3 32->32 refiner convolution at level 0; algorithmic bytes per launch
+        # = one fp32 read + one fp32 write of a (B, 512, 640, 32) activation
+        k_bytes = B * P[0] * 64 * 4
+        k_ms = probe_ms / max(probe_launches, 1)
+        achieved = k_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
+        value = world * B * args.steps / (worst_ms * 1e-3)
+        e2e_value = world * B * e2e_steps / (worst_e2e_ms * 1e-3)
+        t_roof_us = max(byt / (hbm_peak * 1e9), 2 * mac / (0.5 * float(peaks.get("bf16_tflops", 1590.0)) * 1e12)) * 1e6
+
+        cpu = None
+        if world >= 1:
+            dmps, ms, cores, runs = cpu_oracle_throughput(state, 20, 1, budget_s=15.0)
+            cpu = {"value": dmps, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{runs} full forwards of one cfg2 image group (oracle/mvsnet_oracle.py, torch CPU, "
+                             f"{cores} threads), {ms:.0f} ms each"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": worst_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"cfg2: 512x640, 1 comparison view, 64 idepth hypotheses, batch {B} per GPU",
+                       "global_batch": world * B, "parallelism": f"dp{world} (independent image groups, no data-path "
+                       "collective; one all_gather of timings)", "weights": wsrc,
+                       "l2": "256 MiB buffer written between timed steps (outside the event pairs)",
+                       "timing": "CUDA events per step on the launch stream, max over ranks of the per-rank sum",
+                       "wall_s_incl_flush": wall},
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": worst_e2e_ms / e2e_steps,
+                    "what": "MultiViewStereoNet.forward on pinned CPU tensors -> b200mvs_forward_host: H2D of the "
+                            "image pyramids/K/T, full path incl. mask volumes on device, D2H of the 5-level idepth "
+                            "pyramid"},
+            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches_per_step": launches_per_step,
+            "roofline": {"bound": "hbm", "kernel": "conv_kernel<3x3,32->32> (refiner0 residual convs, level 0)",
+                         "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": (achieved / hbm_peak) if achieved else None, "traffic": None,
+                         "peak_source": peak_src, "kernel_ms": k_ms, "kernel_launches": probe_launches,
+                         "algorithmic_bytes_per_launch": k_bytes,
+                         "kernel_share_of_step": probe_ms / total_ms if total_ms > 0 else None},
+            "whole_path": {"algorithmic_gflop_per_depthmap": 2 * mac / 1e9, "algorithmic_mb_per_depthmap": byt / 1e6,
+                           "roofline_us_per_depthmap": t_roof_us,
+                           "frac_of_roofline": t_roof_us / (worst_ms / args.steps / B * 1e3)},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch-per-gpu", type=int, default=1)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        # Launched without torchrun: re-exec under it so that `python bench.py --gpus N` works too.
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"), __file__,
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
+               "--batch-per-gpu", str(args.batch_per_gpu)]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -94,6 +94,16 @@ B200MVS_API int b200mvs_forward_host(b200mvs_net* net, const b200mvs_shape* shap
                          float* const* out_idepth, float* const* out_idepth_raw, uint8_t* const* out_mask,
                          int64_t* h2d_bytes, int64_t* d2h_bytes);
 
+/* Per-kernel-class device timing of the forwards issued since the last reset: when a class is
+ * selected, every launch of that class is bracketed by CUDA events on the launch stream.  Classes:
+ *   "refine_conv32_l0"  the 3x3 32->32 (dilated) convolutions of refiner0 at level 0 (6 per forward)
+ *   "cvf_conv32"        the 3x3x3 32->32 convolutions of the cost-volume filter (4 per forward)
+ *   "none"              disable
+ * b200mvs_probe_read synchronises the recorded events, returns their summed duration in ms and the
+ * number of launches, and resets the accumulation. */
+B200MVS_API int b200mvs_probe_select(b200mvs_net* net, const char* kernel_class);
+B200MVS_API int b200mvs_probe_read(b200mvs_net* net, double* total_ms, int64_t* launches);
+
 /* Number of kernels the last b200mvs_forward on this handle launched. */
 B200MVS_API int64_t b200mvs_last_launch_count(const b200mvs_net* net);
 

@@ -30,6 +30,9 @@ SYMBOLS = {
     "b200mvs_forward_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Shape)]
                              + [ctypes.POINTER(ctypes.c_void_p)] * 8
                              + [ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
+    "b200mvs_probe_select": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p]),
+    "b200mvs_probe_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double),
+                                          ctypes.POINTER(ctypes.c_int64)]),
     "b200mvs_last_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "b200mvs_get_stage": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64,
                                          ctypes.POINTER(ctypes.c_int64), ctypes.c_void_p]),

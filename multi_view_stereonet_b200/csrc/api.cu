@@ -15,6 +15,28 @@ static thread_local int64_t g_launches = 0;
 void set_error(const std::string& msg) { g_error = msg; }
 void note_launch() { ++g_launches; }
 
+// Event-pair probe around launches of one kernel class (b200mvs_probe_select).
+struct Probe {
+  int tag = 0;
+  std::vector<cudaEvent_t> ev;  // pairs
+  size_t used = 0;
+  cudaEvent_t next() {
+    if (used == ev.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      ev.push_back(e);
+    }
+    return ev[used++];
+  }
+};
+static thread_local Probe* g_probe = nullptr;
+void probe_before(int tag, cudaStream_t stream) {
+  if (g_probe != nullptr && g_probe->tag == tag) cudaEventRecord(g_probe->next(), stream);
+}
+void probe_after(int tag, cudaStream_t stream) {
+  if (g_probe != nullptr && g_probe->tag == tag) cudaEventRecord(g_probe->next(), stream);
+}
+
 namespace {
 
 struct ConvW {
@@ -95,6 +117,10 @@ struct b200mvs_net {
 
   Arena arena;
   Workspace ws;
+  Probe probe;
+  // device staging of b200mvs_forward_host (inputs, outputs), grown on demand
+  char* host_stage = nullptr;
+  size_t host_stage_bytes = 0;
   b200mvs_shape ws_shape{};
   bool ws_valid = false;
   bool keep_stages = false;
@@ -334,7 +360,7 @@ struct StatsCursor {
 // (:607-611) folded into the first loader and the last epilogue.
 int run_refiner(b200mvs_net* net, const Refiner& R, StatsCursor& sc, int m, int H, int W, const float* guide_feat,
                 int guide_div, const float* image, int image_div, const float* prior, const float* Kl, int k_div,
-                float* out, cudaStream_t stream) {
+                float* out, int res_tag, cudaStream_t stream) {
   Workspace& ws = net->ws;
   const size_t P = (size_t)H * W;
   const double inv_count = 1.0 / (8.0 * (double)P);
@@ -392,6 +418,7 @@ int run_refiner(b200mvs_net* net, const Refiner& R, StatsCursor& sc, int m, int 
     q.dil = dilations[i];
     q.out = ws.ry[1 - ycur];
     q.out_stats = sc.take(m);
+    q.tag = res_tag;
     RC(launch_conv(CONV_3x3, 32, q, stream));
     st_prev = q.out_stats;
     gn_prev = &R.gn[i];
@@ -451,6 +478,7 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
   const int h4 = L.h[4], w4 = L.w[4];
   const size_t P4 = L.px[4];
   g_launches = 0;
+  g_probe = net->probe.tag != 0 ? &net->probe : nullptr;
 
   B200MVS_CUDA_OK(cudaMemsetAsync(ws.stats, 0, ws.stats_count * sizeof(double), stream));
   StatsCursor sc{ws.stats, 0, ws.stats_count};
@@ -645,6 +673,7 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
       if (i < 4) {
         p.out = bufs[i & 1];
         p.out_stats = sc.take(n);
+        p.tag = TAG_CVF_CONV32;
         RC(launch_conv(CONV_3x3x3, 32, p, stream));
         src = p.out;
         st_prev = p.out_stats;
@@ -663,7 +692,7 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
   // 9. level-4 refiner per view (:605-613)
   if (s.do_refiners[4]) {
     RC(run_refiner(net, net->refiner[4], sc, n, h4, w4, ws.feat4, V, left_pyr[4], V, ws.raw_views, K_pyr[4], V,
-                   ws.refined_views, stream));
+                   ws.refined_views, TAG_NONE, stream));
   }
 
   // 10. baseline un-normalisation, mean over views, mask vote (:616-627)
@@ -689,7 +718,7 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
     if (s.do_refiners[l]) {
       const float* guide = (l == 0) ? nullptr : (l == 1 ? ws.f1 : (l == 2 ? ws.f2 : ws.f3));
       RC(run_refiner(net, net->refiner[l], sc, B, L.h[l], L.w[l], guide, 1, left_pyr[l], 1, prior_l[l], K_pyr[l], 1,
-                     idepth_l[l], stream));
+                     idepth_l[l], l == 0 ? TAG_REFINE_CONV32_L0 : TAG_NONE, stream));
     } else {
       B200MVS_CUDA_OK(cudaMemcpyAsync(idepth_l[l], prior_l[l], (size_t)B * L.px[l] * sizeof(float),
                                       cudaMemcpyDeviceToDevice, stream));
@@ -753,6 +782,8 @@ B200MVS_API void b200mvs_destroy(b200mvs_net* net) {
   cudaSetDevice(net->device);
   for (void* p : net->allocs) cudaFree(p);
   if (net->arena.base != nullptr) cudaFree(net->arena.base);
+  if (net->host_stage != nullptr) cudaFree(net->host_stage);
+  for (cudaEvent_t e : net->probe.ev) cudaEventDestroy(e);
   delete net;
 }
 
@@ -762,6 +793,38 @@ B200MVS_API int b200mvs_set_debug(b200mvs_net* net, int keep_stages) {
     net->keep_stages = keep_stages != 0;
     net->ws_valid = false;  // layout changes
   }
+  return 0;
+}
+
+B200MVS_API int b200mvs_probe_select(b200mvs_net* net, const char* kernel_class) {
+  if (net == nullptr || kernel_class == nullptr) return B200MVS_EINVAL;
+  const std::string k(kernel_class);
+  int tag;
+  if (k == "none") tag = TAG_NONE;
+  else if (k == "refine_conv32_l0") tag = TAG_REFINE_CONV32_L0;
+  else if (k == "cvf_conv32") tag = TAG_CVF_CONV32;
+  else {
+    set_error("b200mvs_probe_select: unknown kernel class '" + k + "'");
+    return B200MVS_EINVAL;
+  }
+  net->probe.tag = tag;
+  net->probe.used = 0;
+  return 0;
+}
+
+B200MVS_API int b200mvs_probe_read(b200mvs_net* net, double* total_ms, int64_t* launches) {
+  if (net == nullptr) return B200MVS_EINVAL;
+  double total = 0.0;
+  const size_t pairs = net->probe.used / 2;
+  for (size_t i = 0; i < pairs; ++i) {
+    B200MVS_CUDA_OK(cudaEventSynchronize(net->probe.ev[2 * i + 1]));
+    float ms = 0.f;
+    B200MVS_CUDA_OK(cudaEventElapsedTime(&ms, net->probe.ev[2 * i], net->probe.ev[2 * i + 1]));
+    total += ms;
+  }
+  if (total_ms != nullptr) *total_ms = total;
+  if (launches != nullptr) *launches = (int64_t)pairs;
+  net->probe.used = 0;
   return 0;
 }
 
@@ -807,12 +870,25 @@ B200MVS_API int b200mvs_forward_host(b200mvs_net* net, const b200mvs_shape* shap
     out_f += 2 * B * L.px[l];
     out_m += B * D * L.px[l];
   }
-  float* din = nullptr;
-  float* dof = nullptr;
-  uint8_t* dom = nullptr;
-  B200MVS_CUDA_OK(cudaMalloc(&din, in_floats * sizeof(float)));
-  B200MVS_CUDA_OK(cudaMalloc(&dof, out_f * sizeof(float)));
-  B200MVS_CUDA_OK(cudaMalloc(&dom, out_m));
+  const size_t in_bytes = (in_floats * sizeof(float) + 255) & ~(size_t)255;
+  const size_t of_bytes = (out_f * sizeof(float) + 255) & ~(size_t)255;
+  const size_t need = in_bytes + of_bytes + out_m;
+  if (need > net->host_stage_bytes) {
+    if (net->host_stage != nullptr) {
+      B200MVS_CUDA_OK(cudaDeviceSynchronize());
+      B200MVS_CUDA_OK(cudaFree(net->host_stage));
+      net->host_stage = nullptr;
+      net->host_stage_bytes = 0;
+    }
+    if (cudaMalloc(reinterpret_cast<void**>(&net->host_stage), need) != cudaSuccess) {
+      set_error("b200mvs_forward_host: staging allocation failed");
+      return B200MVS_ENOMEM;
+    }
+    net->host_stage_bytes = need;
+  }
+  float* din = reinterpret_cast<float*>(net->host_stage);
+  float* dof = reinterpret_cast<float*>(net->host_stage + in_bytes);
+  uint8_t* dom = reinterpret_cast<uint8_t*>(net->host_stage + in_bytes + of_bytes);
   cudaStream_t stream = nullptr;
   int64_t h2d = 0, d2h = 0;
   int rc = 0;
@@ -846,7 +922,7 @@ B200MVS_API int b200mvs_forward_host(b200mvs_net* net, const b200mvs_shape* shap
       c += B * L.px[l];
       orw[l] = c;
       c += B * L.px[l];
-      om[l] = (out_mask != nullptr && out_mask[l] != nullptr) ? m : nullptr;
+      om[l] = m;  // masks are always computed (the reference always returns them)
       m += B * D * L.px[l];
     }
   }
@@ -861,7 +937,7 @@ B200MVS_API int b200mvs_forward_host(b200mvs_net* net, const b200mvs_shape* shap
         cudaMemcpyAsync(out_idepth_raw[l], orw[l], B * L.px[l] * sizeof(float), cudaMemcpyDeviceToHost, stream);
         d2h += (int64_t)(B * L.px[l] * sizeof(float));
       }
-      if (om[l] != nullptr) {
+      if (out_mask != nullptr && out_mask[l] != nullptr) {
         cudaMemcpyAsync(out_mask[l], om[l], B * D * L.px[l], cudaMemcpyDeviceToHost, stream);
         d2h += (int64_t)(B * D * L.px[l]);
       }
@@ -875,9 +951,6 @@ B200MVS_API int b200mvs_forward_host(b200mvs_net* net, const b200mvs_shape* shap
     cudaStreamSynchronize(stream);
     if (rc == -2 && g_error.empty()) set_error("b200mvs_forward_host: upload failed");
   }
-  cudaFree(din);
-  cudaFree(dof);
-  cudaFree(dom);
   if (h2d_bytes != nullptr) *h2d_bytes = h2d;
   if (d2h_bytes != nullptr) *d2h_bytes = d2h;
   return rc;

@@ -334,7 +334,9 @@ int launch_cfg(const ConvParams& p, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid(cdiv(p.Wo, TW) * cdiv(p.Ho, TH) * cdiv(p.Do, TD), p.n_img);
+  if (p.tag != TAG_NONE) probe_before(p.tag, stream);
   conv_kernel<KD, KH, KW, S, COUT, TD, TH, TW, PXT, CSPLIT><<<grid, C::NT, smem, stream>>>(p);
+  if (p.tag != TAG_NONE) probe_after(p.tag, stream);
   B200MVS_LAUNCH_OK("conv_kernel");
   return 0;
 }

@@ -60,7 +60,14 @@ struct ConvParams {
   const float* prior = nullptr;  // [img][Ho][Wo]
   const float* fx = nullptr;     // fx[(img / fx_div) * fx_stride]
   int fx_div = 1, fx_stride = 1;
+  int tag = 0;                   // kernel class for b200mvs_probe_select (host side only)
 };
+
+enum ConvTag : int { TAG_NONE = 0, TAG_REFINE_CONV32_L0 = 1, TAG_CVF_CONV32 = 2 };
+
+// Host hooks called immediately before / after a tagged launch (api.cu).
+void probe_before(int tag, cudaStream_t stream);
+void probe_after(int tag, cudaStream_t stream);
 
 enum ConvKind : int { CONV_3x3 = 0, CONV_5x5_S2 = 1, CONV_3x3x3 = 2 };
 

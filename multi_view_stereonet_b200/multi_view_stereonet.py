@@ -118,6 +118,7 @@ class MultiViewStereoNet(tnn.Module):
         self._handle = None
         self._handle_key = None
         self._keep_stages = False
+        self._host_out = None
 
     # -- native handle ---------------------------------------------------------------------
     def _weights_key(self, device_index):
@@ -172,6 +173,18 @@ class MultiViewStereoNet(tnn.Module):
         _lib.check(lib.b200mvs_get_stage(self._handle, name.encode(), buf.data_ptr(), nbytes.value,
                                          ctypes.byref(nbytes), stream), "b200mvs_get_stage")
         return buf.view(dtype)
+
+    def probe_select(self, kernel_class):
+        """Brackets every launch of `kernel_class` with CUDA events (bench.py roofline leg)."""
+        assert self._handle is not None, "run a forward first"
+        _lib.check(_lib.load().b200mvs_probe_select(self._handle, kernel_class.encode()), "b200mvs_probe_select")
+
+    def probe_read(self):
+        """(summed device ms, launches) of the selected class since the last read."""
+        ms, n = ctypes.c_double(), ctypes.c_int64()
+        _lib.check(_lib.load().b200mvs_probe_read(self._handle, ctypes.byref(ms), ctypes.byref(n)),
+                   "b200mvs_probe_read")
+        return ms.value, n.value
 
     def last_launch_count(self):
         return int(_lib.load().b200mvs_last_launch_count(self._handle)) if self._handle is not None else 0
@@ -245,14 +258,24 @@ class MultiViewStereoNet(tnn.Module):
         b, d = shape.batch, shape.num_idepth_samples
         out_dev = torch.device("cpu") if on_host else dev
         sizes = [tuple(t.shape[-2:]) for t in left]
-        idepth = [torch.empty((b, 1) + s, dtype=torch.float32, device=out_dev) for s in sizes]
-        raw = [torch.empty((b, 1) + s, dtype=torch.float32, device=out_dev) for s in sizes]
-        mask = [torch.empty((b, d) + s, dtype=torch.uint8, device=out_dev) for s in sizes]
+        want_raw, want_masks = True, True
+        if on_host and self._host_out is not None:
+            # bench.py's end-to-end leg: caller-provided (pinned) outputs, possibly a subset
+            idepth = self._host_out["left_idepthmap_pyr"]
+            raw = self._host_out.get("left_idepthmap_raw_pyr")
+            mask = self._host_out.get("left_idepthmap_mask_pyr")
+            want_raw, want_masks = raw is not None, mask is not None
+        else:
+            idepth = [torch.empty((b, 1) + s, dtype=torch.float32, device=out_dev) for s in sizes]
+            raw = [torch.empty((b, 1) + s, dtype=torch.float32, device=out_dev) for s in sizes]
+            mask = [torch.empty((b, d) + s, dtype=torch.uint8, device=out_dev) for s in sizes]
+        null5 = _lib.ptr_array([None] * 5)
         args = [ctypes.byref(shape),
                 _lib.ptr_array([t.data_ptr() for t in left]), _lib.ptr_array([t.data_ptr() for t in Ks]),
                 _lib.ptr_array([t.data_ptr() for t in Ts]), _lib.ptr_array([t.data_ptr() for t in r0]),
                 _lib.ptr_array([t.data_ptr() for t in r4]), _lib.ptr_array([t.data_ptr() for t in idepth]),
-                _lib.ptr_array([t.data_ptr() for t in raw]), _lib.ptr_array([t.data_ptr() for t in mask])]
+                _lib.ptr_array([t.data_ptr() for t in raw]) if want_raw else null5,
+                _lib.ptr_array([t.data_ptr() for t in mask]) if want_masks else null5]
         if on_host:
             h2d, d2h = ctypes.c_int64(), ctypes.c_int64()
             _lib.check(lib.b200mvs_forward_host(handle, *args, ctypes.byref(h2d), ctypes.byref(d2h)),
@@ -265,6 +288,14 @@ class MultiViewStereoNet(tnn.Module):
 
         outputs: Dict[str, List[Optional[torch.Tensor]]] = {}
         outputs["left_idepthmap_pyr"] = idepth
-        outputs["left_idepthmap_raw_pyr"] = raw
-        outputs["left_idepthmap_mask_pyr"] = [m.view(torch.bool) for m in mask]
+        outputs["left_idepthmap_raw_pyr"] = raw if want_raw else [None] * 5
+        outputs["left_idepthmap_mask_pyr"] = ([m.view(torch.bool) if m.dtype == torch.uint8 else m for m in mask]
+                                              if want_masks else [None] * 5)
         return outputs
+
+    def set_host_outputs(self, out):
+        """For CPU-tensor calls: write results into the given (pinned) tensors instead
+        of allocating.  `out` maps "left_idepthmap_pyr" (required) and optionally
+        "left_idepthmap_raw_pyr" / "left_idepthmap_mask_pyr" (uint8) to 5-lists; lists
+        left out are computed on the device but not downloaded.  None restores the default."""
+        self._host_out = out
