@@ -120,6 +120,18 @@ B200MVS_API int b200mvs_get_stage(b200mvs_net* net, const char* name, void* dst,
 /* keep_stages != 0 makes the forward preserve buffers it would otherwise overwrite in place. */
 B200MVS_API int b200mvs_set_debug(b200mvs_net* net, int keep_stages);
 
+/* Options: "tensor_cores" (default 1) -- run the 3x3 32->32 refiner convolutions of levels 0-2 on the
+ * tcgen05 tensor cores with fp16 operands / fp32 accumulation; 0 keeps every layer on the fp32 path. */
+B200MVS_API int b200mvs_set_option(b200mvs_net* net, const char* name, int value);
+
+/* Stage entry for kernel parity tests: y = conv3x3(x, dilation, padding = dilation) + bias on a
+ * channels-last (n, rows, cols, 32) DEVICE tensor; `w_oihw_host` (32,32,3,3) and `bias_host` (32 or
+ * NULL) are HOST pointers.  use_tensor_cores selects the tcgen05 kernel or the fp32 one.
+ * Synchronises `stream` before returning. */
+B200MVS_API int b200mvs_conv3x3_c32(const float* x, const float* w_oihw_host, const float* bias_host, int32_t n,
+                                    int32_t rows, int32_t cols, int32_t dilation, int32_t use_tensor_cores, float* y,
+                                    void* stream);
+
 /* HomographyImagePredictor.forward (stereo/image_predictor.py:470-523) on DEVICE pointers:
  * H (N,3,3), image (N,C,rows,cols) -> pred (N,C,rows,cols), mask (N,rows,cols) uint8.
  * Needs no handle; `zero_invalid` != 0 additionally zeroes masked pixels as PlaneSweepWarper does

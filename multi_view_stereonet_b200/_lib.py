@@ -30,6 +30,10 @@ SYMBOLS = {
     "b200mvs_forward_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Shape)]
                              + [ctypes.POINTER(ctypes.c_void_p)] * 8
                              + [ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
+    "b200mvs_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]),
+    "b200mvs_conv3x3_c32": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+                                           ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                           ctypes.c_void_p, ctypes.c_void_p]),
     "b200mvs_probe_select": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p]),
     "b200mvs_probe_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double),
                                           ctypes.POINTER(ctypes.c_int64)]),

@@ -6,6 +6,7 @@
 
 #include "../../include/b200mvs.h"
 #include "conv.cuh"
+#include "conv_tc.cuh"
 #include "kernels.cuh"
 
 namespace b200mvs {
@@ -42,6 +43,7 @@ namespace {
 struct ConvW {
   float* w = nullptr;
   float* bias = nullptr;
+  uint8_t* w16 = nullptr;  // fp16 UMMA layout, only for 3x3 32->32 layers that may run on tensor cores
 };
 struct GnW {
   float* gamma = nullptr;
@@ -124,6 +126,7 @@ struct b200mvs_net {
   b200mvs_shape ws_shape{};
   bool ws_valid = false;
   bool keep_stages = false;
+  bool use_tensor_cores = true;
   b200mvs_shape last_shape{};
   bool have_last = false;
   int64_t last_launches = 0;
@@ -189,6 +192,17 @@ int pack_conv(b200mvs_net* net, const StateDict& sd, const std::string& name, in
   return 0;
 }
 
+int pack_conv_tc(b200mvs_net* net, const StateDict& sd, const std::string& name, ConvW* out) {
+  const float* w = sd.get(name + ".weight", 32 * 32 * 9);
+  if (w == nullptr) return B200MVS_EWEIGHTS;
+  std::vector<uint8_t> packed;
+  pack_conv3x3_tc_weights(w, &packed);
+  B200MVS_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&out->w16), packed.size()));
+  net->allocs.push_back(out->w16);
+  B200MVS_CUDA_OK(cudaMemcpy(out->w16, packed.data(), packed.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
 int pack_gn(b200mvs_net* net, const StateDict& sd, const std::string& name, GnW* out) {
   const float* g = sd.get(name + ".weight", kC);
   const float* b = sd.get(name + ".bias", kC);
@@ -241,7 +255,9 @@ int build_weights(b200mvs_net* net, const StateDict& sd) {
       RC(pack_conv(net, sd, r + ".conv0", 32, 4, 9, false, 0, {0, 1, 2, 3}, true, &R.conv0));
     RC(pack_gn(net, sd, r + ".bn0", &R.gn0));
     for (int i = 0; i < 6; ++i) {
-      RC(pack_conv(net, sd, r + ".res" + std::to_string(i) + ".conv1", 32, 32, 9, true, 0, {}, true, &R.res[i]));
+      const std::string cn = r + ".res" + std::to_string(i) + ".conv1";
+      RC(pack_conv(net, sd, cn, 32, 32, 9, true, 0, {}, true, &R.res[i]));
+      RC(pack_conv_tc(net, sd, cn, &R.res[i]));
       RC(pack_gn(net, sd, r + ".res" + std::to_string(i) + ".bn1", &R.gn[i]));
     }
     RC(pack_conv(net, sd, r + ".conv_final", 1, 32, 9, true, 0, {}, true, &R.fin));
@@ -419,7 +435,11 @@ int run_refiner(b200mvs_net* net, const Refiner& R, StatsCursor& sc, int m, int 
     q.out = ws.ry[1 - ycur];
     q.out_stats = sc.take(m);
     q.tag = res_tag;
-    RC(launch_conv(CONV_3x3, 32, q, stream));
+    // Levels 0-2 run on the tensor cores (fp16 operands, fp32 accumulate); the small levels stay fp32.
+    if (net->use_tensor_cores && (long long)H * W > 96 * 128 && R.res[i].w16 != nullptr)
+      RC(launch_conv3x3_tc(q, R.res[i].w16, stream));
+    else
+      RC(launch_conv(CONV_3x3, 32, q, stream));
     st_prev = q.out_stats;
     gn_prev = &R.gn[i];
     ycur = 1 - ycur;
@@ -794,6 +814,66 @@ B200MVS_API int b200mvs_set_debug(b200mvs_net* net, int keep_stages) {
     net->ws_valid = false;  // layout changes
   }
   return 0;
+}
+
+B200MVS_API int b200mvs_set_option(b200mvs_net* net, const char* name, int value) {
+  if (net == nullptr || name == nullptr) return B200MVS_EINVAL;
+  const std::string k(name);
+  if (k == "tensor_cores") {
+    net->use_tensor_cores = value != 0;
+    return 0;
+  }
+  set_error("b200mvs_set_option: unknown option '" + k + "'");
+  return B200MVS_EINVAL;
+}
+
+B200MVS_API int b200mvs_conv3x3_c32(const float* x, const float* w_oihw_host, const float* bias_host, int32_t n,
+                                    int32_t rows, int32_t cols, int32_t dilation, int32_t use_tensor_cores, float* y,
+                                    void* stream_) {
+  if (x == nullptr || w_oihw_host == nullptr || y == nullptr || n < 1 || rows < 1 || cols < 1 || dilation < 1 ||
+      dilation > 8) {
+    set_error("b200mvs_conv3x3_c32: bad argument");
+    return B200MVS_EINVAL;
+  }
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  float* dbias = nullptr;
+  void* dw = nullptr;
+  int rc = 0;
+  ConvParams p;
+  p.n_img = n;
+  p.Hi = p.Ho = rows;
+  p.Wi = p.Wo = cols;
+  p.dil = dilation;
+  p.feat.ptr = x;
+  p.feat.mode = FEAT_RAW;
+  p.out = y;
+  if (bias_host != nullptr) {
+    B200MVS_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&dbias), 32 * sizeof(float)));
+    B200MVS_CUDA_OK(cudaMemcpyAsync(dbias, bias_host, 32 * sizeof(float), cudaMemcpyHostToDevice, stream));
+    p.bias = dbias;
+  }
+  if (use_tensor_cores) {
+    std::vector<uint8_t> packed;
+    pack_conv3x3_tc_weights(w_oihw_host, &packed);
+    B200MVS_CUDA_OK(cudaMalloc(&dw, packed.size()));
+    B200MVS_CUDA_OK(cudaMemcpy(dw, packed.data(), packed.size(), cudaMemcpyHostToDevice));
+    rc = launch_conv3x3_tc(p, static_cast<const uint8_t*>(dw), stream);
+  } else {
+    std::vector<float> packed((size_t)4 * 9 * 8 * 32);
+    for (int chunk = 0; chunk < 4; ++chunk)
+      for (int tap = 0; tap < 9; ++tap)
+        for (int k = 0; k < 8; ++k)
+          for (int o = 0; o < 32; ++o)
+            packed[(((size_t)chunk * 9 + tap) * 8 + k) * 32 + o] = w_oihw_host[((size_t)o * 32 + chunk * 8 + k) * 9 + tap];
+    B200MVS_CUDA_OK(cudaMalloc(&dw, packed.size() * sizeof(float)));
+    B200MVS_CUDA_OK(cudaMemcpy(dw, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
+    p.w = static_cast<const float*>(dw);
+    rc = launch_conv(CONV_3x3, 32, p, stream);
+  }
+  cudaStreamSynchronize(stream);
+  cudaFree(dw);
+  if (dbias != nullptr) cudaFree(dbias);
+  return rc;
 }
 
 B200MVS_API int b200mvs_probe_select(b200mvs_net* net, const char* kernel_class) {

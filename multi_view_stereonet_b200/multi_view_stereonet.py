@@ -119,6 +119,7 @@ class MultiViewStereoNet(tnn.Module):
         self._handle_key = None
         self._keep_stages = False
         self._host_out = None
+        self._options = {}
 
     # -- native handle ---------------------------------------------------------------------
     def _weights_key(self, device_index):
@@ -153,6 +154,8 @@ class MultiViewStereoNet(tnn.Module):
         self._handle_key = key
         if self._keep_stages:
             lib.b200mvs_set_debug(handle, 1)
+        for name, value in self._options.items():
+            _lib.check(lib.b200mvs_set_option(handle, name.encode(), value), "b200mvs_set_option")
         return handle
 
     def keep_stages(self, enable=True):
@@ -173,6 +176,12 @@ class MultiViewStereoNet(tnn.Module):
         _lib.check(lib.b200mvs_get_stage(self._handle, name.encode(), buf.data_ptr(), nbytes.value,
                                          ctypes.byref(nbytes), stream), "b200mvs_get_stage")
         return buf.view(dtype)
+
+    def set_option(self, name, value):
+        """Library options (include/b200mvs.h: b200mvs_set_option), e.g. ("tensor_cores", 0)."""
+        self._options[name] = int(value)
+        if self._handle is not None:
+            _lib.check(_lib.load().b200mvs_set_option(self._handle, name.encode(), int(value)), "b200mvs_set_option")
 
     def probe_select(self, kernel_class):
         """Brackets every launch of `kernel_class` with CUDA events (bench.py roofline leg)."""
