@@ -8,6 +8,7 @@
 #include "conv.cuh"
 #include "conv_tc.cuh"
 #include "kernels.cuh"
+#include "recurrence.cuh"
 
 namespace b200mvs {
 
@@ -111,6 +112,7 @@ struct b200mvs_net {
   // FeatureRefiner (multi_view_stereonet.py:398-440)
   ConvW fr_conv0, fr_res0, fr_final;
   GnW fr_gn0, fr_gn1;
+  uint8_t* fr_w16 = nullptr;  // split-fp16 weights of the three layers for the persistent kernel
   // CostVolumeFilter (multi_view_stereonet.py:302-353)
   ConvW cvf[5];
   GnW cvf_gn[4];
@@ -237,6 +239,18 @@ int build_weights(b200mvs_net* net, const StateDict& sd) {
   RC(pack_conv(net, sd, fr + ".res0.conv1", 32, 32, 9, true, 0, {}, true, &net->fr_res0));
   RC(pack_gn(net, sd, fr + ".res0.bn1", &net->fr_gn1));
   RC(pack_conv(net, sd, fr + ".conv_final", 32, 32, 9, true, 0, {}, true, &net->fr_final));
+
+  {
+    const float* w0 = sd.get(fr + ".conv0.weight", 32 * 35 * 9);
+    const float* w1 = sd.get(fr + ".res0.conv1.weight", 32 * 32 * 9);
+    const float* w2 = sd.get(fr + ".conv_final.weight", 32 * 32 * 9);
+    if (w0 == nullptr || w1 == nullptr || w2 == nullptr) return B200MVS_EWEIGHTS;
+    std::vector<uint8_t> packed;
+    pack_recurrence_weights(w0, w1, w2, &packed);
+    B200MVS_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&net->fr_w16), packed.size()));
+    net->allocs.push_back(net->fr_w16);
+    B200MVS_CUDA_OK(cudaMemcpy(net->fr_w16, packed.data(), packed.size(), cudaMemcpyHostToDevice));
+  }
 
   for (int i = 0; i < 4; ++i) {
     RC(pack_conv(net, sd, "volume_filter4.conv" + std::to_string(i), 32, 32, 27, true, 0, {}, true, &net->cvf[i]));
@@ -603,7 +617,25 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
                                     stream));
 
   // 5. the depth-sweep recurrence (multi_view_stereonet.py:279-290)
-  {
+  if (net->use_tensor_cores && recurrence_supported(h4, w4, nullptr, nullptr)) {
+    RecurrenceArgs ra;
+    ra.vol = ws.vol;
+    ra.geo = ws.geo;
+    ra.right_l4 = R4;
+    ra.w16 = net->fr_w16;
+    ra.bias0 = net->fr_conv0.bias;
+    ra.bias1 = net->fr_res0.bias;
+    ra.bias2 = net->fr_final.bias;
+    ra.gamma0 = net->fr_gn0.gamma;
+    ra.beta0 = net->fr_gn0.beta;
+    ra.gamma1 = net->fr_gn1.gamma;
+    ra.beta1 = net->fr_gn1.beta;
+    ra.n = n;
+    ra.D = D;
+    ra.rows = h4;
+    ra.cols = w4;
+    RC(launch_recurrence(ra, stream));
+  } else {
     const double inv_count = 1.0 / (8.0 * (double)P4);
     for (int step = 1; step < D; ++step) {
       RC(launch_step_warp(ws.vol, ws.geo, R4, n, D, step, h4, w4, ws.wf, ws.wimg, stream));

@@ -1,0 +1,24 @@
+// Persistent cluster kernel for the depth-sweep feature recurrence (recurrence.cu).
+#pragma once
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace b200mvs {
+
+struct RecurrenceArgs {
+  float* vol;            // [n][D][rows*cols][32], hypothesis 0 filled; hypotheses 1..D-1 are written
+  GeomOut geo;
+  ViewPtrs right_l4;
+  const uint8_t* w16;    // pack_recurrence_weights
+  const float *bias0, *bias1, *bias2;
+  const float *gamma0, *beta0, *gamma1, *beta1;
+  int n, D, rows, cols;
+};
+
+void pack_recurrence_weights(const float* w0_oihw35, const float* w1_oihw32, const float* w2_oihw32,
+                             std::vector<uint8_t>* out);
+bool recurrence_supported(int rows, int cols, int* n_tiles, size_t* smem_bytes);
+int launch_recurrence(const RecurrenceArgs& a, cudaStream_t stream);
+
+}  // namespace b200mvs
