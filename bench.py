@@ -196,10 +196,12 @@ def run_ours(args, rank, world, local_rank):
         for _ in range(max(args.warmup, 3)):
             net(*inputs, *flags)
         launches_per_step = net.last_launch_count()
-        net.probe_select("refine_conv32_l0")
+        if not os.environ.get("BENCH_NO_PROBE"):
+            net.probe_select("refine_conv32_l0")
         sampler = ClockSampler(local_rank)
-        sampler.start()
-        time.sleep(0.3)
+        if not os.environ.get("BENCH_NO_SAMPLER"):
+            sampler.start()
+            time.sleep(0.3)
         starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
         ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
         barrier()

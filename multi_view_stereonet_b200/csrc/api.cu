@@ -129,6 +129,7 @@ struct b200mvs_net {
   bool ws_valid = false;
   bool keep_stages = false;
   bool use_tensor_cores = true;
+  long long* rec_prof = nullptr;  // device [16][12], allocated when option "recurrence_profile" is set
   b200mvs_shape last_shape{};
   bool have_last = false;
   int64_t last_launches = 0;
@@ -634,6 +635,7 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
     ra.D = D;
     ra.rows = h4;
     ra.cols = w4;
+    ra.prof = net->rec_prof;
     RC(launch_recurrence(ra, stream));
   } else {
     const double inv_count = 1.0 / (8.0 * (double)P4);
@@ -853,6 +855,14 @@ B200MVS_API int b200mvs_set_option(b200mvs_net* net, const char* name, int value
   const std::string k(name);
   if (k == "tensor_cores") {
     net->use_tensor_cores = value != 0;
+    return 0;
+  }
+  if (k == "recurrence_profile") {
+    if (value != 0 && net->rec_prof == nullptr) {
+      B200MVS_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&net->rec_prof), 16 * 12 * sizeof(long long)));
+      B200MVS_CUDA_OK(cudaMemset(net->rec_prof, 0, 16 * 12 * sizeof(long long)));
+      net->allocs.push_back(net->rec_prof);
+    }
     return 0;
   }
   set_error("b200mvs_set_option: unknown option '" + k + "'");
@@ -1102,6 +1112,7 @@ B200MVS_API int b200mvs_get_stage(b200mvs_net* net, const char* name, void* dst,
   }
   else if (k == "cost_filtered") { src = ws.cost1; bytes = n * D * L.px[4] * 4; }
   else if (k == "idepth4_raw_views") { src = ws.raw_views; bytes = n * L.px[4] * 4; }
+  else if (k == "recurrence_profile" && net->rec_prof != nullptr) { src = net->rec_prof; bytes = 16 * 12 * 8; }
   else {
     set_error("b200mvs_get_stage: unknown stage '" + k + "'");
     return B200MVS_EINVAL;

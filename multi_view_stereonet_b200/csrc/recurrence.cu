@@ -46,16 +46,19 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)1 << 46;
   return d;
 }
-constexpr uint32_t kIdescF16 = (1u << 4) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+// kind::f16 instruction descriptors: D = F32, A = B = F16 (K-major), M = 128, N = 32 / 64.
+constexpr uint32_t kIdescN32 = (1u << 4) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t kIdescN64 = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
-__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(kIdescF16), "r"(accumulate)
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 
@@ -130,6 +133,7 @@ struct Layout {
 
 // Planes (each npl_pad x 16 B): [hi f0..f3][hi extra][zero][lo f0..f3][lo extra][zero]
 constexpr int PLANE_HI = 0, PLANE_HI_X = 4, PLANE_LO = 6, PLANE_LO_X = 10, NUM_PLANES = 12;
+constexpr int MAX_TASKS = 4;   // (position, channel octet) staging tasks per thread: npl * 4 <= 4 * NT
 
 __host__ __device__ inline Layout make_layout(int cols) {
   Layout L;
@@ -167,13 +171,37 @@ struct RecParams {
   const float* gamma1;
   const float* beta1;
   int D, rows, cols, n_tiles;
+  long long* prof;       // optional [16][12] phase cycle totals (debug)
 };
+
+// One conv = 9 taps x KSTEPS k-steps; per k-step two MMAs implement the split product
+//   D[:, 0:32]  += A_hi * W_hi      D[:, 32:64] += A_hi * W_lo      (one N=64 MMA on [W_hi | W_lo])
+//   D[:, 0:32]  += A_lo * W_hi                                      (one N=32 MMA)
+// so the A operand -- the shared-memory-bandwidth-bound side at N=32 -- is read twice, not three times.
+// Descriptors differ from precomputed bases only in the 14-bit start-address field.
+template <int KSTEPS>
+__device__ __forceinline__ void issue_conv_mmas(uint32_t tmem_base, uint64_t da_hi0, uint64_t da_lo0, uint64_t db0,
+                                                uint32_t plane_u16, int PW) {
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const uint32_t pos = (uint32_t)((tap / 3) * PW + (tap % 3));  // 16-byte units
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+      // k-steps 0,1 read feature planes (2ks, 2ks+1); k-step 2 reads (extra, zero)
+      const uint32_t pl = (ks < 2) ? 2u * ks : (uint32_t)PLANE_HI_X;
+      const uint64_t a_off = (uint64_t)(pl * plane_u16 + pos);
+      const uint64_t b_off = (uint64_t)((tap * KSTEPS + ks) * (2048 / 16));
+      mma_f16(tmem_base, da_hi0 + a_off, db0 + b_off, kIdescN64, (tap | ks) != 0 ? 1u : 0u);
+      mma_f16(tmem_base, da_lo0 + a_off, db0 + b_off, kIdescN32, 1u);
+    }
+  }
+}
 
 __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ float s_part[2][16][2 * kGroups];  // per-layer partial (sum, sumsq) of every CTA of the cluster
   __shared__ float s_red[NT / 32][2 * kGroups];
-  __shared__ float s_a[kC], s_b[kC], s_bias[3][kC];
+  __shared__ float s_a[kC], s_b[kC], s_bias[3][kC], s_gamma[2][kC], s_beta[2][kC];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t s_tmem;
 
@@ -196,7 +224,7 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
   // ---- one-time setup ----
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
-                 "r"(32u)
+                 "r"(64u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -208,6 +236,10 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
     s_bias[0][tid] = __ldg(p.bias0 + tid);
     s_bias[1][tid] = __ldg(p.bias1 + tid);
     s_bias[2][tid] = __ldg(p.bias2 + tid);
+    s_gamma[0][tid] = __ldg(p.gamma0 + tid);
+    s_beta[0][tid] = __ldg(p.beta0 + tid);
+    s_gamma[1][tid] = __ldg(p.gamma1 + tid);
+    s_beta[1][tid] = __ldg(p.beta1 + tid);
   }
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.w16);
@@ -226,37 +258,15 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
   uint32_t bar_phase = 0;
   cluster_sync_all();  // every CTA's shared memory is initialised before anyone pushes into it
 
-  const uint32_t a_base = smem_u32(s_planes);
-  const uint32_t w_base = smem_u32(s_w);
   const float inv_count = 1.0f / (8.0f * (float)pixels);
+  const uint32_t plane_u16 = L.plane_bytes >> 4;
+  const uint64_t da_hi0 = umma_desc(smem_u32(s_planes) + (uint32_t)PLANE_HI * L.plane_bytes, L.plane_bytes, 128u);
+  const uint64_t da_lo0 = umma_desc(smem_u32(s_planes) + (uint32_t)PLANE_LO * L.plane_bytes, L.plane_bytes, 128u);
+  const uint64_t db_c0 = umma_desc(smem_u32(s_w), 1024u, 128u);
+  const uint64_t db_c1 = db_c0 + (uint64_t)(W0_BLOCKS * (2048 / 16));
+  const uint64_t db_c2 = db_c1 + (uint64_t)(W1_BLOCKS * (2048 / 16));
 
-  // Issues one conv's MMAs: ksteps k-steps per tap, three split terms per k-step.
-  auto issue_conv = [&](int w_block0, int ksteps) {
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      uint32_t acc = 0;
-#pragma unroll 1
-      for (int tap = 0; tap < 9; ++tap) {
-        const uint32_t pos = (uint32_t)((tap / 3) * PW + (tap % 3));
-        for (int ks = 0; ks < ksteps; ++ks) {
-          // k-steps 0,1 read feature planes (2ks, 2ks+1); k-step 2 reads (extra, zero)
-          const int pl = (ks < 2) ? 2 * ks : PLANE_HI_X;
-          const uint32_t a_hi = a_base + (uint32_t)(PLANE_HI + pl) * L.plane_bytes + pos * 16u;
-          const uint32_t a_lo = a_base + (uint32_t)(PLANE_LO + pl) * L.plane_bytes + pos * 16u;
-          const uint32_t b_hi = w_base + (uint32_t)(w_block0 + tap * ksteps + ks) * 2048u;
-          const uint32_t b_lo = b_hi + 1024u;
-          const uint64_t da_hi = umma_desc(a_hi, L.plane_bytes, 128u), da_lo = umma_desc(a_lo, L.plane_bytes, 128u);
-          const uint64_t db_hi = umma_desc(b_hi, 512u, 128u), db_lo = umma_desc(b_lo, 512u, 128u);
-          mma_f16(tmem_base, da_hi, db_hi, acc);
-          acc = 1;
-          mma_f16(tmem_base, da_lo, db_hi, 1u);
-          mma_f16(tmem_base, da_hi, db_lo, 1u);
-        }
-      }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                       smem_u32(&s_bar))
-                   : "memory");
-    }
+  auto wait_mma = [&]() {
     const uint32_t bar = smem_u32(&s_bar);
     uint32_t done = 0;
     while (!done) {
@@ -273,6 +283,10 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
     bar_phase ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   };
+  auto commit_mma = [&]() {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_bar))
+                 : "memory");
+  };
 
   // This thread's slice of the accumulator tile: one output position, 16 channels.
   const int wq = warp & 3, chalf = warp >> 2;
@@ -282,14 +296,35 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
   const bool real_out = active && ox < p.cols && oy < p.rows;
   const uint32_t tmem_my = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(chalf * 16);
 
+  // Staging tasks of this thread, fixed for all steps: (local input position l, channel octet).
+  int t_l[MAX_TASKS], t_gy[MAX_TASKS], t_gx[MAX_TASKS];
+  bool t_real[MAX_TASKS];
+#pragma unroll
+  for (int k = 0; k < MAX_TASKS; ++k) {
+    const int i = tid + k * NT;
+    t_l[k] = i >> 2;
+    const int Lg = pos0 + t_l[k];
+    t_gy[k] = Lg / PW - 1;
+    t_gx[k] = Lg % PW - 1;
+    t_real[k] = active && t_l[k] < npl && t_gy[k] >= 0 && t_gy[k] < p.rows && t_gx[k] >= 0 && t_gx[k] < p.cols;
+  }
+  const int t_oct = tid & 3;  // NT % 4 == 0: the octet is the same for every task of a thread
+  // image-plane task: one local position per thread
+  const int x_l = tid;
+  const int x_gy = (pos0 + x_l) / PW - 1, x_gx = (pos0 + x_l) % PW - 1;
+  const bool x_in = active && x_l < npl;
+  const bool x_real = x_in && x_gy >= 0 && x_gy < p.rows && x_gx >= 0 && x_gx < p.cols;
+
   // Epilogue of conv0 / conv1: raw output (+bias) -> own buffer, neighbours' halo buffers, statistics.
   auto epilogue_raw = [&](int layer) {
     float v[16];
     float gs[2] = {0.f, 0.f}, gq[2] = {0.f, 0.f};
     if (active) {
+      float c[16];
       tmem_ld16(tmem_my, v);
+      tmem_ld16(tmem_my + 32u, c);
 #pragma unroll
-      for (int k = 0; k < 16; ++k) v[k] += s_bias[layer][chalf * 16 + k];
+      for (int k = 0; k < 16; ++k) v[k] = (v[k] + c[k]) + s_bias[layer][chalf * 16 + k];
       float4* own = reinterpret_cast<float4*>(s_own + jl * kC + chalf * 16);
 #pragma unroll
       for (int q = 0; q < 4; ++q) own[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
@@ -347,7 +382,7 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
   };
 
   // GroupNorm coefficients from the cluster-wide partials (fixed summation order: deterministic).
-  auto gn_coeffs = [&](int layer, const float* gamma, const float* beta) {
+  auto gn_coeffs = [&](int layer) {
     if (tid < kC) {
       const int g = tid >> 3;
       double sum = 0.0, sq = 0.0;
@@ -356,11 +391,11 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
         sq += (double)s_part[layer][r][2 * g + 1];
       }
       const double mean = sum * (double)inv_count;
-      double var = sq * (double)inv_count - mean * mean;
-      var = var > 0.0 ? var : 0.0;
-      const double rstd = rsqrt(var + (double)kGnEps);
-      s_a[tid] = (float)((double)__ldg(gamma + tid) * rstd);
-      s_b[tid] = (float)((double)__ldg(beta + tid) - mean * (double)__ldg(gamma + tid) * rstd);
+      const double var = sq * (double)inv_count - mean * mean;   // cancellation handled in double
+      const float rstd = rsqrtf(fmaxf((float)var, 0.f) + kGnEps);
+      const float a = s_gamma[layer][tid] * rstd;
+      s_a[tid] = a;
+      s_b[tid] = s_beta[layer][tid] - (float)mean * a;
     }
     __syncthreads();
   };
@@ -371,135 +406,195 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
     if (l < halo + MTILE) return s_own + (l - halo) * kC;
     return s_halo + ((layer * 2 + 1) * halo + (l - halo - MTILE)) * kC;
   };
-  auto is_real = [&](int l, int* gy, int* gx) -> bool {
-    const int Lg = pos0 + l;
-    *gy = Lg / PW - 1;
-    *gx = Lg % PW - 1;
-    return *gy >= 0 && *gy < p.rows && *gx >= 0 && *gx < p.cols;
+  auto plane_ptr = [&](int plane, int l) -> uint4* {
+    return reinterpret_cast<uint4*>(s_planes + (size_t)plane * L.plane_bytes + (size_t)l * 16);
   };
+
+  long long t_prev = clock64();
+  long long acc_t[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) acc_t[k] = 0;
+#define PROF_MARK(k)                          \
+  do {                                        \
+    if (p.prof != nullptr) {                  \
+      const long long _t = clock64();         \
+      acc_t[k] += _t - t_prev;                \
+      t_prev = _t;                            \
+    }                                         \
+  } while (0)
+
+  const float* img_base = p.right_l4.p[n % p.right_l4.views] + (size_t)(n / p.right_l4.views) * 3 * pixels;
+  // homographies of the coming step, fetched one step ahead
+  float Hinc[9], Hd[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    Hinc[k] = __ldg(p.geo.Hinc + ((size_t)n * p.D + 1) * 9 + k);
+    Hd[k] = __ldg(p.geo.H + ((size_t)n * p.D + 1) * 9 + k);
+  }
 
   for (int step = 1; step < p.D; ++step) {
     // ================= W: warp previous features and the 1/16 image into the conv0 operand =========
-    if (active) {
-      const float* prev = p.vol_in + ((size_t)n * p.D + (step - 1)) * pixels * kC;
-      const float* Hinc = p.geo.Hinc + ((size_t)n * p.D + step) * 9;
-      const float* Hd = p.geo.H + ((size_t)n * p.D + step) * 9;
-      for (int i = tid; i < npl * 5; i += NT) {
-        const int oct = i % 5, l = i / 5;
-        int gy, gx;
-        const bool real = is_real(l, &gy, &gx);
-        float v[8];
+    {
+      const float* prev = p.vol_in + ((size_t)n * p.D + (step - 1)) * pixels * kC + 8 * t_oct;
+      float4 g[MAX_TASKS][8];
+      Bilinear bl[MAX_TASKS];
+      bool ok[MAX_TASKS];
+      // issue every gather of every task before consuming any: one L2 round trip per step
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = 0.f;
-        if (oct < 4) {
-          if (real) {
-            const WarpCoord c = homography_coord(Hinc, (float)gx, (float)gy, p.rows, p.cols);
-            if (!c.invalid) {
-              const Bilinear bl = bilinear_setup(c, p.rows, p.cols);
-              const float* b00 = prev + ((size_t)bl.y0 * p.cols + bl.x0) * kC + 8 * oct;
-              const float* b01 = prev + ((size_t)bl.y0 * p.cols + bl.x1) * kC + 8 * oct;
-              const float* b10 = prev + ((size_t)bl.y1 * p.cols + bl.x0) * kC + 8 * oct;
-              const float* b11 = prev + ((size_t)bl.y1 * p.cols + bl.x1) * kC + 8 * oct;
+      for (int k = 0; k < MAX_TASKS; ++k) {
+        ok[k] = false;
+        if (t_real[k]) {
+          const WarpCoord c = homography_coord(Hinc, (float)t_gx[k], (float)t_gy[k], p.rows, p.cols);
+          ok[k] = !c.invalid;
+          if (ok[k]) {
+            bl[k] = bilinear_setup(c, p.rows, p.cols);
+            const float4* b00 = reinterpret_cast<const float4*>(prev + ((size_t)bl[k].y0 * p.cols + bl[k].x0) * kC);
+            const float4* b01 = reinterpret_cast<const float4*>(prev + ((size_t)bl[k].y0 * p.cols + bl[k].x1) * kC);
+            const float4* b10 = reinterpret_cast<const float4*>(prev + ((size_t)bl[k].y1 * p.cols + bl[k].x0) * kC);
+            const float4* b11 = reinterpret_cast<const float4*>(prev + ((size_t)bl[k].y1 * p.cols + bl[k].x1) * kC);
+            g[k][0] = __ldcg(b00); g[k][1] = __ldcg(b00 + 1);
+            g[k][2] = __ldcg(b01); g[k][3] = __ldcg(b01 + 1);
+            g[k][4] = __ldcg(b10); g[k][5] = __ldcg(b10 + 1);
+            g[k][6] = __ldcg(b11); g[k][7] = __ldcg(b11 + 1);
+          }
+        }
+      }
+      // image planes (3 channels) of this thread's position
+      float xi[8];
 #pragma unroll
-              for (int hq = 0; hq < 2; ++hq) {
-                const float4 a = __ldcg(reinterpret_cast<const float4*>(b00) + hq);
-                const float4 b = __ldcg(reinterpret_cast<const float4*>(b01) + hq);
-                const float4 cc = __ldcg(reinterpret_cast<const float4*>(b10) + hq);
-                const float4 d = __ldcg(reinterpret_cast<const float4*>(b11) + hq);
-                v[4 * hq + 0] = a.x * bl.w00 + b.x * bl.w01 + cc.x * bl.w10 + d.x * bl.w11;
-                v[4 * hq + 1] = a.y * bl.w00 + b.y * bl.w01 + cc.y * bl.w10 + d.y * bl.w11;
-                v[4 * hq + 2] = a.z * bl.w00 + b.z * bl.w01 + cc.z * bl.w10 + d.z * bl.w11;
-                v[4 * hq + 3] = a.w * bl.w00 + b.w * bl.w01 + cc.w * bl.w10 + d.w * bl.w11;
-              }
+      for (int k = 0; k < 8; ++k) xi[k] = 0.f;
+      if (x_real) {
+        const WarpCoord c = homography_coord(Hd, (float)x_gx, (float)x_gy, p.rows, p.cols);
+        if (!c.invalid) {
+          const Bilinear b = bilinear_setup(c, p.rows, p.cols);
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            const float* pl = img_base + (size_t)ch * pixels;
+            xi[ch] = __ldg(pl + b.y0 * p.cols + b.x0) * b.w00 + __ldg(pl + b.y0 * p.cols + b.x1) * b.w01 +
+                     __ldg(pl + b.y1 * p.cols + b.x0) * b.w10 + __ldg(pl + b.y1 * p.cols + b.x1) * b.w11;
+          }
+        }
+      }
+      // prefetch the next step's homographies
+      if (step + 1 < p.D) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          Hinc[k] = __ldg(p.geo.Hinc + ((size_t)n * p.D + step + 1) * 9 + k);
+          Hd[k] = __ldg(p.geo.H + ((size_t)n * p.D + step + 1) * 9 + k);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < MAX_TASKS; ++k) {
+        if (active && t_l[k] < npl) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = 0.f;
+          if (ok[k]) {
+#pragma unroll
+            for (int hq = 0; hq < 2; ++hq) {
+              const float4 a = g[k][hq], b = g[k][2 + hq], cc = g[k][4 + hq], d = g[k][6 + hq];
+              v[4 * hq + 0] = a.x * bl[k].w00 + b.x * bl[k].w01 + cc.x * bl[k].w10 + d.x * bl[k].w11;
+              v[4 * hq + 1] = a.y * bl[k].w00 + b.y * bl[k].w01 + cc.y * bl[k].w10 + d.y * bl[k].w11;
+              v[4 * hq + 2] = a.z * bl[k].w00 + b.z * bl[k].w01 + cc.z * bl[k].w10 + d.z * bl[k].w11;
+              v[4 * hq + 3] = a.w * bl[k].w00 + b.w * bl[k].w01 + cc.w * bl[k].w10 + d.w * bl[k].w11;
             }
           }
+          const int l = t_l[k];
           if (l >= halo && l < halo + MTILE) {
-            float4* wfp = reinterpret_cast<float4*>(s_wf + (l - halo) * kC + 8 * oct);
+            float4* wfp = reinterpret_cast<float4*>(s_wf + (l - halo) * kC + 8 * t_oct);
             wfp[0] = make_float4(v[0], v[1], v[2], v[3]);
             wfp[1] = make_float4(v[4], v[5], v[6], v[7]);
           }
           uint4 hi, lo;
           split8(v, &hi, &lo);
-          *reinterpret_cast<uint4*>(s_planes + (size_t)(PLANE_HI + oct) * L.plane_bytes + (size_t)l * 16) = hi;
-          *reinterpret_cast<uint4*>(s_planes + (size_t)(PLANE_LO + oct) * L.plane_bytes + (size_t)l * 16) = lo;
-        } else {
-          if (real) {
-            const WarpCoord c = homography_coord(Hd, (float)gx, (float)gy, p.rows, p.cols);
-            if (!c.invalid) {
-              const Bilinear bl = bilinear_setup(c, p.rows, p.cols);
-              const float* img = p.right_l4.p[n % p.right_l4.views] + (size_t)(n / p.right_l4.views) * 3 * pixels;
-#pragma unroll
-              for (int ch = 0; ch < 3; ++ch) {
-                const float* pl = img + (size_t)ch * pixels;
-                v[ch] = __ldg(pl + bl.y0 * p.cols + bl.x0) * bl.w00 + __ldg(pl + bl.y0 * p.cols + bl.x1) * bl.w01 +
-                        __ldg(pl + bl.y1 * p.cols + bl.x0) * bl.w10 + __ldg(pl + bl.y1 * p.cols + bl.x1) * bl.w11;
-              }
-            }
-          }
-          uint4 hi, lo;
-          split8(v, &hi, &lo);
-          *reinterpret_cast<uint4*>(s_planes + (size_t)PLANE_HI_X * L.plane_bytes + (size_t)l * 16) = hi;
-          *reinterpret_cast<uint4*>(s_planes + (size_t)PLANE_LO_X * L.plane_bytes + (size_t)l * 16) = lo;
+          *plane_ptr(PLANE_HI + t_oct, l) = hi;
+          *plane_ptr(PLANE_LO + t_oct, l) = lo;
         }
+      }
+      if (x_in) {
+        uint4 hi, lo;
+        split8(xi, &hi, &lo);
+        *plane_ptr(PLANE_HI_X, x_l) = hi;
+        *plane_ptr(PLANE_LO_X, x_l) = lo;
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (active) issue_conv(0, 3);
+    PROF_MARK(0);
+    if (active) {
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        issue_conv_mmas<3>(tmem_base, da_hi0, da_lo0, db_c0, plane_u16, PW);
+        commit_mma();
+      }
+      wait_mma();
+    }
+    PROF_MARK(1);
     epilogue_raw(0);
+    PROF_MARK(2);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     cluster_sync_all();  // A: statistics and halos of y0 are everywhere
+    PROF_MARK(3);
 
     // ================= S1: x0 = lrelu(GN(y0)) over own + halo -> conv1 operand ====================
-    gn_coeffs(0, p.gamma0, p.beta0);
-    if (active) {
-      for (int i = tid; i < npl * 4; i += NT) {
-        const int oct = i & 3, l = i >> 2;
-        int gy, gx;
+    gn_coeffs(0);
+#pragma unroll
+    for (int k = 0; k < MAX_TASKS; ++k) {
+      if (active && t_l[k] < npl) {
         float v[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = 0.f;
-        if (is_real(l, &gy, &gx)) {
-          const float4* src = reinterpret_cast<const float4*>(raw_ptr(0, l) + 8 * oct);
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        if (t_real[k]) {
+          const float4* src = reinterpret_cast<const float4*>(raw_ptr(0, t_l[k]) + 8 * t_oct);
           const float4 a = src[0], b = src[1];
           const float y[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-          for (int k = 0; k < 8; ++k) v[k] = lrelu(fmaf(y[k], s_a[8 * oct + k], s_b[8 * oct + k]));
+          for (int e = 0; e < 8; ++e) v[e] = lrelu(fmaf(y[e], s_a[8 * t_oct + e], s_b[8 * t_oct + e]));
         }
         uint4 hi, lo;
         split8(v, &hi, &lo);
-        *reinterpret_cast<uint4*>(s_planes + (size_t)(PLANE_HI + oct) * L.plane_bytes + (size_t)l * 16) = hi;
-        *reinterpret_cast<uint4*>(s_planes + (size_t)(PLANE_LO + oct) * L.plane_bytes + (size_t)l * 16) = lo;
+        *plane_ptr(PLANE_HI + t_oct, t_l[k]) = hi;
+        *plane_ptr(PLANE_LO + t_oct, t_l[k]) = lo;
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (active) issue_conv(W0_BLOCKS, 2);
+    PROF_MARK(4);
+    if (active) {
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        issue_conv_mmas<2>(tmem_base, da_hi0, da_lo0, db_c1, plane_u16, PW);
+        commit_mma();
+      }
+      wait_mma();
+    }
+    PROF_MARK(5);
     epilogue_raw(1);
+    PROF_MARK(6);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     cluster_sync_all();  // C: statistics and halos of y1 are everywhere
+    PROF_MARK(7);
 
     // ================= S2: x1 = lrelu(GN(y1)) + x0 over own + halo -> conv_final operand ==========
-    gn_coeffs(1, p.gamma1, p.beta1);
-    if (active) {
-      for (int i = tid; i < npl * 4; i += NT) {
-        const int oct = i & 3, l = i >> 2;
-        int gy, gx;
+    gn_coeffs(1);
+#pragma unroll
+    for (int k = 0; k < MAX_TASKS; ++k) {
+      if (active && t_l[k] < npl) {
         float v[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = 0.f;
-        uint4* ph = reinterpret_cast<uint4*>(s_planes + (size_t)(PLANE_HI + oct) * L.plane_bytes + (size_t)l * 16);
-        uint4* plo = reinterpret_cast<uint4*>(s_planes + (size_t)(PLANE_LO + oct) * L.plane_bytes + (size_t)l * 16);
-        if (is_real(l, &gy, &gx)) {
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        uint4* ph = plane_ptr(PLANE_HI + t_oct, t_l[k]);
+        uint4* plo = plane_ptr(PLANE_LO + t_oct, t_l[k]);
+        if (t_real[k]) {
           float x0[8];
           unsplit8(*ph, *plo, x0);
-          const float4* src = reinterpret_cast<const float4*>(raw_ptr(1, l) + 8 * oct);
+          const float4* src = reinterpret_cast<const float4*>(raw_ptr(1, t_l[k]) + 8 * t_oct);
           const float4 a = src[0], b = src[1];
           const float y[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-          for (int k = 0; k < 8; ++k) v[k] = lrelu(fmaf(y[k], s_a[8 * oct + k], s_b[8 * oct + k])) + x0[k];
+          for (int e = 0; e < 8; ++e) v[e] = lrelu(fmaf(y[e], s_a[8 * t_oct + e], s_b[8 * t_oct + e])) + x0[e];
         }
         uint4 hi, lo;
         split8(v, &hi, &lo);
@@ -510,51 +605,66 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (active) issue_conv(W0_BLOCKS + W1_BLOCKS, 2);
+    PROF_MARK(8);
+    if (active) {
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        issue_conv_mmas<2>(tmem_base, da_hi0, da_lo0, db_c2, plane_u16, PW);
+        commit_mma();
+      }
+      wait_mma();
+    }
+    PROF_MARK(9);
 
     // ================= E2: features_step = wf + delta -> global =====================================
     if (active) {
-      float v[16];
+      float v[16], c[16];
       tmem_ld16(tmem_my, v);
+      tmem_ld16(tmem_my + 32u, c);
       if (real_out) {
         float* dst = p.vol + (((size_t)n * p.D + step) * pixels + (size_t)oy * p.cols + ox) * kC + chalf * 16;
         const float* wfp = s_wf + jl * kC + chalf * 16;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           float4 r;
-          r.x = wfp[4 * q + 0] + (v[4 * q + 0] + s_bias[2][chalf * 16 + 4 * q + 0]);
-          r.y = wfp[4 * q + 1] + (v[4 * q + 1] + s_bias[2][chalf * 16 + 4 * q + 1]);
-          r.z = wfp[4 * q + 2] + (v[4 * q + 2] + s_bias[2][chalf * 16 + 4 * q + 2]);
-          r.w = wfp[4 * q + 3] + (v[4 * q + 3] + s_bias[2][chalf * 16 + 4 * q + 3]);
+          r.x = wfp[4 * q + 0] + ((v[4 * q + 0] + c[4 * q + 0]) + s_bias[2][chalf * 16 + 4 * q + 0]);
+          r.y = wfp[4 * q + 1] + ((v[4 * q + 1] + c[4 * q + 1]) + s_bias[2][chalf * 16 + 4 * q + 1]);
+          r.z = wfp[4 * q + 2] + ((v[4 * q + 2] + c[4 * q + 2]) + s_bias[2][chalf * 16 + 4 * q + 2]);
+          r.w = wfp[4 * q + 3] + ((v[4 * q + 3] + c[4 * q + 3]) + s_bias[2][chalf * 16 + 4 * q + 3]);
           __stcg(reinterpret_cast<float4*>(dst) + q, r);
         }
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __threadfence();
+    PROF_MARK(10);
     cluster_sync_all();  // E: hypothesis `step` is visible to every CTA's gathers
+    PROF_MARK(11);
+  }
+  if (p.prof != nullptr && tid == 0 && blockIdx.y == 0) {
+    for (int k = 0; k < 12; ++k) p.prof[rank * 12 + k] = acc_t[k];
   }
 
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64u) : "memory");
   }
 }
 
 }  // namespace
 
-// Weight blocks of 2 KB: [hi 1 KB][lo 1 KB], each [k half (2)][n (32)][8 fp16] (UMMA K-major, no swizzle).
+// Weight blocks of 2 KB = one N=64 B operand [k half (2)][n (64)][8 fp16] (UMMA K-major, no swizzle) whose
+// rows 0..31 hold W_hi and rows 32..63 hold W_lo; an N=32 descriptor on the same block reads W_hi only.
 // Order: conv0 [tap][kstep 3] (k-step 2 = image channels 0..2 then zeros), conv1 [tap][kstep 2], conv2.
 void pack_recurrence_weights(const float* w0_oihw35, const float* w1_oihw32, const float* w2_oihw32,
                              std::vector<uint8_t>* out) {
   out->assign(W_TOTAL_BYTES, 0);
   __half* h = reinterpret_cast<__half*>(out->data());
   auto put = [&](int block, int k, int nn, float w) {
-    const size_t e = (size_t)block * 1024 + (size_t)(k / 8) * 256 + (size_t)nn * 8 + (size_t)(k % 8);  // in halves
+    const size_t e = (size_t)block * 1024 + (size_t)(k / 8) * 512 + (size_t)nn * 8 + (size_t)(k % 8);  // in halves
     const __half hi = __float2half_rn(w);
     const __half lo = __float2half_rn(w - __half2float(hi));
     h[e] = hi;
-    h[e + 512] = lo;
+    h[e + 32 * 8] = lo;
   };
   for (int tap = 0; tap < 9; ++tap)
     for (int nn = 0; nn < 32; ++nn) {
@@ -573,7 +683,7 @@ bool recurrence_supported(int rows, int cols, int* n_tiles, size_t* smem_bytes) 
   const int tiles = cdiv(rows * L.PW, MTILE);
   if (n_tiles != nullptr) *n_tiles = tiles;
   if (smem_bytes != nullptr) *smem_bytes = L.total;
-  return tiles <= 16 && L.halo <= MTILE && L.total <= 225 * 1024;
+  return tiles <= 16 && L.halo <= MTILE && L.npl * 4 <= MAX_TASKS * NT && L.npl <= NT && L.total <= 225 * 1024;
 }
 
 int launch_recurrence(const RecurrenceArgs& a, cudaStream_t stream) {
@@ -607,6 +717,7 @@ int launch_recurrence(const RecurrenceArgs& a, cudaStream_t stream) {
   p.rows = a.rows;
   p.cols = a.cols;
   p.n_tiles = n_tiles;
+  p.prof = a.prof;
 
   // Cluster size: one CTA per M-tile; if that size cannot be scheduled, pad with idle CTAs.
   static int good_cluster[17] = {0};

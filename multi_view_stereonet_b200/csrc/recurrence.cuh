@@ -14,6 +14,7 @@ struct RecurrenceArgs {
   const float *bias0, *bias1, *bias2;
   const float *gamma0, *beta0, *gamma1, *beta1;
   int n, D, rows, cols;
+  long long* prof = nullptr;  // optional [16 ranks][12 phases] cycle totals (debug builds of the tests)
 };
 
 void pack_recurrence_weights(const float* w0_oihw35, const float* w1_oihw32, const float* w2_oihw32,
