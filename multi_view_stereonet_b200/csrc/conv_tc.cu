@@ -147,41 +147,63 @@ __global__ void __launch_bounds__(NT) conv3x3_tc_kernel(const ConvParams p, cons
     const float* rbase = p.feat.resid != nullptr ? p.feat.resid + (size_t)img * vol * kC : nullptr;
     float* xbase = p.feat.x_out != nullptr ? p.feat.x_out + (size_t)img * vol * kC : nullptr;
     const int rows_in = TH + 2 * d;
-    for (int i = tid; i < npos * 4; i += NT) {
-      const int c8 = i & 3;
-      const int L = i >> 2;
-      const int iy = L / PW, ix = L % PW;
-      const int gy = ty0 - d + iy, gx = tx0 - d + ix;
-      float v[8];
+    const int mode = p.feat.mode;
+    constexpr int BATCH = 4;   // tasks whose global loads are all issued before any is consumed
+    for (int i0 = tid; i0 < npos * 4; i0 += NT * BATCH) {
+      float4 ya[BATCH], yb[BATCH], ra[BATCH], rb[BATCH];
+      size_t off[BATCH];
+      bool inb[BATCH];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = 0.f;
-      if (iy < rows_in && gy >= 0 && gy < p.Hi && gx >= 0 && gx < p.Wi) {
-        const size_t off = ((size_t)gy * p.Wi + gx) * kC + 8 * c8;
-        const float4 a = __ldg(reinterpret_cast<const float4*>(fbase + off));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(fbase + off + 4));
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        if (p.feat.mode >= FEAT_GN) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) v[k] = lrelu(fmaf(v[k], s_a[8 * c8 + k], s_b[8 * c8 + k]));
-          if (p.feat.mode == FEAT_GN_RES) {
-            const float4 ra = __ldg(reinterpret_cast<const float4*>(rbase + off));
-            const float4 rb = __ldg(reinterpret_cast<const float4*>(rbase + off + 4));
-            v[0] += ra.x; v[1] += ra.y; v[2] += ra.z; v[3] += ra.w;
-            v[4] += rb.x; v[5] += rb.y; v[6] += rb.z; v[7] += rb.w;
-          }
-          if (xbase != nullptr && iy >= d && iy < d + TH && ix >= d && ix < d + TW) {
-            *reinterpret_cast<float4*>(xbase + off) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(xbase + off + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      for (int k = 0; k < BATCH; ++k) {
+        const int i = i0 + k * NT;
+        const int c8 = i & 3;
+        const int L = i >> 2;
+        const int iy = L / PW, ix = L % PW;
+        const int gy = ty0 - d + iy, gx = tx0 - d + ix;
+        inb[k] = i < npos * 4 && iy < rows_in && gy >= 0 && gy < p.Hi && gx >= 0 && gx < p.Wi;
+        off[k] = inb[k] ? ((size_t)gy * p.Wi + gx) * kC + 8 * c8 : 0;
+        if (inb[k]) {
+          ya[k] = __ldg(reinterpret_cast<const float4*>(fbase + off[k]));
+          yb[k] = __ldg(reinterpret_cast<const float4*>(fbase + off[k] + 4));
+          if (mode == FEAT_GN_RES) {
+            ra[k] = __ldg(reinterpret_cast<const float4*>(rbase + off[k]));
+            rb[k] = __ldg(reinterpret_cast<const float4*>(rbase + off[k] + 4));
           }
         }
       }
-      uint4 h;
-      h.x = pack_half2(v[0], v[1]);
-      h.y = pack_half2(v[2], v[3]);
-      h.z = pack_half2(v[4], v[5]);
-      h.w = pack_half2(v[6], v[7]);
-      *reinterpret_cast<uint4*>(s_in + (size_t)c8 * plane_bytes + (size_t)L * 16) = h;
+#pragma unroll
+      for (int k = 0; k < BATCH; ++k) {
+        const int i = i0 + k * NT;
+        if (i >= npos * 4) continue;
+        const int c8 = i & 3;
+        const int L = i >> 2;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        if (inb[k]) {
+          v[0] = ya[k].x; v[1] = ya[k].y; v[2] = ya[k].z; v[3] = ya[k].w;
+          v[4] = yb[k].x; v[5] = yb[k].y; v[6] = yb[k].z; v[7] = yb[k].w;
+          if (mode >= FEAT_GN) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = lrelu(fmaf(v[e], s_a[8 * c8 + e], s_b[8 * c8 + e]));
+            if (mode == FEAT_GN_RES) {
+              v[0] += ra[k].x; v[1] += ra[k].y; v[2] += ra[k].z; v[3] += ra[k].w;
+              v[4] += rb[k].x; v[5] += rb[k].y; v[6] += rb[k].z; v[7] += rb[k].w;
+            }
+            const int iy = L / PW, ix = L % PW;
+            if (xbase != nullptr && iy >= d && iy < d + TH && ix >= d && ix < d + TW) {
+              *reinterpret_cast<float4*>(xbase + off[k]) = make_float4(v[0], v[1], v[2], v[3]);
+              *reinterpret_cast<float4*>(xbase + off[k] + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            }
+          }
+        }
+        uint4 h;
+        h.x = pack_half2(v[0], v[1]);
+        h.y = pack_half2(v[2], v[3]);
+        h.z = pack_half2(v[4], v[5]);
+        h.w = pack_half2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(s_in + (size_t)c8 * plane_bytes + (size_t)L * 16) = h;
+      }
     }
   }
   // generic-proxy writes -> visible to the tensor core (async proxy)

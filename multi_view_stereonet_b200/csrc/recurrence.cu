@@ -683,7 +683,7 @@ bool recurrence_supported(int rows, int cols, int* n_tiles, size_t* smem_bytes) 
   const int tiles = cdiv(rows * L.PW, MTILE);
   if (n_tiles != nullptr) *n_tiles = tiles;
   if (smem_bytes != nullptr) *smem_bytes = L.total;
-  return tiles <= 16 && L.halo <= MTILE && L.npl * 4 <= MAX_TASKS * NT && L.npl <= NT && L.total <= 225 * 1024;
+  return tiles <= 16 && L.halo <= MTILE && L.npl * 4 <= MAX_TASKS * NT && L.npl <= NT && L.total + 4096 <= 227 * 1024;
 }
 
 int launch_recurrence(const RecurrenceArgs& a, cudaStream_t stream) {
@@ -693,12 +693,11 @@ int launch_recurrence(const RecurrenceArgs& a, cudaStream_t stream) {
     set_error("launch_recurrence: shape not supported by the persistent kernel");
     return -1;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200MVS_CUDA_OK(cudaFuncSetAttribute(recurrence_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         225 * 1024));
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    B200MVS_CUDA_OK(cudaFuncSetAttribute(recurrence_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     B200MVS_CUDA_OK(cudaFuncSetAttribute(recurrence_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    attr_set = true;
+    smem_set = smem;
   }
   RecParams p;
   p.vol_in = a.vol;
