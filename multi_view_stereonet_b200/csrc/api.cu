@@ -7,6 +7,7 @@
 #include "../../include/b200mvs.h"
 #include "conv.cuh"
 #include "conv_tc.cuh"
+#include "cvf_tc.cuh"
 #include "kernels.cuh"
 #include "recurrence.cuh"
 
@@ -254,6 +255,15 @@ int build_weights(b200mvs_net* net, const StateDict& sd) {
   }
 
   for (int i = 0; i < 4; ++i) {
+    {
+      const float* w = sd.get("volume_filter4.conv" + std::to_string(i) + ".weight", 32 * 32 * 27);
+      if (w == nullptr) return B200MVS_EWEIGHTS;
+      std::vector<uint8_t> packed;
+      pack_cvf_tc_weights(w, &packed);
+      B200MVS_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&net->cvf[i].w16), packed.size()));
+      net->allocs.push_back(net->cvf[i].w16);
+      B200MVS_CUDA_OK(cudaMemcpy(net->cvf[i].w16, packed.data(), packed.size(), cudaMemcpyHostToDevice));
+    }
     RC(pack_conv(net, sd, "volume_filter4.conv" + std::to_string(i), 32, 32, 27, true, 0, {}, true, &net->cvf[i]));
     RC(pack_gn(net, sd, "volume_filter4.bn" + std::to_string(i), &net->cvf_gn[i]));
   }
@@ -728,7 +738,27 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
         p.out = bufs[i & 1];
         p.out_stats = sc.take(n);
         p.tag = TAG_CVF_CONV32;
-        RC(launch_conv(CONV_3x3x3, 32, p, stream));
+        if (net->use_tensor_cores && cvf_tc_supported(h4, w4)) {
+          CvfArgs ca;
+          ca.in = p.feat.ptr;
+          ca.mode = p.feat.mode;
+          ca.stats = p.feat.stats;
+          ca.gamma = p.feat.gamma;
+          ca.beta = p.feat.beta;
+          ca.inv_count = p.feat.inv_count;
+          ca.w16 = net->cvf[i].w16;
+          ca.bias = p.bias;
+          ca.out = p.out;
+          ca.out_stats = p.out_stats;
+          ca.n = n;
+          ca.D = D;
+          ca.h = h4;
+          ca.w = w4;
+          ca.tag = p.tag;
+          RC(launch_cvf_tc(ca, stream));
+        } else {
+          RC(launch_conv(CONV_3x3x3, 32, p, stream));
+        }
         src = p.out;
         st_prev = p.out_stats;
       } else {

@@ -1,0 +1,291 @@
+// Conv3d 3x3x3 32->32 of the cost-volume filter (CostVolumeFilter.forward, multi_view_stereonet.py:341-353)
+// on tcgen05 tensor cores with split-fp16 operands (fp32-class accuracy, see recurrence.cu).
+//
+// A CTA owns RT output rows (RT * (w+2) <= 128 positions = one UMMA M-tile) of a chunk of depth slices of one
+// volume and streams through depth: every input slice tile ((RT+2) rows, previous layer's GroupNorm + LeakyReLU
+// applied, split into hi/lo fp16 planes) is staged ONCE into a 4-slot shared-memory ring and used by the three
+// output slices that touch it.  Output slice q = 27 taps x 2 k-steps x 2 MMAs reading ring slots q, q+1, q+2 with
+// the shifted-window descriptors of conv_tc.cu; accumulators are double-buffered in TMEM so the MMAs of slice q
+// run while the epilogue of slice q-1 stores and the loads of input slice q+3 are in flight.
+#include <vector>
+
+#include "conv.cuh"
+#include "cvf_tc.cuh"
+#include "tc_common.cuh"
+
+namespace b200mvs {
+namespace {
+
+constexpr int NT = 256;
+constexpr int MAX_TASKS = 4;
+constexpr int W_BLOCKS = 27 * 2;
+constexpr int W_BYTES = W_BLOCKS * 2048;
+constexpr int RING = 4;
+
+struct Geo {
+  int PW, RT, NP, np_pad;
+  uint32_t plane_bytes, slot_bytes, total;
+};
+__host__ __device__ inline Geo make_geo(int w) {
+  Geo g;
+  g.PW = w + 2;
+  g.RT = 128 / g.PW;
+  g.NP = (g.RT + 2) * g.PW + 2;
+  // the MMA reads 128 rows from every tap offset (up to 2*PW + 2) even when RT * PW < 128
+  if (g.NP < 128 + 2 * g.PW + 2) g.NP = 128 + 2 * g.PW + 2;
+  g.np_pad = (g.NP + 7) & ~7;
+  g.plane_bytes = (uint32_t)g.np_pad * 16u;
+  g.slot_bytes = 8u * g.plane_bytes;  // hi planes 0..3, lo planes 4..7
+  g.total = (uint32_t)W_BYTES + RING * g.slot_bytes;
+  return g;
+}
+
+struct CvfParams {
+  CvfArgs a;
+  int DC, row_tiles;
+};
+
+__global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
+  const CvfArgs& p = P.a;
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ float s_a[kC], s_b[kC], s_bias[kC];
+  __shared__ double s_stats[2 * kGroups];
+  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ uint32_t s_tmem;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = blockIdx.y;
+  const Geo g = make_geo(p.w);
+  const int PW = g.PW, RT = g.RT, NP = g.NP;
+  const int rt = blockIdx.x % P.row_tiles, dc = blockIdx.x / P.row_tiles;
+  const int y0 = rt * RT;
+  const int d0 = dc * P.DC;
+  const int dcount = min(P.DC, p.D - d0);
+  uint8_t* s_w = smem;
+  uint8_t* s_ring = smem + W_BYTES;
+
+  if (warp == 0) tc::tmem_alloc(&s_tmem, 128u);
+  if (tid == 32) {
+    tc::mbar_init(&s_bar[0], 1);
+    tc::mbar_init(&s_bar[1], 1);
+    tc::mbar_init_fence();
+  }
+  if (tid < kC) {
+    s_bias[tid] = p.bias != nullptr ? __ldg(p.bias + tid) : 0.f;
+    if (p.mode >= FEAT_GN) {
+      const int grp = tid >> 3;
+      const double sum = p.stats[(n * kGroups + grp) * 2 + 0];
+      const double sq = p.stats[(n * kGroups + grp) * 2 + 1];
+      const double mean = sum * p.inv_count;
+      double var = sq * p.inv_count - mean * mean;
+      var = var > 0.0 ? var : 0.0;
+      const double rstd = rsqrt(var + (double)kGnEps);
+      s_a[tid] = (float)((double)p.gamma[tid] * rstd);
+      s_b[tid] = (float)((double)p.beta[tid] - mean * (double)p.gamma[tid] * rstd);
+    }
+  }
+  if (tid < 2 * kGroups) s_stats[tid] = 0.0;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.w16);
+    uint4* dst = reinterpret_cast<uint4*>(s_w);
+    for (int i = tid; i < W_BYTES / 16; i += NT) dst[i] = __ldg(src + i);
+    uint4* rz = reinterpret_cast<uint4*>(s_ring);
+    for (int i = tid; i < (int)(RING * g.slot_bytes / 16); i += NT) rz[i] = make_uint4(0, 0, 0, 0);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = s_tmem;
+
+  // staging tasks of this thread (same positions for every slice)
+  const int t_oct = tid & 3;
+  int t_l[MAX_TASKS];
+  size_t t_off[MAX_TASKS];
+  bool t_in[MAX_TASKS], t_real[MAX_TASKS];
+#pragma unroll
+  for (int k = 0; k < MAX_TASKS; ++k) {
+    const int i = tid + k * NT;
+    t_l[k] = i >> 2;
+    const int iy = t_l[k] / PW, ix = t_l[k] % PW;
+    const int gy = y0 - 1 + iy, gx = ix - 1;
+    t_in[k] = t_l[k] < NP;
+    t_real[k] = t_in[k] && iy < RT + 2 && gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;
+    t_off[k] = t_real[k] ? ((size_t)gy * p.w + gx) * kC + 8 * t_oct : 0;
+  }
+  // epilogue slice of this thread: one output position, 16 channels
+  const int wq = warp & 3, chalf = warp >> 2;
+  const int jl = wq * 32 + lane;
+  const int e_oy = jl / PW, e_ox = jl % PW;
+  const bool e_real = e_oy < RT && e_ox < p.w && (y0 + e_oy) < p.h;
+  const size_t e_off = e_real ? ((size_t)(y0 + e_oy) * p.w + e_ox) * kC + chalf * 16 : 0;
+  const uint32_t tmem_my = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(chalf * 16);
+
+  const uint32_t plane_u16 = g.plane_bytes >> 4, slot_u16 = g.slot_bytes >> 4;
+  const uint64_t da0 = tc::umma_desc(tc::smem_u32(s_ring), g.plane_bytes, 128u);
+  const uint64_t db0 = tc::umma_desc(tc::smem_u32(s_w), 1024u, 128u);
+  const size_t slice_elems = (size_t)p.h * p.w * kC;
+  const float* in_n = p.in + (size_t)n * p.D * slice_elems;
+  float* out_n = p.out + (size_t)n * p.D * slice_elems;
+
+  float gs[2] = {0.f, 0.f}, gq[2] = {0.f, 0.f};
+
+  for (int it = 0; it <= dcount + 2; ++it) {
+    // ---- stage input slice `it` (depth d0 - 1 + it) into ring slot it & 3 ----
+    if (it <= dcount + 1) {
+      const int din = d0 - 1 + it;
+      const bool dvalid = din >= 0 && din < p.D;
+      const float* src = in_n + (size_t)(dvalid ? din : 0) * slice_elems;
+      float4 ya[MAX_TASKS], yb[MAX_TASKS];
+#pragma unroll
+      for (int k = 0; k < MAX_TASKS; ++k) {
+        if (t_real[k] && dvalid) {
+          ya[k] = __ldg(reinterpret_cast<const float4*>(src + t_off[k]));
+          yb[k] = __ldg(reinterpret_cast<const float4*>(src + t_off[k] + 4));
+        }
+      }
+      uint8_t* slot = s_ring + (size_t)(it & (RING - 1)) * g.slot_bytes;
+#pragma unroll
+      for (int k = 0; k < MAX_TASKS; ++k) {
+        if (t_in[k]) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = 0.f;
+          if (t_real[k] && dvalid) {
+            v[0] = ya[k].x; v[1] = ya[k].y; v[2] = ya[k].z; v[3] = ya[k].w;
+            v[4] = yb[k].x; v[5] = yb[k].y; v[6] = yb[k].z; v[7] = yb[k].w;
+            if (p.mode >= FEAT_GN) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = lrelu(fmaf(v[e], s_a[8 * t_oct + e], s_b[8 * t_oct + e]));
+            }
+          }
+          uint4 hi, lo;
+          tc::split8(v, &hi, &lo);
+          *reinterpret_cast<uint4*>(slot + (size_t)t_oct * g.plane_bytes + (size_t)t_l[k] * 16) = hi;
+          *reinterpret_cast<uint4*>(slot + (size_t)(4 + t_oct) * g.plane_bytes + (size_t)t_l[k] * 16) = lo;
+        }
+      }
+    }
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+
+    // ---- issue the MMAs of output slice q = it - 2 (input slices q, q+1, q+2) ----
+    const int q = it - 2;
+    if (q >= 0 && q < dcount && tid == 0) {
+      tc::fence_after_sync();
+      const uint32_t acc = tmem_base + (uint32_t)((q & 1) * 64);
+#pragma unroll
+      for (int kz = 0; kz < 3; ++kz) {
+        const uint64_t da_slot = da0 + (uint64_t)(((q + kz) & (RING - 1)) * slot_u16);
+#pragma unroll
+        for (int t2 = 0; t2 < 9; ++t2) {
+          const uint32_t pos = (uint32_t)((t2 / 3) * PW + (t2 % 3));
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint64_t a_hi = da_slot + (uint64_t)(2 * ks * plane_u16 + pos);
+            const uint64_t a_lo = a_hi + (uint64_t)(4 * plane_u16);
+            const uint64_t b = db0 + (uint64_t)((((kz * 9 + t2) * 2) + ks) * 128);
+            tc::mma_f16(acc, a_hi, b, tc::idesc_f16(64), (kz | t2 | ks) != 0 ? 1u : 0u);
+            tc::mma_f16(acc, a_lo, b, tc::idesc_f16(32), 1u);
+          }
+        }
+      }
+      tc::mma_commit(&s_bar[q & 1]);
+    }
+
+    // ---- epilogue of output slice q - 1 (its MMAs were issued one iteration ago) ----
+    const int qe = q - 1;
+    if (qe >= 0 && qe < dcount) {
+      tc::mbar_wait(&s_bar[qe & 1], (uint32_t)((qe >> 1) & 1));
+      tc::fence_after_sync();
+      float v[16], c[16];
+      const uint32_t acc = tmem_my + (uint32_t)((qe & 1) * 64);
+      tc::tmem_ld16(acc, v);
+      tc::tmem_ld16(acc + 32u, c);
+      if (e_real) {
+        float* dst = out_n + (size_t)(d0 + qe) * slice_elems + e_off;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = (v[k] + c[k]) + s_bias[chalf * 16 + k];
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4)
+          *reinterpret_cast<float4*>(dst + 4 * k4) = make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          gs[0] += v[k];
+          gq[0] += v[k] * v[k];
+          gs[1] += v[8 + k];
+          gq[1] += v[8 + k] * v[8 + k];
+        }
+      }
+      tc::fence_before_sync();
+    }
+  }
+
+  // ---- GroupNorm statistics of what this CTA stored ----
+  if (p.out_stats != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      gs[0] += __shfl_xor_sync(0xffffffffu, gs[0], o);
+      gq[0] += __shfl_xor_sync(0xffffffffu, gq[0], o);
+      gs[1] += __shfl_xor_sync(0xffffffffu, gs[1], o);
+      gq[1] += __shfl_xor_sync(0xffffffffu, gq[1], o);
+    }
+    if (lane == 0) {
+      atomicAdd(&s_stats[(2 * chalf) * 2 + 0], (double)gs[0]);
+      atomicAdd(&s_stats[(2 * chalf) * 2 + 1], (double)gq[0]);
+      atomicAdd(&s_stats[(2 * chalf + 1) * 2 + 0], (double)gs[1]);
+      atomicAdd(&s_stats[(2 * chalf + 1) * 2 + 1], (double)gq[1]);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (p.out_stats != nullptr && tid < 2 * kGroups)
+    atomicAdd(p.out_stats + (size_t)n * 2 * kGroups + tid, s_stats[tid]);
+  if (warp == 0) tc::tmem_dealloc(tmem_base, 128u);
+}
+
+}  // namespace
+
+void pack_cvf_tc_weights(const float* w_oidhw, std::vector<uint8_t>* out) {
+  out->assign(W_BYTES, 0);
+  __half* h = reinterpret_cast<__half*>(out->data());
+  for (int tap = 0; tap < 27; ++tap)
+    for (int nn = 0; nn < 32; ++nn)
+      for (int c = 0; c < 32; ++c)
+        tc::put_split_weight(h, tap * 2 + c / 16, c % 16, nn, w_oidhw[((size_t)nn * 32 + c) * 27 + tap]);
+}
+
+bool cvf_tc_supported(int h, int w) {
+  const Geo g = make_geo(w);
+  return g.PW <= 128 && g.RT >= 1 && g.NP * 4 <= MAX_TASKS * NT && g.total + 2048 <= 227 * 1024 && h >= 1;
+}
+
+int launch_cvf_tc(const CvfArgs& a, cudaStream_t stream) {
+  if (a.n <= 0) return 0;
+  if (!cvf_tc_supported(a.h, a.w)) {
+    set_error("launch_cvf_tc: shape not supported");
+    return -1;
+  }
+  const Geo g = make_geo(a.w);
+  static size_t smem_set = 0;
+  if (g.total > smem_set) {
+    B200MVS_CUDA_OK(cudaFuncSetAttribute(cvf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.total));
+    smem_set = g.total;
+  }
+  CvfParams P;
+  P.a = a;
+  P.row_tiles = cdiv(a.h, g.RT);
+  // One CTA per SM (220 KB of shared memory): split depth into as many chunks as fill the chip once.
+  int chunks = 148 / (P.row_tiles * a.n);
+  chunks = chunks < 1 ? 1 : (chunks > a.D ? a.D : chunks);
+  P.DC = cdiv(a.D, chunks);
+  chunks = cdiv(a.D, P.DC);
+  dim3 grid(P.row_tiles * chunks, a.n);
+  if (a.tag != TAG_NONE) probe_before(a.tag, stream);
+  cvf_tc_kernel<<<grid, NT, g.total, stream>>>(P);
+  if (a.tag != TAG_NONE) probe_after(a.tag, stream);
+  B200MVS_LAUNCH_OK("cvf_tc_kernel");
+  return 0;
+}
+
+}  // namespace b200mvs

@@ -18,6 +18,7 @@ CASES = {
     "mv_small": dict(rows=96, cols=128, views=2, hyps=6, batch=2, smooth=True),
     "odd_small": dict(rows=68, cols=90, views=3, hyps=5, batch=1, smooth=True),
     "mid": dict(rows=256, cols=320, views=2, hyps=16, batch=2, smooth=False),
+    "cfg3_b2": dict(rows=512, cols=640, views=4, hyps=64, batch=2, smooth=False),
     "cfg2": dict(rows=512, cols=640, views=1, hyps=64, batch=1, smooth=False),
     "cfg2_smooth": dict(rows=512, cols=640, views=1, hyps=64, batch=1, smooth=True),
 }
