@@ -126,7 +126,8 @@ B200MVS_API int b200mvs_set_option(b200mvs_net* net, const char* name, int value
 
 /* Stage entry for kernel parity tests: y = conv3x3(x, dilation, padding = dilation) + bias on a
  * channels-last (n, rows, cols, 32) DEVICE tensor; `w_oihw_host` (32,32,3,3) and `bias_host` (32 or
- * NULL) are HOST pointers.  use_tensor_cores selects the tcgen05 kernel or the fp32 one.
+ * NULL) are HOST pointers.  use_tensor_cores: 0 = fp32 FFMA kernel, 1 = tcgen05 with fp16 operands,
+ * 2 = tcgen05 with split hi/lo fp16 operands (fp32-class accuracy).
  * Synchronises `stream` before returning. */
 B200MVS_API int b200mvs_conv3x3_c32(const float* x, const float* w_oihw_host, const float* bias_host, int32_t n,
                                     int32_t rows, int32_t cols, int32_t dilation, int32_t use_tensor_cores, float* y,

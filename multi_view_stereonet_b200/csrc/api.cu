@@ -45,7 +45,8 @@ namespace {
 struct ConvW {
   float* w = nullptr;
   float* bias = nullptr;
-  uint8_t* w16 = nullptr;  // fp16 UMMA layout, only for 3x3 32->32 layers that may run on tensor cores
+  uint8_t* w16 = nullptr;   // fp16 UMMA blocks (3x3 layers that may run on tensor cores)
+  uint8_t* w16s = nullptr;  // split hi/lo fp16 UMMA blocks (fp32-class accuracy)
 };
 struct GnW {
   float* gamma = nullptr;
@@ -196,14 +197,18 @@ int pack_conv(b200mvs_net* net, const StateDict& sd, const std::string& name, in
   return 0;
 }
 
-int pack_conv_tc(b200mvs_net* net, const StateDict& sd, const std::string& name, ConvW* out) {
-  const float* w = sd.get(name + ".weight", 32 * 32 * 9);
+int pack_conv_tc(b200mvs_net* net, const StateDict& sd, const std::string& name, int cin, bool has_feat,
+                 int feat_off, const std::vector<int>& extra_idx, ConvW* out) {
+  const float* w = sd.get(name + ".weight", (int64_t)32 * cin * 9);
   if (w == nullptr) return B200MVS_EWEIGHTS;
-  std::vector<uint8_t> packed;
-  pack_conv3x3_tc_weights(w, &packed);
-  B200MVS_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&out->w16), packed.size()));
-  net->allocs.push_back(out->w16);
-  B200MVS_CUDA_OK(cudaMemcpy(out->w16, packed.data(), packed.size(), cudaMemcpyHostToDevice));
+  for (int split = 0; split < 2; ++split) {
+    std::vector<uint8_t> packed;
+    pack_conv3x3_tc_weights(w, cin, has_feat, feat_off, extra_idx, split != 0, &packed);
+    uint8_t** dst = split ? &out->w16s : &out->w16;
+    B200MVS_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(dst), packed.size()));
+    net->allocs.push_back(*dst);
+    B200MVS_CUDA_OK(cudaMemcpy(*dst, packed.data(), packed.size(), cudaMemcpyHostToDevice));
+  }
   return 0;
 }
 
@@ -230,9 +235,11 @@ int build_weights(b200mvs_net* net, const StateDict& sd) {
   for (int i = 0; i < 6; ++i) {
     const std::string r = fe + ".res" + std::to_string(i);
     RC(pack_conv(net, sd, r + ".conv1", 32, 32, 9, true, 0, {}, false, &net->feat_res[i]));
+    RC(pack_conv_tc(net, sd, r + ".conv1", 32, true, 0, {}, &net->feat_res[i]));
     RC(pack_gn(net, sd, r + ".bn1", &net->feat_gn[i]));
   }
   RC(pack_conv(net, sd, fe + ".conv_final", 32, 32, 9, true, 0, {}, true, &net->feat_final));
+  RC(pack_conv_tc(net, sd, fe + ".conv_final", 32, true, 0, {}, &net->feat_final));
 
   const std::string fr = "right_feature_extractor.refiner";
   // input = cat([image(3), features(32)])  (multi_view_stereonet.py:425)
@@ -274,15 +281,18 @@ int build_weights(b200mvs_net* net, const StateDict& sd) {
     Refiner& R = net->refiner[lvl];
     // input = cat([image(3), features(32), idepth(1)]) for levels 1..4, cat([image(3), idepth(1)]) at
     // level 0 (multi_view_stereonet.py:469, 610, 679).
-    if (lvl > 0)
+    if (lvl > 0) {
       RC(pack_conv(net, sd, r + ".conv0", 32, 36, 9, true, 3, {0, 1, 2, 35}, true, &R.conv0));
-    else
+      RC(pack_conv_tc(net, sd, r + ".conv0", 36, true, 3, {0, 1, 2, 35}, &R.conv0));
+    } else {
       RC(pack_conv(net, sd, r + ".conv0", 32, 4, 9, false, 0, {0, 1, 2, 3}, true, &R.conv0));
+      RC(pack_conv_tc(net, sd, r + ".conv0", 4, false, 0, {0, 1, 2, 3}, &R.conv0));
+    }
     RC(pack_gn(net, sd, r + ".bn0", &R.gn0));
     for (int i = 0; i < 6; ++i) {
       const std::string cn = r + ".res" + std::to_string(i) + ".conv1";
       RC(pack_conv(net, sd, cn, 32, 32, 9, true, 0, {}, true, &R.res[i]));
-      RC(pack_conv_tc(net, sd, cn, &R.res[i]));
+      RC(pack_conv_tc(net, sd, cn, 32, true, 0, {}, &R.res[i]));
       RC(pack_gn(net, sd, r + ".res" + std::to_string(i) + ".bn1", &R.gn[i]));
     }
     RC(pack_conv(net, sd, r + ".conv_final", 1, 32, 9, true, 0, {}, true, &R.fin));
@@ -387,6 +397,14 @@ int ensure_workspace(b200mvs_net* net, const b200mvs_shape& s) {
   return 0;
 }
 
+// 3x3 convolution with 32 outputs: tensor cores when enabled (fp16 operands on the large levels, split hi/lo
+// fp16 on the 1/8- and 1/16-scale levels that need fp32-class accuracy), the fp32 FFMA kernel otherwise.
+int conv3x3_c32(b200mvs_net* net, const ConvParams& p, const ConvW& w, bool precise, cudaStream_t stream) {
+  if (net->use_tensor_cores && w.w16 != nullptr && conv3x3_tc_supported(p))
+    return launch_conv3x3_tc(p, precise ? w.w16s : w.w16, precise, stream);
+  return launch_conv(CONV_3x3, 32, p, stream);
+}
+
 struct StatsCursor {
   double* base;
   size_t used = 0, cap;
@@ -434,7 +452,10 @@ int run_refiner(b200mvs_net* net, const Refiner& R, StatsCursor& sc, int m, int 
   p.dil = 1;
   p.out = ws.ry[0];
   p.out_stats = st_prev = sc.take(m);
-  RC(launch_conv(CONV_3x3, 32, p, stream));
+  const bool precise = (long long)H * W <= 96 * 128;  // levels 3 and 4 of a 512x640 input
+  // conv0 sees the idepth channel scaled by fx (values of a few hundred with the signal in the low bits):
+  // always split precision.
+  RC(conv3x3_c32(net, p, R.conv0, true, stream));
 
   static const int dilations[6] = {1, 2, 4, 8, 1, 1};  // multi_view_stereonet.py:457
   const GnW* gn_prev = &R.gn0;
@@ -460,11 +481,7 @@ int run_refiner(b200mvs_net* net, const Refiner& R, StatsCursor& sc, int m, int 
     q.out = ws.ry[1 - ycur];
     q.out_stats = sc.take(m);
     q.tag = res_tag;
-    // Levels 0-2 run on the tensor cores (fp16 operands, fp32 accumulate); the small levels stay fp32.
-    if (net->use_tensor_cores && (long long)H * W > 96 * 128 && R.res[i].w16 != nullptr)
-      RC(launch_conv3x3_tc(q, R.res[i].w16, stream));
-    else
-      RC(launch_conv(CONV_3x3, 32, q, stream));
+    RC(conv3x3_c32(net, q, R.res[i], precise, stream));
     st_prev = q.out_stats;
     gn_prev = &R.gn[i];
     ycur = 1 - ycur;
@@ -613,7 +630,7 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
         p.bias = net->feat_final.bias;
         p.out = ws.feat4;
       }
-      RC(launch_conv(CONV_3x3, 32, p, stream));
+      RC(conv3x3_c32(net, p, i < 6 ? net->feat_res[i] : net->feat_final, true, stream));
       if (i > 0) {
         ycur = 1 - ycur;
         if (i < 6) xcur = 1 - xcur;
@@ -926,10 +943,10 @@ B200MVS_API int b200mvs_conv3x3_c32(const float* x, const float* w_oihw_host, co
   }
   if (use_tensor_cores) {
     std::vector<uint8_t> packed;
-    pack_conv3x3_tc_weights(w_oihw_host, &packed);
+    pack_conv3x3_tc_weights(w_oihw_host, 32, true, 0, {}, use_tensor_cores == 2, &packed);
     B200MVS_CUDA_OK(cudaMalloc(&dw, packed.size()));
     B200MVS_CUDA_OK(cudaMemcpy(dw, packed.data(), packed.size(), cudaMemcpyHostToDevice));
-    rc = launch_conv3x3_tc(p, static_cast<const uint8_t*>(dw), stream);
+    rc = launch_conv3x3_tc(p, static_cast<const uint8_t*>(dw), use_tensor_cores == 2, stream);
   } else {
     std::vector<float> packed((size_t)4 * 9 * 8 * 32);
     for (int chunk = 0; chunk < 4; ++chunk)

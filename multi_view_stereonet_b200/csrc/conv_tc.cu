@@ -23,57 +23,13 @@
 
 #include "conv.cuh"
 #include "conv_tc.cuh"
+#include "tc_common.cuh"
 
 namespace b200mvs {
 namespace {
 
 constexpr int PW = 64;        // positions per tile row (valid outputs: PW - 2*dil)
 constexpr int NT = 256;       // threads per CTA
-constexpr int W_BYTES = 9 * 2 * 1024;   // fp16 weights: [tap][kstep][half(2)][n(32)][8]
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE: start address, leading (K) byte offset,
-// stride (M/N, 8-row group) byte offset, all in 16-byte units; version = 1 (Blackwell).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
-
-// kind::f16 instruction descriptor: D = F32, A = B = F16, K-major both, N = 32, M = 128.
-constexpr uint32_t kIdescF16 = (1u << 4) | (0u << 7) | (0u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
-
-__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(kIdescF16), "r"(accumulate)
-      : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
 
 __host__ __device__ inline int tc_npos(int TH, int dil) {
   int n = (TH + 2 * dil) * PW + 2 * dil;
@@ -85,10 +41,32 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-template <int TH>
+// Stores 8 channels of one position: fp16 (single) or hi/lo split into two plane sets.
+template <bool SPLIT>
+__device__ __forceinline__ void store8(uint8_t* plane_hi, uint32_t lo_offset, int L, const float* v) {
+  if (SPLIT) {
+    uint4 hi, lo;
+    tc::split8(v, &hi, &lo);
+    *reinterpret_cast<uint4*>(plane_hi + (size_t)L * 16) = hi;
+    *reinterpret_cast<uint4*>(plane_hi + lo_offset + (size_t)L * 16) = lo;
+  } else {
+    uint4 h;
+    h.x = pack_half2(v[0], v[1]);
+    h.y = pack_half2(v[2], v[3]);
+    h.z = pack_half2(v[4], v[5]);
+    h.w = pack_half2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(plane_hi + (size_t)L * 16) = h;
+  }
+}
+
+// Plane sets in shared memory: [feat 0..3 (if a 32-channel source)][extra][zero (if planar extras)], and the same
+// again for the lo halves when SPLIT.  K-steps: two over the feature planes, one over (extra, zero).
+template <int TH, bool SPLIT>
 __global__ void __launch_bounds__(NT) conv3x3_tc_kernel(const ConvParams p, const uint8_t* __restrict__ w16) {
-  constexpr int MT = TH * PW / 128;   // M-tiles (two output rows each)
-  constexpr int TMEM_COLS = MT * 32;  // power of two >= 32 for TH in {4, 8, 16}
+  constexpr int MT = TH * PW / 128;             // M-tiles (two output rows each)
+  constexpr int ACC_COLS = SPLIT ? 64 : 32;     // TMEM columns per M-tile
+  constexpr int TMEM_COLS = (MT * ACC_COLS) < 32 ? 32 : MT * ACC_COLS;
+  constexpr uint32_t WBLOCK = SPLIT ? 2048u : 1024u;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ float s_a[kC], s_b[kC], s_bias[kC];
   __shared__ double s_stats[2 * kGroups];
@@ -104,23 +82,27 @@ __global__ void __launch_bounds__(NT) conv3x3_tc_kernel(const ConvParams p, cons
   const int ty0 = (blockIdx.x / tiles_x) * TH;
   const int npos = tc_npos(TH, d);
   const uint32_t plane_bytes = (uint32_t)npos * 16u;
-  uint8_t* s_w = smem;              // W_BYTES
-  uint8_t* s_in = smem + W_BYTES;   // 4 planes x npos x 16 B
+  const int mode = p.feat.mode;
+  const bool has_feat = mode != FEAT_NONE;
+  const bool has_x = p.extra.n > 0;
+  const int ks_feat = has_feat ? 2 : 0;
+  const int KS = ks_feat + (has_x ? 1 : 0);
+  const int fplanes = has_feat ? 4 : 0;
+  const int set_planes = fplanes + (has_x ? 2 : 0);
+  const uint32_t lo_offset = (uint32_t)set_planes * plane_bytes;
+  const uint32_t w_bytes = 9u * (uint32_t)KS * WBLOCK;
+  uint8_t* s_w = smem;
+  uint8_t* s_in = smem + w_bytes;
 
   // ---- one-time setup ----
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
-                 "r"((uint32_t)TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
+  if (warp == 0) tc::tmem_alloc(&s_tmem, (uint32_t)TMEM_COLS);
   if (tid == 32) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_bar)), "r"(1) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tc::mbar_init(&s_bar, 1);
+    tc::mbar_init_fence();
   }
   if (tid < kC) {
     s_bias[tid] = p.bias != nullptr ? __ldg(p.bias + tid) : 0.f;
-    if (p.feat.mode >= FEAT_GN) {
+    if (mode >= FEAT_GN) {
       const int grp = tid >> 3;
       const double sum = p.feat.stats[(img * kGroups + grp) * 2 + 0];
       const double sq = p.feat.stats[(img * kGroups + grp) * 2 + 1];
@@ -135,19 +117,19 @@ __global__ void __launch_bounds__(NT) conv3x3_tc_kernel(const ConvParams p, cons
   if (tid < 2 * kGroups) s_stats[tid] = 0.0;
   __syncthreads();
 
-  // ---- stage weights (already in the canonical fp16 layout) and the transformed input tile ----
+  // ---- stage weights (already in the canonical fp16 layout) ----
   {
     const uint4* src = reinterpret_cast<const uint4*>(w16);
     uint4* dst = reinterpret_cast<uint4*>(s_w);
-    for (int i = tid; i < W_BYTES / 16; i += NT) dst[i] = __ldg(src + i);
+    for (int i = tid; i < (int)(w_bytes / 16); i += NT) dst[i] = __ldg(src + i);
   }
-  {
-    const size_t vol = (size_t)p.Hi * p.Wi;
+  const size_t vol = (size_t)p.Hi * p.Wi;
+  const int rows_in = TH + 2 * d;
+  // ---- stage the transformed 32-channel source ----
+  if (has_feat) {
     const float* fbase = p.feat.ptr + (size_t)(img / p.feat.img_div) * vol * kC;
     const float* rbase = p.feat.resid != nullptr ? p.feat.resid + (size_t)img * vol * kC : nullptr;
     float* xbase = p.feat.x_out != nullptr ? p.feat.x_out + (size_t)img * vol * kC : nullptr;
-    const int rows_in = TH + 2 * d;
-    const int mode = p.feat.mode;
     constexpr int BATCH = 4;   // tasks whose global loads are all issued before any is consumed
     for (int i0 = tid; i0 < npos * 4; i0 += NT * BATCH) {
       float4 ya[BATCH], yb[BATCH], ra[BATCH], rb[BATCH];
@@ -197,61 +179,75 @@ __global__ void __launch_bounds__(NT) conv3x3_tc_kernel(const ConvParams p, cons
             }
           }
         }
-        uint4 h;
-        h.x = pack_half2(v[0], v[1]);
-        h.y = pack_half2(v[2], v[3]);
-        h.z = pack_half2(v[4], v[5]);
-        h.w = pack_half2(v[6], v[7]);
-        *reinterpret_cast<uint4*>(s_in + (size_t)c8 * plane_bytes + (size_t)L * 16) = h;
+        store8<SPLIT>(s_in + (size_t)c8 * plane_bytes, lo_offset, L, v);
       }
     }
   }
-  // generic-proxy writes -> visible to the tensor core (async proxy)
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  // ---- stage the planar extra channels (image planes, scaled idepth) and the zero plane ----
+  if (has_x) {
+    uint8_t* xplane = s_in + (size_t)fplanes * plane_bytes;
+    for (int L = tid; L < npos; L += NT) {
+      const int iy = L / PW, ix = L % PW;
+      const int gy = ty0 - d + iy, gx = tx0 - d + ix;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = 0.f;
+      if (iy < rows_in && gy >= 0 && gy < p.Hi && gx >= 0 && gx < p.Wi) {
+        const size_t pix = (size_t)gy * p.Wi + gx;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (e < p.extra.n) {
+            float x = __ldg(p.extra.ptr[e] + (size_t)(img / p.extra.img_div[e]) * p.extra.img_stride[e] + pix);
+            if (p.extra.scale[e] != nullptr)
+              x = __fmul_rn(x, __ldg(p.extra.scale[e] + (size_t)(img / p.extra.scale_div[e]) * p.extra.scale_stride[e]));
+            v[e] = x;
+          }
+        }
+      }
+      store8<SPLIT>(xplane, lo_offset, L, v);
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(xplane + plane_bytes + (size_t)L * 16) = z;
+      if (SPLIT) *reinterpret_cast<uint4*>(xplane + plane_bytes + lo_offset + (size_t)L * 16) = z;
+    }
+  }
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
   __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  tc::fence_after_sync();
   const uint32_t tmem_base = s_tmem;
 
   // ---- one thread issues every MMA of the tile, then commits to the mbarrier ----
   if (tid == 0) {
-    const uint32_t a0 = smem_u32(s_in);
-    const uint32_t w0 = smem_u32(s_w);
+    const uint32_t plane_u16 = plane_bytes >> 4;
+    const uint64_t da0 = tc::umma_desc(tc::smem_u32(s_in), plane_bytes, 128u);
+    const uint64_t da_lo0 = da0 + (uint64_t)(set_planes * plane_u16);
+    const uint64_t db0 = tc::umma_desc(tc::smem_u32(s_w), SPLIT ? 1024u : 512u, 128u);
 #pragma unroll 1
     for (int mt = 0; mt < MT; ++mt) {
-      const uint32_t dcol = tmem_base + (uint32_t)(mt * 32);
+      const uint32_t dcol = tmem_base + (uint32_t)(mt * ACC_COLS);
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
-        const int ky = tap / 3, kx = tap % 3;
-        const uint32_t pos = (uint32_t)(mt * 128 + ky * d * PW + kx * d);
+        const uint32_t pos = (uint32_t)(mt * 128 + (tap / 3) * d * PW + (tap % 3) * d);
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          const uint64_t adesc = umma_desc(a0 + (uint32_t)(2 * ks) * plane_bytes + pos * 16u, plane_bytes, 128u);
-          const uint64_t bdesc = umma_desc(w0 + (uint32_t)((tap * 2 + ks) * 1024), 512u, 128u);
-          mma_f16(dcol, adesc, bdesc, (tap | ks) != 0 ? 1u : 0u);
+        for (int ks = 0; ks < 3; ++ks) {
+          if (ks < KS) {
+            const uint32_t pl = (ks < ks_feat) ? 2u * ks : (uint32_t)fplanes;
+            const uint64_t a_off = (uint64_t)(pl * plane_u16 + pos);
+            const uint64_t b = db0 + (uint64_t)((tap * KS + ks) * (WBLOCK >> 4));
+            if (SPLIT) {
+              tc::mma_f16(dcol, da0 + a_off, b, tc::idesc_f16(64), (tap | ks) != 0 ? 1u : 0u);
+              tc::mma_f16(dcol, da_lo0 + a_off, b, tc::idesc_f16(32), 1u);
+            } else {
+              tc::mma_f16(dcol, da0 + a_off, b, tc::idesc_f16(32), (tap | ks) != 0 ? 1u : 0u);
+            }
+          }
         }
       }
     }
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_bar))
-                 : "memory");
+    tc::mma_commit(&s_bar);
   }
-  // ---- everyone waits for the accumulators ----
-  {
-    const uint32_t bar = smem_u32(&s_bar);
-    uint32_t done = 0;
-    while (!done) {
-      asm volatile(
-          "{\n\t"
-          ".reg .pred p;\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-          "selp.u32 %0, 1, 0, p;\n\t"
-          "}\n"
-          : "=r"(done)
-          : "r"(bar), "r"(0u)
-          : "memory");
-    }
-  }
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  tc::mbar_wait(&s_bar, 0u);
+  tc::fence_after_sync();
 
   // ---- epilogue: TMEM -> registers -> bias, statistics, channels-last store ----
   const int wq = warp & 3;  // TMEM lane quarter this warp may read
@@ -261,29 +257,41 @@ __global__ void __launch_bounds__(NT) conv3x3_tc_kernel(const ConvParams p, cons
   const size_t ovol = (size_t)p.Ho * p.Wo;
   const size_t ostride = p.out_img_stride != 0 ? (size_t)p.out_img_stride : ovol * kC;
   for (int mt = warp >> 2; mt < MT; mt += NT / 128) {
-    float v[32];
-    tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(mt * 32), v);
     const int j = mt * 128 + wq * 32 + lane;
     const int oy = ty0 + j / PW, ox_t = j % PW;
     const int ox = tx0 + ox_t;
-    if (ox_t < TW && ox < p.Wo && oy < p.Ho) {
-      const size_t opix = (size_t)oy * p.Wo + ox;
-      float* o = p.out + (size_t)img * ostride + opix * kC;
-      const float* add = p.add_src != nullptr ? p.add_src + ((size_t)img * ovol + opix) * kC : nullptr;
+    const bool valid = ox_t < TW && ox < p.Wo && oy < p.Ho;
+    const size_t opix = valid ? (size_t)oy * p.Wo + ox : 0;
+    float* o = p.out + (size_t)img * ostride + opix * kC;
+    const float* add = p.add_src != nullptr ? p.add_src + ((size_t)img * ovol + opix) * kC : nullptr;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float4 r;
-        r.x = v[4 * q + 0] + s_bias[4 * q + 0];
-        r.y = v[4 * q + 1] + s_bias[4 * q + 1];
-        r.z = v[4 * q + 2] + s_bias[4 * q + 2];
-        r.w = v[4 * q + 3] + s_bias[4 * q + 3];
-        if (add != nullptr) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(add + 4 * q));
-          r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w;
+    for (int half = 0; half < 2; ++half) {
+      float v[16];
+      const uint32_t ta = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(mt * ACC_COLS + half * 16);
+      tc::tmem_ld16(ta, v);
+      if (SPLIT) {
+        float c[16];
+        tc::tmem_ld16(ta + 32u, c);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] += c[k];
+      }
+      if (valid) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int ch = half * 16 + 4 * q;
+          float4 r;
+          r.x = v[4 * q + 0] + s_bias[ch + 0];
+          r.y = v[4 * q + 1] + s_bias[ch + 1];
+          r.z = v[4 * q + 2] + s_bias[ch + 2];
+          r.w = v[4 * q + 3] + s_bias[ch + 3];
+          if (add != nullptr) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(add + ch));
+            r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w;
+          }
+          *reinterpret_cast<float4*>(o + ch) = r;
+          gsum[ch >> 3] += (r.x + r.y) + (r.z + r.w);
+          gsq[ch >> 3] += (r.x * r.x + r.y * r.y) + (r.z * r.z + r.w * r.w);
         }
-        *reinterpret_cast<float4*>(o + 4 * q) = r;
-        gsum[q >> 1] += (r.x + r.y) + (r.z + r.w);
-        gsq[q >> 1] += (r.x * r.x + r.y * r.y) + (r.z * r.z + r.w * r.w);
       }
     }
   }
@@ -304,29 +312,32 @@ __global__ void __launch_bounds__(NT) conv3x3_tc_kernel(const ConvParams p, cons
       }
     }
   }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  tc::fence_before_sync();
   __syncthreads();
   if (p.out_stats != nullptr && tid < 2 * kGroups)
     atomicAdd(p.out_stats + (size_t)img * 2 * kGroups + tid, s_stats[tid]);
-  if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
-                 : "memory");
-  }
+  if (warp == 0) tc::tmem_dealloc(tmem_base, (uint32_t)TMEM_COLS);
 }
 
-template <int TH>
+size_t tc_smem_bytes(int TH, bool split, const ConvParams& p) {
+  const int ks = (p.feat.mode != FEAT_NONE ? 2 : 0) + (p.extra.n > 0 ? 1 : 0);
+  const int planes = ((p.feat.mode != FEAT_NONE ? 4 : 0) + (p.extra.n > 0 ? 2 : 0)) * (split ? 2 : 1);
+  return (size_t)9 * ks * (split ? 2048 : 1024) + (size_t)planes * tc_npos(TH, p.dil) * 16;
+}
+
+template <int TH, bool SPLIT>
 int launch_th(const ConvParams& p, const uint8_t* w16, cudaStream_t stream) {
-  const size_t smem = W_BYTES + (size_t)4 * tc_npos(TH, p.dil) * 16;
+  const size_t smem = tc_smem_bytes(TH, SPLIT, p);
   static bool attr_set = false;
   if (!attr_set) {
-    B200MVS_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc_kernel<TH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         200 * 1024));
+    B200MVS_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc_kernel<TH, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         220 * 1024));
     attr_set = true;
   }
   const int TW = PW - 2 * p.dil;
   dim3 grid(cdiv(p.Wo, TW) * cdiv(p.Ho, TH), p.n_img);
   if (p.tag != TAG_NONE) probe_before(p.tag, stream);
-  conv3x3_tc_kernel<TH><<<grid, NT, smem, stream>>>(p, w16);
+  conv3x3_tc_kernel<TH, SPLIT><<<grid, NT, smem, stream>>>(p, w16);
   if (p.tag != TAG_NONE) probe_after(p.tag, stream);
   B200MVS_LAUNCH_OK("conv3x3_tc_kernel");
   return 0;
@@ -334,33 +345,66 @@ int launch_th(const ConvParams& p, const uint8_t* w16, cudaStream_t stream) {
 
 }  // namespace
 
-void pack_conv3x3_tc_weights(const float* w_oihw, std::vector<uint8_t>* out) {
-  out->assign(W_BYTES, 0);
+void pack_conv3x3_tc_weights(const float* w_oihw, int cin, bool has_feat, int feat_off,
+                             const std::vector<int>& extra_idx, bool split, std::vector<uint8_t>* out) {
+  const int ks_feat = has_feat ? 2 : 0;
+  const int KS = ks_feat + (extra_idx.empty() ? 0 : 1);
+  const size_t block_halves = split ? 1024 : 512;
+  out->assign((size_t)9 * KS * block_halves * 2, 0);
   __half* h = reinterpret_cast<__half*>(out->data());
+  auto put = [&](int block, int k, int n, float w) {
+    if (split) {
+      tc::put_split_weight(h, block, k, n, w);
+    } else {
+      h[(size_t)block * 512 + (size_t)(k / 8) * 256 + (size_t)n * 8 + (size_t)(k % 8)] = __float2half_rn(w);
+    }
+  };
   for (int tap = 0; tap < 9; ++tap)
-    for (int c = 0; c < 32; ++c)
-      for (int n = 0; n < 32; ++n) {
-        const int ks = c / 16, k = c % 16;
-        const size_t byte = (size_t)(tap * 2 + ks) * 1024 + (size_t)(k / 8) * 512 + (size_t)n * 16 + (size_t)(k % 8) * 2;
-        h[byte / 2] = __float2half_rn(w_oihw[((size_t)n * 32 + c) * 9 + tap]);
-      }
+    for (int n = 0; n < 32; ++n) {
+      if (has_feat)
+        for (int c = 0; c < 32; ++c) put(tap * KS + c / 16, c % 16, n, w_oihw[((size_t)n * cin + feat_off + c) * 9 + tap]);
+      for (size_t e = 0; e < extra_idx.size(); ++e)
+        put(tap * KS + ks_feat, (int)e, n, w_oihw[((size_t)n * cin + extra_idx[e]) * 9 + tap]);
+    }
 }
 
 bool conv3x3_tc_supported(const ConvParams& p) {
-  return p.feat.mode != FEAT_NONE && p.extra.n == 0 && p.Di == 1 && p.Do == 1 && p.Hi == p.Ho && p.Wi == p.Wo &&
-         p.dil >= 1 && p.dil <= 8;
+  return (p.feat.mode != FEAT_NONE || p.extra.n > 0) && p.extra.n <= 4 && p.Di == 1 && p.Do == 1 && p.Hi == p.Ho &&
+         p.Wi == p.Wo && p.dil >= 1 && p.dil <= 8;
 }
 
-int launch_conv3x3_tc(const ConvParams& p, const uint8_t* w16, cudaStream_t stream) {
+int launch_conv3x3_tc(const ConvParams& p, const uint8_t* w16, bool split, cudaStream_t stream) {
   if (p.n_img <= 0) return 0;
   if (!conv3x3_tc_supported(p)) {
     set_error("launch_conv3x3_tc: unsupported configuration");
     return -1;
   }
-  // Tile height: two CTAs per SM where the halo allows it.
-  if (p.dil <= 2) return launch_th<16>(p, w16, stream);
-  if (p.dil <= 4) return launch_th<8>(p, w16, stream);
-  return launch_th<16>(p, w16, stream);
+  // Tile height: the tallest tile that still gives every SM work and fits two CTAs per SM; small images get
+  // short tiles so that a layer is not a handful of long-running CTAs.
+  const int TW = PW - 2 * p.dil;
+  const int ths[3] = {16, 8, 4};
+  int pick = 4;
+  for (int k = 0; k < 3; ++k) {
+    const int th = ths[k];
+    if (split && th == 16) continue;  // 8 M-tiles x 64 columns would exceed TMEM
+    const long long tiles = (long long)cdiv(p.Wo, TW) * cdiv(p.Ho, th) * p.n_img;
+    const size_t smem = tc_smem_bytes(th, split, p);
+    if (smem > 210 * 1024) continue;
+    if (tiles >= 296 && smem <= 110 * 1024) { pick = th; break; }
+    if (tiles >= 148 && th != 16) { pick = th; break; }
+    if (th == 4) pick = 4;
+  }
+  if (tc_smem_bytes(pick, split, p) > 210 * 1024) {
+    set_error("launch_conv3x3_tc: tile does not fit in shared memory");
+    return -1;
+  }
+  if (split) {
+    if (pick == 8) return launch_th<8, true>(p, w16, stream);
+    return launch_th<4, true>(p, w16, stream);
+  }
+  if (pick == 16) return launch_th<16, false>(p, w16, stream);
+  if (pick == 8) return launch_th<8, false>(p, w16, stream);
+  return launch_th<4, false>(p, w16, stream);
 }
 
 }  // namespace b200mvs

@@ -30,9 +30,11 @@ def conv_stage(x_nhwc, w, bias, dilation, use_tc):
 
 @pytest.mark.parametrize("dilation", [1, 2, 4, 8])
 @pytest.mark.parametrize("shape", [(1, 128, 160), (2, 70, 131), (1, 16, 62)])
-@pytest.mark.parametrize("use_tc", [0, 1])
+@pytest.mark.parametrize("use_tc", [0, 1, 2])
 def test_conv3x3_c32(dilation, shape, use_tc):
     n, h, w = shape
+    if use_tc == 2 and dilation == 8 and h > 100:
+        pass
     g = torch.Generator().manual_seed(dilation * 100 + h)
     x = torch.randn(n, 32, h, w, generator=g)
     wt = torch.randn(32, 32, 3, 3, generator=g) * 0.1
@@ -41,4 +43,4 @@ def test_conv3x3_c32(dilation, shape, use_tc):
     x_nhwc = x.permute(0, 2, 3, 1).contiguous().cuda()
     y = conv_stage(x_nhwc, wt, bias, dilation, use_tc).permute(0, 3, 1, 2).cpu()
     err = float((y - ref).abs().max() / ref.abs().max())
-    assert err <= (TC_TOL if use_tc else FP32_TOL), err
+    assert err <= (TC_TOL if use_tc == 1 else FP32_TOL), err
