@@ -8,6 +8,8 @@
 // [tap][8][COUT] which every lane reads as a broadcast.  Each thread owns PXT pixels x COUT/CSPLIT
 // channels in registers.  The epilogue transposes through shared memory so that global stores are
 // full 128-byte channel vectors, and reduces the GroupNorm statistics of what it stores.
+#include <cuda_fp16.h>
+
 #include "conv.cuh"
 
 namespace b200mvs {
@@ -146,14 +148,31 @@ conv_kernel(const ConvParams p) {
           const size_t pix = ((size_t)gz * p.Hi + gy) * p.Wi + gx;
           const size_t vol = (size_t)p.Di * p.Hi * p.Wi;
           const int c = c0 + 4 * q;
-          v = __ldg(reinterpret_cast<const float4*>(p.feat.ptr + ((size_t)fimg * vol + pix) * kC + c));
+          if (p.feat.half_io) {
+            const uint2 h = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p.feat.ptr) +
+                                                                 ((size_t)fimg * vol + pix) * kC + c));
+            const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&h.x));
+            const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+            v = make_float4(lo.x, lo.y, hi.x, hi.y);
+          } else {
+            v = __ldg(reinterpret_cast<const float4*>(p.feat.ptr + ((size_t)fimg * vol + pix) * kC + c));
+          }
           if (p.feat.mode >= FEAT_GN) {
             v.x = lrelu(fmaf(v.x, s_a[c + 0], s_b[c + 0]));
             v.y = lrelu(fmaf(v.y, s_a[c + 1], s_b[c + 1]));
             v.z = lrelu(fmaf(v.z, s_a[c + 2], s_b[c + 2]));
             v.w = lrelu(fmaf(v.w, s_a[c + 3], s_b[c + 3]));
             if (p.feat.mode == FEAT_GN_RES) {
-              const float4 r = __ldg(reinterpret_cast<const float4*>(p.feat.resid + ((size_t)img * vol + pix) * kC + c));
+              float4 r;
+              if (p.feat.half_io) {
+                const uint2 h = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p.feat.resid) +
+                                                                     ((size_t)img * vol + pix) * kC + c));
+                const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&h.x));
+                const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+                r = make_float4(lo.x, lo.y, hi.x, hi.y);
+              } else {
+                r = __ldg(reinterpret_cast<const float4*>(p.feat.resid + ((size_t)img * vol + pix) * kC + c));
+              }
               v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
             }
             // Only stride-1 same-size layers carry GroupNorm inputs: output pixel == input pixel.

@@ -29,6 +29,9 @@ struct FeatSrc {
   double inv_count = 0.0;        // 1 / (8 * D * H * W)
   const float* resid = nullptr;  // [img][D][H][W][32]
   float* x_out = nullptr;        // if set, the transformed input is written back (tile interior)
+  // fp16 activation storage (refiner levels 0-2 on the tensor-core path): ptr, resid and x_out then point to
+  // __half data of the same [n][H][W][32] shape.  Statistics always come from fp32 accumulators.
+  int half_io = 0;
 };
 
 // Up to 4 planar single-channel sources (image planes, an idepth plane).
@@ -53,6 +56,7 @@ struct ConvParams {
   int dil = 1;
   float* out = nullptr;          // COUT=32: [img][Do][Ho][Wo][32]   COUT=1: [img][Do][Ho][Wo]
   long long out_img_stride = 0;  // elements between output images; 0 = dense (Do*Ho*Wo*COUT)
+  int out_half = 0;              // COUT=32 on the tensor-core path: store the raw output as __half
   double* out_stats = nullptr;   // [img][4][2], COUT=32 only
   const float* add_src = nullptr;  // COUT=32: out += add_src (same layout)
   // COUT=1 epilogue: 0 -> acc + bias ; 1 -> relu(prior * fx + acc + bias) / fx

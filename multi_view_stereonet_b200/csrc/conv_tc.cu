@@ -19,6 +19,7 @@
 // 1/16-scale stages do not and stay on the fp32 path (conv.cu).
 #include <cuda_fp16.h>
 
+#include <cstdlib>
 #include <vector>
 
 #include "conv.cuh"
@@ -39,6 +40,18 @@ __host__ __device__ inline int tc_npos(int TH, int dil) {
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ void unpack8(const uint4& h, float* v) {
+  const uint32_t w[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+    v[2 * k] = f.x;
+    v[2 * k + 1] = f.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  return make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
 }
 
 // Stores 8 channels of one position: fp16 (single) or hi/lo split into two plane sets.
@@ -61,8 +74,8 @@ __device__ __forceinline__ void store8(uint8_t* plane_hi, uint32_t lo_offset, in
 
 // Plane sets in shared memory: [feat 0..3 (if a 32-channel source)][extra][zero (if planar extras)], and the same
 // again for the lo halves when SPLIT.  K-steps: two over the feature planes, one over (extra, zero).
-template <int TH, bool SPLIT>
-__global__ void __launch_bounds__(NT) conv3x3_tc_kernel(const ConvParams p, const uint8_t* __restrict__ w16) {
+template <int TH, bool SPLIT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) conv3x3_tc_kernel(const ConvParams p, const uint8_t* __restrict__ w16) {
   constexpr int MT = TH * PW / 128;             // M-tiles (two output rows each)
   constexpr int ACC_COLS = SPLIT ? 64 : 32;     // TMEM columns per M-tile
   constexpr int TMEM_COLS = (MT * ACC_COLS) < 32 ? 32 : MT * ACC_COLS;
@@ -127,12 +140,16 @@ __global__ void __launch_bounds__(NT) conv3x3_tc_kernel(const ConvParams p, cons
   const int rows_in = TH + 2 * d;
   // ---- stage the transformed 32-channel source ----
   if (has_feat) {
-    const float* fbase = p.feat.ptr + (size_t)(img / p.feat.img_div) * vol * kC;
-    const float* rbase = p.feat.resid != nullptr ? p.feat.resid + (size_t)img * vol * kC : nullptr;
-    float* xbase = p.feat.x_out != nullptr ? p.feat.x_out + (size_t)img * vol * kC : nullptr;
-    constexpr int BATCH = 4;   // tasks whose global loads are all issued before any is consumed
+    const bool hio = p.feat.half_io != 0;
+    const size_t esz = hio ? 2 : 4;   // bytes per stored activation element
+    const uint8_t* fbase = reinterpret_cast<const uint8_t*>(p.feat.ptr) + (size_t)(img / p.feat.img_div) * vol * kC * esz;
+    const uint8_t* rbase = p.feat.resid != nullptr
+                               ? reinterpret_cast<const uint8_t*>(p.feat.resid) + (size_t)img * vol * kC * esz : nullptr;
+    uint8_t* xbase = p.feat.x_out != nullptr ? reinterpret_cast<uint8_t*>(p.feat.x_out) + (size_t)img * vol * kC * esz
+                                             : nullptr;
+    constexpr int BATCH = MINB >= 3 ? 2 : 4;   // tasks whose global loads are all issued before any is consumed
     for (int i0 = tid; i0 < npos * 4; i0 += NT * BATCH) {
-      float4 ya[BATCH], yb[BATCH], ra[BATCH], rb[BATCH];
+      float4 ya[BATCH], yb[BATCH], ra[BATCH], rb[BATCH];   // fp32: two float4; fp16: ya / ra hold 8 halves
       size_t off[BATCH];
       bool inb[BATCH];
 #pragma unroll
@@ -143,13 +160,13 @@ __global__ void __launch_bounds__(NT) conv3x3_tc_kernel(const ConvParams p, cons
         const int iy = L / PW, ix = L % PW;
         const int gy = ty0 - d + iy, gx = tx0 - d + ix;
         inb[k] = i < npos * 4 && iy < rows_in && gy >= 0 && gy < p.Hi && gx >= 0 && gx < p.Wi;
-        off[k] = inb[k] ? ((size_t)gy * p.Wi + gx) * kC + 8 * c8 : 0;
+        off[k] = inb[k] ? (((size_t)gy * p.Wi + gx) * kC + 8 * c8) * esz : 0;
         if (inb[k]) {
           ya[k] = __ldg(reinterpret_cast<const float4*>(fbase + off[k]));
-          yb[k] = __ldg(reinterpret_cast<const float4*>(fbase + off[k] + 4));
+          if (!hio) yb[k] = __ldg(reinterpret_cast<const float4*>(fbase + off[k] + 16));
           if (mode == FEAT_GN_RES) {
             ra[k] = __ldg(reinterpret_cast<const float4*>(rbase + off[k]));
-            rb[k] = __ldg(reinterpret_cast<const float4*>(rbase + off[k] + 4));
+            if (!hio) rb[k] = __ldg(reinterpret_cast<const float4*>(rbase + off[k] + 16));
           }
         }
       }
@@ -163,19 +180,34 @@ __global__ void __launch_bounds__(NT) conv3x3_tc_kernel(const ConvParams p, cons
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = 0.f;
         if (inb[k]) {
-          v[0] = ya[k].x; v[1] = ya[k].y; v[2] = ya[k].z; v[3] = ya[k].w;
-          v[4] = yb[k].x; v[5] = yb[k].y; v[6] = yb[k].z; v[7] = yb[k].w;
+          if (hio) {
+            unpack8(*reinterpret_cast<const uint4*>(&ya[k]), v);
+          } else {
+            v[0] = ya[k].x; v[1] = ya[k].y; v[2] = ya[k].z; v[3] = ya[k].w;
+            v[4] = yb[k].x; v[5] = yb[k].y; v[6] = yb[k].z; v[7] = yb[k].w;
+          }
           if (mode >= FEAT_GN) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = lrelu(fmaf(v[e], s_a[8 * c8 + e], s_b[8 * c8 + e]));
             if (mode == FEAT_GN_RES) {
-              v[0] += ra[k].x; v[1] += ra[k].y; v[2] += ra[k].z; v[3] += ra[k].w;
-              v[4] += rb[k].x; v[5] += rb[k].y; v[6] += rb[k].z; v[7] += rb[k].w;
+              float r[8];
+              if (hio) {
+                unpack8(*reinterpret_cast<const uint4*>(&ra[k]), r);
+              } else {
+                r[0] = ra[k].x; r[1] = ra[k].y; r[2] = ra[k].z; r[3] = ra[k].w;
+                r[4] = rb[k].x; r[5] = rb[k].y; r[6] = rb[k].z; r[7] = rb[k].w;
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] += r[e];
             }
             const int iy = L / PW, ix = L % PW;
             if (xbase != nullptr && iy >= d && iy < d + TH && ix >= d && ix < d + TW) {
-              *reinterpret_cast<float4*>(xbase + off[k]) = make_float4(v[0], v[1], v[2], v[3]);
-              *reinterpret_cast<float4*>(xbase + off[k] + 4) = make_float4(v[4], v[5], v[6], v[7]);
+              if (hio) {
+                *reinterpret_cast<uint4*>(xbase + off[k]) = pack8(v);
+              } else {
+                *reinterpret_cast<float4*>(xbase + off[k]) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(xbase + off[k] + 16) = make_float4(v[4], v[5], v[6], v[7]);
+              }
             }
           }
         }
@@ -245,8 +277,10 @@ __global__ void __launch_bounds__(NT) conv3x3_tc_kernel(const ConvParams p, cons
       }
     }
     tc::mma_commit(&s_bar);
+    tc::mbar_wait(&s_bar, 0u);   // only the issuing thread polls; the rest park at the hardware barrier
+    tc::fence_before_sync();
   }
-  tc::mbar_wait(&s_bar, 0u);
+  __syncthreads();
   tc::fence_after_sync();
 
   // ---- epilogue: TMEM -> registers -> bias, statistics, channels-last store ----
@@ -276,6 +310,7 @@ __global__ void __launch_bounds__(NT) conv3x3_tc_kernel(const ConvParams p, cons
         for (int k = 0; k < 16; ++k) v[k] += c[k];
       }
       if (valid) {
+        float r16[16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int ch = half * 16 + 4 * q;
@@ -288,9 +323,19 @@ __global__ void __launch_bounds__(NT) conv3x3_tc_kernel(const ConvParams p, cons
             const float4 a = __ldg(reinterpret_cast<const float4*>(add + ch));
             r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w;
           }
-          *reinterpret_cast<float4*>(o + ch) = r;
+          r16[4 * q + 0] = r.x; r16[4 * q + 1] = r.y; r16[4 * q + 2] = r.z; r16[4 * q + 3] = r.w;
           gsum[ch >> 3] += (r.x + r.y) + (r.z + r.w);
           gsq[ch >> 3] += (r.x * r.x + r.y * r.y) + (r.z * r.z + r.w * r.w);
+        }
+        if (p.out_half) {
+          __half* oh = reinterpret_cast<__half*>(p.out) + (size_t)img * ostride + opix * kC + half * 16;
+          *reinterpret_cast<uint4*>(oh) = pack8(r16);
+          *reinterpret_cast<uint4*>(oh + 8) = pack8(r16 + 8);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<float4*>(o + half * 16 + 4 * q) =
+                make_float4(r16[4 * q], r16[4 * q + 1], r16[4 * q + 2], r16[4 * q + 3]);
         }
       }
     }
@@ -325,19 +370,19 @@ size_t tc_smem_bytes(int TH, bool split, const ConvParams& p) {
   return (size_t)9 * ks * (split ? 2048 : 1024) + (size_t)planes * tc_npos(TH, p.dil) * 16;
 }
 
-template <int TH, bool SPLIT>
+template <int TH, bool SPLIT, int MINB = 1>
 int launch_th(const ConvParams& p, const uint8_t* w16, cudaStream_t stream) {
   const size_t smem = tc_smem_bytes(TH, SPLIT, p);
   static bool attr_set = false;
   if (!attr_set) {
-    B200MVS_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc_kernel<TH, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B200MVS_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc_kernel<TH, SPLIT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          220 * 1024));
     attr_set = true;
   }
   const int TW = PW - 2 * p.dil;
   dim3 grid(cdiv(p.Wo, TW) * cdiv(p.Ho, TH), p.n_img);
   if (p.tag != TAG_NONE) probe_before(p.tag, stream);
-  conv3x3_tc_kernel<TH, SPLIT><<<grid, NT, smem, stream>>>(p, w16);
+  conv3x3_tc_kernel<TH, SPLIT, MINB><<<grid, NT, smem, stream>>>(p, w16);
   if (p.tag != TAG_NONE) probe_after(p.tag, stream);
   B200MVS_LAUNCH_OK("conv3x3_tc_kernel");
   return 0;
@@ -390,7 +435,7 @@ int launch_conv3x3_tc(const ConvParams& p, const uint8_t* w16, bool split, cudaS
     const long long tiles = (long long)cdiv(p.Wo, TW) * cdiv(p.Ho, th) * p.n_img;
     const size_t smem = tc_smem_bytes(th, split, p);
     if (smem > 210 * 1024) continue;
-    if (tiles >= 296 && smem <= 110 * 1024) { pick = th; break; }
+    if (tiles >= 296 && (smem <= 110 * 1024 || p.dil >= 8)) { pick = th; break; }  // big halo: amortise it
     if (tiles >= 148 && th != 16) { pick = th; break; }
     if (th == 4) pick = 4;
   }
@@ -402,6 +447,10 @@ int launch_conv3x3_tc(const ConvParams& p, const uint8_t* w16, bool split, cudaS
     if (pick == 8) return launch_th<8, true>(p, w16, stream);
     return launch_th<4, true>(p, w16, stream);
   }
+  // Large images, small halo: 8-row tiles at three CTAs per SM overlap one CTA's loads with another's MMAs and
+  // stores better than 16-row tiles at two per SM (measured ~50 vs ~72 us per level-0 layer).
+  static const int variant = getenv("B200MVS_TC_VARIANT") ? atoi(getenv("B200MVS_TC_VARIANT")) : 1;
+  if (variant == 1 && pick == 16 && p.dil <= 2) return launch_th<8, false, 3>(p, w16, stream);
   if (pick == 16) return launch_th<16, false>(p, w16, stream);
   if (pick == 8) return launch_th<8, false>(p, w16, stream);
   return launch_th<4, false>(p, w16, stream);

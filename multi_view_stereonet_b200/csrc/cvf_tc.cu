@@ -196,7 +196,11 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
     // ---- epilogue of output slice q - 1 (its MMAs were issued one iteration ago) ----
     const int qe = q - 1;
     if (qe >= 0 && qe < dcount) {
-      tc::mbar_wait(&s_bar[qe & 1], (uint32_t)((qe >> 1) & 1));
+      if (tid == 0) {  // one poller; the other warps park at the hardware barrier
+        tc::mbar_wait(&s_bar[qe & 1], (uint32_t)((qe >> 1) & 1));
+        tc::fence_before_sync();
+      }
+      __syncthreads();
       tc::fence_after_sync();
       float v[16], c[16];
       const uint32_t acc = tmem_my + (uint32_t)((qe & 1) * 64);

@@ -125,20 +125,28 @@ __global__ void __launch_bounds__(256) cost_norm_kernel(const float* __restrict_
 __global__ void __launch_bounds__(128) softargmin_kernel(const float* __restrict__ cost,
                                                          const float* __restrict__ samples, int D, int pixels,
                                                          float* __restrict__ raw) {
+  // 8 lanes per pixel share the hypothesis axis (lane s handles d = s, s + 8, ...); 16 pixels per CTA.
   const int n = blockIdx.y;
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= pixels) return;
-  const float* c = cost + (size_t)n * D * pixels + p;
+  const int sub = threadIdx.x & 7;
+  const int p = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);
+  const bool ok = p < pixels;
+  const float* c = cost + (size_t)n * D * pixels + (ok ? p : 0);
   float m = -INFINITY;
-  for (int d = 0; d < D; ++d) m = fmaxf(m, -__ldg(c + (size_t)d * pixels));
-  float den = 0.f;
-  for (int d = 0; d < D; ++d) den += expf(-__ldg(c + (size_t)d * pixels) - m);
-  float acc = 0.f;
-  for (int d = 0; d < D; ++d) {
-    const float pr = expf(-__ldg(c + (size_t)d * pixels) - m) / den;
-    acc += pr * __ldg(samples + (size_t)n * D + d);
+  for (int d = sub; d < D; d += 8) m = fmaxf(m, -__ldg(c + (size_t)d * pixels));
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float den = 0.f, num = 0.f;
+  for (int d = sub; d < D; d += 8) {
+    const float e = expf(-__ldg(c + (size_t)d * pixels) - m);
+    den += e;
+    num += e * __ldg(samples + (size_t)n * D + d);
   }
-  raw[(size_t)n * pixels + p] = acc;
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    den += __shfl_xor_sync(0xffffffffu, den, o);
+    num += __shfl_xor_sync(0xffffffffu, num, o);
+  }
+  if (ok && sub == 0) raw[(size_t)n * pixels + p] = num / den;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -150,31 +158,34 @@ __global__ void __launch_bounds__(128) view_reduce_kernel(const float* __restric
                                                           const float* __restrict__ baseline, int views, int D,
                                                           int pixels, int alias, float* __restrict__ raw4,
                                                           float* __restrict__ idepth4, uint8_t* __restrict__ mask4) {
+  // blockIdx.z = 0: the two idepth maps; blockIdx.z = 1 + d: mask plane d
   const int b = blockIdx.y;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= pixels) return;
-  float rs = 0.f, is = 0.f;
-  for (int v = 0; v < views; ++v) {
-    const int n = b * views + v;
-    const float bl = __ldg(baseline + n);
-    float r = __ldg(raw_views + (size_t)n * pixels + p);
-    float f;
-    if (alias) {
-      // do_refiners[4] == False: the reference's two in-place divisions hit the same tensor
-      // (multi_view_stereonet.py:613-619).
-      r = __fdiv_rn(__fdiv_rn(r, bl), bl);
-      f = r;
-    } else {
-      r = __fdiv_rn(r, bl);
-      f = __fdiv_rn(__ldg(refined_views + (size_t)n * pixels + p), bl);
-    }
-    rs += r;
-    is += f;
-  }
   const float nv = (float)views;
-  if (raw4 != nullptr) raw4[(size_t)b * pixels + p] = __fdiv_rn(rs, nv);
-  idepth4[(size_t)b * pixels + p] = __fdiv_rn(is, nv);
-  for (int d = 0; d < D; ++d) {
+  if (blockIdx.z == 0) {
+    float rs = 0.f, is = 0.f;
+    for (int v = 0; v < views; ++v) {
+      const int n = b * views + v;
+      const float bl = __ldg(baseline + n);
+      float r = __ldg(raw_views + (size_t)n * pixels + p);
+      float f;
+      if (alias) {
+        // do_refiners[4] == False: the reference's two in-place divisions hit the same tensor
+        // (multi_view_stereonet.py:613-619).
+        r = __fdiv_rn(__fdiv_rn(r, bl), bl);
+        f = r;
+      } else {
+        r = __fdiv_rn(r, bl);
+        f = __fdiv_rn(__ldg(refined_views + (size_t)n * pixels + p), bl);
+      }
+      rs += r;
+      is += f;
+    }
+    if (raw4 != nullptr) raw4[(size_t)b * pixels + p] = __fdiv_rn(rs, nv);
+    idepth4[(size_t)b * pixels + p] = __fdiv_rn(is, nv);
+  } else {
+    const int d = blockIdx.z - 1;
     float ms = 0.f;
     for (int v = 0; v < views; ++v) ms += (float)__ldg(mask_views + ((size_t)(b * views + v) * D + d) * pixels + p);
     mask4[((size_t)b * D + d) * pixels + p] = (__fdiv_rn(ms, nv) > 0.5f) ? 1 : 0;
@@ -216,7 +227,7 @@ __global__ void __launch_bounds__(256) upsample_f32_kernel(const float* __restri
 }
 
 // Mask volume upsampling: float(mask) -> bilinear -> > 0.5 (multi_view_stereonet.py:389-396).
-// Each thread produces 4 horizontally adjacent outputs (one 32-bit store) when W % 4 == 0.
+// Each thread produces VEC horizontally adjacent outputs (one 32- or 128-bit store) when W % VEC == 0.
 template <int VEC>
 __global__ void __launch_bounds__(256) upsample_mask_kernel(const uint8_t* __restrict__ in, int h, int w, int H, int W,
                                                             uint8_t* __restrict__ out) {
@@ -228,20 +239,24 @@ __global__ void __launch_bounds__(256) upsample_mask_kernel(const uint8_t* __res
   const Lerp ly = lerp_setup(y, (float)h / (float)H, h);
   const uint8_t* r0 = in + (size_t)plane * h * w + (size_t)ly.i0 * w;
   const uint8_t* r1 = in + (size_t)plane * h * w + (size_t)ly.i1 * w;
-  uint32_t packed = 0;
+  uint32_t packed[(VEC + 3) / 4];
+#pragma unroll
+  for (int k = 0; k < (VEC + 3) / 4; ++k) packed[k] = 0;
 #pragma unroll
   for (int k = 0; k < VEC; ++k) {
     const Lerp lx = lerp_setup(xv * VEC + k, (float)w / (float)W, w);
     const float v00 = (float)__ldg(r0 + lx.i0), v01 = (float)__ldg(r0 + lx.i1);
     const float v10 = (float)__ldg(r1 + lx.i0), v11 = (float)__ldg(r1 + lx.i1);
     const float v = ly.l0 * (lx.l0 * v00 + lx.l1 * v01) + ly.l1 * (lx.l0 * v10 + lx.l1 * v11);
-    packed |= (v > 0.5f ? 1u : 0u) << (8 * k);
+    packed[k >> 2] |= (v > 0.5f ? 1u : 0u) << (8 * (k & 3));
   }
   uint8_t* dst = out + (size_t)plane * H * W + (size_t)y * W + xv * VEC;
-  if (VEC == 4) {
-    *reinterpret_cast<uint32_t*>(dst) = packed;
+  if (VEC == 16) {
+    *reinterpret_cast<uint4*>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+  } else if (VEC == 4) {
+    *reinterpret_cast<uint32_t*>(dst) = packed[0];
   } else {
-    dst[0] = (uint8_t)packed;
+    dst[0] = (uint8_t)packed[0];
   }
 }
 
@@ -281,7 +296,7 @@ int launch_cost_norm(const float* cost, long long voxels, float* out, cudaStream
 
 int launch_softargmin(const float* cost, const float* samples, int n, int D, int pixels, float* raw,
                       cudaStream_t stream) {
-  dim3 grid(cdiv(pixels, 128), n);
+  dim3 grid(cdiv(pixels, 16), n);
   softargmin_kernel<<<grid, 128, 0, stream>>>(cost, samples, D, pixels, raw);
   B200MVS_LAUNCH_OK("softargmin_kernel");
   return 0;
@@ -290,7 +305,7 @@ int launch_softargmin(const float* cost, const float* samples, int n, int D, int
 int launch_view_reduce(const float* raw_views, const float* refined_views, const uint8_t* mask_views,
                        const float* baseline, int batch, int views, int D, int pixels, bool refined_is_alias,
                        float* raw4, float* idepth4, uint8_t* mask4, cudaStream_t stream) {
-  dim3 grid(cdiv(pixels, 128), batch);
+  dim3 grid(cdiv(pixels, 128), batch, 1 + D);
   view_reduce_kernel<<<grid, 128, 0, stream>>>(raw_views, refined_views, mask_views, baseline, views, D, pixels,
                                                refined_is_alias ? 1 : 0, raw4, idepth4, mask4);
   B200MVS_LAUNCH_OK("view_reduce_kernel");
@@ -308,11 +323,15 @@ int launch_upsample_mask(const uint8_t* in, long long n_planes, int h, int w, in
                          cudaStream_t stream) {
   // gridDim.y is limited to 65535 planes per launch.
   const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 3) == 0) && (((long long)H * W) % 4 == 0);
+  const bool vec16 = (W % 16 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   for (long long p0 = 0; p0 < n_planes; p0 += 65535) {
     const int np = (int)((n_planes - p0) < 65535 ? (n_planes - p0) : 65535);
     const uint8_t* src = in + (size_t)p0 * h * w;
     uint8_t* dst = out + (size_t)p0 * H * W;
-    if (vec) {
+    if (vec16) {
+      dim3 grid(cdiv(H * (W / 16), 256), np);
+      upsample_mask_kernel<16><<<grid, 256, 0, stream>>>(src, h, w, H, W, dst);
+    } else if (vec) {
       dim3 grid(cdiv(H * (W / 4), 256), np);
       upsample_mask_kernel<4><<<grid, 256, 0, stream>>>(src, h, w, H, W, dst);
     } else {

@@ -30,7 +30,7 @@
 namespace b200mvs {
 namespace {
 
-constexpr int NT = 256;
+constexpr int NT = 512;
 constexpr int MTILE = 128;
 constexpr int W0_BLOCKS = 9 * 3;   // conv0: taps x k-steps (32 feature + 3 image channels, padded to 48)
 constexpr int W1_BLOCKS = 9 * 2;
@@ -133,7 +133,7 @@ struct Layout {
 
 // Planes (each npl_pad x 16 B): [hi f0..f3][hi extra][zero][lo f0..f3][lo extra][zero]
 constexpr int PLANE_HI = 0, PLANE_HI_X = 4, PLANE_LO = 6, PLANE_LO_X = 10, NUM_PLANES = 12;
-constexpr int MAX_TASKS = 4;   // (position, channel octet) staging tasks per thread: npl * 4 <= 4 * NT
+constexpr int MAX_TASKS = 2;   // (position, channel octet) staging tasks per thread: npl * 4 <= 2 * NT
 
 __host__ __device__ inline Layout make_layout(int cols) {
   Layout L;
@@ -147,8 +147,7 @@ __host__ __device__ inline Layout make_layout(int cols) {
   o += W_TOTAL_BYTES;
   L.off_planes = o;
   o += NUM_PLANES * L.plane_bytes;
-  L.off_own = o;           // raw conv output of the own 128 positions, fp32 [128][32]
-  o += MTILE * kC * 4;
+  L.off_own = o;           // (unused: the own tile's raw outputs live in registers)
   L.off_halo = o;          // [layer 2][side 2][halo][32] fp32, written by the neighbour CTAs
   o += 2 * 2 * (uint32_t)L.halo * kC * 4;
   L.off_wf = o;            // warped features of the own positions, fp32 [128][32]
@@ -172,38 +171,63 @@ struct RecParams {
   const float* beta1;
   int D, rows, cols, n_tiles;
   long long* prof;       // optional [16][12] phase cycle totals (debug)
+  int debug;             // timing ablations (wrong results): 1 skip MMAs, 2 skip gathers, 4 skip halo/stat pushes
 };
 
-// One conv = 9 taps x KSTEPS k-steps; per k-step two MMAs implement the split product
+// 8 consecutive fp32 accumulator columns of this thread's TMEM lane.
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// One conv = 9 taps x ksteps k-steps; per k-step two MMAs implement the split product
 //   D[:, 0:32]  += A_hi * W_hi      D[:, 32:64] += A_hi * W_lo      (one N=64 MMA on [W_hi | W_lo])
 //   D[:, 0:32]  += A_lo * W_hi                                      (one N=32 MMA)
 // so the A operand -- the shared-memory-bandwidth-bound side at N=32 -- is read twice, not three times.
-// Descriptors differ from precomputed bases only in the 14-bit start-address field.
-template <int KSTEPS>
-__device__ __forceinline__ void issue_conv_mmas(uint32_t tmem_base, uint64_t da_hi0, uint64_t da_lo0, uint64_t db0,
-                                                uint32_t plane_u16, int PW) {
-#pragma unroll
-  for (int tap = 0; tap < 9; ++tap) {
-    const uint32_t pos = (uint32_t)((tap / 3) * PW + (tap % 3));  // 16-byte units
-#pragma unroll
-    for (int ks = 0; ks < KSTEPS; ++ks) {
-      // k-steps 0,1 read feature planes (2ks, 2ks+1); k-step 2 reads (extra, zero)
-      const uint32_t pl = (ks < 2) ? 2u * ks : (uint32_t)PLANE_HI_X;
-      const uint64_t a_off = (uint64_t)(pl * plane_u16 + pos);
-      const uint64_t b_off = (uint64_t)((tap * KSTEPS + ks) * (2048 / 16));
-      mma_f16(tmem_base, da_hi0 + a_off, db0 + b_off, kIdescN64, (tap | ks) != 0 ? 1u : 0u);
-      mma_f16(tmem_base, da_lo0 + a_off, db0 + b_off, kIdescN32, 1u);
-    }
+// A single thread issues the MMAs, so the issue loop itself is on the critical path: the (A_hi, A_lo, B)
+// descriptors of every k-step are the same in every step of the sweep (fixed shared-memory addresses), are built
+// once into a shared-memory table, and the loop is three loads and two MMAs per k-step.
+struct KStepDesc {
+  uint64_t a_hi, a_lo, b, pad;
+};
+constexpr int KSTEPS_TOTAL = W0_BLOCKS + 2 * W1_BLOCKS;  // 27 + 18 + 18
+
+__device__ __forceinline__ void issue_conv_mmas(const KStepDesc* tbl, int count, uint32_t tmem_base) {
+  const uint32_t taddr = smem_u32(tbl);
+#pragma unroll 3
+  for (int i = 0; i < count; ++i) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pacc, ptrue;\n\t"
+        ".reg .b64 ahi, alo, bd;\n\t"
+        "ld.shared.v2.b64 {ahi, alo}, [%1];\n\t"
+        "ld.shared.b64 bd, [%1+16];\n\t"
+        "setp.ne.b32 pacc, %2, 0;\n\t"
+        "setp.eq.b32 ptrue, %2, %2;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], ahi, bd, %3, pacc;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], alo, bd, %4, ptrue;\n\t"
+        "}\n" ::"r"(tmem_base),
+        "r"(taddr + (uint32_t)i * 32u), "r"((uint32_t)i), "r"(kIdescN64), "r"(kIdescN32)
+        : "memory");
   }
 }
 
+template <bool PROF>
 __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ float s_part[2][16][2 * kGroups];  // per-layer partial (sum, sumsq) of every CTA of the cluster
-  __shared__ float s_red[NT / 32][2 * kGroups];
-  __shared__ float s_a[kC], s_b[kC], s_bias[3][kC], s_gamma[2][kC], s_beta[2][kC];
+  __shared__ float s_red[NT / 32][2];
+  __shared__ float s_bias[3][kC], s_gamma[2][kC], s_beta[2][kC];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t s_tmem;
+  __shared__ __align__(16) KStepDesc s_desc[KSTEPS_TOTAL];
+  __shared__ float s_tot[2 * kGroups];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
@@ -217,7 +241,6 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
 
   uint8_t* s_w = smem + L.off_w;
   uint8_t* s_planes = smem + L.off_planes;
-  float* s_own = reinterpret_cast<float*>(smem + L.off_own);
   float* s_halo = reinterpret_cast<float*>(smem + L.off_halo);
   float* s_wf = reinterpret_cast<float*>(smem + L.off_wf);
 
@@ -263,40 +286,67 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
   const uint64_t da_hi0 = umma_desc(smem_u32(s_planes) + (uint32_t)PLANE_HI * L.plane_bytes, L.plane_bytes, 128u);
   const uint64_t da_lo0 = umma_desc(smem_u32(s_planes) + (uint32_t)PLANE_LO * L.plane_bytes, L.plane_bytes, 128u);
   const uint64_t db_c0 = umma_desc(smem_u32(s_w), 1024u, 128u);
-  const uint64_t db_c1 = db_c0 + (uint64_t)(W0_BLOCKS * (2048 / 16));
-  const uint64_t db_c2 = db_c1 + (uint64_t)(W1_BLOCKS * (2048 / 16));
+  if (tid < KSTEPS_TOTAL) {
+    // entry order = weight block order: conv0 [tap][3 k-steps], conv1 [tap][2], conv2 [tap][2]
+    int i = tid, ksteps = 3;
+    if (i >= W0_BLOCKS) {
+      i = (i - W0_BLOCKS) % W1_BLOCKS;
+      ksteps = 2;
+    }
+    const int tap = i / ksteps, ks = i % ksteps;
+    const uint32_t pos = (uint32_t)((tap / 3) * PW + (tap % 3));        // 16-byte units
+    const uint32_t pl = (ks < 2) ? 2u * ks : (uint32_t)PLANE_HI_X;      // k-step 2 reads (extra, zero)
+    const uint64_t a_off = (uint64_t)(pl * plane_u16 + pos);
+    KStepDesc d;
+    d.a_hi = da_hi0 + a_off;
+    d.a_lo = da_lo0 + a_off;
+    d.b = db_c0 + (uint64_t)(tid * (2048 / 16));
+    d.pad = 0;
+    s_desc[tid] = d;
+  }
+  __syncthreads();
 
-  auto wait_mma = [&]() {
-    const uint32_t bar = smem_u32(&s_bar);
-    uint32_t done = 0;
-    while (!done) {
-      asm volatile(
-          "{\n\t"
-          ".reg .pred q;\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
-          "selp.u32 %0, 1, 0, q;\n\t"
-          "}\n"
-          : "=r"(done)
-          : "r"(bar), "r"(bar_phase)
-          : "memory");
+  // Runs one conv on the tensor core and waits for its accumulators.  Only the issuing thread polls the
+  // mbarrier; everyone else parks at the hardware barrier (polling from 16 warps steals shared-memory bandwidth
+  // from the tensor core's operand fetch).
+  auto run_conv = [&](int first, int count) {
+    if (active && tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (!(p.debug & 1)) issue_conv_mmas(s_desc + first, count, tmem_base);
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                       smem_u32(&s_bar))
+                   : "memory");
+      const uint32_t bar = smem_u32(&s_bar);
+      uint32_t done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred q;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, q;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(bar_phase)
+            : "memory");
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     bar_phase ^= 1u;
+    __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   };
-  auto commit_mma = [&]() {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_bar))
-                 : "memory");
-  };
 
-  // This thread's slice of the accumulator tile: one output position, 16 channels.
-  const int wq = warp & 3, chalf = warp >> 2;
+  // This thread's slice of the accumulator tile: one output position, ONE channel octet (= one GroupNorm group).
+  const int wq = warp & 3, oct_e = warp >> 2;
   const int jl = wq * 32 + lane;                 // local output position
   const int jg = pos0 + jl;                      // global output position
   const int oy = jg / PW, ox = jg % PW;
   const bool real_out = active && ox < p.cols && oy < p.rows;
-  const uint32_t tmem_my = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(chalf * 16);
+  const uint32_t tmem_my = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(oct_e * 8);
+  const int own_l = jl + halo;                   // local input position of the own output
 
   // Staging tasks of this thread, fixed for all steps: (local input position l, channel octet).
+  const int t_oct = tid & 3;  // NT % 4 == 0: the octet is the same for every task of a thread
   int t_l[MAX_TASKS], t_gy[MAX_TASKS], t_gx[MAX_TASKS];
   bool t_real[MAX_TASKS];
 #pragma unroll
@@ -308,115 +358,33 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
     t_gx[k] = Lg % PW - 1;
     t_real[k] = active && t_l[k] < npl && t_gy[k] >= 0 && t_gy[k] < p.rows && t_gx[k] >= 0 && t_gx[k] < p.cols;
   }
-  const int t_oct = tid & 3;  // NT % 4 == 0: the octet is the same for every task of a thread
   // image-plane task: one local position per thread
   const int x_l = tid;
   const int x_gy = (pos0 + x_l) / PW - 1, x_gx = (pos0 + x_l) % PW - 1;
   const bool x_in = active && x_l < npl;
   const bool x_real = x_in && x_gy >= 0 && x_gy < p.rows && x_gx >= 0 && x_gx < p.cols;
+  // halo staging task: (halo position, channel octet); 2 * halo * 4 <= NT
+  const int h_idx = tid >> 2;                               // lower halo then upper halo, as laid out in s_halo
+  const bool h_in = active && h_idx < 2 * halo;
+  const int h_l = h_idx < halo ? h_idx : h_idx + MTILE;     // local input position
+  bool h_real;
+  {
+    const int Lg = pos0 + h_l;
+    const int gy = Lg / PW - 1, gx = Lg % PW - 1;
+    h_real = h_in && gy >= 0 && gy < p.rows && gx >= 0 && gx < p.cols;
+  }
 
-  // Epilogue of conv0 / conv1: raw output (+bias) -> own buffer, neighbours' halo buffers, statistics.
-  auto epilogue_raw = [&](int layer) {
-    float v[16];
-    float gs[2] = {0.f, 0.f}, gq[2] = {0.f, 0.f};
-    if (active) {
-      float c[16];
-      tmem_ld16(tmem_my, v);
-      tmem_ld16(tmem_my + 32u, c);
-#pragma unroll
-      for (int k = 0; k < 16; ++k) v[k] = (v[k] + c[k]) + s_bias[layer][chalf * 16 + k];
-      float4* own = reinterpret_cast<float4*>(s_own + jl * kC + chalf * 16);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) own[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-      // halo pushes: the neighbour indexes its halo buffer [layer][side][i][32]
-      if (jl < halo && rank > 0) {  // upper halo (side 1) of rank-1, index jl
-        const uint32_t la = smem_u32(s_halo + (((layer * 2 + 1) * halo) + jl) * kC + chalf * 16);
-        const uint32_t ra = map_to_rank(la, rank - 1);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) st_cluster_f4(ra + 16u * q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
-      }
-      if (jl >= MTILE - halo && (int)rank + 1 < p.n_tiles) {  // lower halo (side 0) of rank+1
-        const int idx = jl - (MTILE - halo);
-        const uint32_t la = smem_u32(s_halo + (((layer * 2 + 0) * halo) + idx) * kC + chalf * 16);
-        const uint32_t ra = map_to_rank(la, rank + 1);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) st_cluster_f4(ra + 16u * q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
-      }
-      if (real_out) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          gs[0] += v[k];
-          gq[0] += v[k] * v[k];
-          gs[1] += v[8 + k];
-          gq[1] += v[8 + k] * v[8 + k];
-        }
-      }
-    }
-    // CTA partial: warp shuffle, then 8 warps -> one value per (group, moment)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      gs[0] += __shfl_xor_sync(0xffffffffu, gs[0], o);
-      gq[0] += __shfl_xor_sync(0xffffffffu, gq[0], o);
-      gs[1] += __shfl_xor_sync(0xffffffffu, gs[1], o);
-      gq[1] += __shfl_xor_sync(0xffffffffu, gq[1], o);
-    }
-    if (lane == 0) {
-      // this warp covers groups 2*chalf and 2*chalf + 1
-      float* r = s_red[warp];
-#pragma unroll
-      for (int k = 0; k < 2 * kGroups; ++k) r[k] = 0.f;
-      r[(2 * chalf) * 2 + 0] = gs[0];
-      r[(2 * chalf) * 2 + 1] = gq[0];
-      r[(2 * chalf + 1) * 2 + 0] = gs[1];
-      r[(2 * chalf + 1) * 2 + 1] = gq[1];
-    }
-    __syncthreads();
-    if (tid < (int)csize * 2 * kGroups) {
-      const int dst = tid / (2 * kGroups), k = tid % (2 * kGroups);
-      float tot = 0.f;
-#pragma unroll
-      for (int w = 0; w < NT / 32; ++w) tot += s_red[w][k];
-      const uint32_t la = smem_u32(&s_part[layer][rank][k]);
-      st_cluster_f1(map_to_rank(la, (uint32_t)dst), tot);
-    }
-  };
-
-  // GroupNorm coefficients from the cluster-wide partials (fixed summation order: deterministic).
-  auto gn_coeffs = [&](int layer) {
-    if (tid < kC) {
-      const int g = tid >> 3;
-      double sum = 0.0, sq = 0.0;
-      for (int r = 0; r < p.n_tiles; ++r) {
-        sum += (double)s_part[layer][r][2 * g];
-        sq += (double)s_part[layer][r][2 * g + 1];
-      }
-      const double mean = sum * (double)inv_count;
-      const double var = sq * (double)inv_count - mean * mean;   // cancellation handled in double
-      const float rstd = rsqrtf(fmaxf((float)var, 0.f) + kGnEps);
-      const float a = s_gamma[layer][tid] * rstd;
-      s_a[tid] = a;
-      s_b[tid] = s_beta[layer][tid] - (float)mean * a;
-    }
-    __syncthreads();
-  };
-
-  // Raw conv output of local input position l (own tile or a neighbour's pushed halo).
-  auto raw_ptr = [&](int layer, int l) -> const float* {
-    if (l < halo) return s_halo + ((layer * 2 + 0) * halo + l) * kC;
-    if (l < halo + MTILE) return s_own + (l - halo) * kC;
-    return s_halo + ((layer * 2 + 1) * halo + (l - halo - MTILE)) * kC;
-  };
   auto plane_ptr = [&](int plane, int l) -> uint4* {
     return reinterpret_cast<uint4*>(s_planes + (size_t)plane * L.plane_bytes + (size_t)l * 16);
   };
 
-  long long t_prev = clock64();
-  long long acc_t[12];
+  long long t_prev = PROF ? clock64() : 0;
+  long long acc_t[PROF ? 12 : 1];
 #pragma unroll
-  for (int k = 0; k < 12; ++k) acc_t[k] = 0;
+  for (int k = 0; k < (PROF ? 12 : 1); ++k) acc_t[k] = 0;
 #define PROF_MARK(k)                          \
   do {                                        \
-    if (p.prof != nullptr) {                  \
+    if (PROF) {                               \
       const long long _t = clock64();         \
       acc_t[k] += _t - t_prev;                \
       t_prev = _t;                            \
@@ -431,6 +399,9 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
     Hinc[k] = __ldg(p.geo.Hinc + ((size_t)n * p.D + 1) * 9 + k);
     Hd[k] = __ldg(p.geo.H + ((size_t)n * p.D + 1) * 9 + k);
   }
+  float x0own[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) x0own[k] = 0.f;
 
   for (int step = 1; step < p.D; ++step) {
     // ================= W: warp previous features and the 1/16 image into the conv0 operand =========
@@ -443,7 +414,7 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
 #pragma unroll
       for (int k = 0; k < MAX_TASKS; ++k) {
         ok[k] = false;
-        if (t_real[k]) {
+        if (t_real[k] && !(p.debug & 2)) {
           const WarpCoord c = homography_coord(Hinc, (float)t_gx[k], (float)t_gy[k], p.rows, p.cols);
           ok[k] = !c.invalid;
           if (ok[k]) {
@@ -522,115 +493,147 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     PROF_MARK(0);
-    if (active) {
-      if (tid == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        issue_conv_mmas<3>(tmem_base, da_hi0, da_lo0, db_c0, plane_u16, PW);
-        commit_mma();
-      }
-      wait_mma();
-    }
+    run_conv(0, W0_BLOCKS);
     PROF_MARK(1);
-    epilogue_raw(0);
-    PROF_MARK(2);
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    cluster_sync_all();  // A: statistics and halos of y0 are everywhere
-    PROF_MARK(3);
 
-    // ================= S1: x0 = lrelu(GN(y0)) over own + halo -> conv1 operand ====================
-    gn_coeffs(0);
+    // ===== two normalised layers: raw output -> statistics + halo exchange -> barrier -> operand -> conv =====
+#pragma unroll 1
+    for (int layer = 0; layer < 2; ++layer) {
+      // ---- epilogue: raw output (+bias) stays in registers, is pushed to the neighbours' halos, and is reduced
+      float y[8];
+      float gs = 0.f, gq = 0.f;
+      if (active) {
+        float c[8];
+        tmem_ld8(tmem_my, y);
+        tmem_ld8(tmem_my + 32u, c);
 #pragma unroll
-    for (int k = 0; k < MAX_TASKS; ++k) {
-      if (active && t_l[k] < npl) {
-        float v[8];
+        for (int k = 0; k < 8; ++k) y[k] = (y[k] + c[k]) + s_bias[layer][oct_e * 8 + k];
+        // the neighbour indexes its halo buffer [layer][side][i][32]
+        if (jl < halo && rank > 0 && !(p.debug & 4)) {  // upper halo (side 1) of rank-1, index jl
+          const uint32_t ra = map_to_rank(smem_u32(s_halo + (((layer * 2 + 1) * halo) + jl) * kC + oct_e * 8), rank - 1);
+          st_cluster_f4(ra, make_float4(y[0], y[1], y[2], y[3]));
+          st_cluster_f4(ra + 16u, make_float4(y[4], y[5], y[6], y[7]));
+        }
+        if (jl >= MTILE - halo && (int)rank + 1 < p.n_tiles && !(p.debug & 4)) {  // lower halo (side 0) of rank+1
+          const int idx = jl - (MTILE - halo);
+          const uint32_t ra = map_to_rank(smem_u32(s_halo + (((layer * 2 + 0) * halo) + idx) * kC + oct_e * 8), rank + 1);
+          st_cluster_f4(ra, make_float4(y[0], y[1], y[2], y[3]));
+          st_cluster_f4(ra + 16u, make_float4(y[4], y[5], y[6], y[7]));
+        }
+        if (real_out) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = 0.f;
-        if (t_real[k]) {
-          const float4* src = reinterpret_cast<const float4*>(raw_ptr(0, t_l[k]) + 8 * t_oct);
-          const float4 a = src[0], b = src[1];
-          const float y[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+          for (int k = 0; k < 8; ++k) {
+            gs += y[k];
+            gq += y[k] * y[k];
+          }
+        }
+      }
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = lrelu(fmaf(y[e], s_a[8 * t_oct + e], s_b[8 * t_oct + e]));
+      for (int o = 16; o > 0; o >>= 1) {
+        gs += __shfl_xor_sync(0xffffffffu, gs, o);
+        gq += __shfl_xor_sync(0xffffffffu, gq, o);
+      }
+      if (lane == 0) {
+        s_red[warp][0] = gs;
+        s_red[warp][1] = gq;
+      }
+      __syncthreads();
+      if (tid < (int)csize * 2 * kGroups) {
+        // partial of group g = the four warps with oct_e == g
+        const int dst = tid / (2 * kGroups), k = tid % (2 * kGroups);
+        const int g = k >> 1, m = k & 1;
+        const float tot = (s_red[4 * g][m] + s_red[4 * g + 1][m]) + (s_red[4 * g + 2][m] + s_red[4 * g + 3][m]);
+        st_cluster_f1(map_to_rank(smem_u32(&s_part[layer][rank][k]), (uint32_t)dst), tot);
+      }
+      PROF_MARK(2 + 4 * layer);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      cluster_sync_all();  // statistics and halos of this layer's raw output are everywhere
+      PROF_MARK(3 + 4 * layer);
+
+      // ---- GroupNorm coefficients from the cluster-wide partials (fixed reduction tree: deterministic) ----
+      if (warp < 2 * kGroups) {
+        float t = (lane < p.n_tiles) ? s_part[layer][lane][warp] : 0.f;   // n_tiles <= 16
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) s_tot[warp] = t;
+      }
+      __syncthreads();
+      // every thread derives the scale/shift of the two channel octets it touches (own output, halo task)
+      float ca[8], cb[8], ha[8], hb[8];
+      {
+        auto coeffs = [&](int g, float* a, float* b) {
+          const double mean = (double)s_tot[2 * g] * (double)inv_count;
+          const double var = (double)s_tot[2 * g + 1] * (double)inv_count - mean * mean;  // cancellation in double
+          const float rstd = rsqrtf(fmaxf((float)var, 0.f) + kGnEps);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            a[k] = s_gamma[layer][8 * g + k] * rstd;
+            b[k] = s_beta[layer][8 * g + k] - (float)mean * a[k];
+          }
+        };
+        coeffs(oct_e, ca, cb);
+        coeffs(t_oct, ha, hb);
+      }
+
+      // ---- next operand: x = lrelu(GN(y)) (+ x0 for the residual block) over own + halo positions ----
+      if (active) {
+        float x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float t = real_out ? lrelu(fmaf(y[k], ca[k], cb[k])) : 0.f;
+          x[k] = (layer == 0) ? t : t + x0own[k];
+          if (layer == 0) x0own[k] = t;
         }
         uint4 hi, lo;
-        split8(v, &hi, &lo);
-        *plane_ptr(PLANE_HI + t_oct, t_l[k]) = hi;
-        *plane_ptr(PLANE_LO + t_oct, t_l[k]) = lo;
-      }
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    PROF_MARK(4);
-    if (active) {
-      if (tid == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        issue_conv_mmas<2>(tmem_base, da_hi0, da_lo0, db_c1, plane_u16, PW);
-        commit_mma();
-      }
-      wait_mma();
-    }
-    PROF_MARK(5);
-    epilogue_raw(1);
-    PROF_MARK(6);
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    cluster_sync_all();  // C: statistics and halos of y1 are everywhere
-    PROF_MARK(7);
-
-    // ================= S2: x1 = lrelu(GN(y1)) + x0 over own + halo -> conv_final operand ==========
-    gn_coeffs(1);
+        split8(x, &hi, &lo);
+        *plane_ptr(PLANE_HI + oct_e, own_l) = hi;
+        *plane_ptr(PLANE_LO + oct_e, own_l) = lo;
+        if (h_in) {
+          float v[8];
 #pragma unroll
-    for (int k = 0; k < MAX_TASKS; ++k) {
-      if (active && t_l[k] < npl) {
-        float v[8];
+          for (int e = 0; e < 8; ++e) v[e] = 0.f;
+          uint4* ph = plane_ptr(PLANE_HI + t_oct, h_l);
+          uint4* plo = plane_ptr(PLANE_LO + t_oct, h_l);
+          if (h_real) {
+            const float4* src = reinterpret_cast<const float4*>(s_halo + ((layer * 2) * halo + h_idx) * kC + 8 * t_oct);
+            const float4 a = src[0], b = src[1];
+            const float yy[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            float xprev[8];
+            if (layer == 1) unsplit8(*ph, *plo, xprev);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = 0.f;
-        uint4* ph = plane_ptr(PLANE_HI + t_oct, t_l[k]);
-        uint4* plo = plane_ptr(PLANE_LO + t_oct, t_l[k]);
-        if (t_real[k]) {
-          float x0[8];
-          unsplit8(*ph, *plo, x0);
-          const float4* src = reinterpret_cast<const float4*>(raw_ptr(1, t_l[k]) + 8 * t_oct);
-          const float4 a = src[0], b = src[1];
-          const float y[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = lrelu(fmaf(y[e], s_a[8 * t_oct + e], s_b[8 * t_oct + e])) + x0[e];
+            for (int e = 0; e < 8; ++e) {
+              v[e] = lrelu(fmaf(yy[e], ha[e], hb[e]));
+              if (layer == 1) v[e] += xprev[e];
+            }
+          }
+          split8(v, &hi, &lo);
+          *ph = hi;
+          *plo = lo;
         }
-        uint4 hi, lo;
-        split8(v, &hi, &lo);
-        *ph = hi;
-        *plo = lo;
       }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();
+      PROF_MARK(4 + 4 * layer);
+      run_conv(W0_BLOCKS + layer * W1_BLOCKS, W1_BLOCKS);
+      PROF_MARK(5 + 4 * layer);
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    PROF_MARK(8);
-    if (active) {
-      if (tid == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        issue_conv_mmas<2>(tmem_base, da_hi0, da_lo0, db_c2, plane_u16, PW);
-        commit_mma();
-      }
-      wait_mma();
-    }
-    PROF_MARK(9);
 
     // ================= E2: features_step = wf + delta -> global =====================================
     if (active) {
-      float v[16], c[16];
-      tmem_ld16(tmem_my, v);
-      tmem_ld16(tmem_my + 32u, c);
+      float v[8], c[8];
+      tmem_ld8(tmem_my, v);
+      tmem_ld8(tmem_my + 32u, c);
       if (real_out) {
-        float* dst = p.vol + (((size_t)n * p.D + step) * pixels + (size_t)oy * p.cols + ox) * kC + chalf * 16;
-        const float* wfp = s_wf + jl * kC + chalf * 16;
+        float* dst = p.vol + (((size_t)n * p.D + step) * pixels + (size_t)oy * p.cols + ox) * kC + oct_e * 8;
+        const float* wfp = s_wf + jl * kC + oct_e * 8;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 2; ++q) {
           float4 r;
-          r.x = wfp[4 * q + 0] + ((v[4 * q + 0] + c[4 * q + 0]) + s_bias[2][chalf * 16 + 4 * q + 0]);
-          r.y = wfp[4 * q + 1] + ((v[4 * q + 1] + c[4 * q + 1]) + s_bias[2][chalf * 16 + 4 * q + 1]);
-          r.z = wfp[4 * q + 2] + ((v[4 * q + 2] + c[4 * q + 2]) + s_bias[2][chalf * 16 + 4 * q + 2]);
-          r.w = wfp[4 * q + 3] + ((v[4 * q + 3] + c[4 * q + 3]) + s_bias[2][chalf * 16 + 4 * q + 3]);
+          r.x = wfp[4 * q + 0] + ((v[4 * q + 0] + c[4 * q + 0]) + s_bias[2][oct_e * 8 + 4 * q + 0]);
+          r.y = wfp[4 * q + 1] + ((v[4 * q + 1] + c[4 * q + 1]) + s_bias[2][oct_e * 8 + 4 * q + 1]);
+          r.z = wfp[4 * q + 2] + ((v[4 * q + 2] + c[4 * q + 2]) + s_bias[2][oct_e * 8 + 4 * q + 2]);
+          r.w = wfp[4 * q + 3] + ((v[4 * q + 3] + c[4 * q + 3]) + s_bias[2][oct_e * 8 + 4 * q + 3]);
           __stcg(reinterpret_cast<float4*>(dst) + q, r);
         }
       }
@@ -640,8 +643,8 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
     cluster_sync_all();  // E: hypothesis `step` is visible to every CTA's gathers
     PROF_MARK(11);
   }
-  if (p.prof != nullptr && tid == 0 && blockIdx.y == 0) {
-    for (int k = 0; k < 12; ++k) p.prof[rank * 12 + k] = acc_t[k];
+  if (PROF && p.prof != nullptr && tid == 0 && blockIdx.y == 0) {
+    for (int k = 0; k < 12; ++k) p.prof[rank * 12 + k] = acc_t[PROF ? k : 0];
   }
 
   __syncthreads();
@@ -683,7 +686,7 @@ bool recurrence_supported(int rows, int cols, int* n_tiles, size_t* smem_bytes) 
   const int tiles = cdiv(rows * L.PW, MTILE);
   if (n_tiles != nullptr) *n_tiles = tiles;
   if (smem_bytes != nullptr) *smem_bytes = L.total;
-  return tiles <= 16 && L.halo <= MTILE && L.npl * 4 <= MAX_TASKS * NT && L.npl <= NT && L.total + 4096 <= 227 * 1024;
+  return tiles <= 16 && L.halo <= MTILE && L.npl * 4 <= MAX_TASKS * NT && L.npl <= NT && 2 * L.halo * 4 <= NT && L.total + 4096 <= 227 * 1024;
 }
 
 int launch_recurrence(const RecurrenceArgs& a, cudaStream_t stream) {
@@ -695,8 +698,10 @@ int launch_recurrence(const RecurrenceArgs& a, cudaStream_t stream) {
   }
   static size_t smem_set = 0;
   if (smem > smem_set) {
-    B200MVS_CUDA_OK(cudaFuncSetAttribute(recurrence_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B200MVS_CUDA_OK(cudaFuncSetAttribute(recurrence_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    B200MVS_CUDA_OK(cudaFuncSetAttribute(recurrence_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200MVS_CUDA_OK(cudaFuncSetAttribute(recurrence_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    B200MVS_CUDA_OK(cudaFuncSetAttribute(recurrence_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200MVS_CUDA_OK(cudaFuncSetAttribute(recurrence_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     smem_set = smem;
   }
   RecParams p;
@@ -717,6 +722,7 @@ int launch_recurrence(const RecurrenceArgs& a, cudaStream_t stream) {
   p.cols = a.cols;
   p.n_tiles = n_tiles;
   p.prof = a.prof;
+  p.debug = a.debug;
 
   // Cluster size: one CTA per M-tile; if that size cannot be scheduled, pad with idle CTAs.
   static int good_cluster[17] = {0};
@@ -740,14 +746,15 @@ int launch_recurrence(const RecurrenceArgs& a, cudaStream_t stream) {
     cfg.numAttrs = 1;
     if (good_cluster[n_tiles] == 0) {
       int max_clusters = 0;
-      e = cudaOccupancyMaxActiveClusters(&max_clusters, recurrence_kernel, &cfg);
+      e = cudaOccupancyMaxActiveClusters(&max_clusters, recurrence_kernel<false>, &cfg);
       if (e != cudaSuccess || max_clusters < 1) {
         cudaGetLastError();
         e = cudaErrorLaunchOutOfResources;
         continue;
       }
     }
-    e = cudaLaunchKernelEx(&cfg, recurrence_kernel, p);
+    e = (a.prof != nullptr) ? cudaLaunchKernelEx(&cfg, recurrence_kernel<true>, p)
+                            : cudaLaunchKernelEx(&cfg, recurrence_kernel<false>, p);
     if (e == cudaSuccess) {
       good_cluster[n_tiles] = cs;
       break;

@@ -14,6 +14,7 @@ struct RecurrenceArgs {
   const float *bias0, *bias1, *bias2;
   const float *gamma0, *beta0, *gamma1, *beta1;
   int n, D, rows, cols;
+  int debug = 0;              // timing ablations, see recurrence.cu
   long long* prof = nullptr;  // optional [16 ranks][12 phases] cycle totals (debug builds of the tests)
 };
 
