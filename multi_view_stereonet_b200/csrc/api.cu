@@ -17,6 +17,9 @@ static thread_local std::string g_error;
 static thread_local int64_t g_launches = 0;
 void set_error(const std::string& msg) { g_error = msg; }
 void note_launch() { ++g_launches; }
+static bool g_pdl = true;
+bool pdl_enabled() { return g_pdl; }
+void set_pdl_enabled(bool on) { g_pdl = on; }
 
 // Event-pair probe around launches of one kernel class (b200mvs_probe_select).
 struct Probe {
@@ -133,6 +136,11 @@ struct b200mvs_net {
   bool use_tensor_cores = true;
   bool half_activations = true;
   int rec_debug = 0;
+  // Side stream for the work that does not depend on the comparison views (left feature network) or that
+  // nothing downstream waits for (mask upsampling): forked / joined with events inside one forward.
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_left = nullptr, ev_mask_in = nullptr, ev_mask_out = nullptr;
+  bool overlap = true;
   long long* rec_prof = nullptr;  // device [16][12], allocated when option "recurrence_profile" is set
   b200mvs_shape last_shape{};
   bool have_last = false;
@@ -522,6 +530,92 @@ int run_refiner(b200mvs_net* net, const Refiner& R, StatsCursor& sc, int m, int 
   return 0;
 }
 
+// FeatureNetwork.forward (multi_view_stereonet.py:109-129) on images [img0, img0 + cnt) of the (1+V)*B image
+// arrays: conv0 reads `cnt` planar 3-channel images at `planar`; `tail_stats[i]` is layer i's statistics block
+// for all images.
+int run_featnet(b200mvs_net* net, const Levels& L, int img0, int cnt, const float* planar, double* const* tail_stats,
+                float* final_out, long long final_stride, cudaStream_t stream) {
+  Workspace& ws = net->ws;
+  const int h4 = L.h[4], w4 = L.w[4];
+  const size_t P4 = L.px[4];
+  {
+    ConvParams p;
+    p.Hi = L.h[0];
+    p.Wi = L.w[0];
+    p.Ho = L.h[1];
+    p.Wo = L.w[1];
+    p.extra.n = 3;
+    p.w = net->feat_conv[0].w;
+    for (int e = 0; e < 3; ++e) {
+      p.extra.ptr[e] = planar + e * L.px[0];
+      p.extra.img_stride[e] = 3 * (long long)L.px[0];
+    }
+    p.n_img = cnt;
+    p.out = ws.f1 + (size_t)img0 * L.px[1] * kC;
+    RC(launch_conv(CONV_5x5_S2, 32, p, stream));
+  }
+  {
+    const float* src[3] = {ws.f1, ws.f2, ws.f3};
+    float* dst[3] = {ws.f2, ws.f3, ws.l4x[0]};
+    for (int i = 0; i < 3; ++i) {
+      ConvParams p;
+      p.n_img = cnt;
+      p.Hi = L.h[i + 1];
+      p.Wi = L.w[i + 1];
+      p.Ho = L.h[i + 2];
+      p.Wo = L.w[i + 2];
+      p.feat.ptr = src[i] + (size_t)img0 * L.px[i + 1] * kC;
+      p.feat.mode = FEAT_RAW;
+      p.w = net->feat_conv[i + 1].w;
+      p.out = dst[i] + (size_t)img0 * L.px[i + 2] * kC;
+      RC(launch_conv(CONV_5x5_S2, 32, p, stream));
+    }
+  }
+  {
+    // six residual blocks + conv_final at level 4 (multi_view_stereonet.py:119-127)
+    const double inv_count = 1.0 / (8.0 * (double)P4);
+    const size_t ioff = (size_t)img0 * P4 * kC;
+    double* st_prev = nullptr;
+    int xcur = 0, ycur = 0;
+    for (int i = 0; i <= 6; ++i) {
+      ConvParams p;
+      p.n_img = cnt;
+      p.Hi = p.Ho = h4;
+      p.Wi = p.Wo = w4;
+      if (i == 0) {
+        p.feat.ptr = ws.l4x[0] + ioff;
+        p.feat.mode = FEAT_RAW;
+      } else {
+        p.feat.ptr = ws.l4y[ycur] + ioff;
+        p.feat.mode = FEAT_GN_RES;
+        p.feat.stats = st_prev;
+        p.feat.gamma = net->feat_gn[i - 1].gamma;
+        p.feat.beta = net->feat_gn[i - 1].beta;
+        p.feat.inv_count = inv_count;
+        p.feat.resid = ws.l4x[xcur] + ioff;
+        if (i < 6) p.feat.x_out = ws.l4x[1 - xcur] + ioff;
+      }
+      if (i < 6) {
+        p.w = net->feat_res[i].w;
+        p.out = ws.l4y[i == 0 ? 0 : 1 - ycur] + ioff;
+        p.out_stats = tail_stats[i] + (size_t)img0 * 2 * kGroups;
+      } else {
+        p.w = net->feat_final.w;
+        p.bias = net->feat_final.bias;
+        p.out = final_out;
+        p.out_img_stride = final_stride;
+      }
+      RC(conv3x3_c32(net, p, i < 6 ? net->feat_res[i] : net->feat_final, true, stream));
+      if (i > 0) {
+        ycur = 1 - ycur;
+        if (i < 6) xcur = 1 - xcur;
+      }
+      st_prev = p.out_stats;
+    }
+  }
+  return 0;
+}
+
 int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* left_pyr, const float* const* K_pyr,
                  const float* const* Ts, const float* const* right_l0, const float* const* right_l4,
                  float* const* out_idepth, float* const* out_raw, uint8_t* const* out_mask, cudaStream_t stream) {
@@ -563,6 +657,21 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
     R4.p[v] = right_l4[v];
   }
 
+  // The left feature network needs nothing from the comparison views: it runs on the side stream while the main
+  // stream does geometry -> warp -> right feature network -> depth-sweep recurrence (which occupies one
+  // cluster's worth of SMs per view and leaves the rest of the chip idle at small batch).
+  double* tail_stats[6];
+  for (int i = 0; i < 6; ++i) tail_stats[i] = sc.take(NI);
+  const bool overlap = net->overlap && net->side != nullptr;
+  cudaStream_t left_stream = overlap ? net->side : stream;
+  if (overlap) {
+    B200MVS_CUDA_OK(cudaEventRecord(net->ev_fork, stream));
+    B200MVS_CUDA_OK(cudaStreamWaitEvent(net->side, net->ev_fork, 0));
+  }
+  // 3a. FeatureNetwork on the B left images (multi_view_stereonet.py:552)
+  RC(run_featnet(net, L, 0, B, left_pyr[0], tail_stats, ws.feat4, 0, left_stream));
+  if (overlap) B200MVS_CUDA_OK(cudaEventRecord(net->ev_left, net->side));
+
   // 1. geometry
   RC(launch_geometry(Tv, K_pyr[0], K_pyr[4], B, D, h4, w4, ws.geo, stream));
 
@@ -570,89 +679,9 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
   //    (multi_view_stereonet.py:254-258)
   RC(launch_warp_planar(ws.geo.H0, 9, R0, n, 3, L.h[0], L.w[0], true, ws.warped0, ws.l0mask, stream));
 
-  // 3. FeatureNetwork on the B left images and the B*V warped right images (shared weights, :507)
-  {
-    ConvParams p;
-    p.Hi = L.h[0];
-    p.Wi = L.w[0];
-    p.Ho = L.h[1];
-    p.Wo = L.w[1];
-    p.extra.n = 3;
-    p.w = net->feat_conv[0].w;
-    for (int e = 0; e < 3; ++e) {
-      p.extra.ptr[e] = left_pyr[0] + e * L.px[0];
-      p.extra.img_stride[e] = 3 * (long long)L.px[0];
-    }
-    p.n_img = B;
-    p.out = ws.f1;
-    RC(launch_conv(CONV_5x5_S2, 32, p, stream));
-    for (int e = 0; e < 3; ++e) p.extra.ptr[e] = ws.warped0 + e * L.px[0];
-    p.n_img = n;
-    p.out = ws.f1 + (size_t)B * L.px[1] * kC;
-    RC(launch_conv(CONV_5x5_S2, 32, p, stream));
-  }
-  {
-    const float* src[3] = {ws.f1, ws.f2, ws.f3};
-    float* dst[3] = {ws.f2, ws.f3, ws.l4x[0]};
-    for (int i = 0; i < 3; ++i) {
-      ConvParams p;
-      p.n_img = NI;
-      p.Hi = L.h[i + 1];
-      p.Wi = L.w[i + 1];
-      p.Ho = L.h[i + 2];
-      p.Wo = L.w[i + 2];
-      p.feat.ptr = src[i];
-      p.feat.mode = FEAT_RAW;
-      p.w = net->feat_conv[i + 1].w;
-      p.out = dst[i];
-      RC(launch_conv(CONV_5x5_S2, 32, p, stream));
-    }
-  }
-  {
-    // six residual blocks + conv_final at level 4 (multi_view_stereonet.py:119-127)
-    const double inv_count = 1.0 / (8.0 * (double)P4);
-    double* st_prev = nullptr;
-    int xcur = 0, ycur = 0;
-    for (int i = 0; i <= 6; ++i) {
-      ConvParams p;
-      p.n_img = NI;
-      p.Hi = p.Ho = h4;
-      p.Wi = p.Wo = w4;
-      if (i == 0) {
-        p.feat.ptr = ws.l4x[0];
-        p.feat.mode = FEAT_RAW;
-      } else {
-        p.feat.ptr = ws.l4y[ycur];
-        p.feat.mode = FEAT_GN_RES;
-        p.feat.stats = st_prev;
-        p.feat.gamma = net->feat_gn[i - 1].gamma;
-        p.feat.beta = net->feat_gn[i - 1].beta;
-        p.feat.inv_count = inv_count;
-        p.feat.resid = ws.l4x[xcur];
-        if (i < 6) p.feat.x_out = ws.l4x[1 - xcur];
-      }
-      if (i < 6) {
-        p.w = net->feat_res[i].w;
-        p.out = ws.l4y[i == 0 ? 0 : 1 - ycur];
-        p.out_stats = sc.take(NI);
-      } else {
-        p.w = net->feat_final.w;
-        p.bias = net->feat_final.bias;
-        p.out = ws.feat4;
-      }
-      RC(conv3x3_c32(net, p, i < 6 ? net->feat_res[i] : net->feat_final, true, stream));
-      if (i > 0) {
-        ycur = 1 - ycur;
-        if (i < 6) xcur = 1 - xcur;
-      }
-      st_prev = p.out_stats;
-    }
-  }
-
-  // 4. hypothesis 0 of every view's feature volume = features of the warped image (:261, 278)
-  B200MVS_CUDA_OK(cudaMemcpy2DAsync(ws.vol, (size_t)D * P4 * kC * sizeof(float), ws.feat4 + (size_t)B * P4 * kC,
-                                    P4 * kC * sizeof(float), P4 * kC * sizeof(float), n, cudaMemcpyDeviceToDevice,
-                                    stream));
+  // 3b. FeatureNetwork on the B*V warped right images (shared weights, :507)
+  //     conv_final writes hypothesis 0 of every view's feature volume directly (:261, 278)
+  RC(run_featnet(net, L, B, n, ws.warped0, tail_stats, ws.vol, (long long)D * (long long)P4 * kC, stream));
 
   // 5. the depth-sweep recurrence (multi_view_stereonet.py:279-290)
   if (net->use_tensor_cores && recurrence_supported(h4, w4, nullptr, nullptr)) {
@@ -733,6 +762,8 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
       RC(launch_conv(CONV_3x3, 32, c, stream));
     }
   }
+
+  if (overlap) B200MVS_CUDA_OK(cudaStreamWaitEvent(stream, net->ev_left, 0));
 
   // 6. cost volume |L - R| with invalid voxels zeroed (multi_view_stereonet.py:586-592)
   float* cost = net->keep_stages ? ws.cost : ws.vol;
@@ -821,12 +852,19 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
   RC(launch_view_reduce(ws.raw_views, ws.refined_views, ws.mask_views, ws.geo.baseline, B, V, D, (int)P4,
                         !s.do_refiners[4], prior_l[4], idepth_l[4], mask_l[4], stream));
 
-  // 11. coarse-to-fine: bilinear prior, mask upsample, guided refinement (:629-682)
+  // 11. coarse-to-fine: bilinear prior, mask upsample, guided refinement (:629-682).  Nothing on the path reads
+  //     the upsampled mask volumes, so their chain runs on the side stream next to the refiners.
+  cudaStream_t mask_stream = overlap ? net->side : stream;
+  if (overlap && lowest_mask <= 3) {
+    B200MVS_CUDA_OK(cudaEventRecord(net->ev_mask_in, stream));
+    B200MVS_CUDA_OK(cudaStreamWaitEvent(net->side, net->ev_mask_in, 0));
+  }
+  for (int l = 3; l >= lowest_mask; --l)
+    RC(launch_upsample_mask(mask_l[l + 1], (long long)B * D, L.h[l + 1], L.w[l + 1], L.h[l], L.w[l], mask_l[l],
+                            mask_stream));
+  if (overlap && lowest_mask <= 3) B200MVS_CUDA_OK(cudaEventRecord(net->ev_mask_out, net->side));
   for (int l = 3; l >= 0; --l) {
     RC(launch_upsample_f32(idepth_l[l + 1], B, L.h[l + 1], L.w[l + 1], L.h[l], L.w[l], prior_l[l], stream));
-    if (l >= lowest_mask)
-      RC(launch_upsample_mask(mask_l[l + 1], (long long)B * D, L.h[l + 1], L.w[l + 1], L.h[l], L.w[l], mask_l[l],
-                              stream));
     if (s.do_refiners[l]) {
       const float* guide = (l == 0) ? nullptr : (l == 1 ? ws.f1 : (l == 2 ? ws.f2 : ws.f3));
       RC(run_refiner(net, net->refiner[l], sc, B, L.h[l], L.w[l], guide, 1, left_pyr[l], 1, prior_l[l], K_pyr[l], 1,
@@ -836,6 +874,7 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
                                       cudaMemcpyDeviceToDevice, stream));
     }
   }
+  if (overlap && lowest_mask <= 3) B200MVS_CUDA_OK(cudaStreamWaitEvent(stream, net->ev_mask_out, 0));
   if (sc.used > sc.cap) {
     set_error("internal: GroupNorm statistics arena overflow");
     return B200MVS_EINVAL;
@@ -881,6 +920,16 @@ B200MVS_API int b200mvs_create(int device, int num_tensors, const char* const* n
   b200mvs_net* net = new b200mvs_net();
   net->device = device;
   int rc = build_weights(net, sd);
+  if (rc == 0) {
+    if (cudaStreamCreateWithFlags(&net->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&net->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&net->ev_left, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&net->ev_mask_in, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&net->ev_mask_out, cudaEventDisableTiming) != cudaSuccess) {
+      set_error("b200mvs_create: could not create the side stream");
+      rc = B200MVS_ECUDA;
+    }
+  }
   if (rc != 0) {
     b200mvs_destroy(net);
     return rc;
@@ -896,6 +945,9 @@ B200MVS_API void b200mvs_destroy(b200mvs_net* net) {
   if (net->arena.base != nullptr) cudaFree(net->arena.base);
   if (net->host_stage != nullptr) cudaFree(net->host_stage);
   for (cudaEvent_t e : net->probe.ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : {net->ev_fork, net->ev_left, net->ev_mask_in, net->ev_mask_out})
+    if (e != nullptr) cudaEventDestroy(e);
+  if (net->side != nullptr) cudaStreamDestroy(net->side);
   delete net;
 }
 
@@ -917,6 +969,14 @@ B200MVS_API int b200mvs_set_option(b200mvs_net* net, const char* name, int value
   }
   if (k == "half_activations") {
     net->half_activations = value != 0;
+    return 0;
+  }
+  if (k == "pdl") {
+    set_pdl_enabled(value != 0);
+    return 0;
+  }
+  if (k == "overlap") {
+    net->overlap = value != 0;
     return 0;
   }
   if (k == "recurrence_debug") {

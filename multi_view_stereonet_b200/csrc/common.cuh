@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <utility>
 
 namespace b200mvs {
 
@@ -36,6 +37,40 @@ void note_launch();
   } while (0)
 
 __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  The forward is a chain of ~70 short dependent kernels; each one is
+// launched with the programmatic-stream-serialisation attribute so that its CTAs become resident and
+// run their prologue (TMEM allocation, barrier init, weight staging) while the previous kernel
+// drains.  Contract for every kernel of this library:
+//   * acquire on-chip resources (TMEM) first, then pdl_launch_dependents();
+//   * do not read anything a previous kernel wrote before pdl_wait();
+//   * every thread executes pdl_wait() before the kernel exits, so "kernel N complete" implies
+//     "kernels < N complete" (a kernel may read buffers written several launches earlier).
+// ---------------------------------------------------------------------------------------------
+bool pdl_enabled();
+void set_pdl_enabled(bool on);
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Homography pixel transfer with the reference's float32 operation order.

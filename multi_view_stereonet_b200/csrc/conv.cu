@@ -92,6 +92,8 @@ conv_kernel(const ConvParams p) {
   const int iy0 = ty0 * S - (KH / 2) * dil;
   const int iz0 = tz0 - (KD / 2);
 
+  pdl_launch_dependents();
+  pdl_wait();
   // Previous layer's GroupNorm folded into a per-channel scale/shift.
   if (p.feat.mode >= FEAT_GN) {
     if (tid < kC) {
@@ -354,7 +356,7 @@ int launch_cfg(const ConvParams& p, cudaStream_t stream) {
   }
   dim3 grid(cdiv(p.Wo, TW) * cdiv(p.Ho, TH) * cdiv(p.Do, TD), p.n_img);
   if (p.tag != TAG_NONE) probe_before(p.tag, stream);
-  conv_kernel<KD, KH, KW, S, COUT, TD, TH, TW, PXT, CSPLIT><<<grid, C::NT, smem, stream>>>(p);
+  launch_pdl(conv_kernel<KD, KH, KW, S, COUT, TD, TH, TW, PXT, CSPLIT>, grid, dim3(C::NT), smem, stream, p);
   if (p.tag != TAG_NONE) probe_after(p.tag, stream);
   B200MVS_LAUNCH_OK("conv_kernel");
   return 0;

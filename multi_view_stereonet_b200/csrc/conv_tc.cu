@@ -107,28 +107,16 @@ __global__ void __launch_bounds__(NT, MINB) conv3x3_tc_kernel(const ConvParams p
   uint8_t* s_w = smem;
   uint8_t* s_in = smem + w_bytes;
 
-  // ---- one-time setup ----
+  // ---- one-time setup (nothing here depends on earlier kernels: runs under the previous kernel's tail) ----
   if (warp == 0) tc::tmem_alloc(&s_tmem, (uint32_t)TMEM_COLS);
   if (tid == 32) {
     tc::mbar_init(&s_bar, 1);
     tc::mbar_init_fence();
   }
-  if (tid < kC) {
-    s_bias[tid] = p.bias != nullptr ? __ldg(p.bias + tid) : 0.f;
-    if (mode >= FEAT_GN) {
-      const int grp = tid >> 3;
-      const double sum = p.feat.stats[(img * kGroups + grp) * 2 + 0];
-      const double sq = p.feat.stats[(img * kGroups + grp) * 2 + 1];
-      const double mean = sum * p.feat.inv_count;
-      double var = sq * p.feat.inv_count - mean * mean;
-      var = var > 0.0 ? var : 0.0;
-      const double rstd = rsqrt(var + (double)kGnEps);
-      s_a[tid] = (float)((double)p.feat.gamma[tid] * rstd);
-      s_b[tid] = (float)((double)p.feat.beta[tid] - mean * (double)p.feat.gamma[tid] * rstd);
-    }
-  }
+  if (tid < kC) s_bias[tid] = p.bias != nullptr ? __ldg(p.bias + tid) : 0.f;
   if (tid < 2 * kGroups) s_stats[tid] = 0.0;
   __syncthreads();
+  pdl_launch_dependents();   // after the TMEM allocation (see common.cuh)
 
   // ---- stage weights (already in the canonical fp16 layout) ----
   {
@@ -136,6 +124,19 @@ __global__ void __launch_bounds__(NT, MINB) conv3x3_tc_kernel(const ConvParams p
     uint4* dst = reinterpret_cast<uint4*>(s_w);
     for (int i = tid; i < (int)(w_bytes / 16); i += NT) dst[i] = __ldg(src + i);
   }
+  pdl_wait();
+  if (tid < kC && mode >= FEAT_GN) {
+    const int grp = tid >> 3;
+    const double sum = p.feat.stats[(img * kGroups + grp) * 2 + 0];
+    const double sq = p.feat.stats[(img * kGroups + grp) * 2 + 1];
+    const double mean = sum * p.feat.inv_count;
+    double var = sq * p.feat.inv_count - mean * mean;
+    var = var > 0.0 ? var : 0.0;
+    const double rstd = rsqrt(var + (double)kGnEps);
+    s_a[tid] = (float)((double)p.feat.gamma[tid] * rstd);
+    s_b[tid] = (float)((double)p.feat.beta[tid] - mean * (double)p.feat.gamma[tid] * rstd);
+  }
+  __syncthreads();
   const size_t vol = (size_t)p.Hi * p.Wi;
   const int rows_in = TH + 2 * d;
   // ---- stage the transformed 32-channel source ----
@@ -382,7 +383,7 @@ int launch_th(const ConvParams& p, const uint8_t* w16, cudaStream_t stream) {
   const int TW = PW - 2 * p.dil;
   dim3 grid(cdiv(p.Wo, TW) * cdiv(p.Ho, TH), p.n_img);
   if (p.tag != TAG_NONE) probe_before(p.tag, stream);
-  conv3x3_tc_kernel<TH, SPLIT, MINB><<<grid, NT, smem, stream>>>(p, w16);
+  launch_pdl(conv3x3_tc_kernel<TH, SPLIT, MINB>, grid, dim3(NT), smem, stream, p, w16);
   if (p.tag != TAG_NONE) probe_after(p.tag, stream);
   B200MVS_LAUNCH_OK("conv3x3_tc_kernel");
   return 0;

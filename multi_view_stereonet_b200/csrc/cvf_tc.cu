@@ -70,27 +70,28 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
     tc::mbar_init(&s_bar[1], 1);
     tc::mbar_init_fence();
   }
-  if (tid < kC) {
-    s_bias[tid] = p.bias != nullptr ? __ldg(p.bias + tid) : 0.f;
-    if (p.mode >= FEAT_GN) {
-      const int grp = tid >> 3;
-      const double sum = p.stats[(n * kGroups + grp) * 2 + 0];
-      const double sq = p.stats[(n * kGroups + grp) * 2 + 1];
-      const double mean = sum * p.inv_count;
-      double var = sq * p.inv_count - mean * mean;
-      var = var > 0.0 ? var : 0.0;
-      const double rstd = rsqrt(var + (double)kGnEps);
-      s_a[tid] = (float)((double)p.gamma[tid] * rstd);
-      s_b[tid] = (float)((double)p.beta[tid] - mean * (double)p.gamma[tid] * rstd);
-    }
-  }
+  if (tid < kC) s_bias[tid] = p.bias != nullptr ? __ldg(p.bias + tid) : 0.f;
   if (tid < 2 * kGroups) s_stats[tid] = 0.0;
+  __syncthreads();
+  pdl_launch_dependents();   // after the TMEM allocation (see common.cuh)
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.w16);
     uint4* dst = reinterpret_cast<uint4*>(s_w);
     for (int i = tid; i < W_BYTES / 16; i += NT) dst[i] = __ldg(src + i);
     uint4* rz = reinterpret_cast<uint4*>(s_ring);
     for (int i = tid; i < (int)(RING * g.slot_bytes / 16); i += NT) rz[i] = make_uint4(0, 0, 0, 0);
+  }
+  pdl_wait();
+  if (tid < kC && p.mode >= FEAT_GN) {
+    const int grp = tid >> 3;
+    const double sum = p.stats[(n * kGroups + grp) * 2 + 0];
+    const double sq = p.stats[(n * kGroups + grp) * 2 + 1];
+    const double mean = sum * p.inv_count;
+    double var = sq * p.inv_count - mean * mean;
+    var = var > 0.0 ? var : 0.0;
+    const double rstd = rsqrt(var + (double)kGnEps);
+    s_a[tid] = (float)((double)p.gamma[tid] * rstd);
+    s_b[tid] = (float)((double)p.beta[tid] - mean * (double)p.gamma[tid] * rstd);
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -286,7 +287,7 @@ int launch_cvf_tc(const CvfArgs& a, cudaStream_t stream) {
   chunks = cdiv(a.D, P.DC);
   dim3 grid(P.row_tiles * chunks, a.n);
   if (a.tag != TAG_NONE) probe_before(a.tag, stream);
-  cvf_tc_kernel<<<grid, NT, g.total, stream>>>(P);
+  launch_pdl(cvf_tc_kernel, grid, dim3(NT), (size_t)g.total, stream, P);
   if (a.tag != TAG_NONE) probe_after(a.tag, stream);
   B200MVS_LAUNCH_OK("cvf_tc_kernel");
   return 0;

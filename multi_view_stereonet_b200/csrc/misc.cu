@@ -11,6 +11,8 @@ namespace {
 __global__ void __launch_bounds__(256) warp_planar_kernel(const float* __restrict__ H, int h_stride, ViewPtrs src,
                                                           int channels, int rows, int cols, int zero_invalid,
                                                           float* __restrict__ pred, uint8_t* __restrict__ mask) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = blockIdx.y;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= rows * cols) return;
@@ -40,6 +42,8 @@ __global__ void __launch_bounds__(256) warp_planar_kernel(const float* __restric
 __global__ void __launch_bounds__(256) step_warp_kernel(const float* __restrict__ vol, GeomOut geo, ViewPtrs right_l4,
                                                         int D, int step, int rows, int cols,
                                                         float* __restrict__ wf, float* __restrict__ wimg) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int pixels = rows * cols;
@@ -84,6 +88,8 @@ __global__ void __launch_bounds__(256) step_warp_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) cost_kernel(const float* __restrict__ left, const float* vol,
                                                    const float* __restrict__ H, int views, int D, int rows, int cols,
                                                    float* cost, uint8_t* __restrict__ mask) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = blockIdx.z, d = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int pixels = rows * cols;
@@ -106,6 +112,8 @@ __global__ void __launch_bounds__(256) cost_kernel(const float* __restrict__ lef
 
 __global__ void __launch_bounds__(256) cost_norm_kernel(const float* __restrict__ cost, long long voxels,
                                                         float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= voxels) return;
   const float4* c = reinterpret_cast<const float4*>(cost + i * kC);
@@ -125,6 +133,8 @@ __global__ void __launch_bounds__(256) cost_norm_kernel(const float* __restrict_
 __global__ void __launch_bounds__(128) softargmin_kernel(const float* __restrict__ cost,
                                                          const float* __restrict__ samples, int D, int pixels,
                                                          float* __restrict__ raw) {
+  pdl_launch_dependents();
+  pdl_wait();
   // 8 lanes per pixel share the hypothesis axis (lane s handles d = s, s + 8, ...); 16 pixels per CTA.
   const int n = blockIdx.y;
   const int sub = threadIdx.x & 7;
@@ -158,6 +168,8 @@ __global__ void __launch_bounds__(128) view_reduce_kernel(const float* __restric
                                                           const float* __restrict__ baseline, int views, int D,
                                                           int pixels, int alias, float* __restrict__ raw4,
                                                           float* __restrict__ idepth4, uint8_t* __restrict__ mask4) {
+  pdl_launch_dependents();
+  pdl_wait();
   // blockIdx.z = 0: the two idepth maps; blockIdx.z = 1 + d: mask plane d
   const int b = blockIdx.y;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -214,6 +226,8 @@ __device__ __forceinline__ Lerp lerp_setup(int dst, float scale, int in_size) {
 
 __global__ void __launch_bounds__(256) upsample_f32_kernel(const float* __restrict__ in, int h, int w, int H, int W,
                                                            float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int plane = blockIdx.y;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= H * W) return;
@@ -231,6 +245,8 @@ __global__ void __launch_bounds__(256) upsample_f32_kernel(const float* __restri
 template <int VEC>
 __global__ void __launch_bounds__(256) upsample_mask_kernel(const uint8_t* __restrict__ in, int h, int w, int H, int W,
                                                             uint8_t* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long plane = blockIdx.y;
   const int wv = W / VEC;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -266,7 +282,7 @@ int launch_warp_planar(const float* H, int h_stride, const ViewPtrs& src, int n,
                        bool zero_invalid, float* pred, uint8_t* mask, cudaStream_t stream) {
   if (n <= 0) return 0;
   dim3 grid(cdiv(rows * cols, 256), n);
-  warp_planar_kernel<<<grid, 256, 0, stream>>>(H, h_stride, src, channels, rows, cols, zero_invalid ? 1 : 0, pred,
+  launch_pdl(warp_planar_kernel, grid, dim3(256), (size_t)0, stream, H, h_stride, src, channels, rows, cols, zero_invalid ? 1 : 0, pred,
                                                mask);
   B200MVS_LAUNCH_OK("warp_planar_kernel");
   return 0;
@@ -275,7 +291,7 @@ int launch_warp_planar(const float* H, int h_stride, const ViewPtrs& src, int n,
 int launch_step_warp(const float* vol, const GeomOut& geo, const ViewPtrs& right_l4, int n, int D, int step,
                      int rows, int cols, float* wf, float* wimg, cudaStream_t stream) {
   dim3 grid(cdiv(rows * cols * 8, 256), n);
-  step_warp_kernel<<<grid, 256, 0, stream>>>(vol, geo, right_l4, D, step, rows, cols, wf, wimg);
+  launch_pdl(step_warp_kernel, grid, dim3(256), (size_t)0, stream, vol, geo, right_l4, D, step, rows, cols, wf, wimg);
   B200MVS_LAUNCH_OK("step_warp_kernel");
   return 0;
 }
@@ -283,13 +299,13 @@ int launch_step_warp(const float* vol, const GeomOut& geo, const ViewPtrs& right
 int launch_cost(const float* left_feat4, const float* vol, const float* H, int n, int views, int D, int rows,
                 int cols, float* cost, uint8_t* mask, cudaStream_t stream) {
   dim3 grid(cdiv(rows * cols * 8, 256), D, n);
-  cost_kernel<<<grid, 256, 0, stream>>>(left_feat4, vol, H, views, D, rows, cols, cost, mask);
+  launch_pdl(cost_kernel, grid, dim3(256), (size_t)0, stream, left_feat4, vol, H, views, D, rows, cols, cost, mask);
   B200MVS_LAUNCH_OK("cost_kernel");
   return 0;
 }
 
 int launch_cost_norm(const float* cost, long long voxels, float* out, cudaStream_t stream) {
-  cost_norm_kernel<<<(unsigned)((voxels + 255) / 256), 256, 0, stream>>>(cost, voxels, out);
+  launch_pdl(cost_norm_kernel, dim3((unsigned)((voxels + 255) / 256)), dim3(256), (size_t)0, stream, cost, voxels, out);
   B200MVS_LAUNCH_OK("cost_norm_kernel");
   return 0;
 }
@@ -297,7 +313,7 @@ int launch_cost_norm(const float* cost, long long voxels, float* out, cudaStream
 int launch_softargmin(const float* cost, const float* samples, int n, int D, int pixels, float* raw,
                       cudaStream_t stream) {
   dim3 grid(cdiv(pixels, 16), n);
-  softargmin_kernel<<<grid, 128, 0, stream>>>(cost, samples, D, pixels, raw);
+  launch_pdl(softargmin_kernel, grid, dim3(128), (size_t)0, stream, cost, samples, D, pixels, raw);
   B200MVS_LAUNCH_OK("softargmin_kernel");
   return 0;
 }
@@ -306,7 +322,7 @@ int launch_view_reduce(const float* raw_views, const float* refined_views, const
                        const float* baseline, int batch, int views, int D, int pixels, bool refined_is_alias,
                        float* raw4, float* idepth4, uint8_t* mask4, cudaStream_t stream) {
   dim3 grid(cdiv(pixels, 128), batch, 1 + D);
-  view_reduce_kernel<<<grid, 128, 0, stream>>>(raw_views, refined_views, mask_views, baseline, views, D, pixels,
+  launch_pdl(view_reduce_kernel, grid, dim3(128), (size_t)0, stream, raw_views, refined_views, mask_views, baseline, views, D, pixels,
                                                refined_is_alias ? 1 : 0, raw4, idepth4, mask4);
   B200MVS_LAUNCH_OK("view_reduce_kernel");
   return 0;
@@ -314,7 +330,7 @@ int launch_view_reduce(const float* raw_views, const float* refined_views, const
 
 int launch_upsample_f32(const float* in, int n_planes, int h, int w, int H, int W, float* out, cudaStream_t stream) {
   dim3 grid(cdiv(H * W, 256), n_planes);
-  upsample_f32_kernel<<<grid, 256, 0, stream>>>(in, h, w, H, W, out);
+  launch_pdl(upsample_f32_kernel, grid, dim3(256), (size_t)0, stream, in, h, w, H, W, out);
   B200MVS_LAUNCH_OK("upsample_f32_kernel");
   return 0;
 }
@@ -330,13 +346,13 @@ int launch_upsample_mask(const uint8_t* in, long long n_planes, int h, int w, in
     uint8_t* dst = out + (size_t)p0 * H * W;
     if (vec16) {
       dim3 grid(cdiv(H * (W / 16), 256), np);
-      upsample_mask_kernel<16><<<grid, 256, 0, stream>>>(src, h, w, H, W, dst);
+      launch_pdl(upsample_mask_kernel<16>, grid, dim3(256), (size_t)0, stream, src, h, w, H, W, dst);
     } else if (vec) {
       dim3 grid(cdiv(H * (W / 4), 256), np);
-      upsample_mask_kernel<4><<<grid, 256, 0, stream>>>(src, h, w, H, W, dst);
+      launch_pdl(upsample_mask_kernel<4>, grid, dim3(256), (size_t)0, stream, src, h, w, H, W, dst);
     } else {
       dim3 grid(cdiv(H * W, 256), np);
-      upsample_mask_kernel<1><<<grid, 256, 0, stream>>>(src, h, w, H, W, dst);
+      launch_pdl(upsample_mask_kernel<1>, grid, dim3(256), (size_t)0, stream, src, h, w, H, W, dst);
     }
     B200MVS_LAUNCH_OK("upsample_mask_kernel");
   }

@@ -279,6 +279,7 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = s_tmem;
   uint32_t bar_phase = 0;
+  pdl_launch_dependents();
   cluster_sync_all();  // every CTA's shared memory is initialised before anyone pushes into it
 
   const float inv_count = 1.0f / (8.0f * (float)pixels);
@@ -391,6 +392,7 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
     }                                         \
   } while (0)
 
+  pdl_wait();  // everything above ran under the previous kernel's tail; from here on its outputs are read
   const float* img_base = p.right_l4.p[n % p.right_l4.views] + (size_t)(n / p.right_l4.views) * 3 * pixels;
   // homographies of the coming step, fetched one step ahead
   float Hinc[9], Hd[9];
@@ -737,13 +739,15 @@ int launch_recurrence(const RecurrenceArgs& a, cudaStream_t stream) {
     cfg.blockDim = dim3(NT, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cs;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     if (good_cluster[n_tiles] == 0) {
       int max_clusters = 0;
       e = cudaOccupancyMaxActiveClusters(&max_clusters, recurrence_kernel<false>, &cfg);

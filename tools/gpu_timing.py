@@ -44,8 +44,14 @@ def main():
         print(f"{label}: event mean {sum(ms) / steps:.3f} ms (min {min(ms):.3f} max {max(ms):.3f}), "
               f"wall/step {1e3 * wall / steps:.3f} ms, launches {net.last_launch_count()}", flush=True)
 
+    # OPTS="pdl=0,overlap=0" toggles library options for A/B timing
+    for kv in filter(None, os.environ.get("OPTS", "").split(",")):
+        k, v = kv.split("=")
+        net.set_option(k, int(v))
     run("async", False)
     run("sync ", True)
+    if os.environ.get("NOPROF"):
+        return
     net.set_option("recurrence_profile", 1)
     with torch.no_grad():
         net(*inp, *flags)
