@@ -86,7 +86,8 @@ __global__ void __launch_bounds__(NT, MINB) conv3x3_tc_kernel(const ConvParams p
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t s_tmem;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = tc::uniform_warp_index();
   const int img = blockIdx.y;
   const int d = p.dil;
   const int TW = PW - 2 * d;
@@ -249,8 +250,9 @@ __global__ void __launch_bounds__(NT, MINB) conv3x3_tc_kernel(const ConvParams p
   tc::fence_after_sync();
   const uint32_t tmem_base = s_tmem;
 
-  // ---- one thread issues every MMA of the tile, then commits to the mbarrier ----
-  if (tid == 0) {
+  // ---- one elected lane of warp 0 issues every MMA of the tile, then commits to the mbarrier ----
+  if (warp == 0) {
+   if (tc::elect_one()) {
     const uint32_t plane_u16 = plane_bytes >> 4;
     const uint64_t da0 = tc::umma_desc(tc::smem_u32(s_in), plane_bytes, 128u);
     const uint64_t da_lo0 = da0 + (uint64_t)(set_planes * plane_u16);
@@ -280,6 +282,8 @@ __global__ void __launch_bounds__(NT, MINB) conv3x3_tc_kernel(const ConvParams p
     tc::mma_commit(&s_bar);
     tc::mbar_wait(&s_bar, 0u);   // only the issuing thread polls; the rest park at the hardware barrier
     tc::fence_before_sync();
+   }
+   __syncwarp();
   }
   __syncthreads();
   tc::fence_after_sync();

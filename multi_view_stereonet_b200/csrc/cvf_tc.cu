@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
   __shared__ __align__(8) uint64_t s_bar[2];
   __shared__ uint32_t s_tmem;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = tc::uniform_warp_index();
   const int n = blockIdx.y;
   const Geo g = make_geo(p.w);
   const int PW = g.PW, RT = g.RT, NP = g.NP;
@@ -172,7 +173,8 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
 
     // ---- issue the MMAs of output slice q = it - 2 (input slices q, q+1, q+2) ----
     const int q = it - 2;
-    if (q >= 0 && q < dcount && tid == 0) {
+    if (q >= 0 && q < dcount && warp == 0) {
+     if (tc::elect_one()) {
       tc::fence_after_sync();
       const uint32_t acc = tmem_base + (uint32_t)((q & 1) * 64);
 #pragma unroll
@@ -192,14 +194,19 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
         }
       }
       tc::mma_commit(&s_bar[q & 1]);
+     }
+     __syncwarp();
     }
 
     // ---- epilogue of output slice q - 1 (its MMAs were issued one iteration ago) ----
     const int qe = q - 1;
     if (qe >= 0 && qe < dcount) {
-      if (tid == 0) {  // one poller; the other warps park at the hardware barrier
-        tc::mbar_wait(&s_bar[qe & 1], (uint32_t)((qe >> 1) & 1));
-        tc::fence_before_sync();
+      if (warp == 0) {  // one poller; the other warps park at the hardware barrier
+        if (tc::elect_one()) {
+          tc::mbar_wait(&s_bar[qe & 1], (uint32_t)((qe >> 1) & 1));
+          tc::fence_before_sync();
+        }
+        __syncwarp();
       }
       __syncthreads();
       tc::fence_after_sync();

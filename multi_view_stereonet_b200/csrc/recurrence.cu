@@ -193,28 +193,30 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 // A single thread issues the MMAs, so the issue loop itself is on the critical path: the (A_hi, A_lo, B)
 // descriptors of every k-step are the same in every step of the sweep (fixed shared-memory addresses), are built
 // once into a shared-memory table, and the loop is three loads and two MMAs per k-step.
-struct KStepDesc {
-  uint64_t a_hi, a_lo, b, pad;
-};
-constexpr int KSTEPS_TOTAL = W0_BLOCKS + 2 * W1_BLOCKS;  // 27 + 18 + 18
+// A single elected lane of warp 0 issues the MMAs from warp-uniform control flow with descriptors computed from
+// warp-uniform values, so that ptxas keeps them in uniform registers and emits back-to-back UTCHMMA.  (Issuing
+// from an `if (tid == 0)` branch, or loading descriptors from memory, makes it wrap every MMA in an
+// ELECT / R2UR / BRA.U.ANY waterfall loop: ~70 cycles per MMA, more than the MMA itself.)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
 
-__device__ __forceinline__ void issue_conv_mmas(const KStepDesc* tbl, int count, uint32_t tmem_base) {
-  const uint32_t taddr = smem_u32(tbl);
-#pragma unroll 3
-  for (int i = 0; i < count; ++i) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred pacc, ptrue;\n\t"
-        ".reg .b64 ahi, alo, bd;\n\t"
-        "ld.shared.v2.b64 {ahi, alo}, [%1];\n\t"
-        "ld.shared.b64 bd, [%1+16];\n\t"
-        "setp.ne.b32 pacc, %2, 0;\n\t"
-        "setp.eq.b32 ptrue, %2, %2;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], ahi, bd, %3, pacc;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], alo, bd, %4, ptrue;\n\t"
-        "}\n" ::"r"(tmem_base),
-        "r"(taddr + (uint32_t)i * 32u), "r"((uint32_t)i), "r"(kIdescN64), "r"(kIdescN32)
-        : "memory");
+template <int KS>
+__device__ __forceinline__ void issue_conv_mmas(uint64_t da_hi0, uint64_t da_lo0, uint64_t db, uint32_t plane_u16,
+                                                uint32_t PW, uint32_t tmem_base) {
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const uint32_t pos = (uint32_t)(tap / 3) * PW + (uint32_t)(tap % 3);   // 16-byte units
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const uint32_t pl = (ks < 2) ? 2u * ks : (uint32_t)PLANE_HI_X;       // k-step 2 reads (extra, zero)
+      const uint64_t a_off = (uint64_t)(pl * plane_u16 + pos);
+      const uint64_t b = db + (uint64_t)((tap * KS + ks) * (2048 / 16));
+      mma_f16(tmem_base, da_hi0 + a_off, b, kIdescN64, (tap | ks) != 0 ? 1u : 0u);
+      mma_f16(tmem_base, da_lo0 + a_off, b, kIdescN32, 1u);
+    }
   }
 }
 
@@ -226,10 +228,11 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
   __shared__ float s_bias[3][kC], s_gamma[2][kC], s_beta[2][kC];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t s_tmem;
-  __shared__ __align__(16) KStepDesc s_desc[KSTEPS_TOTAL];
   __shared__ float s_tot[2 * kGroups];
+  __shared__ float s_H[2][18];   // [step parity][H_inc (9), H_d (9)], fetched one step ahead
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform
   const uint32_t rank = cluster_ctarank();
   const uint32_t csize = gridDim.x;  // cluster == all CTAs of blockIdx.y
   const int n = blockIdx.y;
@@ -287,50 +290,40 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
   const uint64_t da_hi0 = umma_desc(smem_u32(s_planes) + (uint32_t)PLANE_HI * L.plane_bytes, L.plane_bytes, 128u);
   const uint64_t da_lo0 = umma_desc(smem_u32(s_planes) + (uint32_t)PLANE_LO * L.plane_bytes, L.plane_bytes, 128u);
   const uint64_t db_c0 = umma_desc(smem_u32(s_w), 1024u, 128u);
-  if (tid < KSTEPS_TOTAL) {
-    // entry order = weight block order: conv0 [tap][3 k-steps], conv1 [tap][2], conv2 [tap][2]
-    int i = tid, ksteps = 3;
-    if (i >= W0_BLOCKS) {
-      i = (i - W0_BLOCKS) % W1_BLOCKS;
-      ksteps = 2;
-    }
-    const int tap = i / ksteps, ks = i % ksteps;
-    const uint32_t pos = (uint32_t)((tap / 3) * PW + (tap % 3));        // 16-byte units
-    const uint32_t pl = (ks < 2) ? 2u * ks : (uint32_t)PLANE_HI_X;      // k-step 2 reads (extra, zero)
-    const uint64_t a_off = (uint64_t)(pl * plane_u16 + pos);
-    KStepDesc d;
-    d.a_hi = da_hi0 + a_off;
-    d.a_lo = da_lo0 + a_off;
-    d.b = db_c0 + (uint64_t)(tid * (2048 / 16));
-    d.pad = 0;
-    s_desc[tid] = d;
-  }
-  __syncthreads();
-
   // Runs one conv on the tensor core and waits for its accumulators.  Only the issuing thread polls the
   // mbarrier; everyone else parks at the hardware barrier (polling from 16 warps steals shared-memory bandwidth
   // from the tensor core's operand fetch).
-  auto run_conv = [&](int first, int count) {
-    if (active && tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (!(p.debug & 1)) issue_conv_mmas(s_desc + first, count, tmem_base);
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                       smem_u32(&s_bar))
-                   : "memory");
-      const uint32_t bar = smem_u32(&s_bar);
-      uint32_t done = 0;
-      while (!done) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred q;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, q;\n\t"
-            "}\n"
-            : "=r"(done)
-            : "r"(bar), "r"(bar_phase)
-            : "memory");
+  auto run_conv = [&](int layer) {
+    if (warp == 0) {
+      if (active && elect_one()) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (!(p.debug & 1)) {
+          if (layer == 0)
+            issue_conv_mmas<3>(da_hi0, da_lo0, db_c0, plane_u16, (uint32_t)PW, tmem_base);
+          else
+            issue_conv_mmas<2>(da_hi0, da_lo0,
+                               db_c0 + (uint64_t)((W0_BLOCKS + (layer - 1) * W1_BLOCKS) * (2048 / 16)), plane_u16,
+                               (uint32_t)PW, tmem_base);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                         smem_u32(&s_bar))
+                     : "memory");
+        const uint32_t bar = smem_u32(&s_bar);
+        uint32_t done = 0;
+        while (!done) {
+          asm volatile(
+              "{\n\t"
+              ".reg .pred q;\n\t"
+              "mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
+              "selp.u32 %0, 1, 0, q;\n\t"
+              "}\n"
+              : "=r"(done)
+              : "r"(bar), "r"(bar_phase)
+              : "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
     }
     bar_phase ^= 1u;
     __syncthreads();
@@ -394,13 +387,10 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
 
   pdl_wait();  // everything above ran under the previous kernel's tail; from here on its outputs are read
   const float* img_base = p.right_l4.p[n % p.right_l4.views] + (size_t)(n / p.right_l4.views) * 3 * pixels;
-  // homographies of the coming step, fetched one step ahead
-  float Hinc[9], Hd[9];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    Hinc[k] = __ldg(p.geo.Hinc + ((size_t)n * p.D + 1) * 9 + k);
-    Hd[k] = __ldg(p.geo.H + ((size_t)n * p.D + 1) * 9 + k);
-  }
+  // homographies of the coming step, fetched one step ahead into shared memory
+  if (tid < 18)
+    s_H[1][tid] = __ldg((tid < 9 ? p.geo.Hinc : p.geo.H - 9) + ((size_t)n * p.D + 1) * 9 + tid);
+  __syncthreads();
   float x0own[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) x0own[k] = 0.f;
@@ -408,6 +398,8 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
   for (int step = 1; step < p.D; ++step) {
     // ================= W: warp previous features and the 1/16 image into the conv0 operand =========
     {
+      const float* Hinc = s_H[step & 1];
+      const float* Hd = Hinc + 9;
       const float* prev = p.vol_in + ((size_t)n * p.D + (step - 1)) * pixels * kC + 8 * t_oct;
       float4 g[MAX_TASKS][8];
       Bilinear bl[MAX_TASKS];
@@ -448,14 +440,9 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
           }
         }
       }
-      // prefetch the next step's homographies
-      if (step + 1 < p.D) {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          Hinc[k] = __ldg(p.geo.Hinc + ((size_t)n * p.D + step + 1) * 9 + k);
-          Hd[k] = __ldg(p.geo.H + ((size_t)n * p.D + step + 1) * 9 + k);
-        }
-      }
+      // prefetch the next step's homographies (read after several block-wide barriers)
+      if (step + 1 < p.D && tid < 18)
+        s_H[(step + 1) & 1][tid] = __ldg((tid < 9 ? p.geo.Hinc : p.geo.H - 9) + ((size_t)n * p.D + step + 1) * 9 + tid);
 #pragma unroll
       for (int k = 0; k < MAX_TASKS; ++k) {
         if (active && t_l[k] < npl) {
@@ -495,7 +482,7 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     PROF_MARK(0);
-    run_conv(0, W0_BLOCKS);
+    run_conv(0);
     PROF_MARK(1);
 
     // ===== two normalised layers: raw output -> statistics + halo exchange -> barrier -> operand -> conv =====
@@ -617,7 +604,7 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();
       PROF_MARK(4 + 4 * layer);
-      run_conv(W0_BLOCKS + layer * W1_BLOCKS, W1_BLOCKS);
+      run_conv(1 + layer);
       PROF_MARK(5 + 4 * layer);
     }
 

@@ -9,6 +9,17 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a fully active warp.  The MMA-issuing code must sit in warp-uniform control flow
+// (`if (warp == 0)` with a provably uniform warp index, then `if (elect_one())`) with descriptors computed from
+// warp-uniform values: ptxas then keeps them in uniform registers and emits back-to-back UTCHMMA.  Issuing from
+// `if (tid == 0)` makes it wrap every MMA in an ELECT / R2UR / BRA.U.ANY waterfall loop (~70 cycles per MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ int uniform_warp_index() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 // UMMA shared-memory descriptor, K-major, SWIZZLE_NONE.  Canonical layout (16-byte units):
 // ((8, m), 2) : ((1, SBO), LBO) -- a core matrix is 8 rows x 16 bytes stored contiguously, the next
 // 8-row group is SBO bytes further, the second 16-byte K chunk of the MMA is LBO bytes further.
