@@ -85,6 +85,7 @@ struct Workspace {
   float *f1 = nullptr, *f2 = nullptr, *f3 = nullptr, *feat4 = nullptr;
   float *l4x[2] = {nullptr, nullptr}, *l4y[2] = {nullptr, nullptr};
   // recurrence
+  float* imgconv = nullptr;
   float *vol = nullptr, *wf = nullptr, *wimg = nullptr, *sy0 = nullptr, *sx0 = nullptr, *sy1 = nullptr;
   // cost volume
   float *cost = nullptr, *cvfA = nullptr, *cost1 = nullptr;
@@ -139,7 +140,7 @@ struct b200mvs_net {
   // Side stream for the work that does not depend on the comparison views (left feature network) or that
   // nothing downstream waits for (mask upsampling): forked / joined with events inside one forward.
   cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_left = nullptr, ev_mask_in = nullptr, ev_mask_out = nullptr;
+  cudaEvent_t ev_geo = nullptr, ev_fork = nullptr, ev_left = nullptr, ev_mask_in = nullptr, ev_mask_out = nullptr;
   bool overlap = true;
   long long* rec_prof = nullptr;  // device [16][12], allocated when option "recurrence_profile" is set
   b200mvs_shape last_shape{};
@@ -351,6 +352,7 @@ void layout(b200mvs_net* net, const b200mvs_shape& s, bool dry) {
     W.l4y[i] = A.take<float>(NI * L.px[4] * kC);
   }
   W.vol = A.take<float>(n * D * L.px[4] * kC);
+  W.imgconv = A.take<float>(n * D * L.px[4] * kC);
   W.wf = A.take<float>(n * L.px[4] * kC);
   W.wimg = A.take<float>(n * 3 * L.px[4]);
   W.sy0 = A.take<float>(n * L.px[4] * kC);
@@ -670,10 +672,21 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
   }
   // 3a. FeatureNetwork on the B left images (multi_view_stereonet.py:552)
   RC(run_featnet(net, L, 0, B, left_pyr[0], tail_stats, ws.feat4, 0, left_stream));
-  if (overlap) B200MVS_CUDA_OK(cudaEventRecord(net->ev_left, net->side));
 
   // 1. geometry
   RC(launch_geometry(Tv, K_pyr[0], K_pyr[4], B, D, h4, w4, ws.geo, stream));
+
+  // 1b. image half of FeatureRefiner.conv0 for every hypothesis (needs only the homographies): side stream
+  const bool persistent = net->use_tensor_cores && recurrence_supported(h4, w4, nullptr, nullptr);
+  if (persistent) {
+    if (overlap) {
+      B200MVS_CUDA_OK(cudaEventRecord(net->ev_geo, stream));
+      B200MVS_CUDA_OK(cudaStreamWaitEvent(net->side, net->ev_geo, 0));
+    }
+    RC(launch_image_conv(ws.geo.H, R4, net->fr_conv0.w + (size_t)4 * 9 * 8 * 32, net->fr_conv0.bias, n, D, h4, w4,
+                         ws.imgconv, left_stream));
+  }
+  if (overlap) B200MVS_CUDA_OK(cudaEventRecord(net->ev_left, net->side));
 
   // 2. full-resolution warp of every comparison image by the idepth-0 homography
   //    (multi_view_stereonet.py:254-258)
@@ -684,8 +697,10 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
   RC(run_featnet(net, L, B, n, ws.warped0, tail_stats, ws.vol, (long long)D * (long long)P4 * kC, stream));
 
   // 5. the depth-sweep recurrence (multi_view_stereonet.py:279-290)
-  if (net->use_tensor_cores && recurrence_supported(h4, w4, nullptr, nullptr)) {
+  if (overlap) B200MVS_CUDA_OK(cudaStreamWaitEvent(stream, net->ev_left, 0));
+  if (persistent) {
     RecurrenceArgs ra;
+    ra.imgconv = ws.imgconv;
     ra.vol = ws.vol;
     ra.geo = ws.geo;
     ra.right_l4 = R4;
@@ -762,8 +777,6 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
       RC(launch_conv(CONV_3x3, 32, c, stream));
     }
   }
-
-  if (overlap) B200MVS_CUDA_OK(cudaStreamWaitEvent(stream, net->ev_left, 0));
 
   // 6. cost volume |L - R| with invalid voxels zeroed (multi_view_stereonet.py:586-592)
   float* cost = net->keep_stages ? ws.cost : ws.vol;
@@ -923,6 +936,7 @@ B200MVS_API int b200mvs_create(int device, int num_tensors, const char* const* n
   if (rc == 0) {
     if (cudaStreamCreateWithFlags(&net->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&net->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&net->ev_geo, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&net->ev_left, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&net->ev_mask_in, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&net->ev_mask_out, cudaEventDisableTiming) != cudaSuccess) {
@@ -945,7 +959,7 @@ B200MVS_API void b200mvs_destroy(b200mvs_net* net) {
   if (net->arena.base != nullptr) cudaFree(net->arena.base);
   if (net->host_stage != nullptr) cudaFree(net->host_stage);
   for (cudaEvent_t e : net->probe.ev) cudaEventDestroy(e);
-  for (cudaEvent_t e : {net->ev_fork, net->ev_left, net->ev_mask_in, net->ev_mask_out})
+  for (cudaEvent_t e : {net->ev_geo, net->ev_fork, net->ev_left, net->ev_mask_in, net->ev_mask_out})
     if (e != nullptr) cudaEventDestroy(e);
   if (net->side != nullptr) cudaStreamDestroy(net->side);
   delete net;

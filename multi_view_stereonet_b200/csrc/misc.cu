@@ -36,6 +36,77 @@ __global__ void __launch_bounds__(256) warp_planar_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// Image part of FeatureRefiner.conv0 for every hypothesis at once.  conv0 acts on cat([warped 1/16 image (3),
+// warped features (32)]) (multi_view_stereonet.py:425-426); convolution is linear in its input channels, and the
+// image half depends only on H_d (multi_view_stereonet.py:270-275), not on the recurrence.  This kernel computes
+//   out[n][d] = conv3x3(warp(right_l4, H_d) zeroed outside, W0[:, 0:3]) + bias0        for d = 1..D-1
+// so that the persistent recurrence kernel only runs the 32-channel half on the tensor core.  fp32 FFMA.
+// ---------------------------------------------------------------------------------------------
+constexpr int kIcRows = 8;
+__global__ void __launch_bounds__(256) image_conv_kernel(const float* __restrict__ H, ViewPtrs right_l4,
+                                                         const float* __restrict__ w, const float* __restrict__ bias,
+                                                         int D, int rows, int cols, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ float s_ic[];
+  const int PWc = cols + 2;
+  float* s_img = s_ic;                              // [3][kIcRows + 2][PWc]
+  float* s_w = s_ic + 3 * (kIcRows + 2) * PWc;      // [tap][3][32]
+  float* s_b = s_w + 27 * 32;
+  const int tid = threadIdx.x;
+  const int d = blockIdx.y + 1, n = blockIdx.z, y0 = blockIdx.x * kIcRows;
+  const int pixels = rows * cols;
+  for (int i = tid; i < 27 * 32; i += 256) {
+    const int tap = i / 96, c = (i / 32) % 3, o = i % 32;
+    s_w[i] = __ldg(w + (tap * 8 + c) * 32 + o);     // packed [tap][8][32], image channels are k = 0..2
+  }
+  if (tid < 32) s_b[tid] = __ldg(bias + tid);
+  const float* Hd = H + ((size_t)n * D + d) * 9;
+  const float* img = right_l4.p[n % right_l4.views] + (size_t)(n / right_l4.views) * 3 * pixels;
+  for (int i = tid; i < (kIcRows + 2) * PWc; i += 256) {
+    const int iy = i / PWc, ix = i % PWc;
+    const int gy = y0 - 1 + iy, gx = ix - 1;
+    float v[3] = {0.f, 0.f, 0.f};
+    if (gy >= 0 && gy < rows && gx >= 0 && gx < cols) {
+      const WarpCoord c = homography_coord(Hd, (float)gx, (float)gy, rows, cols);
+      if (!c.invalid) {
+        const Bilinear b = bilinear_setup(c, rows, cols);
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          const float* pl = img + (size_t)ch * pixels;
+          v[ch] = __ldg(pl + b.y0 * cols + b.x0) * b.w00 + __ldg(pl + b.y0 * cols + b.x1) * b.w01 +
+                  __ldg(pl + b.y1 * cols + b.x0) * b.w10 + __ldg(pl + b.y1 * cols + b.x1) * b.w11;
+        }
+      }
+    }
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) s_img[(ch * (kIcRows + 2) + iy) * PWc + ix] = v[ch];
+  }
+  __syncthreads();
+  for (int t = tid; t < kIcRows * cols * 4; t += 256) {
+    const int oct = t & 3, pix = t >> 2;
+    const int y = pix / cols, x = pix % cols;
+    if (y0 + y >= rows) continue;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = s_b[oct * 8 + k];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float a = s_img[(c * (kIcRows + 2) + y + tap / 3) * PWc + x + tap % 3];
+        const float* wr = s_w + (tap * 3 + c) * 32 + oct * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(a, wr[k], acc[k]);
+      }
+    }
+    float4* o = reinterpret_cast<float4*>(out + (((size_t)n * D + d) * pixels + (size_t)(y0 + y) * cols + x) * kC + oct * 8);
+    o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // One recurrence step's warps (multi_view_stereonet.py:275, 285).  8 lanes per pixel, one float4
 // of the 32 feature channels each; lanes 0..2 additionally warp one plane of the 1/16 right image.
 // ---------------------------------------------------------------------------------------------
@@ -285,6 +356,20 @@ int launch_warp_planar(const float* H, int h_stride, const ViewPtrs& src, int n,
   launch_pdl(warp_planar_kernel, grid, dim3(256), (size_t)0, stream, H, h_stride, src, channels, rows, cols, zero_invalid ? 1 : 0, pred,
                                                mask);
   B200MVS_LAUNCH_OK("warp_planar_kernel");
+  return 0;
+}
+
+int launch_image_conv(const float* H, const ViewPtrs& right_l4, const float* w_tap8x32, const float* bias, int n,
+                      int D, int rows, int cols, float* out, cudaStream_t stream) {
+  if (D < 2) return 0;
+  dim3 grid(cdiv(rows, kIcRows), D - 1, n);
+  const size_t smem = ((size_t)3 * (kIcRows + 2) * (cols + 2) + 27 * 32 + 32) * sizeof(float);
+  if (smem > 48 * 1024) {
+    set_error("launch_image_conv: image too wide");
+    return -1;
+  }
+  launch_pdl(image_conv_kernel, grid, dim3(256), smem, stream, H, right_l4, w_tap8x32, bias, D, rows, cols, out);
+  B200MVS_LAUNCH_OK("image_conv_kernel");
   return 0;
 }
 

@@ -8,18 +8,24 @@
 //            y1   = conv3x3(x0) + b           ; x1 = lrelu(GN(y1)) + x0
 //            features_i = wf + conv3x3(x1) + b                        (FeatureRefiner, :424-440)
 //
+// The image half of the first convolution, conv3x3(img, W0[:, 0:3]) + b, does not depend on the recurrence: it is
+// computed for all hypotheses beforehand (image_conv_kernel, misc.cu) and added in the first epilogue, so the
+// tensor core only sees 32-channel operands.
+//
 // Decomposition.  The 1/16-scale image is linearised with a zero column on each side (pitch
 // PW = w + 2); CTA r of the cluster owns output positions [128 r, 128 r + 128) = one UMMA M-tile.
-// Each 3x3 conv is 9 taps x K/16 k-steps of tcgen05.mma.kind::f16 (M=128, N=32) whose A operand
+// Each 3x3 conv is 9 taps x 2 k-steps of tcgen05.mma.kind::f16 (M=128, N=32) whose A operand
 // for tap (ky, kx) is the staged activation plane started ky*PW + kx positions later (see
 // conv_tc.cu).  The 1/16-scale stages need ~fp32 operand accuracy, so every
-// operand is split x = hi + lo into two fp16 values and each k-step issues three MMAs
-// (hi*hi + lo*hi + hi*lo), fp32 accumulation in TMEM: ~22 significant bits.
-// GroupNorm needs whole-image statistics twice per step: CTAs push their partial sums into every
-// CTA's shared memory (DSMEM) and meet at a hardware cluster barrier; the raw conv outputs of the
-// PW+1 positions next to a tile boundary are pushed into the neighbour CTA's halo buffer at the same
-// time, so each CTA normalises its own tile plus halo locally.  Three cluster barriers per step.
-// All weights (hi and lo, three layers, 126 KB) stay resident in shared memory for all steps.
+// operand is split x = hi + lo into two fp16 values and each k-step issues the three products
+// (hi*hi + lo*hi + hi*lo) as two MMAs, fp32 accumulation in TMEM: ~22 significant bits.
+// GroupNorm needs whole-image statistics twice per step: every warp pushes its partial sums into every CTA's
+// shared memory and the raw conv outputs of the PW+1 positions next to a tile boundary into the neighbour CTA's
+// halo buffer with st.async, which completes bytes on the RECEIVER's mbarrier; each CTA waits for its own expected
+// byte count (no cluster-wide barrier) and normalises its tile plus halo locally.  One cluster barrier per step
+// publishes the new hypothesis; the next step's gather source (own tile + halo + margin, a contiguous pixel
+// range) is then pulled into shared memory by one 1-D TMA bulk copy and gathered from there.
+// All weights (hi and lo, three layers, 108 KB) stay resident in shared memory for all steps.
 #include <cuda_fp16.h>
 
 #include <vector>
@@ -32,7 +38,7 @@ namespace {
 
 constexpr int NT = 512;
 constexpr int MTILE = 128;
-constexpr int W0_BLOCKS = 9 * 3;   // conv0: taps x k-steps (32 feature + 3 image channels, padded to 48)
+constexpr int W0_BLOCKS = 9 * 2;   // taps x k-steps (32 input channels)
 constexpr int W1_BLOCKS = 9 * 2;
 constexpr int W_TOTAL_BYTES = (W0_BLOCKS + 2 * W1_BLOCKS) * 2 * 1024;  // hi + lo
 
@@ -126,16 +132,19 @@ __device__ __forceinline__ void unsplit8(const uint4& hi, const uint4& lo, float
 
 struct Layout {
   int PW, halo, npl, npl_pad;
+  int stage_px;            // pixels of the previous hypothesis staged per step (own + halo + margin)
+  int margin;              // pixels staged before / after the own + halo range
   uint32_t plane_bytes;
   // byte offsets into dynamic shared memory
-  uint32_t off_w, off_planes, off_own, off_halo, off_wf, total;
+  uint32_t off_w, off_planes, off_halo, off_wf, off_stage, total;
 };
 
-// Planes (each npl_pad x 16 B): [hi f0..f3][hi extra][zero][lo f0..f3][lo extra][zero]
-constexpr int PLANE_HI = 0, PLANE_HI_X = 4, PLANE_LO = 6, PLANE_LO_X = 10, NUM_PLANES = 12;
+// Planes (each npl_pad x 16 B): [hi f0..f3][lo f0..f3]
+constexpr int PLANE_HI = 0, PLANE_LO = 4, NUM_PLANES = 8;
 constexpr int MAX_TASKS = 2;   // (position, channel octet) staging tasks per thread: npl * 4 <= 2 * NT
+constexpr uint32_t kSmemBudget = 227u * 1024u - 8u * 1024u;   // dynamic part; static arrays take the rest
 
-__host__ __device__ inline Layout make_layout(int cols) {
+__host__ __device__ inline Layout make_layout(int rows, int cols) {
   Layout L;
   L.PW = cols + 2;
   L.halo = L.PW + 1;
@@ -147,11 +156,20 @@ __host__ __device__ inline Layout make_layout(int cols) {
   o += W_TOTAL_BYTES;
   L.off_planes = o;
   o += NUM_PLANES * L.plane_bytes;
-  L.off_own = o;           // (unused: the own tile's raw outputs live in registers)
   L.off_halo = o;          // [layer 2][side 2][halo][32] fp32, written by the neighbour CTAs
   o += 2 * 2 * (uint32_t)L.halo * kC * 4;
   L.off_wf = o;            // warped features of the own positions, fp32 [128][32]
   o += MTILE * kC * 4;
+  L.off_stage = o;         // previous hypothesis, pixels [q_lo, q_lo + stage_px), fp32 [px][32]
+  // own + halo positions cover at most this many consecutive pixels; the rest of the budget is margin
+  const int span = ((L.npl - 1) / L.PW + 2) * cols;
+  int cap = o < kSmemBudget ? (int)((kSmemBudget - o) / (kC * 4)) : 0;
+  const int want = span + 2 * (2 * cols + 4);
+  if (cap > want) cap = want;
+  if (cap > rows * cols) cap = rows * cols;
+  L.stage_px = cap;
+  L.margin = (cap - span) / 2;
+  o += (uint32_t)(cap > 0 ? cap : 0) * kC * 4;
   L.total = o;
   return L;
 }
@@ -169,9 +187,10 @@ struct RecParams {
   const float* beta0;
   const float* gamma1;
   const float* beta1;
+  const float* imgconv;  // [n][D][rows*cols][32]: image half of conv0 + bias0 (image_conv_kernel)
   int D, rows, cols, n_tiles;
   long long* prof;       // optional [16][12] phase cycle totals (debug)
-  int debug;             // timing ablations (wrong results): 1 skip MMAs, 2 skip gathers, 4 skip halo/stat pushes
+  int debug;             // timing ablations (wrong results): 1 skip MMAs, 2 skip gathers
 };
 
 // 8 consecutive fp32 accumulator columns of this thread's TMEM lane.
@@ -203,40 +222,85 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-template <int KS>
 __device__ __forceinline__ void issue_conv_mmas(uint64_t da_hi0, uint64_t da_lo0, uint64_t db, uint32_t plane_u16,
                                                 uint32_t PW, uint32_t tmem_base) {
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
     const uint32_t pos = (uint32_t)(tap / 3) * PW + (uint32_t)(tap % 3);   // 16-byte units
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {
-      const uint32_t pl = (ks < 2) ? 2u * ks : (uint32_t)PLANE_HI_X;       // k-step 2 reads (extra, zero)
-      const uint64_t a_off = (uint64_t)(pl * plane_u16 + pos);
-      const uint64_t b = db + (uint64_t)((tap * KS + ks) * (2048 / 16));
+    for (int ks = 0; ks < 2; ++ks) {
+      const uint64_t a_off = (uint64_t)(2u * ks * plane_u16 + pos);
+      const uint64_t b = db + (uint64_t)((tap * 2 + ks) * (2048 / 16));
       mma_f16(tmem_base, da_hi0 + a_off, b, kIdescN64, (tap | ks) != 0 ? 1u : 0u);
       mma_f16(tmem_base, da_lo0 + a_off, b, kIdescN32, 1u);
     }
   }
 }
 
+// Remote shared-memory store that signals `bytes stored` on an mbarrier of the destination CTA: the receiver
+// waits for its expected byte count instead of the whole cluster meeting at a barrier.
+__device__ __forceinline__ void st_async_f4(uint32_t raddr, float4 v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
+               "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(rbar)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_f1(uint32_t raddr, float v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(raddr), "f"(v),
+               "r"(rbar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arm_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 q, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  }
+}
+
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// Per-step schedule of one CTA (one 128-position M-tile of one view):
+//   T   one lane: TMA bulk copy of the previous hypothesis' pixels [q_lo, q_lo + count) into shared memory
+//   W   gather-warp from shared memory (plan computed during the previous step; taps outside the staged range
+//       fall back to global memory) -> split-fp16 conv0 operand
+//   MMA0 | E0: raw output + image half -> st.async pushes of boundary rows to the neighbours and of the GroupNorm
+//             partial sums to every CTA, each completing bytes on the receiver's mbarrier
+//   wait own mbarrier | S1: normalise own + halo -> operand | MMA1 (meanwhile: next step's gather plan)
+//   E1 / wait / S2 | MMA2 | E2: features = warped + delta -> global
+//   one cluster barrier: hypothesis `step` is published, exchange buffers are free again
 template <bool PROF>
 __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ float s_part[2][16][2 * kGroups];  // per-layer partial (sum, sumsq) of every CTA of the cluster
-  __shared__ float s_red[NT / 32][2];
-  __shared__ float s_bias[3][kC], s_gamma[2][kC], s_beta[2][kC];
-  __shared__ __align__(8) uint64_t s_bar;
+  // GroupNorm partial (sum, sumsq) of [layer][source CTA][group][warp quarter]
+  __shared__ __align__(16) float s_part[2][16][kGroups][4][2];
+  __shared__ float s_bias[2][kC], s_gamma[2][kC], s_beta[2][kC];   // biases of conv1, conv2 (conv0's is in imgconv)
+  __shared__ __align__(8) uint64_t s_bar;        // MMA completion
+  __shared__ __align__(8) uint64_t s_xbar[2];    // per layer: bytes pushed into this CTA by the cluster
+  __shared__ __align__(8) uint64_t s_tbar;       // TMA staging of the previous hypothesis
   __shared__ uint32_t s_tmem;
-  __shared__ float s_tot[2 * kGroups];
-  __shared__ float s_H[2][18];   // [step parity][H_inc (9), H_d (9)], fetched one step ahead
+  __shared__ float s_H[2][9];    // [step parity] H_inc, fetched one step ahead
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform
   const uint32_t rank = cluster_ctarank();
-  const uint32_t csize = gridDim.x;  // cluster == all CTAs of blockIdx.y
   const int n = blockIdx.y;
-  const Layout L = make_layout(p.cols);
+  const Layout L = make_layout(p.rows, p.cols);
   const int PW = L.PW, halo = L.halo, npl = L.npl;
   const int pixels = p.rows * p.cols;
   const bool active = (int)rank < p.n_tiles;
@@ -246,6 +310,7 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
   uint8_t* s_planes = smem + L.off_planes;
   float* s_halo = reinterpret_cast<float*>(smem + L.off_halo);
   float* s_wf = reinterpret_cast<float*>(smem + L.off_wf);
+  const float* s_stage = reinterpret_cast<const float*>(smem + L.off_stage);
 
   // ---- one-time setup ----
   if (warp == 0) {
@@ -256,12 +321,14 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
   }
   if (tid == 32) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_bar)), "r"(1) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_xbar[0])), "r"(1) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_xbar[1])), "r"(1) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_tbar)), "r"(1) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < kC) {
-    s_bias[0][tid] = __ldg(p.bias0 + tid);
-    s_bias[1][tid] = __ldg(p.bias1 + tid);
-    s_bias[2][tid] = __ldg(p.bias2 + tid);
+    s_bias[0][tid] = __ldg(p.bias1 + tid);
+    s_bias[1][tid] = __ldg(p.bias2 + tid);
     s_gamma[0][tid] = __ldg(p.gamma0 + tid);
     s_beta[0][tid] = __ldg(p.beta0 + tid);
     s_gamma[1][tid] = __ldg(p.gamma1 + tid);
@@ -271,7 +338,7 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
     const uint4* src = reinterpret_cast<const uint4*>(p.w16);
     uint4* dst = reinterpret_cast<uint4*>(s_w);
     for (int i = tid; i < W_TOTAL_BYTES / 16; i += NT) dst[i] = __ldg(src + i);
-    // zero every plane once: the two zero planes and the padding lanes of the extra planes stay zero
+    // zero every plane once: padding lanes stay zero
     uint4* pl = reinterpret_cast<uint4*>(s_planes);
     for (int i = tid; i < NUM_PLANES * L.npl_pad; i += NT) pl[i] = make_uint4(0, 0, 0, 0);
     float4* hz = reinterpret_cast<float4*>(s_halo);
@@ -283,31 +350,33 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
   const uint32_t tmem_base = s_tmem;
   uint32_t bar_phase = 0;
   pdl_launch_dependents();
-  cluster_sync_all();  // every CTA's shared memory is initialised before anyone pushes into it
+  cluster_sync_all();  // every CTA's shared memory and mbarriers are initialised before anyone pushes into them
 
   const float inv_count = 1.0f / (8.0f * (float)pixels);
   const uint32_t plane_u16 = L.plane_bytes >> 4;
   const uint64_t da_hi0 = umma_desc(smem_u32(s_planes) + (uint32_t)PLANE_HI * L.plane_bytes, L.plane_bytes, 128u);
   const uint64_t da_lo0 = umma_desc(smem_u32(s_planes) + (uint32_t)PLANE_LO * L.plane_bytes, L.plane_bytes, 128u);
   const uint64_t db_c0 = umma_desc(smem_u32(s_w), 1024u, 128u);
-  // Runs one conv on the tensor core and waits for its accumulators.  Only the issuing thread polls the
-  // mbarrier; everyone else parks at the hardware barrier (polling from 16 warps steals shared-memory bandwidth
-  // from the tensor core's operand fetch).
-  auto run_conv = [&](int layer) {
+
+  // Tensor-core conv: an elected lane of warp 0 issues and commits; later the same lane polls the completion
+  // mbarrier while everyone else parks at the hardware barrier.  Work placed between the two overlaps the MMAs.
+  auto issue_conv = [&](int layer) {
     if (warp == 0) {
       if (active && elect_one()) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (!(p.debug & 1)) {
-          if (layer == 0)
-            issue_conv_mmas<3>(da_hi0, da_lo0, db_c0, plane_u16, (uint32_t)PW, tmem_base);
-          else
-            issue_conv_mmas<2>(da_hi0, da_lo0,
-                               db_c0 + (uint64_t)((W0_BLOCKS + (layer - 1) * W1_BLOCKS) * (2048 / 16)), plane_u16,
-                               (uint32_t)PW, tmem_base);
-        }
+        if (!(p.debug & 1))
+          issue_conv_mmas(da_hi0, da_lo0, db_c0 + (uint64_t)(layer * W1_BLOCKS * (2048 / 16)), plane_u16, (uint32_t)PW,
+                          tmem_base);
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                          smem_u32(&s_bar))
                      : "memory");
+      }
+      __syncwarp();
+    }
+  };
+  auto wait_conv = [&]() {
+    if (warp == 0) {
+      if (active && elect_one()) {
         const uint32_t bar = smem_u32(&s_bar);
         uint32_t done = 0;
         while (!done) {
@@ -338,9 +407,12 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
   const bool real_out = active && ox < p.cols && oy < p.rows;
   const uint32_t tmem_my = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(oct_e * 8);
   const int own_l = jl + halo;                   // local input position of the own output
+  const size_t own_pix = real_out ? (size_t)oy * p.cols + ox : 0;
 
-  // Staging tasks of this thread, fixed for all steps: (local input position l, channel octet).
+  // Gather tasks of this thread, fixed for all steps: (local input position l, channel octet).  The four lanes of
+  // a quad share the position and take one octet each.
   const int t_oct = tid & 3;  // NT % 4 == 0: the octet is the same for every task of a thread
+  const int sw = (tid >> 2) & 1;   // which 16-byte half of the octet is read first (shared-memory bank spread)
   int t_l[MAX_TASKS], t_gy[MAX_TASKS], t_gx[MAX_TASKS];
   bool t_real[MAX_TASKS];
 #pragma unroll
@@ -352,13 +424,8 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
     t_gx[k] = Lg % PW - 1;
     t_real[k] = active && t_l[k] < npl && t_gy[k] >= 0 && t_gy[k] < p.rows && t_gx[k] >= 0 && t_gx[k] < p.cols;
   }
-  // image-plane task: one local position per thread
-  const int x_l = tid;
-  const int x_gy = (pos0 + x_l) / PW - 1, x_gx = (pos0 + x_l) % PW - 1;
-  const bool x_in = active && x_l < npl;
-  const bool x_real = x_in && x_gy >= 0 && x_gy < p.rows && x_gx >= 0 && x_gx < p.cols;
-  // halo staging task: (halo position, channel octet); 2 * halo * 4 <= NT
-  const int h_idx = tid >> 2;                               // lower halo then upper halo, as laid out in s_halo
+  // halo staging task: halo position (tid & 127) of the thread's own octet; 2 * halo <= 128
+  const int h_idx = tid & 127;                              // lower halo then upper halo, as laid out in s_halo
   const bool h_in = active && h_idx < 2 * halo;
   const int h_l = h_idx < halo ? h_idx : h_idx + MTILE;     // local input position
   bool h_real;
@@ -367,6 +434,24 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
     const int gy = Lg / PW - 1, gx = Lg % PW - 1;
     h_real = h_in && gy >= 0 && gy < p.rows && gx >= 0 && gx < p.cols;
   }
+  // bytes the cluster pushes into this CTA per layer: every active CTA's 16 warp partials (sum, sumsq) and the
+  // boundary rows of the two neighbours
+  const uint32_t xbytes = (uint32_t)p.n_tiles * 16u * 2u * 4u +
+                          (rank > 0 ? (uint32_t)halo * kC * 4u : 0u) +
+                          ((int)rank + 1 < p.n_tiles ? (uint32_t)halo * kC * 4u : 0u);
+  // staged pixel range of the previous hypothesis: the pixels under the own + halo positions, plus a margin
+  int q_lo, q_cnt;
+  {
+    const int gy0 = pos0 / PW - 1;
+    int gx0 = pos0 % PW - 1;
+    gx0 = gx0 < 0 ? 0 : (gx0 > p.cols - 1 ? p.cols - 1 : gx0);
+    int first = gy0 * p.cols + gx0 - L.margin;
+    first = first < 0 ? 0 : first;
+    if (first > pixels - L.stage_px) first = pixels - L.stage_px;   // stage_px <= pixels
+    q_lo = first;
+    q_cnt = L.stage_px;
+  }
+  const int st_lo = q_lo * kC, st_n = q_cnt * kC;   // in floats, relative to the hypothesis base
 
   auto plane_ptr = [&](int plane, int l) -> uint4* {
     return reinterpret_cast<uint4*>(s_planes + (size_t)plane * L.plane_bytes + (size_t)l * 16);
@@ -386,77 +471,113 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
   } while (0)
 
   pdl_wait();  // everything above ran under the previous kernel's tail; from here on its outputs are read
-  const float* img_base = p.right_l4.p[n % p.right_l4.views] + (size_t)(n / p.right_l4.views) * 3 * pixels;
-  // homographies of the coming step, fetched one step ahead into shared memory
-  if (tid < 18)
-    s_H[1][tid] = __ldg((tid < 9 ? p.geo.Hinc : p.geo.H - 9) + ((size_t)n * p.D + 1) * 9 + tid);
+
+  // Gather plan of the coming step (element offsets of the four bilinear taps and their weights), computed one
+  // step ahead while the tensor core runs: quad lane k evaluates task k's homography and broadcasts it.
+  int g_off[MAX_TASKS][4];
+  float g_w[MAX_TASKS][4];
+  bool g_ok[MAX_TASKS];
+  auto plan_gathers = [&](int step) {
+    const float* Hinc = s_H[step & 1];
+    int mo[4] = {0, 0, 0, 0};
+    float mw[4] = {0.f, 0.f, 0.f, 0.f};
+    int mok = 0;
+    const int kq = t_oct & 1;   // lanes 0/2 of the quad evaluate task 0, lanes 1/3 task 1 (2 and 3 redundantly)
+    if ((kq == 0 ? t_real[0] : t_real[1]) && !(p.debug & 2)) {
+      const WarpCoord c = homography_coord(Hinc, (float)(kq == 0 ? t_gx[0] : t_gx[1]),
+                                           (float)(kq == 0 ? t_gy[0] : t_gy[1]), p.rows, p.cols);
+      if (!c.invalid) {
+        const Bilinear b = bilinear_setup(c, p.rows, p.cols);
+        mok = 1;
+        mo[0] = (b.y0 * p.cols + b.x0) * kC;
+        mo[1] = (b.y0 * p.cols + b.x1) * kC;
+        mo[2] = (b.y1 * p.cols + b.x0) * kC;
+        mo[3] = (b.y1 * p.cols + b.x1) * kC;
+        mw[0] = b.w00;
+        mw[1] = b.w01;
+        mw[2] = b.w10;
+        mw[3] = b.w11;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < MAX_TASKS; ++k) {
+      const int srcl = (lane & ~3) + k;
+      g_ok[k] = __shfl_sync(0xffffffffu, mok, srcl) != 0;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        g_off[k][t] = __shfl_sync(0xffffffffu, mo[t], srcl);
+        g_w[k][t] = __shfl_sync(0xffffffffu, mw[t], srcl);
+      }
+    }
+  };
+  auto fetch_H = [&](int step) {
+    if (step < p.D && tid < 9) s_H[step & 1][tid] = __ldg(p.geo.Hinc + ((size_t)n * p.D + step) * 9 + tid);
+  };
+  // one lane: bulk copy of hypothesis `step - 1`, pixels [q_lo, q_lo + q_cnt), into the staging buffer
+  auto stage_prev = [&](int step) {
+    if (warp == 1) {
+      if (active && elect_one()) {
+        asm volatile("fence.proxy.async;" ::: "memory");   // other CTAs' generic-proxy stores -> this async-proxy read
+        mbar_arm_tx(&s_tbar, (uint32_t)st_n * 4u);
+        tma_load_1d(smem + L.off_stage, p.vol_in + ((size_t)n * p.D + (step - 1)) * pixels * kC + st_lo,
+                    (uint32_t)st_n * 4u, &s_tbar);
+      }
+      __syncwarp();
+    }
+  };
+
+  stage_prev(1);
+  fetch_H(1);
   __syncthreads();
+  plan_gathers(1);
+
   float x0own[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) x0own[k] = 0.f;
 
   for (int step = 1; step < p.D; ++step) {
-    // ================= W: warp previous features and the 1/16 image into the conv0 operand =========
+    if (active && tid == 0) {
+      mbar_arm_tx(&s_xbar[0], xbytes);
+      mbar_arm_tx(&s_xbar[1], xbytes);
+    }
+    // image half of conv0 (+ bias) at this thread's output position, consumed in the first epilogue
+    float4 ic0 = make_float4(0.f, 0.f, 0.f, 0.f), ic1 = ic0;
+    if (real_out) {
+      const float4* icp =
+          reinterpret_cast<const float4*>(p.imgconv + (((size_t)n * p.D + step) * pixels + own_pix) * kC + oct_e * 8);
+      ic0 = __ldg(icp);
+      ic1 = __ldg(icp + 1);
+    }
+    fetch_H(step + 1);   // read after several block-wide barriers
+    // ================= W: warp previous features into the conv0 operand ============================
+    if (active) mbar_wait_cluster(&s_tbar, (uint32_t)((step - 1) & 1));
     {
-      const float* Hinc = s_H[step & 1];
-      const float* Hd = Hinc + 9;
       const float* prev = p.vol_in + ((size_t)n * p.D + (step - 1)) * pixels * kC + 8 * t_oct;
-      float4 g[MAX_TASKS][8];
-      Bilinear bl[MAX_TASKS];
-      bool ok[MAX_TASKS];
-      // issue every gather of every task before consuming any: one L2 round trip per step
-#pragma unroll
-      for (int k = 0; k < MAX_TASKS; ++k) {
-        ok[k] = false;
-        if (t_real[k] && !(p.debug & 2)) {
-          const WarpCoord c = homography_coord(Hinc, (float)t_gx[k], (float)t_gy[k], p.rows, p.cols);
-          ok[k] = !c.invalid;
-          if (ok[k]) {
-            bl[k] = bilinear_setup(c, p.rows, p.cols);
-            const float4* b00 = reinterpret_cast<const float4*>(prev + ((size_t)bl[k].y0 * p.cols + bl[k].x0) * kC);
-            const float4* b01 = reinterpret_cast<const float4*>(prev + ((size_t)bl[k].y0 * p.cols + bl[k].x1) * kC);
-            const float4* b10 = reinterpret_cast<const float4*>(prev + ((size_t)bl[k].y1 * p.cols + bl[k].x0) * kC);
-            const float4* b11 = reinterpret_cast<const float4*>(prev + ((size_t)bl[k].y1 * p.cols + bl[k].x1) * kC);
-            g[k][0] = __ldcg(b00); g[k][1] = __ldcg(b00 + 1);
-            g[k][2] = __ldcg(b01); g[k][3] = __ldcg(b01 + 1);
-            g[k][4] = __ldcg(b10); g[k][5] = __ldcg(b10 + 1);
-            g[k][6] = __ldcg(b11); g[k][7] = __ldcg(b11 + 1);
-          }
-        }
-      }
-      // image planes (3 channels) of this thread's position
-      float xi[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) xi[k] = 0.f;
-      if (x_real) {
-        const WarpCoord c = homography_coord(Hd, (float)x_gx, (float)x_gy, p.rows, p.cols);
-        if (!c.invalid) {
-          const Bilinear b = bilinear_setup(c, p.rows, p.cols);
-#pragma unroll
-          for (int ch = 0; ch < 3; ++ch) {
-            const float* pl = img_base + (size_t)ch * pixels;
-            xi[ch] = __ldg(pl + b.y0 * p.cols + b.x0) * b.w00 + __ldg(pl + b.y0 * p.cols + b.x1) * b.w01 +
-                     __ldg(pl + b.y1 * p.cols + b.x0) * b.w10 + __ldg(pl + b.y1 * p.cols + b.x1) * b.w11;
-          }
-        }
-      }
-      // prefetch the next step's homographies (read after several block-wide barriers)
-      if (step + 1 < p.D && tid < 18)
-        s_H[(step + 1) & 1][tid] = __ldg((tid < 9 ? p.geo.Hinc : p.geo.H - 9) + ((size_t)n * p.D + step + 1) * 9 + tid);
+      const float* stg = s_stage + 8 * t_oct;
 #pragma unroll
       for (int k = 0; k < MAX_TASKS; ++k) {
         if (active && t_l[k] < npl) {
           float v[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) v[e] = 0.f;
-          if (ok[k]) {
+          if (g_ok[k]) {
 #pragma unroll
-            for (int hq = 0; hq < 2; ++hq) {
-              const float4 a = g[k][hq], b = g[k][2 + hq], cc = g[k][4 + hq], d = g[k][6 + hq];
-              v[4 * hq + 0] = a.x * bl[k].w00 + b.x * bl[k].w01 + cc.x * bl[k].w10 + d.x * bl[k].w11;
-              v[4 * hq + 1] = a.y * bl[k].w00 + b.y * bl[k].w01 + cc.y * bl[k].w10 + d.y * bl[k].w11;
-              v[4 * hq + 2] = a.z * bl[k].w00 + b.z * bl[k].w01 + cc.z * bl[k].w10 + d.z * bl[k].w11;
-              v[4 * hq + 3] = a.w * bl[k].w00 + b.w * bl[k].w01 + cc.w * bl[k].w10 + d.w * bl[k].w11;
+            for (int t = 0; t < 4; ++t) {
+              const int loc = g_off[k][t] - st_lo;
+              float4 a, b;
+              if ((unsigned)loc < (unsigned)st_n) {
+                const float4* sp = reinterpret_cast<const float4*>(stg + loc);
+                const float4 f = sp[sw], s2 = sp[sw ^ 1];
+                a = sw ? s2 : f;
+                b = sw ? f : s2;
+              } else {   // tap outside the staged range (large incremental motion): global memory
+                const float4* gp = reinterpret_cast<const float4*>(prev + g_off[k][t]);
+                a = __ldcg(gp);
+                b = __ldcg(gp + 1);
+              }
+              const float wt = g_w[k][t];
+              v[0] = fmaf(a.x, wt, v[0]); v[1] = fmaf(a.y, wt, v[1]); v[2] = fmaf(a.z, wt, v[2]); v[3] = fmaf(a.w, wt, v[3]);
+              v[4] = fmaf(b.x, wt, v[4]); v[5] = fmaf(b.y, wt, v[5]); v[6] = fmaf(b.z, wt, v[6]); v[7] = fmaf(b.w, wt, v[7]);
             }
           }
           const int l = t_l[k];
@@ -471,44 +592,47 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
           *plane_ptr(PLANE_LO + t_oct, l) = lo;
         }
       }
-      if (x_in) {
-        uint4 hi, lo;
-        split8(xi, &hi, &lo);
-        *plane_ptr(PLANE_HI_X, x_l) = hi;
-        *plane_ptr(PLANE_LO_X, x_l) = lo;
-      }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     PROF_MARK(0);
-    run_conv(0);
+    issue_conv(0);
+    wait_conv();
     PROF_MARK(1);
 
-    // ===== two normalised layers: raw output -> statistics + halo exchange -> barrier -> operand -> conv =====
+    // ===== two normalised layers: raw output -> statistics + halo exchange -> wait -> operand -> conv =====
 #pragma unroll 1
     for (int layer = 0; layer < 2; ++layer) {
       // ---- epilogue: raw output (+bias) stays in registers, is pushed to the neighbours' halos, and is reduced
       float y[8];
-      float gs = 0.f, gq = 0.f;
       if (active) {
         float c[8];
         tmem_ld8(tmem_my, y);
         tmem_ld8(tmem_my + 32u, c);
+        if (layer == 0) {
+          const float add[8] = {ic0.x, ic0.y, ic0.z, ic0.w, ic1.x, ic1.y, ic1.z, ic1.w};
 #pragma unroll
-        for (int k = 0; k < 8; ++k) y[k] = (y[k] + c[k]) + s_bias[layer][oct_e * 8 + k];
-        // the neighbour indexes its halo buffer [layer][side][i][32]
-        if (jl < halo && rank > 0 && !(p.debug & 4)) {  // upper halo (side 1) of rank-1, index jl
-          const uint32_t ra = map_to_rank(smem_u32(s_halo + (((layer * 2 + 1) * halo) + jl) * kC + oct_e * 8), rank - 1);
-          st_cluster_f4(ra, make_float4(y[0], y[1], y[2], y[3]));
-          st_cluster_f4(ra + 16u, make_float4(y[4], y[5], y[6], y[7]));
+          for (int k = 0; k < 8; ++k) y[k] = (y[k] + c[k]) + add[k];
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) y[k] = (y[k] + c[k]) + s_bias[0][oct_e * 8 + k];
         }
-        if (jl >= MTILE - halo && (int)rank + 1 < p.n_tiles && !(p.debug & 4)) {  // lower halo (side 0) of rank+1
+        // the neighbour indexes its halo buffer [layer][side][i][32]
+        if (jl < halo && rank > 0) {  // upper halo (side 1) of rank-1, index jl
+          const uint32_t ra = map_to_rank(smem_u32(s_halo + (((layer * 2 + 1) * halo) + jl) * kC + oct_e * 8), rank - 1);
+          const uint32_t rb = map_to_rank(smem_u32(&s_xbar[layer]), rank - 1);
+          st_async_f4(ra, make_float4(y[0], y[1], y[2], y[3]), rb);
+          st_async_f4(ra + 16u, make_float4(y[4], y[5], y[6], y[7]), rb);
+        }
+        if (jl >= MTILE - halo && (int)rank + 1 < p.n_tiles) {  // lower halo (side 0) of rank+1
           const int idx = jl - (MTILE - halo);
           const uint32_t ra = map_to_rank(smem_u32(s_halo + (((layer * 2 + 0) * halo) + idx) * kC + oct_e * 8), rank + 1);
-          st_cluster_f4(ra, make_float4(y[0], y[1], y[2], y[3]));
-          st_cluster_f4(ra + 16u, make_float4(y[4], y[5], y[6], y[7]));
+          const uint32_t rb = map_to_rank(smem_u32(&s_xbar[layer]), rank + 1);
+          st_async_f4(ra, make_float4(y[0], y[1], y[2], y[3]), rb);
+          st_async_f4(ra + 16u, make_float4(y[4], y[5], y[6], y[7]), rb);
         }
+        float gs = 0.f, gq = 0.f;
         if (real_out) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
@@ -516,85 +640,83 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
             gq += y[k] * y[k];
           }
         }
-      }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        gs += __shfl_xor_sync(0xffffffffu, gs, o);
-        gq += __shfl_xor_sync(0xffffffffu, gq, o);
+        for (int o = 16; o > 0; o >>= 1) {
+          gs += __shfl_xor_sync(0xffffffffu, gs, o);
+          gq += __shfl_xor_sync(0xffffffffu, gq, o);
+        }
+        // lane 2d + m pushes this warp's (sum | sumsq) to CTA d
+        if (lane < 2 * p.n_tiles) {
+          const uint32_t dst = (uint32_t)(lane >> 1);
+          const int m = lane & 1;
+          st_async_f1(map_to_rank(smem_u32(&s_part[layer][rank][oct_e][wq][m]), dst), m ? gq : gs,
+                      map_to_rank(smem_u32(&s_xbar[layer]), dst));
+        }
       }
-      if (lane == 0) {
-        s_red[warp][0] = gs;
-        s_red[warp][1] = gq;
-      }
-      __syncthreads();
-      if (tid < (int)csize * 2 * kGroups) {
-        // partial of group g = the four warps with oct_e == g
-        const int dst = tid / (2 * kGroups), k = tid % (2 * kGroups);
-        const int g = k >> 1, m = k & 1;
-        const float tot = (s_red[4 * g][m] + s_red[4 * g + 1][m]) + (s_red[4 * g + 2][m] + s_red[4 * g + 3][m]);
-        st_cluster_f1(map_to_rank(smem_u32(&s_part[layer][rank][k]), (uint32_t)dst), tot);
-      }
-      PROF_MARK(2 + 4 * layer);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      cluster_sync_all();  // statistics and halos of this layer's raw output are everywhere
+      PROF_MARK(2 + 4 * layer);
+      if (active) mbar_wait_cluster(&s_xbar[layer], (uint32_t)((step - 1) & 1));
       PROF_MARK(3 + 4 * layer);
 
-      // ---- GroupNorm coefficients from the cluster-wide partials (fixed reduction tree: deterministic) ----
-      if (warp < 2 * kGroups) {
-        float t = (lane < p.n_tiles) ? s_part[layer][lane][warp] : 0.f;   // n_tiles <= 16
+      if (active) {
+        // ---- GroupNorm coefficients of the own octet's group: lane r sums CTA r's four warp partials, then a
+        //      butterfly over the lanes (every lane ends with the same bits: deterministic) ----
+        float ca[8], cb[8];
+        {
+          float ts = 0.f, tq = 0.f;
+          if (lane < p.n_tiles) {
+            const float4 u = *reinterpret_cast<const float4*>(&s_part[layer][lane][oct_e][0][0]);
+            const float4 w = *reinterpret_cast<const float4*>(&s_part[layer][lane][oct_e][2][0]);
+            ts = (u.x + u.z) + (w.x + w.z);
+            tq = (u.y + u.w) + (w.y + w.w);
+          }
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (lane == 0) s_tot[warp] = t;
-      }
-      __syncthreads();
-      // every thread derives the scale/shift of the two channel octets it touches (own output, halo task)
-      float ca[8], cb[8], ha[8], hb[8];
-      {
-        auto coeffs = [&](int g, float* a, float* b) {
-          const double mean = (double)s_tot[2 * g] * (double)inv_count;
-          const double var = (double)s_tot[2 * g + 1] * (double)inv_count - mean * mean;  // cancellation in double
+          for (int o = 16; o > 0; o >>= 1) {
+            ts += __shfl_xor_sync(0xffffffffu, ts, o);
+            tq += __shfl_xor_sync(0xffffffffu, tq, o);
+          }
+          const double mean = (double)ts * (double)inv_count;
+          const double var = (double)tq * (double)inv_count - mean * mean;  // cancellation in double
           const float rstd = rsqrtf(fmaxf((float)var, 0.f) + kGnEps);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            a[k] = s_gamma[layer][8 * g + k] * rstd;
-            b[k] = s_beta[layer][8 * g + k] - (float)mean * a[k];
+            ca[k] = s_gamma[layer][8 * oct_e + k] * rstd;
+            cb[k] = s_beta[layer][8 * oct_e + k] - (float)mean * ca[k];
           }
-        };
-        coeffs(oct_e, ca, cb);
-        coeffs(t_oct, ha, hb);
-      }
-
-      // ---- next operand: x = lrelu(GN(y)) (+ x0 for the residual block) over own + halo positions ----
-      if (active) {
-        float x[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float t = real_out ? lrelu(fmaf(y[k], ca[k], cb[k])) : 0.f;
-          x[k] = (layer == 0) ? t : t + x0own[k];
-          if (layer == 0) x0own[k] = t;
         }
-        uint4 hi, lo;
-        split8(x, &hi, &lo);
-        *plane_ptr(PLANE_HI + oct_e, own_l) = hi;
-        *plane_ptr(PLANE_LO + oct_e, own_l) = lo;
+        // ---- next operand: x = lrelu(GN(y)) (+ x0 for the residual block) over own + halo positions ----
+        {
+          float x[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float t = real_out ? lrelu(fmaf(y[k], ca[k], cb[k])) : 0.f;
+            x[k] = (layer == 0) ? t : t + x0own[k];
+            if (layer == 0) x0own[k] = t;
+          }
+          uint4 hi, lo;
+          split8(x, &hi, &lo);
+          *plane_ptr(PLANE_HI + oct_e, own_l) = hi;
+          *plane_ptr(PLANE_LO + oct_e, own_l) = lo;
+        }
         if (h_in) {
           float v[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) v[e] = 0.f;
-          uint4* ph = plane_ptr(PLANE_HI + t_oct, h_l);
-          uint4* plo = plane_ptr(PLANE_LO + t_oct, h_l);
+          uint4* ph = plane_ptr(PLANE_HI + oct_e, h_l);
+          uint4* plo = plane_ptr(PLANE_LO + oct_e, h_l);
           if (h_real) {
-            const float4* src = reinterpret_cast<const float4*>(s_halo + ((layer * 2) * halo + h_idx) * kC + 8 * t_oct);
+            const float4* src = reinterpret_cast<const float4*>(s_halo + ((layer * 2) * halo + h_idx) * kC + 8 * oct_e);
             const float4 a = src[0], b = src[1];
             const float yy[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
             float xprev[8];
             if (layer == 1) unsplit8(*ph, *plo, xprev);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              v[e] = lrelu(fmaf(yy[e], ha[e], hb[e]));
+              v[e] = lrelu(fmaf(yy[e], ca[e], cb[e]));
               if (layer == 1) v[e] += xprev[e];
             }
           }
+          uint4 hi, lo;
           split8(v, &hi, &lo);
           *ph = hi;
           *plo = lo;
@@ -604,7 +726,10 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();
       PROF_MARK(4 + 4 * layer);
-      run_conv(1 + layer);
+      issue_conv(1 + layer);
+      // ---- work for the NEXT step, overlapped with this conv's MMAs ----
+      if (layer == 0 && step + 1 < p.D) plan_gathers(step + 1);
+      wait_conv();
       PROF_MARK(5 + 4 * layer);
     }
 
@@ -614,22 +739,23 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
       tmem_ld8(tmem_my, v);
       tmem_ld8(tmem_my + 32u, c);
       if (real_out) {
-        float* dst = p.vol + (((size_t)n * p.D + step) * pixels + (size_t)oy * p.cols + ox) * kC + oct_e * 8;
+        float* dst = p.vol + (((size_t)n * p.D + step) * pixels + own_pix) * kC + oct_e * 8;
         const float* wfp = s_wf + jl * kC + oct_e * 8;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           float4 r;
-          r.x = wfp[4 * q + 0] + ((v[4 * q + 0] + c[4 * q + 0]) + s_bias[2][oct_e * 8 + 4 * q + 0]);
-          r.y = wfp[4 * q + 1] + ((v[4 * q + 1] + c[4 * q + 1]) + s_bias[2][oct_e * 8 + 4 * q + 1]);
-          r.z = wfp[4 * q + 2] + ((v[4 * q + 2] + c[4 * q + 2]) + s_bias[2][oct_e * 8 + 4 * q + 2]);
-          r.w = wfp[4 * q + 3] + ((v[4 * q + 3] + c[4 * q + 3]) + s_bias[2][oct_e * 8 + 4 * q + 3]);
+          r.x = wfp[4 * q + 0] + ((v[4 * q + 0] + c[4 * q + 0]) + s_bias[1][oct_e * 8 + 4 * q + 0]);
+          r.y = wfp[4 * q + 1] + ((v[4 * q + 1] + c[4 * q + 1]) + s_bias[1][oct_e * 8 + 4 * q + 1]);
+          r.z = wfp[4 * q + 2] + ((v[4 * q + 2] + c[4 * q + 2]) + s_bias[1][oct_e * 8 + 4 * q + 2]);
+          r.w = wfp[4 * q + 3] + ((v[4 * q + 3] + c[4 * q + 3]) + s_bias[1][oct_e * 8 + 4 * q + 3]);
           __stcg(reinterpret_cast<float4*>(dst) + q, r);
         }
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     PROF_MARK(10);
-    cluster_sync_all();  // E: hypothesis `step` is visible to every CTA's gathers
+    cluster_sync_all();  // hypothesis `step` is visible to every CTA; exchange buffers are free again
+    if (step + 1 < p.D) stage_prev(step + 1);
     PROF_MARK(11);
   }
   if (PROF && p.prof != nullptr && tid == 0 && blockIdx.y == 0) {
@@ -646,7 +772,7 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
 
 // Weight blocks of 2 KB = one N=64 B operand [k half (2)][n (64)][8 fp16] (UMMA K-major, no swizzle) whose
 // rows 0..31 hold W_hi and rows 32..63 hold W_lo; an N=32 descriptor on the same block reads W_hi only.
-// Order: conv0 [tap][kstep 3] (k-step 2 = image channels 0..2 then zeros), conv1 [tap][kstep 2], conv2.
+// Order: conv0 (feature channels only, reference input channels 3..34) [tap][kstep 2], conv1, conv2.
 void pack_recurrence_weights(const float* w0_oihw35, const float* w1_oihw32, const float* w2_oihw32,
                              std::vector<uint8_t>* out) {
   out->assign(W_TOTAL_BYTES, 0);
@@ -659,23 +785,22 @@ void pack_recurrence_weights(const float* w0_oihw35, const float* w1_oihw32, con
     h[e + 32 * 8] = lo;
   };
   for (int tap = 0; tap < 9; ++tap)
-    for (int nn = 0; nn < 32; ++nn) {
-      // reference conv0 input order: [image 0..2, features 0..31]  (multi_view_stereonet.py:425)
-      for (int c = 0; c < 32; ++c) put(tap * 3 + c / 16, c % 16, nn, w0_oihw35[((size_t)nn * 35 + 3 + c) * 9 + tap]);
-      for (int c = 0; c < 3; ++c) put(tap * 3 + 2, c, nn, w0_oihw35[((size_t)nn * 35 + c) * 9 + tap]);
+    for (int nn = 0; nn < 32; ++nn)
       for (int c = 0; c < 32; ++c) {
+        // reference conv0 input order: [image 0..2, features 0..31]  (multi_view_stereonet.py:425)
+        put(tap * 2 + c / 16, c % 16, nn, w0_oihw35[((size_t)nn * 35 + 3 + c) * 9 + tap]);
         put(W0_BLOCKS + tap * 2 + c / 16, c % 16, nn, w1_oihw32[((size_t)nn * 32 + c) * 9 + tap]);
         put(W0_BLOCKS + W1_BLOCKS + tap * 2 + c / 16, c % 16, nn, w2_oihw32[((size_t)nn * 32 + c) * 9 + tap]);
       }
-    }
 }
 
 bool recurrence_supported(int rows, int cols, int* n_tiles, size_t* smem_bytes) {
-  const Layout L = make_layout(cols);
+  const Layout L = make_layout(rows, cols);
   const int tiles = cdiv(rows * L.PW, MTILE);
   if (n_tiles != nullptr) *n_tiles = tiles;
   if (smem_bytes != nullptr) *smem_bytes = L.total;
-  return tiles <= 16 && L.halo <= MTILE && L.npl * 4 <= MAX_TASKS * NT && L.npl <= NT && 2 * L.halo * 4 <= NT && L.total + 4096 <= 227 * 1024;
+  return tiles <= 16 && L.halo <= MTILE && L.npl * 4 <= MAX_TASKS * NT && 2 * L.halo <= 128 &&
+         L.stage_px >= 1 && L.margin >= cols + 2 && L.total <= kSmemBudget;
 }
 
 int launch_recurrence(const RecurrenceArgs& a, cudaStream_t stream) {
@@ -706,6 +831,7 @@ int launch_recurrence(const RecurrenceArgs& a, cudaStream_t stream) {
   p.beta0 = a.beta0;
   p.gamma1 = a.gamma1;
   p.beta1 = a.beta1;
+  p.imgconv = a.imgconv;
   p.D = a.D;
   p.rows = a.rows;
   p.cols = a.cols;

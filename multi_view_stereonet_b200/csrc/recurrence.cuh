@@ -13,6 +13,7 @@ struct RecurrenceArgs {
   const uint8_t* w16;    // pack_recurrence_weights
   const float *bias0, *bias1, *bias2;
   const float *gamma0, *beta0, *gamma1, *beta1;
+  const float* imgconv;  // [n][D][rows*cols][32] image half of conv0 + bias0 (launch_image_conv)
   int n, D, rows, cols;
   int debug = 0;              // timing ablations, see recurrence.cu
   long long* prof = nullptr;  // optional [16 ranks][12 phases] cycle totals (debug builds of the tests)
