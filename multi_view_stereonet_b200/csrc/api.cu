@@ -7,6 +7,7 @@
 #include "../../include/b200mvs.h"
 #include "conv.cuh"
 #include "conv_tc.cuh"
+#include "conv5_tc.cuh"
 #include "cvf_tc.cuh"
 #include "kernels.cuh"
 #include "recurrence.cuh"
@@ -243,6 +244,17 @@ int build_weights(b200mvs_net* net, const StateDict& sd) {
   RC(pack_conv(net, sd, fe + ".conv0", 32, 3, 25, false, 0, {0, 1, 2}, false, &net->feat_conv[0]));
   for (int i = 1; i < 4; ++i)
     RC(pack_conv(net, sd, fe + ".conv" + std::to_string(i), 32, 32, 25, true, 0, {}, false, &net->feat_conv[i]));
+  for (int i = 0; i < 4; ++i) {
+    const int cin = i == 0 ? 3 : 32;
+    const float* w = sd.get(fe + ".conv" + std::to_string(i) + ".weight", (int64_t)32 * cin * 25);
+    if (w == nullptr) return B200MVS_EWEIGHTS;
+    std::vector<uint8_t> packed;
+    if (i == 0) pack_conv5_c3_weights(w, &packed);
+    else pack_conv5_c32_weights(w, &packed);
+    B200MVS_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&net->feat_conv[i].w16s), packed.size()));
+    net->allocs.push_back(net->feat_conv[i].w16s);
+    B200MVS_CUDA_OK(cudaMemcpy(net->feat_conv[i].w16s, packed.data(), packed.size(), cudaMemcpyHostToDevice));
+  }
   for (int i = 0; i < 6; ++i) {
     const std::string r = fe + ".res" + std::to_string(i);
     RC(pack_conv(net, sd, r + ".conv1", 32, 32, 9, true, 0, {}, false, &net->feat_res[i]));
@@ -540,23 +552,32 @@ int run_featnet(b200mvs_net* net, const Levels& L, int img0, int cnt, const floa
   Workspace& ws = net->ws;
   const int h4 = L.h[4], w4 = L.w[4];
   const size_t P4 = L.px[4];
-  {
-    ConvParams p;
-    p.Hi = L.h[0];
-    p.Wi = L.w[0];
-    p.Ho = L.h[1];
-    p.Wo = L.w[1];
-    p.extra.n = 3;
-    p.w = net->feat_conv[0].w;
-    for (int e = 0; e < 3; ++e) {
-      p.extra.ptr[e] = planar + e * L.px[0];
-      p.extra.img_stride[e] = 3 * (long long)L.px[0];
+  if (net->use_tensor_cores) {
+    // conv0..conv3: 5x5 stride 2 on the tensor cores (split fp16), multi_view_stereonet.py:113-116
+    RC(launch_conv5x5s2_c3_tc(planar, net->feat_conv[0].w16s, cnt, L.h[0], L.w[0], ws.f1 + (size_t)img0 * L.px[1] * kC,
+                              stream));
+    const float* src[3] = {ws.f1, ws.f2, ws.f3};
+    float* dst[3] = {ws.f2, ws.f3, ws.l4x[0]};
+    for (int i = 0; i < 3; ++i)
+      RC(launch_conv5x5s2_c32_tc(src[i] + (size_t)img0 * L.px[i + 1] * kC, net->feat_conv[i + 1].w16s, cnt, L.h[i + 1],
+                                 L.w[i + 1], dst[i] + (size_t)img0 * L.px[i + 2] * kC, stream));
+  } else {
+    {
+      ConvParams p;
+      p.Hi = L.h[0];
+      p.Wi = L.w[0];
+      p.Ho = L.h[1];
+      p.Wo = L.w[1];
+      p.extra.n = 3;
+      p.w = net->feat_conv[0].w;
+      for (int e = 0; e < 3; ++e) {
+        p.extra.ptr[e] = planar + e * L.px[0];
+        p.extra.img_stride[e] = 3 * (long long)L.px[0];
+      }
+      p.n_img = cnt;
+      p.out = ws.f1 + (size_t)img0 * L.px[1] * kC;
+      RC(launch_conv(CONV_5x5_S2, 32, p, stream));
     }
-    p.n_img = cnt;
-    p.out = ws.f1 + (size_t)img0 * L.px[1] * kC;
-    RC(launch_conv(CONV_5x5_S2, 32, p, stream));
-  }
-  {
     const float* src[3] = {ws.f1, ws.f2, ws.f3};
     float* dst[3] = {ws.f2, ws.f3, ws.l4x[0]};
     for (int i = 0; i < 3; ++i) {
