@@ -11,6 +11,7 @@
 #include "cvf_tc.cuh"
 #include "kernels.cuh"
 #include "recurrence.cuh"
+#include "tail.cuh"
 
 namespace b200mvs {
 
@@ -60,6 +61,7 @@ struct GnW {
 struct Refiner {
   ConvW conv0, res[6], fin;
   GnW gn0, gn[6];
+  RefineFinalW finw;
 };
 
 // Bump allocator over one device allocation; sizes are computed from the call shape.
@@ -123,6 +125,7 @@ struct b200mvs_net {
   // CostVolumeFilter (multi_view_stereonet.py:302-353)
   ConvW cvf[5];
   GnW cvf_gn[4];
+  CvfFinalW cvf_finw;
   // IDepthmapRefiner x5 (multi_view_stereonet.py:442-484)
   Refiner refiner[5];
 
@@ -298,6 +301,13 @@ int build_weights(b200mvs_net* net, const StateDict& sd) {
     RC(pack_gn(net, sd, "volume_filter4.bn" + std::to_string(i), &net->cvf_gn[i]));
   }
   RC(pack_conv(net, sd, "volume_filter4.conv4", 1, 32, 27, true, 0, {}, true, &net->cvf[4]));
+  {
+    const float* w = sd.get("volume_filter4.conv4.weight", 32 * 27);
+    const float* b = sd.get("volume_filter4.conv4.bias", 1);
+    if (w == nullptr || b == nullptr) return B200MVS_EWEIGHTS;
+    std::memcpy(net->cvf_finw.w, w, sizeof(net->cvf_finw.w));
+    net->cvf_finw.bias = b[0];
+  }
 
   for (int lvl = 0; lvl < 5; ++lvl) {
     const std::string r = "refiner" + std::to_string(lvl);
@@ -319,6 +329,13 @@ int build_weights(b200mvs_net* net, const StateDict& sd) {
       RC(pack_gn(net, sd, r + ".res" + std::to_string(i) + ".bn1", &R.gn[i]));
     }
     RC(pack_conv(net, sd, r + ".conv_final", 1, 32, 9, true, 0, {}, true, &R.fin));
+    {
+      const float* w = sd.get(r + ".conv_final.weight", 32 * 9);
+      const float* b = sd.get(r + ".conv_final.bias", 1);
+      if (w == nullptr || b == nullptr) return B200MVS_EWEIGHTS;
+      std::memcpy(R.finw.w, w, sizeof(R.finw.w));
+      R.finw.bias = b[0];
+    }
   }
   return 0;
 }
@@ -519,28 +536,8 @@ int run_refiner(b200mvs_net* net, const Refiner& R, StatsCursor& sc, int m, int 
     xres = xnew;
   }
   // conv_final 32 -> 1 on x6 = lrelu(gn(y)) + x5, then relu(prior * fx + delta) / fx
-  ConvParams f;
-  f.n_img = m;
-  f.Hi = f.Ho = H;
-  f.Wi = f.Wo = W;
-  f.feat.ptr = ws.ry[ycur];
-  f.feat.mode = FEAT_GN_RES;
-  f.feat.stats = st_prev;
-  f.feat.gamma = gn_prev->gamma;
-  f.feat.beta = gn_prev->beta;
-  f.feat.inv_count = inv_count;
-  f.feat.resid = ws.rx[xres];
-  f.feat.half_io = half_act;
-  f.w = R.fin.w;
-  f.bias = R.fin.bias;
-  f.dil = 1;
-  f.out = out;
-  f.epi1_mode = 1;
-  f.prior = prior;
-  f.fx = Kl;
-  f.fx_div = k_div;
-  f.fx_stride = 16;
-  RC(launch_conv(CONV_3x3, 1, f, stream));
+  RC(launch_refine_final(ws.ry[ycur], ws.rx[xres], half_act != 0, st_prev, gn_prev->gamma, gn_prev->beta, inv_count,
+                         R.finw, prior, Kl, k_div, 16, m, H, W, out, stream));
   return 0;
 }
 
@@ -804,6 +801,7 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
   RC(launch_cost(ws.feat4, ws.vol, ws.geo.H, n, V, D, h4, w4, cost, ws.mask_views, stream));
 
   // 7. CostVolumeFilter (five Conv3d, :341-353) or the channel norm (:598)
+  bool softargmin_done = false;
   if (s.do_cost_volume_filter) {
     const double inv_count = 1.0 / (8.0 * (double)D * (double)P4);
     float* bufs[2] = {ws.cvfA, cost};
@@ -854,6 +852,11 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
         }
         src = p.out;
         st_prev = p.out_stats;
+      } else if (cvf_final_supported(D)) {
+        // conv4 (32 -> 1) fused with the soft-argmin (:350-352, 602); the idle ping-pong buffer holds the partials
+        RC(launch_cvf_final(src, st_prev, net->cvf_gn[3].gamma, net->cvf_gn[3].beta, inv_count, net->cvf_finw,
+                            ws.geo.samples, n, D, h4, w4, bufs[0], ws.cost1, ws.raw_views, stream));
+        softargmin_done = true;
       } else {
         p.out = ws.cost1;
         RC(launch_conv(CONV_3x3x3, 1, p, stream));
@@ -864,7 +867,7 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
   }
 
   // 8. soft-argmin (:602)
-  RC(launch_softargmin(ws.cost1, ws.geo.samples, n, D, (int)P4, ws.raw_views, stream));
+  if (!softargmin_done) RC(launch_softargmin(ws.cost1, ws.geo.samples, n, D, (int)P4, ws.raw_views, stream));
 
   // 9. level-4 refiner per view (:605-613)
   if (s.do_refiners[4]) {

@@ -12,6 +12,7 @@
 // its input tile in shared memory and builds the im2col operand [position][80] explicitly (5 k-steps of 16).
 #include <cuda_fp16.h>
 
+#include <type_traits>
 #include <vector>
 
 #include "conv5_tc.cuh"
@@ -183,20 +184,26 @@ __global__ void __launch_bounds__(NT, 1) conv5x5s2_c32_tc_kernel(const float* __
 // ------------------------------------------------------------------------------------------------------------
 // 3 -> 32 (planar input)
 // ------------------------------------------------------------------------------------------------------------
-constexpr int B_TH = 8, B_TW = 64;                 // output tile: 512 positions = 4 M-tiles
-constexpr int B_MT = B_TH * B_TW / 128;
-constexpr int B_IR = 2 * B_TH + 3, B_IC = 2 * B_TW + 3;
+constexpr int B_TW = 64;                           // output tile: TH x 64 positions = TH / 2 M-tiles
+constexpr int B_IC = 2 * B_TW + 3;
 constexpr int B_PITCH = B_IC + 2;                  // 133: odd pitch, rows start in different banks
-constexpr int B_PLANE = B_IR * B_PITCH;
 constexpr int B_KSTEPS = 5;                        // K = 75 padded to 80
 constexpr uint32_t B_WBYTES = B_KSTEPS * 2048u;
 constexpr uint32_t B_CHUNK = 128u * 16u;           // one 8-wide K chunk of an M-tile: 128 rows x 16 B
 constexpr uint32_t B_ATILE = 2u * B_KSTEPS * B_CHUNK;   // one M-tile of the operand (hi or lo)
-constexpr uint32_t B_SMEM = B_WBYTES + 2u * B_MT * B_ATILE + 3u * B_PLANE * 4u;
+template <int TH>
+struct BCfg {
+  static constexpr int MT = TH * B_TW / 128;
+  static constexpr int IR = 2 * TH + 3;
+  static constexpr int PLANE = IR * B_PITCH;
+  static constexpr uint32_t SMEM = B_WBYTES + 2u * MT * B_ATILE + 3u * PLANE * 4u;
+};
 
-__global__ void __launch_bounds__(NT, 1) conv5x5s2_c3_tc_kernel(const float* __restrict__ in,
+template <int TH, int MINB>
+__global__ void __launch_bounds__(NT, MINB) conv5x5s2_c3_tc_kernel(const float* __restrict__ in,
                                                                  const uint8_t* __restrict__ w16, int Hi, int Wi,
                                                                  int Ho, int Wo, float* __restrict__ out) {
+  constexpr int B_TH = TH, B_MT = BCfg<TH>::MT, B_IR = BCfg<TH>::IR, B_PLANE = BCfg<TH>::PLANE;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t s_tmem;
@@ -228,23 +235,29 @@ __global__ void __launch_bounds__(NT, 1) conv5x5s2_c3_tc_kernel(const float* __r
     const size_t plane = (size_t)Hi * Wi;
     const float* base = in + (size_t)img * 3 * plane;
     const int iy0 = 2 * oy0 - 2, ix0 = 2 * ox0 - 2;
-    for (int i = tid; i < 3 * B_IR * B_IC; i += NT) {
-      const int x = i % B_IC, y = (i / B_IC) % B_IR, c = i / (B_IC * B_IR);
-      const int gy = iy0 + y, gx = ix0 + x;
-      float v = 0.f;
-      if (gy >= 0 && gy < Hi && gx >= 0 && gx < Wi) v = __ldg(base + c * plane + (size_t)gy * Wi + gx);
-      s_t[(c * B_IR + y) * B_PITCH + x] = v;
+    for (int row = warp; row < 3 * B_IR; row += NT / 32) {   // one warp per tile row: coalesced, no index divisions
+      const int c = row / B_IR, y = row % B_IR;
+      const int gy = iy0 + y;
+      const bool rowok = gy >= 0 && gy < Hi;
+      const float* rp = base + c * plane + (size_t)(rowok ? gy : 0) * Wi;
+      float* dp = s_t + (c * B_IR + y) * B_PITCH;
+#pragma unroll
+      for (int x0 = 0; x0 < B_IC; x0 += 32) {
+        const int x = x0 + lane, gx = ix0 + x;
+        if (x < B_IC) dp[x] = (rowok && gx >= 0 && gx < Wi) ? __ldg(rp + gx) : 0.f;
+      }
     }
   }
   __syncthreads();
-  // ---- im2col: thread = output position, k = tap * 3 + channel ----
-  for (int pos = tid; pos < B_TH * B_TW; pos += NT) {
+  // ---- im2col: task = (output position, half of the K chunks), k = tap * 3 + channel; the half is warp-uniform ----
+  auto build = [&](int pos, auto first_chunk) {
+    constexpr int J0 = decltype(first_chunk)::value;
     const int oyl = pos / B_TW, oxl = pos % B_TW;
     const float* src = s_t + (2 * oyl) * B_PITCH + 2 * oxl;
     const int mt = pos >> 7, m = pos & 127;
     uint8_t* dst = s_a + (size_t)mt * B_ATILE + (size_t)(m >> 3) * 128 + (size_t)(m & 7) * 16;
 #pragma unroll
-    for (int j = 0; j < 2 * B_KSTEPS; ++j) {
+    for (int j = J0; j < J0 + B_KSTEPS; ++j) {
       float v[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -261,6 +274,11 @@ __global__ void __launch_bounds__(NT, 1) conv5x5s2_c3_tc_kernel(const float* __r
       *reinterpret_cast<uint4*>(dst + (size_t)j * B_CHUNK) = hi;
       *reinterpret_cast<uint4*>(dst + (size_t)j * B_CHUNK + (size_t)B_MT * B_ATILE) = lo;
     }
+  };
+  for (int task = tid; task < 2 * B_TH * B_TW; task += NT) {
+    const int pos = task % (B_TH * B_TW);
+    if (task < B_TH * B_TW) build(pos, std::integral_constant<int, 0>{});
+    else build(pos, std::integral_constant<int, B_KSTEPS>{});
   }
   tc::fence_proxy_async();
   tc::fence_before_sync();
@@ -362,19 +380,29 @@ int launch_conv5x5s2_c32_tc(const float* in, const uint8_t* w16, int n, int Hi, 
   return 0;
 }
 
-int launch_conv5x5s2_c3_tc(const float* in, const uint8_t* w16, int n, int Hi, int Wi, float* out,
-                           cudaStream_t stream) {
-  if (n <= 0) return 0;
+template <int TH, int MINB>
+int launch_c3(const float* in, const uint8_t* w16, int n, int Hi, int Wi, float* out, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    B200MVS_CUDA_OK(cudaFuncSetAttribute(conv5x5s2_c3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B_SMEM));
+    B200MVS_CUDA_OK(cudaFuncSetAttribute(conv5x5s2_c3_tc_kernel<TH, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)BCfg<TH>::SMEM));
     attr_set = true;
   }
   const int Ho = (Hi + 1) / 2, Wo = (Wi + 1) / 2;
-  dim3 grid(cdiv(Wo, B_TW) * cdiv(Ho, B_TH), n);
-  launch_pdl(conv5x5s2_c3_tc_kernel, grid, dim3(NT), (size_t)B_SMEM, stream, in, w16, Hi, Wi, Ho, Wo, out);
+  dim3 grid(cdiv(Wo, B_TW) * cdiv(Ho, TH), n);
+  launch_pdl(conv5x5s2_c3_tc_kernel<TH, MINB>, grid, dim3(NT), (size_t)BCfg<TH>::SMEM, stream, in, w16, Hi, Wi, Ho, Wo, out);
   B200MVS_LAUNCH_OK("conv5x5s2_c3_tc_kernel");
   return 0;
+}
+
+int launch_conv5x5s2_c3_tc(const float* in, const uint8_t* w16, int n, int Hi, int Wi, float* out,
+                           cudaStream_t stream) {
+  if (n <= 0) return 0;
+  const int Ho = (Hi + 1) / 2, Wo = (Wi + 1) / 2;
+  // Few image groups: short tiles (three CTAs per SM, fine-grained tail); many: tall tiles amortise the weights.
+  const long long tall = (long long)cdiv(Wo, B_TW) * cdiv(Ho, 8) * n;
+  if (tall >= 296) return launch_c3<8, 1>(in, w16, n, Hi, Wi, out, stream);
+  return launch_c3<2, 3>(in, w16, n, Hi, Wi, out, stream);
 }
 
 }  // namespace b200mvs

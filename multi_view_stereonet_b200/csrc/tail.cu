@@ -1,0 +1,293 @@
+// The 32 -> 1 convolutions that close IDepthmapRefiner (multi_view_stereonet.py:479-483) and CostVolumeFilter
+// (:350-352), restructured as  pointwise 32 -> taps linear map  +  shifted sum over the taps:
+//     out(p) = b + sum_t sum_c x_c(p + o_t) w[c][t] = b + sum_t P_t(p + o_t),      P_t(q) = sum_c x_c(q) w[c][t]
+// Every input pixel is read and normalised once, its 9 (27) partial products are kept in shared memory (L2 for the
+// 3-D filter), and an output is 9 (27) adds.  The weights travel as kernel parameters, so every FFMA takes its
+// weight operand straight from the constant bank.  Both are pure bandwidth kernels: one read of the activation.
+#include <cuda_fp16.h>
+
+#include "conv.cuh"
+#include "tail.cuh"
+
+namespace b200mvs {
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------
+// IDepthmapRefiner tail:  x = lrelu(GN(y)) + resid ; delta = conv3x3(x, 32 -> 1) + b ;
+//                         out = relu(prior * fx + delta) / fx          (:482 and the caller's scaling :607-611)
+// ------------------------------------------------------------------------------------------------------------
+constexpr int F_TH = 14, F_TW = 30;            // output tile; the halo-extended tile is 16 x 32 = 2 pixels per thread
+constexpr int F_HH = F_TH + 2, F_HW = F_TW + 2;
+constexpr int F_NT = 256;
+
+struct FinalParams {
+  const void* y;        // raw output of the last residual conv, [n][H][W][32] fp32 or fp16
+  const void* resid;    // the residual stream, same type
+  const double* stats;  // [n][4][2]
+  const float* gamma;
+  const float* beta;
+  double inv_count;
+  const float* prior;   // [n][H][W]
+  const float* fx;
+  int fx_div, fx_stride;
+  float* out;           // [n][H][W]
+  int H, W;
+};
+
+__device__ __forceinline__ void load32(const float* p, float* v) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 f = __ldg(reinterpret_cast<const float4*>(p) + q);
+    v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
+  }
+}
+__device__ __forceinline__ void load32(const __half* p, float* v) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint4 h = __ldg(reinterpret_cast<const uint4*>(p) + q);
+    const uint32_t w[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+      v[8 * q + 2 * k] = f.x;
+      v[8 * q + 2 * k + 1] = f.y;
+    }
+  }
+}
+
+template <class T>
+__global__ void __launch_bounds__(F_NT) refine_final_kernel(const FinalParams p, const RefineFinalW W) {
+  __shared__ float s_part[9][F_HH * F_HW];
+  __shared__ float s_a[kC], s_b[kC];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int tid = threadIdx.x, img = blockIdx.y;
+  const int tiles_x = cdiv(p.W, F_TW);
+  const int tx0 = (blockIdx.x % tiles_x) * F_TW, ty0 = (blockIdx.x / tiles_x) * F_TH;
+  if (tid < kC) {
+    const int grp = tid >> 3;
+    const double sum = p.stats[(img * kGroups + grp) * 2 + 0];
+    const double sq = p.stats[(img * kGroups + grp) * 2 + 1];
+    const double mean = sum * p.inv_count;
+    double var = sq * p.inv_count - mean * mean;
+    var = var > 0.0 ? var : 0.0;
+    const double rstd = rsqrt(var + (double)kGnEps);
+    s_a[tid] = (float)((double)p.gamma[tid] * rstd);
+    s_b[tid] = (float)((double)p.beta[tid] - mean * (double)p.gamma[tid] * rstd);
+  }
+  __syncthreads();
+  const size_t ibase = (size_t)img * p.H * p.W;
+#pragma unroll
+  for (int r = 0; r < F_HH * F_HW / F_NT; ++r) {
+    const int hp = tid + r * F_NT;
+    const int gy = ty0 - 1 + hp / F_HW, gx = tx0 - 1 + hp % F_HW;
+    float acc[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+    if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
+      const size_t off = (ibase + (size_t)gy * p.W + gx) * kC;
+      float v[32], rs[32];
+      load32(reinterpret_cast<const T*>(p.y) + off, v);
+      load32(reinterpret_cast<const T*>(p.resid) + off, rs);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const float x = lrelu(fmaf(v[c], s_a[c], s_b[c])) + rs[c];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc[t] = fmaf(x, W.w[c * 9 + t], acc[t]);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) s_part[t][hp] = acc[t];
+  }
+  __syncthreads();
+  const float f = __ldg(p.fx + (size_t)(img / p.fx_div) * p.fx_stride);
+  for (int o = tid; o < F_TH * F_TW; o += F_NT) {
+    const int ly = o / F_TW, lx = o % F_TW;
+    const int oy = ty0 + ly, ox = tx0 + lx;
+    if (oy >= p.H || ox >= p.W) continue;
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc += s_part[t][(ly + t / 3) * F_HW + lx + t % 3];
+    const size_t opix = ibase + (size_t)oy * p.W + ox;
+    const float v = acc + W.bias;
+    const float scaled = __fmul_rn(__ldg(p.prior + opix), f);
+    p.out[opix] = __fdiv_rn(fmaxf(__fadd_rn(scaled, v), 0.f), f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// CostVolumeFilter tail: conv3d 3x3x3 32 -> 1 on lrelu(GN(y3)), then the soft-argmin over the hypothesis axis
+// (extract_idepthmap, :486-492).
+// ------------------------------------------------------------------------------------------------------------
+struct CvfPartialParams {
+  const float* y;       // [n][D][P][32]
+  const double* stats;  // [n][4][2]
+  const float* gamma;
+  const float* beta;
+  double inv_count;
+  float* part;          // [n][D][27][P]
+  int D, P;
+};
+
+__global__ void __launch_bounds__(128) cvf_final_partial_kernel(const CvfPartialParams p, const CvfFinalW W) {
+  __shared__ float s_a[kC], s_b[kC];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int tid = threadIdx.x, n = blockIdx.y;
+  if (tid < kC) {
+    const int grp = tid >> 3;
+    const double sum = p.stats[(n * kGroups + grp) * 2 + 0];
+    const double sq = p.stats[(n * kGroups + grp) * 2 + 1];
+    const double mean = sum * p.inv_count;
+    double var = sq * p.inv_count - mean * mean;
+    var = var > 0.0 ? var : 0.0;
+    const double rstd = rsqrt(var + (double)kGnEps);
+    s_a[tid] = (float)((double)p.gamma[tid] * rstd);
+    s_b[tid] = (float)((double)p.beta[tid] - mean * (double)p.gamma[tid] * rstd);
+  }
+  __syncthreads();
+  const int vox = blockIdx.x * blockDim.x + tid;   // d * P + pixel
+  if (vox >= p.D * p.P) return;
+  const int d = vox / p.P, pix = vox % p.P;
+  float acc[27];
+#pragma unroll
+  for (int t = 0; t < 27; ++t) acc[t] = 0.f;
+  const float* src = p.y + ((size_t)n * p.D * p.P + vox) * kC;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 f = __ldg(reinterpret_cast<const float4*>(src) + q);
+    const float v[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = 4 * q + e;
+      const float x = lrelu(fmaf(v[e], s_a[c], s_b[c]));
+#pragma unroll
+      for (int t = 0; t < 27; ++t) acc[t] = fmaf(x, W.w[c * 27 + t], acc[t]);
+    }
+  }
+  float* dst = p.part + ((size_t)(n * p.D + d) * 27) * p.P + pix;
+#pragma unroll
+  for (int t = 0; t < 27; ++t) dst[(size_t)t * p.P] = acc[t];
+}
+
+// 16 consecutive pixels per CTA, 1024 threads: thread (pixel, slot) sums the 27 shifted partials of hypotheses
+// slot, slot + 64, ... (all 27 loads of a hypothesis in flight at once), then 8 lanes per pixel run the soft-argmin
+// exactly as softargmin_kernel.
+constexpr int S_PX = 16, S_SLOTS = 64;
+__global__ void __launch_bounds__(S_PX * S_SLOTS) cvf_final_sum_softargmin_kernel(const float* __restrict__ part,
+                                                                                  const float* __restrict__ samples,
+                                                                                  float bias, int D, int h, int w,
+                                                                                  float* __restrict__ cost1,
+                                                                                  float* __restrict__ raw) {
+  extern __shared__ float s_cost[];   // [D][S_PX]
+  pdl_launch_dependents();
+  pdl_wait();
+  const int tid = threadIdx.x;
+  const int n = blockIdx.y, P = h * w;
+  {
+    const int lp = tid % S_PX, slot = tid / S_PX;
+    const int pix = blockIdx.x * S_PX + lp;
+    const bool okp = pix < P;
+    const int y = okp ? pix / w : 0, x = okp ? pix % w : 0;
+    for (int d = slot; d < D; d += S_SLOTS) {
+      float t[27];
+#pragma unroll
+      for (int kd = 0; kd < 3; ++kd) {
+        const int dd = d + kd - 1;
+        const bool okd = okp && dd >= 0 && dd < D;
+        const float* pl = part + ((size_t)(n * D + (okd ? dd : 0)) * 27 + kd * 9) * P;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const int yy = y + ky - 1;
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int xx = x + kx - 1;
+            const bool ok = okd && yy >= 0 && yy < h && xx >= 0 && xx < w;
+            t[kd * 9 + ky * 3 + kx] = ok ? __ldg(pl + (size_t)(ky * 3 + kx) * P + yy * w + xx) : 0.f;
+          }
+        }
+      }
+      float acc = bias;
+#pragma unroll
+      for (int k = 0; k < 27; ++k) acc += t[k];
+      if (okp) cost1[((size_t)n * D + d) * P + pix] = acc;
+      s_cost[d * S_PX + lp] = acc;
+    }
+  }
+  __syncthreads();
+  if (tid >= S_PX * 8) return;
+  const int sub = tid & 7, pl = tid >> 3;
+  const int p2 = blockIdx.x * S_PX + pl;
+  float m = -INFINITY;
+  for (int d = sub; d < D; d += 8) m = fmaxf(m, -s_cost[d * S_PX + pl]);
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float den = 0.f, num = 0.f;
+  for (int d = sub; d < D; d += 8) {
+    const float e = expf(-s_cost[d * S_PX + pl] - m);
+    den += e;
+    num += e * __ldg(samples + (size_t)n * D + d);
+  }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    den += __shfl_xor_sync(0xffffffffu, den, o);
+    num += __shfl_xor_sync(0xffffffffu, num, o);
+  }
+  if (p2 < P && sub == 0) raw[(size_t)n * P + p2] = num / den;
+}
+
+}  // namespace
+
+int launch_refine_final(const void* y, const void* resid, bool half_io, const double* stats, const float* gamma,
+                        const float* beta, double inv_count, const RefineFinalW& w, const float* prior,
+                        const float* fx, int fx_div, int fx_stride, int n, int H, int W, float* out,
+                        cudaStream_t stream) {
+  if (n <= 0) return 0;
+  FinalParams p;
+  p.y = y;
+  p.resid = resid;
+  p.stats = stats;
+  p.gamma = gamma;
+  p.beta = beta;
+  p.inv_count = inv_count;
+  p.prior = prior;
+  p.fx = fx;
+  p.fx_div = fx_div;
+  p.fx_stride = fx_stride;
+  p.out = out;
+  p.H = H;
+  p.W = W;
+  dim3 grid(cdiv(W, F_TW) * cdiv(H, F_TH), n);
+  if (half_io)
+    launch_pdl(refine_final_kernel<__half>, grid, dim3(F_NT), (size_t)0, stream, p, w);
+  else
+    launch_pdl(refine_final_kernel<float>, grid, dim3(F_NT), (size_t)0, stream, p, w);
+  B200MVS_LAUNCH_OK("refine_final_kernel");
+  return 0;
+}
+
+bool cvf_final_supported(int D) { return (size_t)D * S_PX * sizeof(float) <= 48 * 1024; }
+
+int launch_cvf_final(const float* y, const double* stats, const float* gamma, const float* beta, double inv_count,
+                     const CvfFinalW& w, const float* samples, int n, int D, int h, int wd, float* part, float* cost1,
+                     float* raw, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  CvfPartialParams p;
+  p.y = y;
+  p.stats = stats;
+  p.gamma = gamma;
+  p.beta = beta;
+  p.inv_count = inv_count;
+  p.part = part;
+  p.D = D;
+  p.P = h * wd;
+  launch_pdl(cvf_final_partial_kernel, dim3(cdiv(D * h * wd, 128), n), dim3(128), (size_t)0, stream, p, w);
+  B200MVS_LAUNCH_OK("cvf_final_partial_kernel");
+  launch_pdl(cvf_final_sum_softargmin_kernel, dim3(cdiv(h * wd, S_PX), n), dim3(S_PX * S_SLOTS),
+             (size_t)D * S_PX * sizeof(float),
+             stream, (const float*)part, samples, w.bias, D, h, wd, cost1, raw);
+  B200MVS_LAUNCH_OK("cvf_final_sum_softargmin_kernel");
+  return 0;
+}
+
+}  // namespace b200mvs

@@ -1,0 +1,31 @@
+// 32 -> 1 tail convolutions of IDepthmapRefiner and CostVolumeFilter (tail.cu).
+#pragma once
+#include "common.cuh"
+
+namespace b200mvs {
+
+// Reference weight layouts: conv_final.weight (1, 32, 3, 3) -> w[c * 9 + tap]; volume_filter4.conv4.weight
+// (1, 32, 3, 3, 3) -> w[c * 27 + tap].  Passed to the kernels by value (constant bank).
+struct RefineFinalW {
+  float w[32 * 9];
+  float bias;
+};
+struct CvfFinalW {
+  float w[32 * 27];
+  float bias;
+};
+
+// out = relu(prior * fx + conv3x3(lrelu(GN(y)) + resid) + b) / fx     (multi_view_stereonet.py:479-483, 607-611)
+int launch_refine_final(const void* y, const void* resid, bool half_io, const double* stats, const float* gamma,
+                        const float* beta, double inv_count, const RefineFinalW& w, const float* prior,
+                        const float* fx, int fx_div, int fx_stride, int n, int H, int W, float* out,
+                        cudaStream_t stream);
+
+// cost1 = conv3d(lrelu(GN(y)), 32 -> 1) + b ; raw = soft-argmin over D (:350-352, 486-492).
+// `part` is scratch of n * D * 27 * h * w floats.
+bool cvf_final_supported(int D);
+int launch_cvf_final(const float* y, const double* stats, const float* gamma, const float* beta, double inv_count,
+                     const CvfFinalW& w, const float* samples, int n, int D, int h, int wd, float* part, float* cost1,
+                     float* raw, cudaStream_t stream);
+
+}  // namespace b200mvs
