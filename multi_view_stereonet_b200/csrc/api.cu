@@ -7,6 +7,7 @@
 #include "../../include/b200mvs.h"
 #include "conv.cuh"
 #include "conv_tc.cuh"
+#include "conv_ws.cuh"
 #include "conv5_tc.cuh"
 #include "cvf_tc.cuh"
 #include "kernels.cuh"
@@ -140,6 +141,7 @@ struct b200mvs_net {
   bool keep_stages = false;
   bool use_tensor_cores = true;
   bool half_activations = true;
+  bool warp_specialized = true;
   int rec_debug = 0;
   // Side stream for the work that does not depend on the comparison views (left feature network) or that
   // nothing downstream waits for (mask upsampling): forked / joined with events inside one forward.
@@ -441,6 +443,8 @@ int ensure_workspace(b200mvs_net* net, const b200mvs_shape& s) {
 // 3x3 convolution with 32 outputs: tensor cores when enabled (fp16 operands on the large levels, split hi/lo
 // fp16 on the 1/8- and 1/16-scale levels that need fp32-class accuracy), the fp32 FFMA kernel otherwise.
 int conv3x3_c32(b200mvs_net* net, const ConvParams& p, const ConvW& w, bool precise, cudaStream_t stream) {
+  if (net->use_tensor_cores && net->warp_specialized && !precise && w.w16 != nullptr && conv3x3_ws_supported(p))
+    return launch_conv3x3_ws(p, w.w16, stream);
   if (net->use_tensor_cores && w.w16 != nullptr && conv3x3_tc_supported(p))
     return launch_conv3x3_tc(p, precise ? w.w16s : w.w16, precise, stream);
   return launch_conv(CONV_3x3, 32, p, stream);
@@ -1003,6 +1007,10 @@ B200MVS_API int b200mvs_set_option(b200mvs_net* net, const char* name, int value
   const std::string k(name);
   if (k == "tensor_cores") {
     net->use_tensor_cores = value != 0;
+    return 0;
+  }
+  if (k == "warp_specialized") {
+    net->warp_specialized = value != 0;
     return 0;
   }
   if (k == "half_activations") {

@@ -52,6 +52,32 @@ bool pdl_enabled();
 void set_pdl_enabled(bool on);
 
 #ifdef __CUDACC__
+// L2 residency hints.  The refiner activations ping-pong between four buffers that together fit in the 126 MB L2:
+// stores of tensors the next layer reads are marked evict_last, loads of tensors that are dead after this layer
+// evict_first, so the live set stays on chip instead of round-tripping through HBM.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint4 ldg_hint(const void* ptr, uint64_t policy) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(ptr), "l"(policy));
+  return v;
+}
+__device__ __forceinline__ void stg_hint(void* ptr, const uint4& v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w), "l"(policy)
+               : "memory");
+}
+
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 

@@ -74,6 +74,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane polls (with a hardware suspend-time hint), the warp then reconverges: hundreds of threads spinning on
+// try_wait flood the shared-memory pipe and starve the warps that do the work.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) {
+    const uint32_t a = smem_u32(bar);
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t"
+          ".reg .pred q;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2, %3;\n\t"
+          "selp.u32 %0, 1, 0, q;\n\t"
+          "}\n"
+          : "=r"(done)
+          : "r"(a), "r"(parity), "r"(2000u)
+          : "memory");
+    }
+  }
+  __syncwarp();
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
                "r"(cols)
