@@ -76,7 +76,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 // One lane polls (with a hardware suspend-time hint), the warp then reconverges: hundreds of threads spinning on
 // try_wait flood the shared-memory pipe and starve the warps that do the work.
+// One try_wait per lane; true if the phase has completed.
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, q;\n\t"
+      "}\n"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  if (__all_sync(0xffffffffu, mbar_test(bar, parity))) return;   // fast path: already complete
   if ((threadIdx.x & 31) == 0) {
     const uint32_t a = smem_u32(bar);
     uint32_t done = 0;
@@ -93,7 +109,9 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
     }
   }
   __syncwarp();
+  mbar_wait(bar, parity);   // completes at once; gives every lane its own acquire of the phase
 }
+
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
