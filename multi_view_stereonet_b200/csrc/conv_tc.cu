@@ -448,10 +448,16 @@ int launch_conv3x3_tc(const ConvParams& p, const uint8_t* w16, bool split, cudaS
     set_error("launch_conv3x3_tc: tile does not fit in shared memory");
     return -1;
   }
+  // Small images (a few dozen tiles at most): the layer is one dependent latency chain, so halve the chain of every
+  // CTA -- two-row tiles = one M-tile each -- rather than amortise the halo.
+  static const int small_th = getenv("B200MVS_TC_SMALL_TH") ? atoi(getenv("B200MVS_TC_SMALL_TH")) : 2;
+  const bool tiny = pick == 4 && (long long)cdiv(p.Wo, TW) * cdiv(p.Ho, 4) * p.n_img < 74 && small_th == 2;
   if (split) {
     if (pick == 8) return launch_th<8, true>(p, w16, stream);
+    if (tiny) return launch_th<2, true>(p, w16, stream);
     return launch_th<4, true>(p, w16, stream);
   }
+  if (tiny) return launch_th<2, false>(p, w16, stream);
   // Large images, small halo: 8-row tiles at three CTAs per SM overlap one CTA's loads with another's MMAs and
   // stores better than 16-row tiles at two per SM (measured ~50 vs ~72 us per level-0 layer).
   static const int variant = getenv("B200MVS_TC_VARIANT") ? atoi(getenv("B200MVS_TC_VARIANT")) : 1;
