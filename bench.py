@@ -290,7 +290,7 @@ def run_ours(args, rank, world, local_rank):
                             "pyramid"},
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
-            "roofline": {"bound": "hbm", "kernel": "conv_kernel<3x3,32->32> (refiner0 residual convs, level 0)",
+            "roofline": {"bound": "hbm", "kernel": "conv3x3_ws_kernel (refiner0 residual 3x3 32->32 convs, level 0)",
                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": (achieved / hbm_peak) if achieved else None, "traffic": None,
                          "peak_source": peak_src, "kernel_ms": k_ms, "kernel_launches": probe_launches,

@@ -65,6 +65,7 @@ struct Refiner {
   RefineFinalW finw;
 };
 
+
 // Bump allocator over one device allocation; sizes are computed from the call shape.
 struct Arena {
   char* base = nullptr;
@@ -127,6 +128,7 @@ struct b200mvs_net {
   ConvW cvf[5];
   GnW cvf_gn[4];
   CvfFinalW cvf_finw;
+  RefineHeadW head0;   // refiner0.conv0 (level 0: image + idepth only)
   // IDepthmapRefiner x5 (multi_view_stereonet.py:442-484)
   Refiner refiner[5];
 
@@ -323,6 +325,13 @@ int build_weights(b200mvs_net* net, const StateDict& sd) {
       RC(pack_conv(net, sd, r + ".conv0", 32, 4, 9, false, 0, {0, 1, 2, 3}, true, &R.conv0));
       RC(pack_conv_tc(net, sd, r + ".conv0", 4, false, 0, {0, 1, 2, 3}, &R.conv0));
     }
+    if (lvl == 0) {
+      const float* w = sd.get(r + ".conv0.weight", 32 * 4 * 9);
+      const float* b = sd.get(r + ".conv0.bias", 32);
+      if (w == nullptr || b == nullptr) return B200MVS_EWEIGHTS;
+      std::memcpy(net->head0.w, w, sizeof(net->head0.w));
+      std::memcpy(net->head0.bias, b, sizeof(net->head0.bias));
+    }
     RC(pack_gn(net, sd, r + ".bn0", &R.gn0));
     for (int i = 0; i < 6; ++i) {
       const std::string cn = r + ".res" + std::to_string(i) + ".conv1";
@@ -505,7 +514,12 @@ int run_refiner(b200mvs_net* net, const Refiner& R, StatsCursor& sc, int m, int 
   p.out_stats = st_prev = sc.take(m);
   // conv0 sees the idepth channel scaled by fx (values of a few hundred with the signal in the low bits):
   // always split precision.
-  RC(conv3x3_c32(net, p, R.conv0, true, stream));
+  if (guide_feat == nullptr && image_div == 1 && net->use_tensor_cores) {
+    // level 0: four planar inputs only -- dedicated fp32 kernel (tail.cu)
+    RC(launch_refine_head_l0(image, prior, Kl, k_div, 16, net->head0, m, H, W, ws.ry[0], half_act != 0, st_prev, stream));
+  } else {
+    RC(conv3x3_c32(net, p, R.conv0, true, stream));
+  }
 
   static const int dilations[6] = {1, 2, 4, 8, 1, 1};  // multi_view_stereonet.py:457
   const GnW* gn_prev = &R.gn0;

@@ -19,6 +19,7 @@
 // 1/16-scale stages do not and stay on the fp32 path (conv.cu).
 #include <cuda_fp16.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
@@ -72,6 +73,20 @@ __device__ __forceinline__ void store8(uint8_t* plane_hi, uint32_t lo_offset, in
   }
 }
 
+// Optional timeline of CTA (0,0) in globaltimer ns (B200MVS_TC_PROFILE=1): kernel entry, prologue done (before
+// griddepcontrol.wait), dependencies met, coefficients ready, operand staged, MMAs complete, stores issued, exit.
+__device__ long long g_tc_prof[8];
+__device__ int g_tc_prof_on;
+__device__ __forceinline__ long long tc_gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TC_STAMP(k)                                                                             \
+  do {                                                                                          \
+    if (g_tc_prof_on && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) g_tc_prof[k] = tc_gtime(); \
+  } while (0)
+
 // Plane sets in shared memory: [feat 0..3 (if a 32-channel source)][extra][zero (if planar extras)], and the same
 // again for the lo halves when SPLIT.  K-steps: two over the feature planes, one over (extra, zero).
 template <int TH, bool SPLIT, int MINB>
@@ -86,6 +101,7 @@ __global__ void __launch_bounds__(NT, MINB) conv3x3_tc_kernel(const ConvParams p
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t s_tmem;
 
+  TC_STAMP(0);
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = tc::uniform_warp_index();
   const int img = blockIdx.y;
@@ -125,7 +141,9 @@ __global__ void __launch_bounds__(NT, MINB) conv3x3_tc_kernel(const ConvParams p
     uint4* dst = reinterpret_cast<uint4*>(s_w);
     for (int i = tid; i < (int)(w_bytes / 16); i += NT) dst[i] = __ldg(src + i);
   }
+  TC_STAMP(1);
   pdl_wait();
+  TC_STAMP(2);
   if (tid < kC && mode >= FEAT_GN) {
     const int grp = tid >> 3;
     const double sum = p.feat.stats[(img * kGroups + grp) * 2 + 0];
@@ -138,6 +156,7 @@ __global__ void __launch_bounds__(NT, MINB) conv3x3_tc_kernel(const ConvParams p
     s_b[tid] = (float)((double)p.feat.beta[tid] - mean * (double)p.feat.gamma[tid] * rstd);
   }
   __syncthreads();
+  TC_STAMP(3);
   const size_t vol = (size_t)p.Hi * p.Wi;
   const int rows_in = TH + 2 * d;
   // ---- stage the transformed 32-channel source ----
@@ -249,6 +268,7 @@ __global__ void __launch_bounds__(NT, MINB) conv3x3_tc_kernel(const ConvParams p
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = s_tmem;
+  TC_STAMP(4);
 
   // ---- one elected lane of warp 0 issues every MMA of the tile, then commits to the mbarrier ----
   if (warp == 0) {
@@ -288,6 +308,7 @@ __global__ void __launch_bounds__(NT, MINB) conv3x3_tc_kernel(const ConvParams p
   __syncthreads();
   tc::fence_after_sync();
 
+  TC_STAMP(5);
   // ---- epilogue: TMEM -> registers -> bias, statistics, channels-last store ----
   const int wq = warp & 3;  // TMEM lane quarter this warp may read
   float gsum[kGroups], gsq[kGroups];
@@ -345,6 +366,7 @@ __global__ void __launch_bounds__(NT, MINB) conv3x3_tc_kernel(const ConvParams p
       }
     }
   }
+  TC_STAMP(6);
   if (p.out_stats != nullptr) {
 #pragma unroll
     for (int g = 0; g < kGroups; ++g) {
@@ -366,6 +388,7 @@ __global__ void __launch_bounds__(NT, MINB) conv3x3_tc_kernel(const ConvParams p
   __syncthreads();
   if (p.out_stats != nullptr && tid < 2 * kGroups)
     atomicAdd(p.out_stats + (size_t)img * 2 * kGroups + tid, s_stats[tid]);
+  TC_STAMP(7);
   if (warp == 0) tc::tmem_dealloc(tmem_base, (uint32_t)TMEM_COLS);
 }
 
@@ -387,7 +410,19 @@ int launch_th(const ConvParams& p, const uint8_t* w16, cudaStream_t stream) {
   const int TW = PW - 2 * p.dil;
   dim3 grid(cdiv(p.Wo, TW) * cdiv(p.Ho, TH), p.n_img);
   if (p.tag != TAG_NONE) probe_before(p.tag, stream);
+  static const bool prof = getenv("B200MVS_TC_PROFILE") != nullptr;
+  if (prof) {
+    const int one = 1;
+    cudaMemcpyToSymbol(g_tc_prof_on, &one, sizeof(int));
+  }
   launch_pdl(conv3x3_tc_kernel<TH, SPLIT, MINB>, grid, dim3(NT), smem, stream, p, w16);
+  if (prof) {
+    long long h[8];
+    cudaStreamSynchronize(stream);
+    cudaMemcpyFromSymbol(h, g_tc_prof, sizeof(h));
+    fprintf(stderr, "tc TH=%d split=%d grid=%dx%d dil=%d: prologue %lld | dep wait %lld | coeffs %lld | stage %lld | mma %lld | epilogue %lld | stats+exit %lld (ns)\n",
+            TH, (int)SPLIT, grid.x, grid.y, p.dil, h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6]);
+  }
   if (p.tag != TAG_NONE) probe_after(p.tag, stream);
   B200MVS_LAUNCH_OK("conv3x3_tc_kernel");
   return 0;

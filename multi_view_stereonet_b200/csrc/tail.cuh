@@ -10,6 +10,11 @@ struct RefineFinalW {
   float w[32 * 9];
   float bias;
 };
+// refiner0.conv0.weight (32, 4, 3, 3) in the reference's order w[(o * 4 + c) * 9 + tap], and its bias.
+struct RefineHeadW {
+  float w[32 * 4 * 9];
+  float bias[32];
+};
 struct CvfFinalW {
   float w[32 * 27];
   float bias;
@@ -20,6 +25,12 @@ int launch_refine_final(const void* y, const void* resid, bool half_io, const do
                         const float* beta, double inv_count, const RefineFinalW& w, const float* prior,
                         const float* fx, int fx_div, int fx_stride, int n, int H, int W, float* out,
                         cudaStream_t stream);
+
+// IDepthmapRefiner.conv0 at level 0 (4 planar input channels: image (3) and idepth * fx; :469-470, 679-681):
+// y = conv3x3(cat[image, prior * fx]) + b as fp16 or fp32 channels-last, plus the GroupNorm statistics of y.
+int launch_refine_head_l0(const float* image, const float* prior, const float* fx, int fx_div, int fx_stride,
+                          const RefineHeadW& w, int n, int H, int W, void* out, bool out_half, double* out_stats,
+                          cudaStream_t stream);
 
 // cost1 = conv3d(lrelu(GN(y)), 32 -> 1) + b ; raw = soft-argmin over D (:350-352, 486-492).
 // `part` is scratch of n * D * 27 * h * w floats.
