@@ -140,6 +140,21 @@ B200MVS_API int b200mvs_conv3x3_c32(const float* x, const float* w_oihw_host, co
 B200MVS_API int b200mvs_homography_warp(const float* H, const float* image, int32_t n, int32_t channels, int32_t rows,
                             int32_t cols, int32_t zero_invalid, float* pred, uint8_t* mask, void* stream);
 
+/* The reprojection layers of stereo/image_predictor.py next to the hot path, one fused per-pixel
+ * kernel on DEVICE pointers; needs no handle.  K (N,4,4), T_right_in_left (N,4,4), map (N,1,rows,cols):
+ *   map_kind 0: inverse depthmap   -> IDepthmapProjector.forward (:525-576) / IDepthImagePredictor.forward (:347-398)
+ *   map_kind 1: disparity map      -> DisparityToIDepth.forward (:120-218) then the above = ImagePredictor.forward (:578-601)
+ *   map_kind 2: rectified disparity-> RectifiedImagePredictor.forward (:275-345)
+ * Outputs (any may be NULL): pred (N,C,rows,cols) sampled from right_image (N,C,rows,cols) with bilinear /
+ * border / align_corners=False; mask (N,1,rows,cols) uint8, 1 = projects outside the image; right_pixels
+ * (N,rows,cols,2) normalised grid coordinates; right_idepths (N,1,rows,cols); idepth_out (N,1,rows,cols) the
+ * converted inverse depths (map_kind 1); disparity_out (N,1,rows,cols) = IDepthToDisparity.forward (:220-273) of the
+ * inverse depths (map_kind 0 or 1). */
+B200MVS_API int b200mvs_reproject(const float* K, const float* T_right_in_left, const float* map, int32_t map_kind,
+                                  const float* right_image, int32_t n, int32_t channels, int32_t rows, int32_t cols,
+                                  float* pred, uint8_t* mask, float* right_pixels, float* right_idepths,
+                                  float* idepth_out, float* disparity_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,5 +1,7 @@
 """B200-native depth-inference hot path of MultiViewStereoNet."""
-__all__ = ["MultiViewStereoNet", "HomographyImagePredictor", "ImagePredictor"]
+_LAYERS = ("HomographyImagePredictor", "ImagePredictor", "IDepthImagePredictor", "IDepthmapProjector",
+           "DisparityToIDepth", "IDepthToDisparity", "RectifiedImagePredictor")
+__all__ = ["MultiViewStereoNet"] + list(_LAYERS)
 
 
 def __getattr__(name):
@@ -8,7 +10,7 @@ def __getattr__(name):
     if name == "MultiViewStereoNet":
         from .multi_view_stereonet import MultiViewStereoNet
         return MultiViewStereoNet
-    if name in ("HomographyImagePredictor", "ImagePredictor"):
+    if name in _LAYERS:
         from . import image_predictor
         return getattr(image_predictor, name)
     raise AttributeError(name)

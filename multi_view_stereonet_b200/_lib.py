@@ -44,6 +44,9 @@ SYMBOLS = {
     "b200mvs_homography_warp": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
                                                ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
                                                ctypes.c_void_p, ctypes.c_void_p]),
+    "b200mvs_reproject": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+                                         ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                         ctypes.c_int32] + [ctypes.c_void_p] * 7),
 }
 
 _lib = None

@@ -1330,4 +1330,21 @@ B200MVS_API int b200mvs_homography_warp(const float* H, const float* image, int3
                             static_cast<cudaStream_t>(stream));
 }
 
+B200MVS_API int b200mvs_reproject(const float* K, const float* T_right_in_left, const float* map, int32_t map_kind,
+                                  const float* right_image, int32_t n, int32_t channels, int32_t rows, int32_t cols,
+                                  float* pred, uint8_t* mask, float* right_pixels, float* right_idepths,
+                                  float* idepth_out, float* disparity_out, void* stream) {
+  if (K == nullptr || T_right_in_left == nullptr || map == nullptr || n < 0 || rows < 1 || cols < 1 || map_kind < 0 ||
+      map_kind > 2 || (pred != nullptr && (right_image == nullptr || channels < 1))) {
+    set_error("b200mvs_reproject: bad argument");
+    return B200MVS_EINVAL;
+  }
+  if (n > 65535) {
+    set_error("b200mvs_reproject: at most 65535 images per call");
+    return B200MVS_EINVAL;
+  }
+  return launch_reproject(K, T_right_in_left, map, map_kind, right_image, n, channels, rows, cols, pred, mask,
+                          right_pixels, right_idepths, idepth_out, disparity_out, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

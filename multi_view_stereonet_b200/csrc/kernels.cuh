@@ -56,6 +56,12 @@ int launch_view_reduce(const float* raw_views, const float* refined_views, const
                        const float* baseline, int batch, int views, int D, int pixels, bool refined_is_alias,
                        float* raw4, float* idepth4, uint8_t* mask4, cudaStream_t stream);
 
+// The reprojection layers of stereo/image_predictor.py (reproject.cu).  kind: 0 = `map` is an inverse depthmap,
+// 1 = a general (non-rectified) disparity map, 2 = a rectified disparity map.  Every output pointer is optional.
+int launch_reproject(const float* K, const float* T, const float* map, int kind, const float* right, int n,
+                     int channels, int rows, int cols, float* pred, uint8_t* mask, float* right_pixels,
+                     float* right_idepths, float* idepth_out, float* disparity_out, cudaStream_t stream);
+
 // F.interpolate(bilinear, align_corners=False) of a (N, planes, h, w) float map, and the
 // float->bilinear->(>0.5) mask variant (multi_view_stereonet.py:372-396).
 int launch_upsample_f32(const float* in, int n_planes, int h, int w, int H, int W, float* out, cudaStream_t stream);
