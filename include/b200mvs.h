@@ -155,6 +155,21 @@ B200MVS_API int b200mvs_reproject(const float* K, const float* T_right_in_left, 
                                   float* pred, uint8_t* mask, float* right_pixels, float* right_idepths,
                                   float* idepth_out, float* disparity_out, void* stream);
 
+/* Input preparation before the hot path (multi_view_unpack_batch, multi_view_stereonet_utils.py:541-604), DEVICE
+ * pointers, no handle.
+ * b200mvs_area_downsample: one level of build_image_pyramid (utils/image_utils.py:111-128): `planes` images of
+ * (rows, cols) -> ((rows+1)/2, (cols+1)/2) by area averaging (F.interpolate(mode="area")).
+ * b200mvs_prepare_cameras: K (B,4,4); T_right_in_lefts[v] (B,4,4), v < views; level_sizes = HOST int32[2*levels]
+ * (rows_l, cols_l) of the pyramid.  Writes K_pyr (levels,B,4,4) (:555-582), T_right_in_left / T_left_in_right
+ * (views,B,4,4) with translations divided by the baseline to the first comparison camera (:585-604) and
+ * baseline (B).  The caller checks baseline > 0 as the reference asserts (:598-599). */
+B200MVS_API int b200mvs_area_downsample(const float* in, int32_t planes, int32_t rows, int32_t cols, float* out,
+                                        void* stream);
+B200MVS_API int b200mvs_prepare_cameras(const float* K, const float* const* T_right_in_lefts, int32_t batch,
+                                        int32_t views, int32_t levels, const int32_t* level_sizes, float* K_pyr,
+                                        float* T_right_in_left_out, float* T_left_in_right_out, float* baseline,
+                                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

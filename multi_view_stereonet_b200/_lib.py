@@ -47,6 +47,12 @@ SYMBOLS = {
     "b200mvs_reproject": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
                                          ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                          ctypes.c_int32] + [ctypes.c_void_p] * 7),
+    "b200mvs_area_downsample": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                               ctypes.c_void_p, ctypes.c_void_p]),
+    "b200mvs_prepare_cameras": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int32,
+                                               ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32),
+                                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                               ctypes.c_void_p]),
 }
 
 _lib = None

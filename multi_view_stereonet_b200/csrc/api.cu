@@ -1347,4 +1347,42 @@ B200MVS_API int b200mvs_reproject(const float* K, const float* T_right_in_left, 
                           right_pixels, right_idepths, idepth_out, disparity_out, static_cast<cudaStream_t>(stream));
 }
 
+B200MVS_API int b200mvs_area_downsample(const float* in, int32_t planes, int32_t rows, int32_t cols, float* out,
+                                        void* stream) {
+  if (in == nullptr || out == nullptr || planes < 0 || rows < 1 || cols < 1) {
+    set_error("b200mvs_area_downsample: bad argument");
+    return B200MVS_EINVAL;
+  }
+  return launch_area_downsample(in, planes, rows, cols, out, static_cast<cudaStream_t>(stream));
+}
+
+B200MVS_API int b200mvs_prepare_cameras(const float* K, const float* const* T_right_in_lefts, int32_t batch,
+                                        int32_t views, int32_t levels, const int32_t* level_sizes, float* K_pyr,
+                                        float* T_right_in_left_out, float* T_left_in_right_out, float* baseline,
+                                        void* stream_) {
+  if (K == nullptr || T_right_in_lefts == nullptr || level_sizes == nullptr || K_pyr == nullptr ||
+      T_right_in_left_out == nullptr || T_left_in_right_out == nullptr || baseline == nullptr || batch < 0 ||
+      views < 1 || views > kMaxViews || levels < 1 || levels > 16) {
+    set_error("b200mvs_prepare_cameras: bad argument");
+    return B200MVS_EINVAL;
+  }
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ViewPtrs T{};
+  T.views = views;
+  for (int v = 0; v < views; ++v) {
+    if (T_right_in_lefts[v] == nullptr) {
+      set_error("b200mvs_prepare_cameras: missing pose");
+      return B200MVS_EINVAL;
+    }
+    T.p[v] = T_right_in_lefts[v];
+  }
+  int* dsizes = nullptr;
+  B200MVS_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&dsizes), sizeof(int) * 2 * levels, stream));
+  B200MVS_CUDA_OK(cudaMemcpyAsync(dsizes, level_sizes, sizeof(int) * 2 * levels, cudaMemcpyHostToDevice, stream));
+  const int rc = launch_prepare_cameras(K, T, batch, levels, dsizes, K_pyr, T_right_in_left_out, T_left_in_right_out,
+                                        baseline, stream);
+  cudaFreeAsync(dsizes, stream);
+  return rc;
+}
+
 }  // extern "C"

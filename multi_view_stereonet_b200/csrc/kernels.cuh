@@ -56,6 +56,13 @@ int launch_view_reduce(const float* raw_views, const float* refined_views, const
                        const float* baseline, int batch, int views, int D, int pixels, bool refined_is_alias,
                        float* raw4, float* idepth4, uint8_t* mask4, cudaStream_t stream);
 
+// Input preparation (multi_view_unpack_batch, multi_view_stereonet_utils.py:541-604): one pyramid level by area
+// averaging, and the per-level intrinsics / inverse poses / baseline normalisation of a batch of image groups.
+// level_sizes_dev: DEVICE int[2 * levels] = (rows_l, cols_l).
+int launch_area_downsample(const float* in, int planes, int rows, int cols, float* out, cudaStream_t stream);
+int launch_prepare_cameras(const float* K, const ViewPtrs& T, int batch, int levels, const int* level_sizes_dev,
+                           float* K_pyr, float* T_norm, float* Tinv_norm, float* baseline, cudaStream_t stream);
+
 // The reprojection layers of stereo/image_predictor.py (reproject.cu).  kind: 0 = `map` is an inverse depthmap,
 // 1 = a general (non-rectified) disparity map, 2 = a rectified disparity map.  Every output pointer is optional.
 int launch_reproject(const float* K, const float* T, const float* map, int kind, const float* right, int n,

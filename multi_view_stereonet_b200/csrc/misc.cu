@@ -107,6 +107,102 @@ __global__ void __launch_bounds__(256) image_conv_kernel(const float* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------
+// Input preparation: what multi_view_unpack_batch does before the hot path
+// (multi_view_stereonet_utils.py:541-604).
+// ---------------------------------------------------------------------------------------------
+// One level of build_image_pyramid (utils/image_utils.py:111-128): F.interpolate(mode="area") to
+// ((h+1)/2, (w+1)/2) = adaptive average pooling with windows [floor(i*in/out), ceil((i+1)*in/out)).
+__global__ void __launch_bounds__(256) area_downsample_kernel(const float* __restrict__ in, int rows, int cols,
+                                                              int orows, int ocols, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int plane = blockIdx.y;
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= orows * ocols) return;
+  const int ox = o % ocols, oy = o / ocols;
+  const int y0 = (int)(((long long)oy * rows) / orows), y1 = (int)((((long long)oy + 1) * rows + orows - 1) / orows);
+  const int x0 = (int)(((long long)ox * cols) / ocols), x1 = (int)((((long long)ox + 1) * cols + ocols - 1) / ocols);
+  const float* src = in + (size_t)plane * rows * cols;
+  float sum = 0.f;
+  for (int y = y0; y < y1; ++y)
+    for (int x = x0; x < x1; ++x) sum = __fadd_rn(sum, __ldg(src + (size_t)y * cols + x));
+  out[(size_t)plane * orows * ocols + o] = __fdiv_rn(sum, (float)((y1 - y0) * (x1 - x0)));
+}
+
+// Per image group: the per-level intrinsics (:555-582), T_left_in_right = inverse(T_right_in_left) (:590) and the
+// normalisation of all translations by the baseline to the first comparison camera (:596-604).
+__global__ void __launch_bounds__(32) prepare_cameras_kernel(const float* __restrict__ K, ViewPtrs T, int batch,
+                                                             int levels, const int* __restrict__ level_sizes,
+                                                             float* __restrict__ K_pyr, float* __restrict__ T_norm,
+                                                             float* __restrict__ Tinv_norm,
+                                                             float* __restrict__ baseline) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const float* Kb = K + (size_t)b * 16;
+  for (int l = 0; l < levels; ++l) {
+    float* Ko = K_pyr + ((size_t)l * batch + b) * 16;
+    for (int i = 0; i < 16; ++i) Ko[i] = Kb[i];
+    if (l > 0) {
+      const float sx = (float)level_sizes[2 * l + 1] / (float)level_sizes[1];
+      const float sy = (float)level_sizes[2 * l] / (float)level_sizes[0];
+      Ko[0] = __fmul_rn(Kb[0], sx);
+      Ko[5] = __fmul_rn(Kb[5], sy);
+      Ko[2] = __fsub_rn(__fmul_rn(sx, __fadd_rn(Kb[2], 0.5f)), 0.5f);
+      Ko[6] = __fsub_rn(__fmul_rn(sy, __fadd_rn(Kb[6], 0.5f)), 0.5f);
+    }
+  }
+  const float* T0 = T.p[0] + (size_t)b * 16;
+  const float bl = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(T0[3], T0[3]), __fmul_rn(T0[7], T0[7])), __fmul_rn(T0[11], T0[11])));
+  baseline[b] = bl;
+  for (int v = 0; v < T.views; ++v) {
+    const float* Tv = T.p[v] + (size_t)b * 16;
+    // general 4x4 inverse (the reference calls torch.inverse), Gauss-Jordan with partial pivoting in float64
+    double m[4][8];
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) {
+        m[i][j] = (double)Tv[i * 4 + j];
+        m[i][4 + j] = (i == j) ? 1.0 : 0.0;
+      }
+    for (int c = 0; c < 4; ++c) {
+      int piv = c;
+      double best = fabs(m[c][c]);
+      for (int r = c + 1; r < 4; ++r)
+        if (fabs(m[r][c]) > best) {
+          best = fabs(m[r][c]);
+          piv = r;
+        }
+      if (piv != c)
+        for (int j = 0; j < 8; ++j) {
+          const double tmp = m[c][j];
+          m[c][j] = m[piv][j];
+          m[piv][j] = tmp;
+        }
+      const double dd = 1.0 / m[c][c];
+      for (int j = 0; j < 8; ++j) m[c][j] *= dd;
+      for (int r = 0; r < 4; ++r)
+        if (r != c) {
+          const double f = m[r][c];
+          for (int j = 0; j < 8; ++j) m[r][j] -= f * m[c][j];
+        }
+    }
+    float* To = T_norm + ((size_t)v * batch + b) * 16;
+    float* Io = Tinv_norm + ((size_t)v * batch + b) * 16;
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) {
+        float t = Tv[i * 4 + j], ti = (float)m[i][4 + j];
+        if (j == 3 && i < 3) {
+          t = __fdiv_rn(t, bl);
+          ti = __fdiv_rn(ti, bl);
+        }
+        To[i * 4 + j] = t;
+        Io[i * 4 + j] = ti;
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // One recurrence step's warps (multi_view_stereonet.py:275, 285).  8 lanes per pixel, one float4
 // of the 32 feature channels each; lanes 0..2 additionally warp one plane of the 1/16 right image.
 // ---------------------------------------------------------------------------------------------
@@ -370,6 +466,28 @@ int launch_image_conv(const float* H, const ViewPtrs& right_l4, const float* w_t
   }
   launch_pdl(image_conv_kernel, grid, dim3(256), smem, stream, H, right_l4, w_tap8x32, bias, D, rows, cols, out);
   B200MVS_LAUNCH_OK("image_conv_kernel");
+  return 0;
+}
+
+int launch_area_downsample(const float* in, int planes, int rows, int cols, float* out, cudaStream_t stream) {
+  if (planes <= 0) return 0;
+  const int orows = (rows + 1) / 2, ocols = (cols + 1) / 2;
+  for (int p0 = 0; p0 < planes; p0 += 65535) {
+    const int np = planes - p0 < 65535 ? planes - p0 : 65535;
+    dim3 grid(cdiv(orows * ocols, 256), np);
+    launch_pdl(area_downsample_kernel, grid, dim3(256), (size_t)0, stream, in + (size_t)p0 * rows * cols, rows, cols, orows,
+               ocols, out + (size_t)p0 * orows * ocols);
+    B200MVS_LAUNCH_OK("area_downsample_kernel");
+  }
+  return 0;
+}
+
+int launch_prepare_cameras(const float* K, const ViewPtrs& T, int batch, int levels, const int* level_sizes_dev,
+                           float* K_pyr, float* T_norm, float* Tinv_norm, float* baseline, cudaStream_t stream) {
+  if (batch <= 0) return 0;
+  launch_pdl(prepare_cameras_kernel, dim3(cdiv(batch, 32)), dim3(32), (size_t)0, stream, K, T, batch, levels,
+             level_sizes_dev, K_pyr, T_norm, Tinv_norm, baseline);
+  B200MVS_LAUNCH_OK("prepare_cameras_kernel");
   return 0;
 }
 

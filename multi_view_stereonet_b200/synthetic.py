@@ -129,3 +129,29 @@ def to_device(inputs, device):
     mv = lambda t: t.to(device)
     return ([mv(t) for t in left_pyr], [mv(t) for t in K_pyr], [mv(t) for t in Ts],
             [[mv(t) for t in p] for p in right_pyrs])
+
+
+def make_raw_batch(B=2, V=2, rows=38, cols=51, seed=99):
+    """Raw dataset-style batch: odd image size (exercises the non-2x2 pooling windows), un-normalised poses."""
+    g = torch.Generator().manual_seed(seed)
+    K = torch.eye(4).repeat(B, 1, 1, 1)                         # (B, 1, 4, 4) as the datasets deliver it
+    K[:, 0, 0, 0] = torch.tensor([0.8 * cols, 0.9 * cols])[:B]
+    K[:, 0, 1, 1] = torch.tensor([0.8 * cols, 0.85 * cols])[:B]
+    K[:, 0, 0, 2] = (cols - 1) / 2.0
+    K[:, 0, 1, 2] = (rows - 1) / 2.0
+    Ts = []
+    for v in range(V):
+        T = torch.eye(4).repeat(B, 1, 1, 1)
+        a = 0.03 * (v + 1)
+        T[:, 0, 0, 0] = T[:, 0, 2, 2] = math.cos(a)
+        T[:, 0, 0, 2] = math.sin(a)
+        T[:, 0, 2, 0] = -math.sin(a)
+        T[:, 0, :3, 3] = torch.tensor([0.4 * (v + 1), -0.07, 0.11 * (v + 1)]) * torch.tensor([[1.0], [2.5]])[:B]
+        Ts.append(T)
+    batch = {"left_image": torch.rand(B, 3, rows, cols, generator=g) * 2 - 1,
+             "right_image": [torch.rand(B, 3, rows, cols, generator=g) * 2 - 1 for _ in range(V)],
+             "K": K, "T_right_in_left": Ts, "left_filename": ["l"] * B, "right_filename": [["r"] * B] * V,
+             "left_depthmap_true": torch.rand(B, 1, rows, cols, generator=g) * 10,
+             "right_depthmap_true": [torch.rand(B, 1, rows, cols, generator=g) * 10 for _ in range(V)]}
+    batch["left_depthmap_true"][:, :, :5] = 0.0                  # invalid (zero) depths stay zero
+    return batch

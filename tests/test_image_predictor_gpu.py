@@ -40,10 +40,16 @@ def test_image_predictor_matches_oracle_at_full_resolution():
     g = torch.Generator().manual_seed(7)
     disparity = 2.0 + 20.0 * torch.rand(n, 1, rows, cols, generator=g)
     ref_pred, ref_mask = ipo.image_predictor(K, T, disparity, image)
+    truth, truth_mask = ipo.image_predictor(K, T, disparity, image, dtype=torch.float64)
     pred, mask = ip.ImagePredictor()(K.cuda(), T.cuda(), disparity.cuda(), image.cuda())
     ref_px, _, _ = ipo.idepthmap_projector(K, T, ipo.disparity_to_idepth(K, T, disparity))
     assert masks_agree(mask.cpu(), ref_mask, ref_px)
-    ok = ~(mask.cpu() | ref_mask)
-    assert float(((pred.cpu() - ref_pred) * ok).abs().max()) <= 2e-3     # bilinear weights near 640 px: ~1e-4 px
+    # Two float32 evaluations of the same chain differ by ~1e-4 px in the sampling coordinate at 640 px; judge both
+    # against the float64 evaluation: the kernel must be as close to it as the float32 restatement is.
+    ok = ~(mask.cpu() | ref_mask | truth_mask)
+    err_cuda = float(((pred.cpu().double() - truth) * ok).abs().max())
+    err_ref = float(((ref_pred.double() - truth) * ok).abs().max())
+    assert err_cuda <= max(4.0 * err_ref, 1e-4), (err_cuda, err_ref)
+    assert float(((pred.cpu() - ref_pred) * ok).abs().mean()) <= 1e-5
     with pytest.raises(RuntimeError):
         ip.ImagePredictor()(K, T, disparity, image)                       # no CPU path
