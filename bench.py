@@ -26,11 +26,37 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
+# Rank 0 must print exactly one JSON line on stdout: NCCL's version banner (NCCL_DEBUG=VERSION) goes there too.
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 import torch  # noqa: E402
 
 ROWS, COLS, VIEWS, HYPS = 512, 640, 1, 64       # BASELINE cfg2 / cfg4 per-item shape
 METRIC = "depthmaps/sec at 512x640, 2-view, 64 hyp"
 UNIT = "depthmaps/s"
+
+
+_REAL_STDOUT = None
+
+
+def reserve_stdout():
+    """Keeps the process's stdout for the one JSON line: everything else that writes to fd 1 (NCCL's banner, library
+    chatter) is sent to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def log(*a):
@@ -162,7 +188,7 @@ def run_reference(args, rank):
         "e2e": {"value": dmps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args, rank, world, local_rank):
@@ -301,7 +327,7 @@ def run_ours(args, rank, world, local_rank):
                            "frac_of_roofline": t_roof_us / (worst_ms / args.steps / B * 1e3)},
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -318,6 +344,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    reserve_stdout()
     if args.impl == "reference":
         run_reference(args, rank)
         return
