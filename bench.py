@@ -245,6 +245,15 @@ def run_ours(args, rank, world, local_rank):
         net.probe_select("none")
         time.sleep(0.2)
         sampler.stop()
+        # the longest single kernel (latency bound: 63 dependent steps) -- probed in a short untimed pass
+        rec_ms, rec_launches = 0.0, 0
+        if not os.environ.get("BENCH_NO_PROBE"):
+            net.probe_select("recurrence")
+            for _ in range(5):
+                net(*inputs, *flags)
+            torch.cuda.synchronize(dev)
+            rec_ms, rec_launches = net.probe_read()
+            net.probe_select("none")
     total_ms = sum(step_ms)
 
     # ---- end to end through the host entry: pinned inputs -> H2D -> forward -> D2H ----
@@ -285,6 +294,11 @@ def run_ours(args, rank, world, local_rank):
         # dominant kernel: the 3x3 32->32 refiner convolution at level 0; algorithmic bytes per launch
         # = one fp32 read + one fp32 write of a (B, 512, 640, 32) activation
         k_bytes = B * P[0] * 64 * 4
+        traffic = None
+        tpath = os.path.join(REPO, "profiles", "r1_traffic.json")
+        if os.path.exists(tpath) and B == 1:
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel from the committed ncu --set full capture
+            traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")
         k_ms = probe_ms / max(probe_launches, 1)
         achieved = k_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
         value = world * B * args.steps / (worst_ms * 1e-3)
@@ -318,10 +332,14 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches_per_step": launches_per_step,
             "roofline": {"bound": "hbm", "kernel": "conv3x3_ws_kernel (refiner0 residual 3x3 32->32 convs, level 0)",
                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": (achieved / hbm_peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / hbm_peak) if achieved else None, "traffic": traffic,
                          "peak_source": peak_src, "kernel_ms": k_ms, "kernel_launches": probe_launches,
                          "algorithmic_bytes_per_launch": k_bytes,
                          "kernel_share_of_step": probe_ms / total_ms if total_ms > 0 else None},
+            "latency_kernel": {"kernel": "recurrence_kernel (persistent cluster, D-1 dependent steps)",
+                               "kernel_ms": rec_ms / max(rec_launches, 1), "kernel_launches": rec_launches,
+                               "us_per_step": 1e3 * rec_ms / max(rec_launches, 1) / max(B * (HYPS - 1), 1) * B,
+                               "share_of_step": (rec_ms / max(rec_launches, 1)) / (total_ms / args.steps) if total_ms > 0 else None},
             "whole_path": {"algorithmic_gflop_per_depthmap": 2 * mac / 1e9, "algorithmic_mb_per_depthmap": byt / 1e6,
                            "roofline_us_per_depthmap": t_roof_us,
                            "frac_of_roofline": t_roof_us / (worst_ms / args.steps / B * 1e3)},

@@ -98,6 +98,7 @@ B200MVS_API int b200mvs_forward_host(b200mvs_net* net, const b200mvs_shape* shap
  * selected, every launch of that class is bracketed by CUDA events on the launch stream.  Classes:
  *   "refine_conv32_l0"  the 3x3 32->32 (dilated) convolutions of refiner0 at level 0 (6 per forward)
  *   "cvf_conv32"        the 3x3x3 32->32 convolutions of the cost-volume filter (4 per forward)
+ *   "recurrence"        the persistent depth-sweep recurrence kernel (1 per forward)
  *   "none"              disable
  * b200mvs_probe_read synchronises the recorded events, returns their summed duration in ms and the
  * number of launches, and resets the accumulation. */

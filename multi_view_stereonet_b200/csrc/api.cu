@@ -754,7 +754,9 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
     ra.cols = w4;
     ra.prof = net->rec_prof;
     ra.debug = net->rec_debug;
+    probe_before(TAG_RECURRENCE, stream);
     RC(launch_recurrence(ra, stream));
+    probe_after(TAG_RECURRENCE, stream);
   } else {
     const double inv_count = 1.0 / (8.0 * (double)P4);
     for (int step = 1; step < D; ++step) {
@@ -1111,6 +1113,7 @@ B200MVS_API int b200mvs_probe_select(b200mvs_net* net, const char* kernel_class)
   if (k == "none") tag = TAG_NONE;
   else if (k == "refine_conv32_l0") tag = TAG_REFINE_CONV32_L0;
   else if (k == "cvf_conv32") tag = TAG_CVF_CONV32;
+  else if (k == "recurrence") tag = TAG_RECURRENCE;
   else {
     set_error("b200mvs_probe_select: unknown kernel class '" + k + "'");
     return B200MVS_EINVAL;

@@ -67,7 +67,7 @@ struct ConvParams {
   int tag = 0;                   // kernel class for b200mvs_probe_select (host side only)
 };
 
-enum ConvTag : int { TAG_NONE = 0, TAG_REFINE_CONV32_L0 = 1, TAG_CVF_CONV32 = 2 };
+enum ConvTag : int { TAG_NONE = 0, TAG_REFINE_CONV32_L0 = 1, TAG_CVF_CONV32 = 2, TAG_RECURRENCE = 3 };
 
 // Host hooks called immediately before / after a tagged launch (api.cu).
 void probe_before(int tag, cudaStream_t stream);
