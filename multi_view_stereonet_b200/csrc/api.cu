@@ -1,4 +1,7 @@
 // C ABI (include/b200mvs.h): handle, weight packing, workspace and the forward orchestration.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -148,8 +151,13 @@ struct b200mvs_net {
   // Side stream for the work that does not depend on the comparison views (left feature network) or that
   // nothing downstream waits for (mask upsampling): forked / joined with events inside one forward.
   cudaStream_t side = nullptr;
-  cudaEvent_t ev_geo = nullptr, ev_fork = nullptr, ev_left = nullptr, ev_mask_in = nullptr, ev_mask_out = nullptr;
+  cudaEvent_t ev_geo = nullptr, ev_imgconv = nullptr, ev_fork = nullptr, ev_left = nullptr, ev_mask_in = nullptr, ev_mask_out = nullptr;
   bool overlap = true;
+  // b200mvs_forward_host: uploads run on their own stream in the order the path needs them, compute waits per piece
+  cudaStream_t copy_stream = nullptr, host_stream = nullptr;
+  cudaEvent_t ev_up[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // cameras, right l0, right l4, left l0, rest
+  float* pinned_small = nullptr;
+  size_t pinned_small_floats = 0;
   long long* rec_prof = nullptr;  // device [16][12], allocated when option "recurrence_profile" is set
   b200mvs_shape last_shape{};
   bool have_last = false;
@@ -656,7 +664,14 @@ int run_featnet(b200mvs_net* net, const Levels& L, int img0, int cnt, const floa
 
 int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* left_pyr, const float* const* K_pyr,
                  const float* const* Ts, const float* const* right_l0, const float* const* right_l4,
-                 float* const* out_idepth, float* const* out_raw, uint8_t* const* out_mask, cudaStream_t stream) {
+                 float* const* out_idepth, float* const* out_raw, uint8_t* const* out_mask, cudaStream_t stream,
+                 const cudaEvent_t* uploaded = nullptr) {
+  // `uploaded` (b200mvs_forward_host): events after which [0] K/T, [1] right level 0, [2] right level 4, [3] left
+  // level 0, [4] left levels 1-4 are resident; null = all inputs already resident.
+  auto wait_upload = [&](int which, cudaStream_t on) -> int {
+    if (uploaded != nullptr) B200MVS_CUDA_OK(cudaStreamWaitEvent(on, uploaded[which], 0));
+    return 0;
+  };
   if (s.batch < 1 || s.views < 1 || s.views > kMaxViews || s.rows < 16 || s.cols < 16 ||
       s.num_idepth_samples < 2 || s.num_idepth_samples > 4096) {
     set_error("b200mvs_forward: bad shape (need batch>=1, 1<=views<=16, rows,cols>=16, 2<=D<=4096)");
@@ -706,34 +721,42 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
     B200MVS_CUDA_OK(cudaEventRecord(net->ev_fork, stream));
     B200MVS_CUDA_OK(cudaStreamWaitEvent(net->side, net->ev_fork, 0));
   }
-  // 3a. FeatureNetwork on the B left images (multi_view_stereonet.py:552)
-  RC(run_featnet(net, L, 0, B, left_pyr[0], tail_stats, ws.feat4, 0, left_stream));
-
   // 1. geometry
+  RC(wait_upload(0, stream));
   RC(launch_geometry(Tv, K_pyr[0], K_pyr[4], B, D, h4, w4, ws.geo, stream));
 
-  // 1b. image half of FeatureRefiner.conv0 for every hypothesis (needs only the homographies): side stream
+  // 1b. image half of FeatureRefiner.conv0 for every hypothesis (needs only the homographies and the 1/16-scale
+  //     comparison images): first thing on the side stream, the recurrence waits for it
   const bool persistent = net->use_tensor_cores && recurrence_supported(h4, w4, nullptr, nullptr);
   if (persistent) {
     if (overlap) {
       B200MVS_CUDA_OK(cudaEventRecord(net->ev_geo, stream));
       B200MVS_CUDA_OK(cudaStreamWaitEvent(net->side, net->ev_geo, 0));
     }
+    RC(wait_upload(2, left_stream));
     RC(launch_image_conv(ws.geo.H, R4, net->fr_conv0.w + (size_t)4 * 9 * 8 * 32, net->fr_conv0.bias, n, D, h4, w4,
                          ws.imgconv, left_stream));
+    if (overlap) B200MVS_CUDA_OK(cudaEventRecord(net->ev_imgconv, net->side));
   }
-  if (overlap) B200MVS_CUDA_OK(cudaEventRecord(net->ev_left, net->side));
 
   // 2. full-resolution warp of every comparison image by the idepth-0 homography
   //    (multi_view_stereonet.py:254-258)
+  RC(wait_upload(1, stream));
   RC(launch_warp_planar(ws.geo.H0, 9, R0, n, 3, L.h[0], L.w[0], true, ws.warped0, ws.l0mask, stream));
 
   // 3b. FeatureNetwork on the B*V warped right images (shared weights, :507)
   //     conv_final writes hypothesis 0 of every view's feature volume directly (:261, 278)
   RC(run_featnet(net, L, B, n, ws.warped0, tail_stats, ws.vol, (long long)D * (long long)P4 * kC, stream));
 
+  // 3a. FeatureNetwork on the B left images (multi_view_stereonet.py:552): side stream, needed by the cost volume
+  //     (enqueued after the critical path's launches)
+  RC(wait_upload(3, left_stream));
+  RC(run_featnet(net, L, 0, B, left_pyr[0], tail_stats, ws.feat4, 0, left_stream));
+  if (overlap) B200MVS_CUDA_OK(cudaEventRecord(net->ev_left, net->side));
+
   // 5. the depth-sweep recurrence (multi_view_stereonet.py:279-290)
-  if (overlap) B200MVS_CUDA_OK(cudaStreamWaitEvent(stream, net->ev_left, 0));
+  RC(wait_upload(2, stream));
+  if (overlap && persistent) B200MVS_CUDA_OK(cudaStreamWaitEvent(stream, net->ev_imgconv, 0));
   if (persistent) {
     RecurrenceArgs ra;
     ra.imgconv = ws.imgconv;
@@ -817,6 +840,7 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
   }
 
   // 6. cost volume |L - R| with invalid voxels zeroed (multi_view_stereonet.py:586-592)
+  if (overlap) B200MVS_CUDA_OK(cudaStreamWaitEvent(stream, net->ev_left, 0));
   float* cost = net->keep_stages ? ws.cost : ws.vol;
   RC(launch_cost(ws.feat4, ws.vol, ws.geo.H, n, V, D, h4, w4, cost, ws.mask_views, stream));
 
@@ -890,6 +914,7 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
   if (!softargmin_done) RC(launch_softargmin(ws.cost1, ws.geo.samples, n, D, (int)P4, ws.raw_views, stream));
 
   // 9. level-4 refiner per view (:605-613)
+  RC(wait_upload(4, stream));
   if (s.do_refiners[4]) {
     RC(run_refiner(net, net->refiner[4], sc, n, h4, w4, ws.feat4, V, left_pyr[4], V, ws.raw_views, K_pyr[4], V,
                    ws.refined_views, TAG_NONE, stream));
@@ -981,9 +1006,17 @@ B200MVS_API int b200mvs_create(int device, int num_tensors, const char* const* n
     if (cudaStreamCreateWithFlags(&net->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&net->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&net->ev_geo, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&net->ev_imgconv, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&net->ev_left, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&net->ev_mask_in, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&net->ev_mask_out, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&net->ev_mask_out, cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&net->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&net->host_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&net->ev_up[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&net->ev_up[1], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&net->ev_up[2], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&net->ev_up[3], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&net->ev_up[4], cudaEventDisableTiming) != cudaSuccess) {
       set_error("b200mvs_create: could not create the side stream");
       rc = B200MVS_ECUDA;
     }
@@ -1003,9 +1036,14 @@ B200MVS_API void b200mvs_destroy(b200mvs_net* net) {
   if (net->arena.base != nullptr) cudaFree(net->arena.base);
   if (net->host_stage != nullptr) cudaFree(net->host_stage);
   for (cudaEvent_t e : net->probe.ev) cudaEventDestroy(e);
-  for (cudaEvent_t e : {net->ev_geo, net->ev_fork, net->ev_left, net->ev_mask_in, net->ev_mask_out})
+  for (cudaEvent_t e : {net->ev_geo, net->ev_imgconv, net->ev_fork, net->ev_left, net->ev_mask_in, net->ev_mask_out})
     if (e != nullptr) cudaEventDestroy(e);
   if (net->side != nullptr) cudaStreamDestroy(net->side);
+  for (cudaEvent_t e : net->ev_up)
+    if (e != nullptr) cudaEventDestroy(e);
+  if (net->copy_stream != nullptr) cudaStreamDestroy(net->copy_stream);
+  if (net->host_stream != nullptr) cudaStreamDestroy(net->host_stream);
+  if (net->pinned_small != nullptr) cudaFreeHost(net->pinned_small);
   delete net;
 }
 
@@ -1200,29 +1238,61 @@ B200MVS_API int b200mvs_forward_host(b200mvs_net* net, const b200mvs_shape* shap
   float* din = reinterpret_cast<float*>(net->host_stage);
   float* dof = reinterpret_cast<float*>(net->host_stage + in_bytes);
   uint8_t* dom = reinterpret_cast<uint8_t*>(net->host_stage + in_bytes + of_bytes);
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = net->host_stream;
+  cudaStream_t cs = net->copy_stream;
+  static const bool hprof = getenv("B200MVS_HOST_PROFILE") != nullptr;
+  auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_entry = hprof ? now() : 0.0;
   int64_t h2d = 0, d2h = 0;
   int rc = 0;
   auto up = [&](const float* src, size_t count, float*& cursor) -> const float* {
     float* dst = cursor;
     cursor += count;
-    if (cudaMemcpyAsync(dst, src, count * sizeof(float), cudaMemcpyHostToDevice, stream) != cudaSuccess) rc = -2;
+    if (cudaMemcpyAsync(dst, src, count * sizeof(float), cudaMemcpyHostToDevice, cs) != cudaSuccess) rc = -2;
     h2d += (int64_t)(count * sizeof(float));
     return dst;
   };
+  // Uploads in the order the path consumes them, each piece followed by an event the compute streams wait on:
+  // cameras (packed into one pinned buffer: one copy instead of 5 + V tiny ones), comparison images at level 0
+  // (warp -> right feature network -> recurrence: the critical path), reference image at level 0 (left feature
+  // network, side stream), then everything the refiners and the 1/16-scale warps need.
   float* cur = din;
   const float* dl[5];
   const float* dk[5];
   const float *dT[kMaxViews], *dr0[kMaxViews], *dr4[kMaxViews];
-  for (int l = 0; l < 5; ++l) {
-    dl[l] = up(left_image_pyr[l], B * 3 * L.px[l], cur);
-    dk[l] = up(K_pyr[l], B * 16, cur);
+  {
+    const size_t small = (5 + V) * B * 16;
+    if (small > net->pinned_small_floats) {
+      if (net->pinned_small != nullptr) {
+        B200MVS_CUDA_OK(cudaStreamSynchronize(cs));
+        cudaFreeHost(net->pinned_small);
+        net->pinned_small = nullptr;
+      }
+      B200MVS_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&net->pinned_small), small * sizeof(float)));
+      net->pinned_small_floats = small;
+    } else {
+      // the previous call's copy out of this buffer completed before that call returned (it synchronised)
+    }
+    float* hp = net->pinned_small;
+    for (int l = 0; l < 5; ++l) {
+      std::memcpy(hp + (size_t)l * B * 16, K_pyr[l], B * 16 * sizeof(float));
+      dk[l] = cur + (size_t)l * B * 16;
+    }
+    for (size_t v = 0; v < V; ++v) {
+      std::memcpy(hp + (5 + v) * B * 16, T_right_in_lefts[v], B * 16 * sizeof(float));
+      dT[v] = cur + (5 + v) * B * 16;
+    }
+    up(hp, small, cur);
+    cudaEventRecord(net->ev_up[0], cs);
   }
-  for (size_t v = 0; v < V; ++v) {
-    dT[v] = up(T_right_in_lefts[v], B * 16, cur);
-    dr0[v] = up(right_image_l0[v], B * 3 * L.px[0], cur);
-    dr4[v] = up(right_image_l4[v], B * 3 * L.px[4], cur);
-  }
+  for (size_t v = 0; v < V; ++v) dr0[v] = up(right_image_l0[v], B * 3 * L.px[0], cur);
+  cudaEventRecord(net->ev_up[1], cs);
+  for (size_t v = 0; v < V; ++v) dr4[v] = up(right_image_l4[v], B * 3 * L.px[4], cur);
+  cudaEventRecord(net->ev_up[2], cs);
+  dl[0] = up(left_image_pyr[0], B * 3 * L.px[0], cur);
+  cudaEventRecord(net->ev_up[3], cs);
+  for (int l = 1; l < 5; ++l) dl[l] = up(left_image_pyr[l], B * 3 * L.px[l], cur);
+  cudaEventRecord(net->ev_up[4], cs);
   float *oi[5], *orw[5];
   uint8_t* om[5];
   {
@@ -1237,7 +1307,9 @@ B200MVS_API int b200mvs_forward_host(b200mvs_net* net, const b200mvs_shape* shap
       m += B * D * L.px[l];
     }
   }
-  if (rc == 0) rc = forward_impl(net, s, dl, dk, dT, dr0, dr4, oi, orw, om, stream);
+  const double t_up = hprof ? now() : 0.0;
+  if (rc == 0) rc = forward_impl(net, s, dl, dk, dT, dr0, dr4, oi, orw, om, stream, net->ev_up);
+  const double t_enq = hprof ? now() : 0.0;
   if (rc == 0) {
     for (int l = 0; l < 5; ++l) {
       if (out_idepth != nullptr && out_idepth[l] != nullptr) {
@@ -1254,11 +1326,15 @@ B200MVS_API int b200mvs_forward_host(b200mvs_net* net, const b200mvs_shape* shap
       }
     }
     cudaError_t e = cudaStreamSynchronize(stream);
+    if (hprof)
+      fprintf(stderr, "forward_host: uploads enqueued %.0f us | kernels enqueued %.0f us | wait for completion %.0f us\n",
+              t_up - t_entry, t_enq - t_up, now() - t_enq);
     if (e != cudaSuccess) {
       set_error(std::string("b200mvs_forward_host: ") + cudaGetErrorString(e));
       rc = B200MVS_ECUDA;
     }
   } else {
+    cudaStreamSynchronize(cs);
     cudaStreamSynchronize(stream);
     if (rc == -2 && g_error.empty()) set_error("b200mvs_forward_host: upload failed");
   }

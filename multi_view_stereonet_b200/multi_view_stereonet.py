@@ -125,6 +125,20 @@ class MultiViewStereoNet(tnn.Module):
     def _weights_key(self, device_index):
         return (device_index,) + tuple((id(p), p._version) for p in self.parameters())
 
+    # Walking 226 parameters to build the key costs ~0.1 ms per forward, so the full check only runs when something
+    # may have changed the weights: the standard entry points below mark the native copy stale; code that edits
+    # parameters in place some other way calls `refresh_weights()`.
+    def refresh_weights(self):
+        self._weights_stale = True
+
+    def load_state_dict(self, *args, **kwargs):
+        self._weights_stale = True
+        return super().load_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._weights_stale = True
+        return super()._apply(fn, *args, **kwargs)
+
     def _release(self):
         if self._handle is not None:
             _lib.load().b200mvs_destroy(self._handle)
@@ -138,7 +152,11 @@ class MultiViewStereoNet(tnn.Module):
             pass
 
     def _native(self, device_index):
+        if (self._handle is not None and not getattr(self, "_weights_stale", True)
+                and self._handle_key[0] == device_index):
+            return self._handle
         key = self._weights_key(device_index)
+        self._weights_stale = False
         if self._handle is not None and key == self._handle_key:
             return self._handle
         lib = _lib.load()
