@@ -7,6 +7,7 @@
 // output slices that touch it.  Output slice q = 27 taps x 2 k-steps x 2 MMAs reading ring slots q, q+1, q+2 with
 // the shifted-window descriptors of conv_tc.cu; accumulators are double-buffered in TMEM so the MMAs of slice q
 // run while the epilogue of slice q-1 stores and the loads of input slice q+3 are in flight.
+#include <cstdlib>
 #include <vector>
 
 #include "conv.cuh"
@@ -43,6 +44,7 @@ __host__ __device__ inline Geo make_geo(int w) {
 struct CvfParams {
   CvfArgs a;
   int DC, row_tiles;
+  int dbg;   // timing ablation (wrong results): 1 = issue no MMAs
 };
 
 __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
@@ -131,20 +133,32 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
 
   float gs[2] = {0.f, 0.f}, gq[2] = {0.f, 0.f};
 
-  for (int it = 0; it <= dcount + 2; ++it) {
-    // ---- stage input slice `it` (depth d0 - 1 + it) into ring slot it & 3 ----
-    if (it <= dcount + 1) {
-      const int din = d0 - 1 + it;
-      const bool dvalid = din >= 0 && din < p.D;
-      const float* src = in_n + (size_t)(dvalid ? din : 0) * slice_elems;
-      float4 ya[MAX_TASKS], yb[MAX_TASKS];
+  // Software pipeline over depth.  Iteration `it`:
+  //   transform + stage input slice it (its global loads were issued one iteration earlier)   -> ring slot it & 3
+  //   issue the MMAs of output slice it - 2 (queued right behind those of slice it - 3: the tensor pipe stays busy)
+  //   issue the global loads of input slice it + 1
+  //   epilogue of output slice it - 3 (overlaps the MMAs just issued and the loads in flight)
+  float4 ya[MAX_TASKS], yb[MAX_TASKS];
+  bool loaded_valid = false;
+  auto issue_loads = [&](int slice) {
+    const int din = d0 - 1 + slice;
+    loaded_valid = slice <= dcount + 1 && din >= 0 && din < p.D;
+    if (loaded_valid) {
+      const float* src = in_n + (size_t)din * slice_elems;
 #pragma unroll
       for (int k = 0; k < MAX_TASKS; ++k) {
-        if (t_real[k] && dvalid) {
+        if (t_real[k]) {
           ya[k] = __ldg(reinterpret_cast<const float4*>(src + t_off[k]));
           yb[k] = __ldg(reinterpret_cast<const float4*>(src + t_off[k] + 4));
         }
       }
+    }
+  };
+  issue_loads(0);
+  for (int it = 0; it <= dcount + 2; ++it) {
+    // ---- transform and stage input slice `it` into ring slot it & 3 (last read by the MMAs of output slice it - 4,
+    //      whose completion the epilogue of slice it - 4 observed one iteration ago) ----
+    if (it <= dcount + 1) {
       uint8_t* slot = s_ring + (size_t)(it & (RING - 1)) * g.slot_bytes;
 #pragma unroll
       for (int k = 0; k < MAX_TASKS; ++k) {
@@ -152,7 +166,7 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
           float v[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) v[e] = 0.f;
-          if (t_real[k] && dvalid) {
+          if (t_real[k] && loaded_valid) {
             v[0] = ya[k].x; v[1] = ya[k].y; v[2] = ya[k].z; v[3] = ya[k].w;
             v[4] = yb[k].x; v[5] = yb[k].y; v[6] = yb[k].z; v[7] = yb[k].w;
             if (p.mode >= FEAT_GN) {
@@ -178,7 +192,7 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
       tc::fence_after_sync();
       const uint32_t acc = tmem_base + (uint32_t)((q & 1) * 64);
 #pragma unroll
-      for (int kz = 0; kz < 3; ++kz) {
+      for (int kz = 0; kz < ((P.dbg & 1) ? 0 : 3); ++kz) {
         const uint64_t da_slot = da0 + (uint64_t)(((q + kz) & (RING - 1)) * slot_u16);
 #pragma unroll
         for (int t2 = 0; t2 < 9; ++t2) {
@@ -198,8 +212,10 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
      __syncwarp();
     }
 
-    // ---- epilogue of output slice q - 1 (its MMAs were issued one iteration ago) ----
-    const int qe = q - 1;
+    issue_loads(it + 1);
+
+    // ---- epilogue of output slice it - 3 (its MMAs were issued one iteration ago) ----
+    const int qe = it - 3;
     if (qe >= 0 && qe < dcount) {
       if (warp == 0) {  // one poller; the other warps park at the hardware barrier
         if (tc::elect_one()) {
@@ -287,6 +303,8 @@ int launch_cvf_tc(const CvfArgs& a, cudaStream_t stream) {
   CvfParams P;
   P.a = a;
   P.row_tiles = cdiv(a.h, g.RT);
+  static const int dbg = getenv("B200MVS_CVF_DEBUG") ? atoi(getenv("B200MVS_CVF_DEBUG")) : 0;
+  P.dbg = dbg;
   // One CTA per SM (220 KB of shared memory): split depth into as many chunks as fill the chip once.
   int chunks = 148 / (P.row_tiles * a.n);
   chunks = chunks < 1 ? 1 : (chunks > a.D ? a.D : chunks);
