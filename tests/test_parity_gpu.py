@@ -99,6 +99,16 @@ def test_cfg3_item_multiview(net, gta_state):
         assert bool((out1["left_idepthmap_mask_pyr"][lvl][0] == out2["left_idepthmap_mask_pyr"][lvl][0]).all())
 
 
+def test_cfg5_item_large_image(net, gta_state):
+    """One image group of BASELINE cfg5 (1024x1280, 4 comparison views, 128 hypotheses): the 1/16-scale image
+    (64x80 = 41 M-tiles) is beyond the persistent recurrence kernel's cluster, so this exercises the multi-launch
+    fallback of the depth sweep, and the full-resolution warp has a knife-edge mask pixel on these inputs
+    (tests/_gpu_util.py re-runs the oracle with the CUDA path's tie-break after checking it is one)."""
+    from tests._gpu_util import run_case
+    rep, _, _ = run_case(net, gta_state, synthetic.make_inputs(1024, 1280, 4, 1), 128, stages=False)
+    _assert_report(rep)
+
+
 def test_homography_image_predictor(net):
     from multi_view_stereonet_b200 import HomographyImagePredictor
     from oracle import mvsnet_oracle as oracle
