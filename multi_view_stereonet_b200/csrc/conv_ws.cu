@@ -100,6 +100,7 @@ struct WsParams {
   double inv_count;
   int n_img, H, W, dil;
   int tiles_x, tiles_y, stages, has_res, prof;
+  int dbg;   // timing ablations (wrong results): 1 transform warps only wait / arrive, 2 no MMAs, 4 no output stores
 };
 
 template <int TH>
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(NT, 1) conv3x3_ws_kernel(const WsParams p, con
         const int gy = ty0 - d + r;
         const uint8_t* raw = s_ring + (size_t)q * 2u * CHUNK_HALF + (size_t)(rr * PW + ix) * 64 + c8 * 16;
         uint4 h = make_uint4(0, 0, 0, 0);
-        if (col_ok && gy >= 0 && gy < p.H) {
+        if (col_ok && gy >= 0 && gy < p.H && !(p.dbg & 1)) {
           float v[8];
           unpack8(*reinterpret_cast<const uint4*>(raw), v);
 #pragma unroll
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(NT, 1) conv3x3_ws_kernel(const WsParams p, con
           h = pack8(v);
           if (xg != nullptr && col_int && r >= d && r < d + TH) stg_hint(xg + (ptrdiff_t)r * p.W * kC, h, pol_keep);
         }
-        *reinterpret_cast<uint4*>(xpl + (size_t)r * (PW * 16)) = h;
+        if (!(p.dbg & 1)) *reinterpret_cast<uint4*>(xpl + (size_t)r * (PW * 16)) = h;
         mbar_arrive(&s_rfree[q]);   // this thread is done reading the slot
       }
       tc::fence_proxy_async();
@@ -284,7 +285,7 @@ __global__ void __launch_bounds__(NT, 1) conv3x3_ws_kernel(const WsParams p, con
         tc::fence_after_sync();
         const uint64_t da = da0 + (uint64_t)(s * (stage_bytes >> 4));
 #pragma unroll 1
-        for (int mt = 0; mt < MT; ++mt) {
+        for (int mt = 0; mt < ((p.dbg & 2) ? 0 : MT); ++mt) {
           const uint32_t dcol = tmem_base + (uint32_t)(a * ACC_COLS + mt * 32);
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
@@ -355,9 +356,31 @@ __global__ void __launch_bounds__(NT, 1) conv3x3_ws_kernel(const WsParams p, con
             gsum[c >> 3] += v[c];
             gsq[c >> 3] = fmaf(v[c], v[c], gsq[c >> 3]);
           }
-          __half* o = p.out + (size_t)img * img_elems + ((size_t)oy * p.W + ox) * kC;
+        }
+        // Store through a lane transpose: in every store instruction two adjacent lanes write the two 16-byte halves
+        // of one 32-byte sector (a lane writing its own pixel's 64 bytes with four instructions would touch every
+        // sector twice, half-filled).  Instruction k covers pixels 16 (k >> 1) .. + 15, channel octets 2 (k & 1) + {0, 1}.
+        uint4 ch[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) stg_hint(o + 8 * q, pack8(v + 8 * q), pol_keep);
+        for (int q = 0; q < 4; ++q) ch[q] = pack8(v + 8 * q);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int src = (lane >> 1) + 16 * (k >> 1);
+          uint4 lo, hi;
+          lo.x = __shfl_sync(0xffffffffu, ch[2 * (k & 1)].x, src);
+          lo.y = __shfl_sync(0xffffffffu, ch[2 * (k & 1)].y, src);
+          lo.z = __shfl_sync(0xffffffffu, ch[2 * (k & 1)].z, src);
+          lo.w = __shfl_sync(0xffffffffu, ch[2 * (k & 1)].w, src);
+          hi.x = __shfl_sync(0xffffffffu, ch[2 * (k & 1) + 1].x, src);
+          hi.y = __shfl_sync(0xffffffffu, ch[2 * (k & 1) + 1].y, src);
+          hi.z = __shfl_sync(0xffffffffu, ch[2 * (k & 1) + 1].z, src);
+          hi.w = __shfl_sync(0xffffffffu, ch[2 * (k & 1) + 1].w, src);
+          const int js = mt * 128 + wq * 32 + src;
+          const int oys = ty0 + js / PW, oxts = js % PW, oxs = tx0 + oxts;
+          if (oxts < TW && oxs < p.W && oys < p.H && !(p.dbg & 4)) {
+            __half* o = p.out + (size_t)img * img_elems + ((size_t)oys * p.W + oxs) * kC + 8 * (2 * (k & 1) + (lane & 1));
+            stg_hint(o, (lane & 1) ? hi : lo, pol_keep);
+          }
         }
       }
       tc::fence_before_sync();
@@ -490,6 +513,8 @@ int launch_conv3x3_ws(const ConvParams& p, const uint8_t* w16, cudaStream_t stre
   q.has_res = has_res ? 1 : 0;
   static const bool prof = getenv("B200MVS_WS_PROFILE") != nullptr;
   q.prof = prof ? 1 : 0;
+  static const int dbg = getenv("B200MVS_WS_DEBUG") ? atoi(getenv("B200MVS_WS_DEBUG")) : 0;
+  q.dbg = dbg;
   CUtensorMap tm_y, tm_r;
   if (!make_map(p.feat.ptr, p.n_img, p.Hi, p.Wi, &tm_y) ||
       !make_map(has_res ? (const void*)p.feat.resid : (const void*)p.feat.ptr, p.n_img, p.Hi, p.Wi, &tm_r)) {
