@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(NT, 1) conv5x5s2_c32_tc_kernel(const float* __
                                                                   const uint8_t* __restrict__ w16, int Hi, int Wi,
                                                                   int Ho, int Wo, float* __restrict__ out) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ __align__(8) uint64_t s_bar, s_wbar;
   __shared__ uint32_t s_tmem;
   uint8_t* s_w = smem;
   uint8_t* s_pl = smem + A_WBYTES;   // planes [hi | lo][phase (py * 2 + px)][octet]
@@ -55,14 +55,13 @@ __global__ void __launch_bounds__(NT, 1) conv5x5s2_c32_tc_kernel(const float* __
   if (warp == 0) tc::tmem_alloc(&s_tmem, 64u);
   if (tid == 32) {
     tc::mbar_init(&s_bar, 1);
+    tc::mbar_init(&s_wbar, 1);
     tc::mbar_init_fence();
+    tc::bulk_load_weights(s_w, w16, A_WBYTES, &s_wbar);   // constant data: before griddepcontrol.wait
   }
   __syncthreads();
   pdl_launch_dependents();
   {
-    const uint4* src = reinterpret_cast<const uint4*>(w16);
-    uint4* dst = reinterpret_cast<uint4*>(s_w);
-    for (int i = tid; i < (int)(A_WBYTES / 16); i += NT) dst[i] = __ldg(src + i);
     // positions past the last staged row are read by the garbage columns only, but must not hold NaN patterns
     for (int i = tid; i < 32 * (A_NPOS - A_IN_ROWS / 2 * A_PW); i += NT) {
       const int pl = i / (A_NPOS - A_IN_ROWS / 2 * A_PW), r = i % (A_NPOS - A_IN_ROWS / 2 * A_PW);
@@ -125,6 +124,7 @@ __global__ void __launch_bounds__(NT, 1) conv5x5s2_c32_tc_kernel(const float* __
 
   if (warp == 0) {
     if (tc::elect_one()) {
+      tc::mbar_wait(&s_wbar, 0u);   // the bulk-copied weights have landed
       const uint64_t da0 = tc::umma_desc(tc::smem_u32(s_pl), A_PLANE, 128u);
       const uint64_t db0 = tc::umma_desc(tc::smem_u32(s_w), 1024u, 128u);
       constexpr uint32_t plane_u16 = A_PLANE >> 4;

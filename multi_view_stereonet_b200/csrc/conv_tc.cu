@@ -35,7 +35,7 @@ constexpr int NT = 256;       // threads per CTA
 
 __host__ __device__ inline int tc_npos(int TH, int dil) {
   int n = (TH + 2 * dil) * PW + 2 * dil;
-  return (n + 7) & ~7;
+  return ((n + 5) & ~7) + 2;   // 2 (mod 8): the four octet planes a lane quad writes start in distinct banks
 }
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {

@@ -34,7 +34,9 @@ __host__ __device__ inline Geo make_geo(int w) {
   g.NP = (g.RT + 2) * g.PW + 2;
   // the MMA reads 128 rows from every tap offset (up to 2*PW + 2) even when RT * PW < 128
   if (g.NP < 128 + 2 * g.PW + 2) g.NP = 128 + 2 * g.PW + 2;
-  g.np_pad = (g.NP + 7) & ~7;
+  // padded to 2 (mod 8) positions: consecutive planes then start 32 bytes apart modulo 128, so the four octet planes
+  // the lanes of a quad write at once fall into distinct shared-memory banks
+  g.np_pad = ((g.NP + 5) & ~7) + 2;
   g.plane_bytes = (uint32_t)g.np_pad * 16u;
   g.slot_bytes = 8u * g.plane_bytes;  // hi planes 0..3, lo planes 4..7
   g.total = (uint32_t)W_BYTES + RING * g.slot_bytes;
@@ -44,7 +46,7 @@ __host__ __device__ inline Geo make_geo(int w) {
 struct CvfParams {
   CvfArgs a;
   int DC, row_tiles;
-  int dbg;   // timing ablation (wrong results): 1 = issue no MMAs
+  int dbg;   // timing ablations (wrong results): 1 no MMAs, 2 no operand staging stores, 4 no output stores, 8 no input loads
 };
 
 __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
@@ -52,7 +54,7 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ float s_a[kC], s_b[kC], s_bias[kC];
   __shared__ double s_stats[2 * kGroups];
-  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ __align__(8) uint64_t s_bar[2], s_wbar;
   __shared__ uint32_t s_tmem;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -71,19 +73,15 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
   if (tid == 32) {
     tc::mbar_init(&s_bar[0], 1);
     tc::mbar_init(&s_bar[1], 1);
+    tc::mbar_init(&s_wbar, 1);
     tc::mbar_init_fence();
+    tc::bulk_load_weights(s_w, p.w16, (uint32_t)W_BYTES, &s_wbar);   // constant data: before griddepcontrol.wait
   }
   if (tid < kC) s_bias[tid] = p.bias != nullptr ? __ldg(p.bias + tid) : 0.f;
   if (tid < 2 * kGroups) s_stats[tid] = 0.0;
   __syncthreads();
   pdl_launch_dependents();   // after the TMEM allocation (see common.cuh)
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(p.w16);
-    uint4* dst = reinterpret_cast<uint4*>(s_w);
-    for (int i = tid; i < W_BYTES / 16; i += NT) dst[i] = __ldg(src + i);
-    uint4* rz = reinterpret_cast<uint4*>(s_ring);
-    for (int i = tid; i < (int)(RING * g.slot_bytes / 16); i += NT) rz[i] = make_uint4(0, 0, 0, 0);
-  }
+  // (no ring initialisation: every position an MMA reads, [0, NP), is written by the staging of its slice)
   pdl_wait();
   if (tid < kC && p.mode >= FEAT_GN) {
     const int grp = tid >> 3;
@@ -142,7 +140,7 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
   bool loaded_valid = false;
   auto issue_loads = [&](int slice) {
     const int din = d0 - 1 + slice;
-    loaded_valid = slice <= dcount + 1 && din >= 0 && din < p.D;
+    loaded_valid = slice <= dcount + 1 && din >= 0 && din < p.D && !(P.dbg & 8);
     if (loaded_valid) {
       const float* src = in_n + (size_t)din * slice_elems;
 #pragma unroll
@@ -176,8 +174,10 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
           }
           uint4 hi, lo;
           tc::split8(v, &hi, &lo);
-          *reinterpret_cast<uint4*>(slot + (size_t)t_oct * g.plane_bytes + (size_t)t_l[k] * 16) = hi;
-          *reinterpret_cast<uint4*>(slot + (size_t)(4 + t_oct) * g.plane_bytes + (size_t)t_l[k] * 16) = lo;
+          if (!(P.dbg & 2)) {
+            *reinterpret_cast<uint4*>(slot + (size_t)t_oct * g.plane_bytes + (size_t)t_l[k] * 16) = hi;
+            *reinterpret_cast<uint4*>(slot + (size_t)(4 + t_oct) * g.plane_bytes + (size_t)t_l[k] * 16) = lo;
+          }
         }
       }
     }
@@ -189,6 +189,7 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
     const int q = it - 2;
     if (q >= 0 && q < dcount && warp == 0) {
      if (tc::elect_one()) {
+      if (q == 0) tc::mbar_wait(&s_wbar, 0u);   // the bulk-copied weights have landed
       tc::fence_after_sync();
       const uint32_t acc = tmem_base + (uint32_t)((q & 1) * 64);
 #pragma unroll
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
       const uint32_t acc = tmem_my + (uint32_t)((qe & 1) * 64);
       tc::tmem_ld16(acc, v);
       tc::tmem_ld16(acc + 32u, c);
-      if (e_real) {
+      if (e_real && !(P.dbg & 4)) {
         float* dst = out_n + (size_t)(d0 + qe) * slice_elems + e_off;
 #pragma unroll
         for (int k = 0; k < 16; ++k) v[k] = (v[k] + c[k]) + s_bias[chalf * 16 + k];

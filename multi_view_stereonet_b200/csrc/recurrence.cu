@@ -149,7 +149,9 @@ __host__ __device__ inline Layout make_layout(int rows, int cols) {
   L.PW = cols + 2;
   L.halo = L.PW + 1;
   L.npl = MTILE + 2 * L.halo;
-  L.npl_pad = (L.npl + 7) & ~7;
+  // padded to 2 (mod 8) positions: consecutive planes then start 32 bytes apart modulo 128, so the four octet planes
+  // the lanes of a quad write at once fall into distinct shared-memory banks
+  L.npl_pad = ((L.npl + 5) & ~7) + 2;
   L.plane_bytes = (uint32_t)L.npl_pad * 16u;
   uint32_t o = 0;
   L.off_w = o;

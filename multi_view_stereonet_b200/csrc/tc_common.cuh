@@ -113,6 +113,20 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
 }
 
 
+// Weights into shared memory with the bulk-copy engine: one thread arms `bar` with the byte count and issues 1-D
+// cp.async.bulk copies (chunks of at most 32 KB); whoever consumes the weights waits on `bar` (parity 0).  A
+// 100 KB weight set staged with LDG/STS costs every thread ~25 dependent vector loads in the prologue.
+__device__ __forceinline__ void bulk_load_weights(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  for (uint32_t off = 0; off < bytes; off += 32768u) {
+    const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst) + off),
+                 "l"(reinterpret_cast<const uint8_t*>(gsrc) + off), "r"(n), "r"(smem_u32(bar))
+                 : "memory");
+  }
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
                "r"(cols)
