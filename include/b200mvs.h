@@ -171,6 +171,28 @@ B200MVS_API int b200mvs_prepare_cameras(const float* K, const float* const* T_ri
                                         float* T_right_in_left_out, float* T_left_in_right_out, float* baseline,
                                         void* stream);
 
+/* Post-processing after the hot path, DEVICE pointers, no handle: what test.py does with
+ * `left_idepthmap_pyr[0]` once the forward has returned, as one pass over the maps.
+ *   est (batch, pixels)        est_is_depth == 0: inverse depth maps in baseline-normalised units; the function
+ *                              divides by `baseline` and inverts the positive values (test.py:211-214).
+ *                              est_is_depth != 0: depth maps, used as they are.
+ *   baseline (batch)           inputs["baseline"] (multi_view_stereonet_utils.py:596-604); NULL = 1
+ *   depth_true (batch, pixels) baseline-normalised ground-truth depth as multi_view_unpack_batch holds it; it is
+ *                              multiplied back by the baseline as get_groundtruth_depthmap does (test.py:167-186).
+ *                              NULL = conversion only.
+ *   min_depth, max_depth       validity range, exclusive on both sides, applied to ground truth AND estimate
+ *                              (test.py:222, 236): gta_sfm 0 / 1e3, demon 0.5 / 10.
+ * outputs (any may be NULL):
+ *   idepth_out, depth_out (batch, pixels)   batch_left_idepthmap_est / batch_left_depthmap_est (test.py:211-213)
+ *   metrics (batch, 8) float64              abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3 (get_depth_prediction_metrics,
+ *                                           test.py:41-71) over the valid pixels, then the valid-pixel count; the
+ *                                           seven metrics are NaN where the count is 0 (the reference skips such
+ *                                           images, test.py:224-226). */
+B200MVS_API int b200mvs_depth_metrics(const float* est, const float* baseline, const float* depth_true,
+                                      int32_t est_is_depth, float min_depth, float max_depth, int32_t batch,
+                                      int64_t pixels, float* idepth_out, float* depth_out, double* metrics,
+                                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,9 @@ SYMBOLS = {
                                                ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32),
                                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                ctypes.c_void_p]),
+    "b200mvs_depth_metrics": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+                                             ctypes.c_float, ctypes.c_float, ctypes.c_int32, ctypes.c_int64,
+                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
 }
 
 _lib = None

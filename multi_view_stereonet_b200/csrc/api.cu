@@ -13,6 +13,7 @@
 #include "conv_ws.cuh"
 #include "conv5_tc.cuh"
 #include "cvf_tc.cuh"
+#include "evalpost.cuh"
 #include "kernels.cuh"
 #include "recurrence.cuh"
 #include "tail.cuh"
@@ -698,6 +699,18 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
   const size_t P4 = L.px[4];
   g_launches = 0;
   g_probe = net->probe.tag != 0 ? &net->probe : nullptr;
+  // Debug hook (B200MVS_STAGE_PROFILE=1): events at the stage boundaries of the main stream, printed to stderr
+  // after a synchronise.  Perturbs the pipeline slightly (an event between two kernels ends their PDL overlap).
+  static const bool sprof = getenv("B200MVS_STAGE_PROFILE") != nullptr;
+  std::vector<std::pair<const char*, cudaEvent_t>> marks;
+  auto mark = [&](const char* what) {
+    if (!sprof) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, stream);
+    marks.emplace_back(what, e);
+  };
+  mark("begin");
 
   B200MVS_CUDA_OK(cudaMemsetAsync(ws.stats, 0, ws.stats_count * sizeof(double), stream));
   StatsCursor sc{ws.stats, 0, ws.stats_count};
@@ -748,6 +761,7 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
   //     conv_final writes hypothesis 0 of every view's feature volume directly (:261, 278)
   RC(run_featnet(net, L, B, n, ws.warped0, tail_stats, ws.vol, (long long)D * (long long)P4 * kC, stream));
 
+  mark("geometry+warp+right featnet");
   // 3a. FeatureNetwork on the B left images (multi_view_stereonet.py:552): side stream, needed by the cost volume
   //     (enqueued after the critical path's launches)
   RC(wait_upload(3, left_stream));
@@ -839,6 +853,7 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
     }
   }
 
+  mark("recurrence");
   // 6. cost volume |L - R| with invalid voxels zeroed (multi_view_stereonet.py:586-592)
   if (overlap) B200MVS_CUDA_OK(cudaStreamWaitEvent(stream, net->ev_left, 0));
   float* cost = net->keep_stages ? ws.cost : ws.vol;
@@ -913,6 +928,7 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
   // 8. soft-argmin (:602)
   if (!softargmin_done) RC(launch_softargmin(ws.cost1, ws.geo.samples, n, D, (int)P4, ws.raw_views, stream));
 
+  mark("cost+cvf+softargmin");
   // 9. level-4 refiner per view (:605-613)
   RC(wait_upload(4, stream));
   if (s.do_refiners[4]) {
@@ -934,6 +950,7 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
   RC(launch_view_reduce(ws.raw_views, ws.refined_views, ws.mask_views, ws.geo.baseline, B, V, D, (int)P4,
                         !s.do_refiners[4], prior_l[4], idepth_l[4], mask_l[4], stream));
 
+  mark("refiner4+view_reduce");
   // 11. coarse-to-fine: bilinear prior, mask upsample, guided refinement (:629-682).  Nothing on the path reads
   //     the upsampled mask volumes, so their chain runs on the side stream next to the refiners.
   cudaStream_t mask_stream = overlap ? net->side : stream;
@@ -955,8 +972,24 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
       B200MVS_CUDA_OK(cudaMemcpyAsync(idepth_l[l], prior_l[l], (size_t)B * L.px[l] * sizeof(float),
                                       cudaMemcpyDeviceToDevice, stream));
     }
+    static const char* names[4] = {"upsample+refiner0", "upsample+refiner1", "upsample+refiner2", "upsample+refiner3"};
+    mark(names[l]);
   }
   if (overlap && lowest_mask <= 3) B200MVS_CUDA_OK(cudaStreamWaitEvent(stream, net->ev_mask_out, 0));
+  if (sprof) {
+    mark("join mask chain");
+    cudaEventSynchronize(marks.back().second);
+    float total = 0.f;
+    cudaEventElapsedTime(&total, marks.front().second, marks.back().second);
+    fprintf(stderr, "stage profile (us):");
+    for (size_t i = 1; i < marks.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+      fprintf(stderr, " [%s] %.0f", marks[i].first, ms * 1e3f);
+    }
+    fprintf(stderr, " | total %.0f\n", total * 1e3f);
+    for (auto& m : marks) cudaEventDestroy(m.second);
+  }
   if (sc.used > sc.cap) {
     set_error("internal: GroupNorm statistics arena overflow");
     return B200MVS_EINVAL;
@@ -1462,6 +1495,22 @@ B200MVS_API int b200mvs_prepare_cameras(const float* K, const float* const* T_ri
                                         baseline, stream);
   cudaFreeAsync(dsizes, stream);
   return rc;
+}
+
+B200MVS_API int b200mvs_depth_metrics(const float* est, const float* baseline, const float* depth_true,
+                                      int32_t est_is_depth, float min_depth, float max_depth, int32_t batch,
+                                      int64_t pixels, float* idepth_out, float* depth_out, double* metrics,
+                                      void* stream) {
+  if (est == nullptr || batch < 1 || pixels < 1) {
+    set_error("b200mvs_depth_metrics: bad argument");
+    return B200MVS_EINVAL;
+  }
+  if (metrics != nullptr && depth_true == nullptr) {
+    set_error("b200mvs_depth_metrics: metrics need depth_true");
+    return B200MVS_EINVAL;
+  }
+  return launch_depth_metrics(est, baseline, depth_true, est_is_depth != 0, min_depth, max_depth, batch, pixels,
+                              idepth_out, depth_out, metrics, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"
