@@ -207,6 +207,26 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Two 8-column slices of this thread's TMEM lane (the hi*hi+lo*hi and hi*lo accumulators): both loads in flight,
+// one wait.
+__device__ __forceinline__ void tmem_ld8x2(uint32_t taddr0, uint32_t taddr1, float* v, float* c) {
+  uint32_t r[8], q[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr0)
+               : "memory");
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7])
+               : "r"(taddr1)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[i] = __uint_as_float(r[i]);
+    c[i] = __uint_as_float(q[i]);
+  }
+}
+
 // One conv = 9 taps x ksteps k-steps; per k-step two MMAs implement the split product
 //   D[:, 0:32]  += A_hi * W_hi      D[:, 32:64] += A_hi * W_lo      (one N=64 MMA on [W_hi | W_lo])
 //   D[:, 0:32]  += A_lo * W_hi                                      (one N=32 MMA)
@@ -600,6 +620,9 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
     __syncthreads();
     PROF_MARK(0);
     issue_conv(0);
+    // the NEXT step's gather plan, overlapped with conv0's MMAs (this step's plan was consumed above; H_inc of the
+    // next step was fetched before the barrier above)
+    if (step + 1 < p.D) plan_gathers(step + 1);
     wait_conv();
     PROF_MARK(1);
 
@@ -610,8 +633,7 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
       float y[8];
       if (active) {
         float c[8];
-        tmem_ld8(tmem_my, y);
-        tmem_ld8(tmem_my + 32u, c);
+        tmem_ld8x2(tmem_my, tmem_my + 32u, y, c);
         if (layer == 0) {
           const float add[8] = {ic0.x, ic0.y, ic0.z, ic0.w, ic1.x, ic1.y, ic1.z, ic1.w};
 #pragma unroll
@@ -729,8 +751,6 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
       __syncthreads();
       PROF_MARK(4 + 4 * layer);
       issue_conv(1 + layer);
-      // ---- work for the NEXT step, overlapped with this conv's MMAs ----
-      if (layer == 0 && step + 1 < p.D) plan_gathers(step + 1);
       wait_conv();
       PROF_MARK(5 + 4 * layer);
     }
@@ -738,8 +758,7 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
     // ================= E2: features_step = wf + delta -> global =====================================
     if (active) {
       float v[8], c[8];
-      tmem_ld8(tmem_my, v);
-      tmem_ld8(tmem_my + 32u, c);
+      tmem_ld8x2(tmem_my, tmem_my + 32u, v, c);
       if (real_out) {
         float* dst = p.vol + (((size_t)n * p.D + step) * pixels + own_pix) * kC + oct_e * 8;
         const float* wfp = s_wf + jl * kC + oct_e * 8;
