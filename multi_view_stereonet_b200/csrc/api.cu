@@ -67,6 +67,7 @@ struct Refiner {
   ConvW conv0, res[6], fin;
   GnW gn0, gn[6];
   RefineFinalW finw;
+  RefineHeadIdW idw;   // conv0's idepth-channel taps (the last input channel), for the precomputed-guide path
 };
 
 
@@ -102,6 +103,8 @@ struct Workspace {
   float *raw_views = nullptr, *refined_views = nullptr;
   // refiners (shared by all levels)
   float *rx[2] = {nullptr, nullptr}, *ry[2] = {nullptr, nullptr};
+  // guide part of every refiner's conv0 (+ bias), computed while the depth sweep runs: [B][H_l][W_l][32] fp32
+  float* pre[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   // output scratch
   float* idepth[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   float* prior[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -148,10 +151,12 @@ struct b200mvs_net {
   bool use_tensor_cores = true;
   bool half_activations = true;
   bool warp_specialized = true;
+  bool conv0_precompute = true;   // refiner conv0 = precomputed guide part + idepth part (tail.cu)
   int rec_debug = 0;
   // Side stream for the work that does not depend on the comparison views (left feature network) or that
   // nothing downstream waits for (mask upsampling): forked / joined with events inside one forward.
   cudaStream_t side = nullptr;
+  cudaEvent_t ev_pre = nullptr, ev_right = nullptr;
   cudaEvent_t ev_geo = nullptr, ev_imgconv = nullptr, ev_fork = nullptr, ev_left = nullptr, ev_mask_in = nullptr, ev_mask_out = nullptr;
   bool overlap = true;
   // b200mvs_forward_host: uploads run on their own stream in the order the path needs them, compute waits per piece
@@ -334,6 +339,13 @@ int build_weights(b200mvs_net* net, const StateDict& sd) {
       RC(pack_conv(net, sd, r + ".conv0", 32, 4, 9, false, 0, {0, 1, 2, 3}, true, &R.conv0));
       RC(pack_conv_tc(net, sd, r + ".conv0", 4, false, 0, {0, 1, 2, 3}, &R.conv0));
     }
+    {
+      const int cin = lvl > 0 ? 36 : 4;
+      const float* w = sd.get(r + ".conv0.weight", 32 * cin * 9);
+      if (w == nullptr) return B200MVS_EWEIGHTS;
+      for (int t = 0; t < 9; ++t)
+        for (int o = 0; o < 32; ++o) R.idw.w[t * 32 + o] = w[((size_t)o * cin + (cin - 1)) * 9 + t];
+    }
     if (lvl == 0) {
       const float* w = sd.get(r + ".conv0.weight", 32 * 4 * 9);
       const float* b = sd.get(r + ".conv0.bias", 32);
@@ -419,6 +431,7 @@ void layout(b200mvs_net* net, const b200mvs_shape& s, bool dry) {
     W.rx[i] = A.take<float>(rmax * kC);
     W.ry[i] = A.take<float>(rmax * kC);
   }
+  for (int l = 0; l < 5; ++l) W.pre[l] = A.take<float>(B * L.px[l] * kC);
   for (int l = 0; l < 5; ++l) {
     W.idepth[l] = A.take<float>(B * L.px[l]);
     W.prior[l] = A.take<float>(B * L.px[l]);
@@ -480,9 +493,11 @@ struct StatsCursor {
 
 // One IDepthmapRefiner (multi_view_stereonet.py:468-484) with the caller-side fx scaling
 // (:607-611) folded into the first loader and the last epilogue.
+// `pre` != nullptr: the guide part of conv0 (+ bias) was computed ahead of time by run_refiner_guide (image m reads
+// pre[m / guide_div]); conv0 is then only the idepth channel on top of it.
 int run_refiner(b200mvs_net* net, const Refiner& R, StatsCursor& sc, int m, int H, int W, const float* guide_feat,
                 int guide_div, const float* image, int image_div, const float* prior, const float* Kl, int k_div,
-                float* out, int res_tag, cudaStream_t stream) {
+                float* out, int res_tag, cudaStream_t stream, const float* pre = nullptr) {
   Workspace& ws = net->ws;
   const size_t P = (size_t)H * W;
   const double inv_count = 1.0 / (8.0 * (double)P);
@@ -523,7 +538,10 @@ int run_refiner(b200mvs_net* net, const Refiner& R, StatsCursor& sc, int m, int 
   p.out_stats = st_prev = sc.take(m);
   // conv0 sees the idepth channel scaled by fx (values of a few hundred with the signal in the low bits):
   // always split precision.
-  if (guide_feat == nullptr && image_div == 1 && net->use_tensor_cores) {
+  if (pre != nullptr) {
+    RC(launch_refine_head_pre(pre, guide_div, prior, Kl, k_div, 16, R.idw, m, H, W, ws.ry[0], half_act != 0, st_prev,
+                              stream));
+  } else if (guide_feat == nullptr && image_div == 1 && net->use_tensor_cores) {
     // level 0: four planar inputs only -- dedicated fp32 kernel (tail.cu)
     RC(launch_refine_head_l0(image, prior, Kl, k_div, 16, net->head0, m, H, W, ws.ry[0], half_act != 0, st_prev, stream));
   } else {
@@ -566,6 +584,32 @@ int run_refiner(b200mvs_net* net, const Refiner& R, StatsCursor& sc, int m, int 
   RC(launch_refine_final(ws.ry[ycur], ws.rx[xres], half_act != 0, st_prev, gn_prev->gamma, gn_prev->beta, inv_count,
                          R.finw, prior, Kl, k_div, 16, m, H, W, out, stream));
   return 0;
+}
+
+// Guide part of an IDepthmapRefiner.conv0 (+ bias) for the B reference images of one level: conv0 over
+// cat[image, features] with the idepth channel left out (level 0: the image alone), fp32 channels-last.
+int run_refiner_guide(b200mvs_net* net, const Refiner& R, int B, int H, int W, const float* guide_feat,
+                      const float* image, float* pre, cudaStream_t stream) {
+  if (guide_feat == nullptr) return launch_refine_head_image_l0(image, net->head0, B, H, W, pre, stream);
+  const size_t P = (size_t)H * W;
+  ConvParams p;
+  p.n_img = B;
+  p.Hi = p.Ho = H;
+  p.Wi = p.Wo = W;
+  p.feat.ptr = guide_feat;
+  p.feat.mode = FEAT_RAW;
+  p.feat.img_div = 1;
+  p.extra.n = 3;   // the fourth planar slot (idepth * fx) stays zero
+  for (int e = 0; e < 3; ++e) {
+    p.extra.ptr[e] = image + e * P;
+    p.extra.img_stride[e] = 3 * (long long)P;
+    p.extra.img_div[e] = 1;
+  }
+  p.w = R.conv0.w;
+  p.bias = R.conv0.bias;
+  p.dil = 1;
+  p.out = pre;
+  return launch_conv3x3_tc(p, R.conv0.w16s, true, stream);
 }
 
 // FeatureNetwork.forward (multi_view_stereonet.py:109-129) on images [img0, img0 + cnt) of the (1+V)*B image
@@ -760,6 +804,7 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
   // 3b. FeatureNetwork on the B*V warped right images (shared weights, :507)
   //     conv_final writes hypothesis 0 of every view's feature volume directly (:261, 278)
   RC(run_featnet(net, L, B, n, ws.warped0, tail_stats, ws.vol, (long long)D * (long long)P4 * kC, stream));
+  if (overlap) B200MVS_CUDA_OK(cudaEventRecord(net->ev_right, stream));
 
   mark("geometry+warp+right featnet");
   // 3a. FeatureNetwork on the B left images (multi_view_stereonet.py:552): side stream, needed by the cost volume
@@ -767,6 +812,24 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
   RC(wait_upload(3, left_stream));
   RC(run_featnet(net, L, 0, B, left_pyr[0], tail_stats, ws.feat4, 0, left_stream));
   if (overlap) B200MVS_CUDA_OK(cudaEventRecord(net->ev_left, net->side));
+
+  // 3c. every refiner's conv0 is linear in its inputs and all but one of them (image, left features) are known
+  //     now: their part is computed here, next to the depth sweep; the idepth channel is added when the coarser
+  //     level has produced it (run_refiner)
+  bool use_pre[5] = {false, false, false, false, false};
+  if (net->conv0_precompute && net->use_tensor_cores) {
+    // not before the depth sweep is ready to start: its cluster needs 11 free SMs in one GPC, and a large grid
+    // already resident there would hold it back (measured: +29 us on the sweep); smallest level first
+    if (overlap) B200MVS_CUDA_OK(cudaStreamWaitEvent(net->side, net->ev_right, 0));
+    RC(wait_upload(4, left_stream));
+    for (int l = 4; l >= 0; --l) {
+      if (!s.do_refiners[l]) continue;
+      const float* guide = (l == 0) ? nullptr : (l == 1 ? ws.f1 : (l == 2 ? ws.f2 : (l == 3 ? ws.f3 : ws.feat4)));
+      RC(run_refiner_guide(net, net->refiner[l], B, L.h[l], L.w[l], guide, left_pyr[l], ws.pre[l], left_stream));
+      use_pre[l] = true;
+    }
+    if (overlap) B200MVS_CUDA_OK(cudaEventRecord(net->ev_pre, net->side));
+  }
 
   // 5. the depth-sweep recurrence (multi_view_stereonet.py:279-290)
   RC(wait_upload(2, stream));
@@ -931,9 +994,10 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
   mark("cost+cvf+softargmin");
   // 9. level-4 refiner per view (:605-613)
   RC(wait_upload(4, stream));
+  if (overlap && net->conv0_precompute && net->use_tensor_cores) B200MVS_CUDA_OK(cudaStreamWaitEvent(stream, net->ev_pre, 0));
   if (s.do_refiners[4]) {
     RC(run_refiner(net, net->refiner[4], sc, n, h4, w4, ws.feat4, V, left_pyr[4], V, ws.raw_views, K_pyr[4], V,
-                   ws.refined_views, TAG_NONE, stream));
+                   ws.refined_views, TAG_NONE, stream, use_pre[4] ? ws.pre[4] : nullptr));
   }
 
   // 10. baseline un-normalisation, mean over views, mask vote (:616-627)
@@ -967,7 +1031,7 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
     if (s.do_refiners[l]) {
       const float* guide = (l == 0) ? nullptr : (l == 1 ? ws.f1 : (l == 2 ? ws.f2 : ws.f3));
       RC(run_refiner(net, net->refiner[l], sc, B, L.h[l], L.w[l], guide, 1, left_pyr[l], 1, prior_l[l], K_pyr[l], 1,
-                     idepth_l[l], l == 0 ? TAG_REFINE_CONV32_L0 : TAG_NONE, stream));
+                     idepth_l[l], l == 0 ? TAG_REFINE_CONV32_L0 : TAG_NONE, stream, use_pre[l] ? ws.pre[l] : nullptr));
     } else {
       B200MVS_CUDA_OK(cudaMemcpyAsync(idepth_l[l], prior_l[l], (size_t)B * L.px[l] * sizeof(float),
                                       cudaMemcpyDeviceToDevice, stream));
@@ -1041,6 +1105,8 @@ B200MVS_API int b200mvs_create(int device, int num_tensors, const char* const* n
         cudaEventCreateWithFlags(&net->ev_geo, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&net->ev_imgconv, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&net->ev_left, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&net->ev_pre, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&net->ev_right, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&net->ev_mask_in, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&net->ev_mask_out, cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithFlags(&net->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -1069,7 +1135,7 @@ B200MVS_API void b200mvs_destroy(b200mvs_net* net) {
   if (net->arena.base != nullptr) cudaFree(net->arena.base);
   if (net->host_stage != nullptr) cudaFree(net->host_stage);
   for (cudaEvent_t e : net->probe.ev) cudaEventDestroy(e);
-  for (cudaEvent_t e : {net->ev_geo, net->ev_imgconv, net->ev_fork, net->ev_left, net->ev_mask_in, net->ev_mask_out})
+  for (cudaEvent_t e : {net->ev_geo, net->ev_imgconv, net->ev_fork, net->ev_left, net->ev_pre, net->ev_right, net->ev_mask_in, net->ev_mask_out})
     if (e != nullptr) cudaEventDestroy(e);
   if (net->side != nullptr) cudaStreamDestroy(net->side);
   for (cudaEvent_t e : net->ev_up)
@@ -1098,6 +1164,10 @@ B200MVS_API int b200mvs_set_option(b200mvs_net* net, const char* name, int value
   }
   if (k == "warp_specialized") {
     net->warp_specialized = value != 0;
+    return 0;
+  }
+  if (k == "conv0_precompute") {
+    net->conv0_precompute = value != 0;
     return 0;
   }
   if (k == "half_activations") {

@@ -135,10 +135,12 @@ struct HeadParams {
 // Thread = (4 vertically adjacent output pixels, one channel octet): the octet's 8 weights of a (channel, tap) are
 // two shared-memory vector loads reused by 32 FFMAs; the four lanes of a quad cover a pixel's 32 channels, so stores
 // are full 64-byte (fp16) or 128-byte (fp32) pixel records.
-template <bool HALF>
+// NC = 4: image + prior * fx (the whole conv0).  NC = 3: image channels only (+ bias) -- the part of conv0 that does
+// not depend on the coarser level's result, computed ahead of time (see refine_head_pre_kernel).
+template <bool HALF, int NC>
 __global__ void __launch_bounds__(H_TH * H_TW, 4) refine_head_l0_kernel(const HeadParams p,
                                                                       const __grid_constant__ RefineHeadW W) {
-  __shared__ float s_in[4][H_TH + 2][H_TW + 2];
+  __shared__ float s_in[NC][H_TH + 2][H_TW + 2];
   __shared__ __align__(16) float s_w[4 * 9][32];
   __shared__ float s_bias[32];
   __shared__ double s_stats[2 * kGroups];
@@ -154,10 +156,10 @@ __global__ void __launch_bounds__(H_TH * H_TW, 4) refine_head_l0_kernel(const He
   const int tiles_x = cdiv(p.W, H_TW);
   const int tx0 = (blockIdx.x % tiles_x) * H_TW, ty0 = (blockIdx.x / tiles_x) * H_TH;
   const size_t plane = (size_t)p.H * p.W;
-  const float f = __ldg(p.fx + (size_t)(img / p.fx_div) * p.fx_stride);
+  const float f = NC == 4 ? __ldg(p.fx + (size_t)(img / p.fx_div) * p.fx_stride) : 1.0f;
   {
     // all loads of the tile are issued before any is stored: one memory round trip per CTA
-    constexpr int N_IN = 4 * (H_TH + 2) * (H_TW + 2);
+    constexpr int N_IN = NC * (H_TH + 2) * (H_TW + 2);
     constexpr int ITERS = (N_IN + H_TH * H_TW - 1) / (H_TH * H_TW);
     float v[ITERS];
 #pragma unroll
@@ -185,7 +187,7 @@ __global__ void __launch_bounds__(H_TH * H_TW, 4) refine_head_l0_kernel(const He
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[k][e] = s_bias[8 * o8 + e];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < NC; ++c) {
     float in[6][3];
 #pragma unroll
     for (int r = 0; r < 6; ++r)
@@ -233,6 +235,135 @@ __global__ void __launch_bounds__(H_TH * H_TW, 4) refine_head_l0_kernel(const He
   }
   if (p.out_stats != nullptr) {
     // lanes with equal (lane & 3) hold the same GroupNorm group
+#pragma unroll
+    for (int o = 16; o >= 4; o >>= 1) {
+      gs += __shfl_xor_sync(0xffffffffu, gs, o);
+      gq += __shfl_xor_sync(0xffffffffu, gq, o);
+    }
+    if ((tid & 31) < 4) {
+      atomicAdd(&s_stats[2 * o8 + 0], (double)gs);
+      atomicAdd(&s_stats[2 * o8 + 1], (double)gq);
+    }
+    __syncthreads();
+    if (tid < 2 * kGroups) atomicAdd(p.out_stats + (size_t)img * 2 * kGroups + tid, s_stats[tid]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// IDepthmapRefiner.conv0 with the guide part precomputed.  conv0 is linear in its input channels:
+//   conv0(cat[guide, idepth * fx]) = [conv(guide) + b] + conv(idepth * fx)
+// The bracket (35 of the 36 input channels at levels 1-4, 3 of 4 at level 0) depends only on the reference image and
+// its features, so it is computed on the side stream while the depth sweep runs (`pre`, fp32 channels-last).  What
+// is left on the critical path when the coarser level's idepth arrives is this kernel: 9 taps of one planar
+// channel per output, one read of `pre`, the GroupNorm statistics of the sum.  Same thread mapping as above.
+// ------------------------------------------------------------------------------------------------------------
+struct HeadPreParams {
+  const float* pre;     // [n / pre_div][H][W][32] fp32
+  int pre_div;
+  const float* prior;   // [n][H][W]
+  const float* fx;
+  int fx_div, fx_stride;
+  void* out;            // [n][H][W][32] fp16 or fp32
+  double* out_stats;    // [n][4][2]
+  int H, W;
+};
+
+template <bool HALF>
+__global__ void __launch_bounds__(H_TH * H_TW, 4) refine_head_pre_kernel(const HeadPreParams p,
+                                                                       const __grid_constant__ RefineHeadIdW W) {
+  __shared__ float s_in[H_TH + 2][H_TW + 2];
+  __shared__ __align__(16) float s_w[9][32];
+  __shared__ double s_stats[2 * kGroups];
+  const int tid = threadIdx.x, img = blockIdx.y;
+  for (int i = tid; i < 9 * 32; i += H_TH * H_TW) s_w[i >> 5][i & 31] = W.w[i];
+  if (tid < 2 * kGroups) s_stats[tid] = 0.0;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int tiles_x = cdiv(p.W, H_TW);
+  const int tx0 = (blockIdx.x % tiles_x) * H_TW, ty0 = (blockIdx.x / tiles_x) * H_TH;
+  const size_t plane = (size_t)p.H * p.W;
+  const float f = __ldg(p.fx + (size_t)(img / p.fx_div) * p.fx_stride);
+  const int o8 = tid & 3, g = tid >> 2;
+  const int lx = g % H_TW, ly0 = (g / H_TW) * 4;
+  const int ox = tx0 + lx;
+  // every global load of the thread is in flight before the first use
+  constexpr int N_IN = (H_TH + 2) * (H_TW + 2);
+  constexpr int ITERS = (N_IN + H_TH * H_TW - 1) / (H_TH * H_TW);
+  float v[ITERS];
+#pragma unroll
+  for (int k = 0; k < ITERS; ++k) {
+    const int i = tid + k * H_TH * H_TW;
+    const int x = i % (H_TW + 2), y = i / (H_TW + 2);
+    const int gy = ty0 - 1 + y, gx = tx0 - 1 + x;
+    v[k] = 0.f;
+    if (i < N_IN && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) v[k] = __ldg(p.prior + (size_t)img * plane + (size_t)gy * p.W + gx);
+  }
+  float acc[4][8];
+  const float* pre = p.pre + (size_t)(img / p.pre_div) * plane * kC + 8 * o8;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int oy = ty0 + ly0 + k;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (ox < p.W && oy < p.H) {
+      const float4* src = reinterpret_cast<const float4*>(pre + ((size_t)oy * p.W + ox) * kC);
+      a = __ldg(src);
+      b = __ldg(src + 1);
+    }
+    acc[k][0] = a.x; acc[k][1] = a.y; acc[k][2] = a.z; acc[k][3] = a.w;
+    acc[k][4] = b.x; acc[k][5] = b.y; acc[k][6] = b.z; acc[k][7] = b.w;
+  }
+#pragma unroll
+  for (int k = 0; k < ITERS; ++k) {
+    const int i = tid + k * H_TH * H_TW;
+    if (i < N_IN) s_in[i / (H_TW + 2)][i % (H_TW + 2)] = __fmul_rn(v[k], f);
+  }
+  __syncthreads();
+  {
+    float in[6][3];
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int x = 0; x < 3; ++x) in[r][x] = s_in[ly0 + r][lx + x];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float4 w0 = *reinterpret_cast<const float4*>(&s_w[t][8 * o8]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&s_w[t][8 * o8 + 4]);
+      const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float x = in[k + t / 3][t % 3];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[k][e] = fmaf(x, w[e], acc[k][e]);
+      }
+    }
+  }
+  float gs = 0.f, gq = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int oy = ty0 + ly0 + k;
+    if (ox < p.W && oy < p.H) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        gs += acc[k][e];
+        gq = fmaf(acc[k][e], acc[k][e], gq);
+      }
+      const size_t opix = ((size_t)img * p.H + oy) * p.W + ox;
+      if (HALF) {
+        uint32_t h[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const __half2 hh = __floats2half2_rn(acc[k][2 * q], acc[k][2 * q + 1]);
+          h[q] = *reinterpret_cast<const uint32_t*>(&hh);
+        }
+        *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + opix * kC + 8 * o8) = make_uint4(h[0], h[1], h[2], h[3]);
+      } else {
+        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix * kC + 8 * o8);
+        o[0] = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+        o[1] = make_float4(acc[k][4], acc[k][5], acc[k][6], acc[k][7]);
+      }
+    }
+  }
+  if (p.out_stats != nullptr) {
 #pragma unroll
     for (int o = 16; o >= 4; o >>= 1) {
       gs += __shfl_xor_sync(0xffffffffu, gs, o);
@@ -415,10 +546,53 @@ int launch_refine_head_l0(const float* image, const float* prior, const float* f
   p.W = W;
   dim3 grid(cdiv(W, H_TW) * cdiv(H, H_TH), n);
   if (out_half)
-    launch_pdl(refine_head_l0_kernel<true>, grid, dim3(H_TH * H_TW), (size_t)0, stream, p, w);
+    launch_pdl(refine_head_l0_kernel<true, 4>, grid, dim3(H_TH * H_TW), (size_t)0, stream, p, w);
   else
-    launch_pdl(refine_head_l0_kernel<false>, grid, dim3(H_TH * H_TW), (size_t)0, stream, p, w);
+    launch_pdl(refine_head_l0_kernel<false, 4>, grid, dim3(H_TH * H_TW), (size_t)0, stream, p, w);
   B200MVS_LAUNCH_OK("refine_head_l0_kernel");
+  return 0;
+}
+
+int launch_refine_head_image_l0(const float* image, const RefineHeadW& w, int n, int H, int W, float* pre,
+                                cudaStream_t stream) {
+  if (n <= 0) return 0;
+  HeadParams p;
+  p.image = image;
+  p.prior = nullptr;
+  p.fx = nullptr;
+  p.fx_div = 1;
+  p.fx_stride = 0;
+  p.out = pre;
+  p.out_stats = nullptr;
+  p.H = H;
+  p.W = W;
+  dim3 grid(cdiv(W, H_TW) * cdiv(H, H_TH), n);
+  launch_pdl(refine_head_l0_kernel<false, 3>, grid, dim3(H_TH * H_TW), (size_t)0, stream, p, w);
+  B200MVS_LAUNCH_OK("refine_head_l0_kernel<image>");
+  return 0;
+}
+
+int launch_refine_head_pre(const float* pre, int pre_div, const float* prior, const float* fx, int fx_div,
+                           int fx_stride, const RefineHeadIdW& w, int n, int H, int W, void* out, bool out_half,
+                           double* out_stats, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  HeadPreParams p;
+  p.pre = pre;
+  p.pre_div = pre_div;
+  p.prior = prior;
+  p.fx = fx;
+  p.fx_div = fx_div;
+  p.fx_stride = fx_stride;
+  p.out = out;
+  p.out_stats = out_stats;
+  p.H = H;
+  p.W = W;
+  dim3 grid(cdiv(W, H_TW) * cdiv(H, H_TH), n);
+  if (out_half)
+    launch_pdl(refine_head_pre_kernel<true>, grid, dim3(H_TH * H_TW), (size_t)0, stream, p, w);
+  else
+    launch_pdl(refine_head_pre_kernel<false>, grid, dim3(H_TH * H_TW), (size_t)0, stream, p, w);
+  B200MVS_LAUNCH_OK("refine_head_pre_kernel");
   return 0;
 }
 

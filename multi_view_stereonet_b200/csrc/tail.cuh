@@ -15,6 +15,10 @@ struct RefineHeadW {
   float w[32 * 4 * 9];
   float bias[32];
 };
+// The idepth channel of an IDepthmapRefiner.conv0 (the last input channel): w[tap * 32 + o].
+struct RefineHeadIdW {
+  float w[9 * 32];
+};
 struct CvfFinalW {
   float w[32 * 27];
   float bias;
@@ -31,6 +35,15 @@ int launch_refine_final(const void* y, const void* resid, bool half_io, const do
 int launch_refine_head_l0(const float* image, const float* prior, const float* fx, int fx_div, int fx_stride,
                           const RefineHeadW& w, int n, int H, int W, void* out, bool out_half, double* out_stats,
                           cudaStream_t stream);
+
+// conv0 split into its guide part and its idepth part (tail.cu: refine_head_pre_kernel).
+//   launch_refine_head_image_l0: pre = conv3x3(image) + b at level 0, fp32 channels-last (no statistics)
+//   launch_refine_head_pre:      y = pre[img / pre_div] + conv3x3(prior * fx; idepth-channel weights), statistics of y
+int launch_refine_head_image_l0(const float* image, const RefineHeadW& w, int n, int H, int W, float* pre,
+                                cudaStream_t stream);
+int launch_refine_head_pre(const float* pre, int pre_div, const float* prior, const float* fx, int fx_div,
+                           int fx_stride, const RefineHeadIdW& w, int n, int H, int W, void* out, bool out_half,
+                           double* out_stats, cudaStream_t stream);
 
 // cost1 = conv3d(lrelu(GN(y)), 32 -> 1) + b ; raw = soft-argmin over D (:350-352, 486-492).
 // `part` is scratch of n * D * 27 * h * w floats.
