@@ -497,7 +497,8 @@ struct StatsCursor {
 // pre[m / guide_div]); conv0 is then only the idepth channel on top of it.
 int run_refiner(b200mvs_net* net, const Refiner& R, StatsCursor& sc, int m, int H, int W, const float* guide_feat,
                 int guide_div, const float* image, int image_div, const float* prior, const float* Kl, int k_div,
-                float* out, int res_tag, cudaStream_t stream, const float* pre = nullptr) {
+                float* out, int res_tag, cudaStream_t stream, const float* pre = nullptr,
+                const float* coarse = nullptr, int ch = 0, int cw = 0) {
   Workspace& ws = net->ws;
   const size_t P = (size_t)H * W;
   const double inv_count = 1.0 / (8.0 * (double)P);
@@ -539,8 +540,9 @@ int run_refiner(b200mvs_net* net, const Refiner& R, StatsCursor& sc, int m, int 
   // conv0 sees the idepth channel scaled by fx (values of a few hundred with the signal in the low bits):
   // always split precision.
   if (pre != nullptr) {
-    RC(launch_refine_head_pre(pre, guide_div, prior, Kl, k_div, 16, R.idw, m, H, W, ws.ry[0], half_act != 0, st_prev,
-                              stream));
+    // with `coarse` the head also upsamples the coarser level's idepth into `prior` (one launch less per level)
+    RC(launch_refine_head_pre(pre, guide_div, prior, coarse, ch, cw, const_cast<float*>(prior), Kl, k_div, 16, R.idw, m, H,
+                              W, ws.ry[0], half_act != 0, st_prev, stream));
   } else if (guide_feat == nullptr && image_div == 1 && net->use_tensor_cores) {
     // level 0: four planar inputs only -- dedicated fp32 kernel (tail.cu)
     RC(launch_refine_head_l0(image, prior, Kl, k_div, 16, net->head0, m, H, W, ws.ry[0], half_act != 0, st_prev, stream));
@@ -1027,11 +1029,13 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
                             mask_stream));
   if (overlap && lowest_mask <= 3) B200MVS_CUDA_OK(cudaEventRecord(net->ev_mask_out, net->side));
   for (int l = 3; l >= 0; --l) {
-    RC(launch_upsample_f32(idepth_l[l + 1], B, L.h[l + 1], L.w[l + 1], L.h[l], L.w[l], prior_l[l], stream));
+    const bool fused_up = s.do_refiners[l] && use_pre[l];   // the refiner's head upsamples its own prior
+    if (!fused_up) RC(launch_upsample_f32(idepth_l[l + 1], B, L.h[l + 1], L.w[l + 1], L.h[l], L.w[l], prior_l[l], stream));
     if (s.do_refiners[l]) {
       const float* guide = (l == 0) ? nullptr : (l == 1 ? ws.f1 : (l == 2 ? ws.f2 : ws.f3));
       RC(run_refiner(net, net->refiner[l], sc, B, L.h[l], L.w[l], guide, 1, left_pyr[l], 1, prior_l[l], K_pyr[l], 1,
-                     idepth_l[l], l == 0 ? TAG_REFINE_CONV32_L0 : TAG_NONE, stream, use_pre[l] ? ws.pre[l] : nullptr));
+                     idepth_l[l], l == 0 ? TAG_REFINE_CONV32_L0 : TAG_NONE, stream, use_pre[l] ? ws.pre[l] : nullptr,
+                     fused_up ? idepth_l[l + 1] : nullptr, L.h[l + 1], L.w[l + 1]));
     } else {
       B200MVS_CUDA_OK(cudaMemcpyAsync(idepth_l[l], prior_l[l], (size_t)B * L.px[l] * sizeof(float),
                                       cudaMemcpyDeviceToDevice, stream));

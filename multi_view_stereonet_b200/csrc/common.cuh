@@ -154,6 +154,37 @@ __device__ __forceinline__ Bilinear bilinear_setup(const WarpCoord& c, int rows,
   return b;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Bilinear resize, align_corners=False (ATen upsample_bilinear2d): src = scale*(dst+0.5)-0.5
+// clamped at 0, i1 = i0 + (i0 < in-1), l1 = src - i0.
+// ---------------------------------------------------------------------------------------------
+struct Lerp {
+  int i0, i1;
+  float l0, l1;
+};
+__device__ __forceinline__ Lerp lerp_setup(int dst, float scale, int in_size) {
+  float src = __fsub_rn(__fmul_rn(scale, __fadd_rn((float)dst, 0.5f)), 0.5f);
+  src = src < 0.f ? 0.f : src;
+  Lerp r;
+  r.i0 = (int)src;
+  if (r.i0 > in_size - 1) r.i0 = in_size - 1;
+  r.i1 = r.i0 + (r.i0 < in_size - 1 ? 1 : 0);
+  r.l1 = __fsub_rn(src, (float)r.i0);
+  r.l0 = __fsub_rn(1.0f, r.l1);
+  return r;
+}
+// One output pixel of F.interpolate(size=(H, W), mode="bilinear", align_corners=False) of a (h, w) map
+// (Upsampler.forward, multi_view_stereonet.py:372-380); shared by the stand-alone upsampling kernel and the
+// refiner head that upsamples its prior on the fly, so both produce the same bits.
+__device__ __forceinline__ float upsample_bilinear_at(const float* __restrict__ src, int h, int w, int H, int W, int y,
+                                                      int x) {
+  const Lerp ly = lerp_setup(y, (float)h / (float)H, h);
+  const Lerp lx = lerp_setup(x, (float)w / (float)W, w);
+  const float v00 = __ldg(src + ly.i0 * w + lx.i0), v01 = __ldg(src + ly.i0 * w + lx.i1);
+  const float v10 = __ldg(src + ly.i1 * w + lx.i0), v11 = __ldg(src + ly.i1 * w + lx.i1);
+  return ly.l0 * (lx.l0 * v00 + lx.l1 * v01) + ly.l1 * (lx.l0 * v10 + lx.l1 * v11);
+}
+
 __device__ __forceinline__ float lrelu(float v) { return v > 0.0f ? v : kLreluSlope * v; }
 
 }  // namespace b200mvs

@@ -371,26 +371,6 @@ __global__ void __launch_bounds__(128) view_reduce_kernel(const float* __restric
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Bilinear resize, align_corners=False (ATen upsample_bilinear2d): src = scale*(dst+0.5)-0.5
-// clamped at 0, i1 = i0 + (i0 < in-1), l1 = src - i0.
-// ---------------------------------------------------------------------------------------------
-struct Lerp {
-  int i0, i1;
-  float l0, l1;
-};
-__device__ __forceinline__ Lerp lerp_setup(int dst, float scale, int in_size) {
-  float src = __fsub_rn(__fmul_rn(scale, __fadd_rn((float)dst, 0.5f)), 0.5f);
-  src = src < 0.f ? 0.f : src;
-  Lerp r;
-  r.i0 = (int)src;
-  if (r.i0 > in_size - 1) r.i0 = in_size - 1;
-  r.i1 = r.i0 + (r.i0 < in_size - 1 ? 1 : 0);
-  r.l1 = __fsub_rn(src, (float)r.i0);
-  r.l0 = __fsub_rn(1.0f, r.l1);
-  return r;
-}
-
 __global__ void __launch_bounds__(256) upsample_f32_kernel(const float* __restrict__ in, int h, int w, int H, int W,
                                                            float* __restrict__ out) {
   pdl_launch_dependents();
@@ -399,12 +379,7 @@ __global__ void __launch_bounds__(256) upsample_f32_kernel(const float* __restri
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= H * W) return;
   const int x = p % W, y = p / W;
-  const Lerp ly = lerp_setup(y, (float)h / (float)H, h);
-  const Lerp lx = lerp_setup(x, (float)w / (float)W, w);
-  const float* src = in + (size_t)plane * h * w;
-  const float v00 = __ldg(src + ly.i0 * w + lx.i0), v01 = __ldg(src + ly.i0 * w + lx.i1);
-  const float v10 = __ldg(src + ly.i1 * w + lx.i0), v11 = __ldg(src + ly.i1 * w + lx.i1);
-  out[(size_t)plane * H * W + p] = ly.l0 * (lx.l0 * v00 + lx.l1 * v01) + ly.l1 * (lx.l0 * v10 + lx.l1 * v11);
+  out[(size_t)plane * H * W + p] = upsample_bilinear_at(in + (size_t)plane * h * w, h, w, H, W, y, x);
 }
 
 // Mask volume upsampling: float(mask) -> bilinear -> > 0.5 (multi_view_stereonet.py:389-396).

@@ -260,7 +260,10 @@ __global__ void __launch_bounds__(H_TH * H_TW, 4) refine_head_l0_kernel(const He
 struct HeadPreParams {
   const float* pre;     // [n / pre_div][H][W][32] fp32
   int pre_div;
-  const float* prior;   // [n][H][W]
+  const float* prior;   // [n][H][W], read when coarse == nullptr
+  const float* coarse;  // [n][ch][cw]: the coarser level's idepth; the prior is its bilinear upsampling
+  int ch, cw;           // (Upsampler.forward, multi_view_stereonet.py:372-380, 630), computed on the fly and
+  float* prior_out;     // written to prior_out [n][H][W] for the tile interior ("left_idepthmap_raw_pyr")
   const float* fx;
   int fx_div, fx_stride;
   void* out;            // [n][H][W][32] fp16 or fp32
@@ -296,7 +299,14 @@ __global__ void __launch_bounds__(H_TH * H_TW, 4) refine_head_pre_kernel(const H
     const int x = i % (H_TW + 2), y = i / (H_TW + 2);
     const int gy = ty0 - 1 + y, gx = tx0 - 1 + x;
     v[k] = 0.f;
-    if (i < N_IN && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) v[k] = __ldg(p.prior + (size_t)img * plane + (size_t)gy * p.W + gx);
+    if (i < N_IN && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
+      if (p.coarse != nullptr) {
+        v[k] = upsample_bilinear_at(p.coarse + (size_t)img * p.ch * p.cw, p.ch, p.cw, p.H, p.W, gy, gx);
+        if (y >= 1 && y <= H_TH && x >= 1 && x <= H_TW) p.prior_out[(size_t)img * plane + (size_t)gy * p.W + gx] = v[k];
+      } else {
+        v[k] = __ldg(p.prior + (size_t)img * plane + (size_t)gy * p.W + gx);
+      }
+    }
   }
   float acc[4][8];
   const float* pre = p.pre + (size_t)(img / p.pre_div) * plane * kC + 8 * o8;
@@ -572,14 +582,18 @@ int launch_refine_head_image_l0(const float* image, const RefineHeadW& w, int n,
   return 0;
 }
 
-int launch_refine_head_pre(const float* pre, int pre_div, const float* prior, const float* fx, int fx_div,
-                           int fx_stride, const RefineHeadIdW& w, int n, int H, int W, void* out, bool out_half,
-                           double* out_stats, cudaStream_t stream) {
+int launch_refine_head_pre(const float* pre, int pre_div, const float* prior, const float* coarse, int ch, int cw,
+                           float* prior_out, const float* fx, int fx_div, int fx_stride, const RefineHeadIdW& w, int n,
+                           int H, int W, void* out, bool out_half, double* out_stats, cudaStream_t stream) {
   if (n <= 0) return 0;
   HeadPreParams p;
   p.pre = pre;
   p.pre_div = pre_div;
   p.prior = prior;
+  p.coarse = coarse;
+  p.ch = ch;
+  p.cw = cw;
+  p.prior_out = prior_out;
   p.fx = fx;
   p.fx_div = fx_div;
   p.fx_stride = fx_stride;

@@ -41,9 +41,11 @@ int launch_refine_head_l0(const float* image, const float* prior, const float* f
 //   launch_refine_head_pre:      y = pre[img / pre_div] + conv3x3(prior * fx; idepth-channel weights), statistics of y
 int launch_refine_head_image_l0(const float* image, const RefineHeadW& w, int n, int H, int W, float* pre,
                                 cudaStream_t stream);
-int launch_refine_head_pre(const float* pre, int pre_div, const float* prior, const float* fx, int fx_div,
-                           int fx_stride, const RefineHeadIdW& w, int n, int H, int W, void* out, bool out_half,
-                           double* out_stats, cudaStream_t stream);
+//                                coarse != nullptr: the prior is the bilinear upsampling of coarse (n, ch, cw),
+//                                computed on the fly and also written to prior_out (n, H, W); else `prior` is read
+int launch_refine_head_pre(const float* pre, int pre_div, const float* prior, const float* coarse, int ch, int cw,
+                           float* prior_out, const float* fx, int fx_div, int fx_stride, const RefineHeadIdW& w, int n,
+                           int H, int W, void* out, bool out_half, double* out_stats, cudaStream_t stream);
 
 // cost1 = conv3d(lrelu(GN(y)), 32 -> 1) + b ; raw = soft-argmin over D (:350-352, 486-492).
 // `part` is scratch of n * D * 27 * h * w floats.
