@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(NT, MINB) conv3x3_tc_kernel(const ConvParams p
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ float s_a[kC], s_b[kC], s_bias[kC];
   __shared__ double s_stats[2 * kGroups];
-  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ __align__(8) uint64_t s_bar, s_wbar;
   __shared__ uint32_t s_tmem;
 
   TC_STAMP(0);
@@ -128,19 +128,15 @@ __global__ void __launch_bounds__(NT, MINB) conv3x3_tc_kernel(const ConvParams p
   if (warp == 0) tc::tmem_alloc(&s_tmem, (uint32_t)TMEM_COLS);
   if (tid == 32) {
     tc::mbar_init(&s_bar, 1);
+    tc::mbar_init(&s_wbar, 1);
     tc::mbar_init_fence();
+    // weights (already in the canonical fp16 layout): constant data, fetched by the copy engine; the MMA lane waits
+    tc::bulk_load_weights(s_w, w16, w_bytes, &s_wbar);
   }
   if (tid < kC) s_bias[tid] = p.bias != nullptr ? __ldg(p.bias + tid) : 0.f;
   if (tid < 2 * kGroups) s_stats[tid] = 0.0;
   __syncthreads();
   pdl_launch_dependents();   // after the TMEM allocation (see common.cuh)
-
-  // ---- stage weights (already in the canonical fp16 layout) ----
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(w16);
-    uint4* dst = reinterpret_cast<uint4*>(s_w);
-    for (int i = tid; i < (int)(w_bytes / 16); i += NT) dst[i] = __ldg(src + i);
-  }
   TC_STAMP(1);
   pdl_wait();
   TC_STAMP(2);
@@ -277,6 +273,7 @@ __global__ void __launch_bounds__(NT, MINB) conv3x3_tc_kernel(const ConvParams p
     const uint64_t da0 = tc::umma_desc(tc::smem_u32(s_in), plane_bytes, 128u);
     const uint64_t da_lo0 = da0 + (uint64_t)(set_planes * plane_u16);
     const uint64_t db0 = tc::umma_desc(tc::smem_u32(s_w), SPLIT ? 1024u : 512u, 128u);
+    tc::mbar_wait(&s_wbar, 0u);   // the bulk-copied weights have landed
 #pragma unroll 1
     for (int mt = 0; mt < MT; ++mt) {
       const uint32_t dcol = tmem_base + (uint32_t)(mt * ACC_COLS);

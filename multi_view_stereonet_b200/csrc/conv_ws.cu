@@ -32,9 +32,9 @@ constexpr int NT = (N_EPI + 2 + N_XF) * 32;
 constexpr int NXF_T = N_XF * 32;
 constexpr uint32_t W_BYTES = 9u * 2u * 1024u;
 constexpr int MAX_STAGES = 2;
-constexpr int RING = 6;                        // raw chunks (2 tile rows of y and of resid) in flight
+constexpr int MAX_RING = 6;                    // raw chunks (2 tile rows of y and of resid) in flight, at most
 constexpr uint32_t CHUNK_HALF = 2u * PW * 64u;  // one tensor's part of a chunk: 2 rows x 64 positions x 64 B
-constexpr uint32_t RING_BYTES = RING * 2u * CHUNK_HALF;
+__host__ __device__ inline uint32_t ring_bytes(int ring) { return (uint32_t)ring * 2u * CHUNK_HALF; }
 constexpr size_t kSmemBudget = 220 * 1024;
 
 // positions per plane, padded to 2 (mod 8): consecutive planes then start 32 bytes apart modulo 128, so the four
@@ -99,7 +99,7 @@ struct WsParams {
   const float* bias;
   double inv_count;
   int n_img, H, W, dil;
-  int tiles_x, tiles_y, stages, has_res, prof;
+  int tiles_x, tiles_y, stages, ring, has_res, prof;
   int dbg;   // timing ablations (wrong results): 1 transform warps only wait / arrive, 2 no MMAs, 4 no output stores
 };
 
@@ -111,8 +111,9 @@ __global__ void __launch_bounds__(NT, 1) conv3x3_ws_kernel(const WsParams p, con
   constexpr int ACC_COLS = MT * 32;      // TMEM columns of one accumulator set
   constexpr uint32_t TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t s_raw[RING], s_rfree[RING], s_full[MAX_STAGES], s_empty[MAX_STAGES], s_tfull[2],
+  __shared__ __align__(8) uint64_t s_raw[MAX_RING], s_rfree[MAX_RING], s_full[MAX_STAGES], s_empty[MAX_STAGES], s_tfull[2],
       s_tempty[2];
+  __shared__ __align__(8) uint64_t s_wbar;   // bulk copy of the weights
   __shared__ float s_bias[kC];
   __shared__ uint32_t s_tmem;
 
@@ -129,12 +130,13 @@ __global__ void __launch_bounds__(NT, 1) conv3x3_ws_kernel(const WsParams p, con
   const int total = tiles_img * p.n_img;
   uint8_t* s_w = smem;
   uint8_t* s_ring = smem + W_BYTES;            // [slot][y | resid][2 rows][64 positions][32 channels]
-  uint8_t* s_st = smem + W_BYTES + RING_BYTES;
+  const int RING = p.ring;
+  uint8_t* s_st = smem + W_BYTES + ring_bytes(RING);
 
   // ---- prologue: nothing here depends on earlier kernels ----
   if (warp == 0) tc::tmem_alloc(&s_tmem, TMEM_COLS);
   if (tid == 32) {
-    for (int q = 0; q < RING; ++q) {
+    for (int q = 0; q < MAX_RING; ++q) {
       tc::mbar_init(&s_raw[q], 1);
       tc::mbar_init(&s_rfree[q], NXF_T);
     }
@@ -146,13 +148,15 @@ __global__ void __launch_bounds__(NT, 1) conv3x3_ws_kernel(const WsParams p, con
       tc::mbar_init(&s_tfull[a], 1);
       tc::mbar_init(&s_tempty[a], N_EPI * 32);
     }
+    tc::mbar_init(&s_wbar, 1);
     tc::mbar_init_fence();
+    // constant data, fetched by the copy engine while the CTA sets itself up; only the MMA lane waits for it.
+    // Two of these CTAs cannot share an SM, so this prologue runs AFTER the previous layer's CTA has left the SM --
+    // on the critical path between two layers.
+    tc::bulk_load_weights(s_w, w16, W_BYTES, &s_wbar);
   }
   if (tid < kC) s_bias[tid] = p.bias != nullptr ? __ldg(p.bias + tid) : 0.f;
   {
-    const uint4* src = reinterpret_cast<const uint4*>(w16);
-    uint4* dst = reinterpret_cast<uint4*>(s_w);
-    for (int i = tid; i < (int)(W_BYTES / 16); i += NT) dst[i] = __ldg(src + i);
     // the tail positions past the last staged row are read by the garbage columns only; keep them zero
     const int tail = npos - rows_in * PW;
     for (int i = tid; i < S * 4 * tail; i += NT) {
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(NT, 1) conv3x3_ws_kernel(const WsParams p, con
     float ca[8], cb[8];
     int cur_img = -1;
     int it = 0;
-    uint32_t cq = 0;   // running chunk counter (ring slot = cq % RING)
+    uint32_t q = 0, qph = 0;   // ring slot of the running chunk counter and the parity of its lap
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
       const int s = it % S;
       const int img = t / tiles_img, tt = t - img * tiles_img;
@@ -215,9 +219,8 @@ __global__ void __launch_bounds__(NT, 1) conv3x3_ws_kernel(const WsParams p, con
                                             ((ptrdiff_t)(ty0 - d) * p.W + (col_ok ? gx : 0)) * kC + 8 * c8
                                       : nullptr;
       tc::mbar_wait_warp(&s_empty[s], (uint32_t)(((it / S) & 1) ^ 1));   // the MMAs that read this stage completed
-      for (int c = 0; c < nchunks; ++c, ++cq) {
-        const uint32_t q = cq % RING;
-        tc::mbar_wait_warp(&s_raw[q], (cq / RING) & 1u);   // this chunk's TMA boxes have landed
+      for (int c = 0; c < nchunks; ++c) {
+        tc::mbar_wait_warp(&s_raw[q], qph);   // this chunk's TMA boxes have landed
         if (c == 0) WS_STAMP(xw == 0 && lane == 0, 1);
         const int r = 2 * c + rr;
         const int gy = ty0 - d + r;
@@ -239,6 +242,10 @@ __global__ void __launch_bounds__(NT, 1) conv3x3_ws_kernel(const WsParams p, con
         }
         if (!(p.dbg & 1)) *reinterpret_cast<uint4*>(xpl + (size_t)r * (PW * 16)) = h;
         mbar_arrive(&s_rfree[q]);   // this thread is done reading the slot
+        if (++q == (uint32_t)RING) {
+          q = 0;
+          qph ^= 1u;
+        }
       }
       tc::fence_proxy_async();
       mbar_arrive(&s_full[s]);
@@ -250,19 +257,22 @@ __global__ void __launch_bounds__(NT, 1) conv3x3_ws_kernel(const WsParams p, con
       const uint32_t tx_bytes = (p.has_res ? 2u : 1u) * CHUNK_HALF;
       const int nchunks = rows_in / 2;
       int it = 0;
-      uint32_t cq = 0;
+      uint32_t q = 0, qph = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
         const int img = t / tiles_img, tt = t - img * tiles_img;
         const int tyi = tt / p.tiles_x;
         const int tx0 = (tt - tyi * p.tiles_x) * TW, ty0 = tyi * TH;
-        for (int c = 0; c < nchunks; ++c, ++cq) {
-          const uint32_t q = cq % RING;
-          tc::mbar_wait(&s_rfree[q], ((cq / RING) & 1u) ^ 1u);   // every transform warp has read the slot
+        for (int c = 0; c < nchunks; ++c) {
+          tc::mbar_wait(&s_rfree[q], qph ^ 1u);   // every transform warp has read the slot
           mbar_arrive_tx(&s_raw[q], tx_bytes);
           if (c == 0) WS_STAMP(true, 0);
           uint8_t* slot = s_ring + (size_t)q * 2u * CHUNK_HALF;
           tma_load_4d(slot, &tm_y, 0, tx0 - d, ty0 - d + 2 * c, img, &s_raw[q]);
           if (p.has_res) tma_load_4d(slot + CHUNK_HALF, &tm_r, 0, tx0 - d, ty0 - d + 2 * c, img, &s_raw[q]);
+          if (++q == (uint32_t)RING) {
+            q = 0;
+            qph ^= 1u;
+          }
         }
       }
     }
@@ -273,6 +283,7 @@ __global__ void __launch_bounds__(NT, 1) conv3x3_ws_kernel(const WsParams p, con
       const uint32_t plane_u16 = plane_bytes >> 4;
       const uint64_t da0 = tc::umma_desc(tc::smem_u32(s_st), plane_bytes, 128u);   // stage and plane strides: 16 B units
       const uint64_t db0 = tc::umma_desc(tc::smem_u32(s_w), 512u, 128u);
+      tc::mbar_wait(&s_wbar, 0u);   // the bulk-copied weights have landed
       int it = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
         const int s = it % S;
@@ -428,19 +439,26 @@ bool make_map(const void* base, int n, int H, int W, CUtensorMap* out) {
 }
 
 struct WsPlan {
-  int th, stages;
+  int th, stages, ring;
 };
-bool plan_for(int dil, WsPlan* plan) {
-  const size_t budget = kSmemBudget - W_BYTES - RING_BYTES;
-  const int ths[2] = {8, 4};
-  // prefer two stages (loads of the next tile overlap this tile's transform and MMAs), then the taller tile
-  for (int want = 2; want >= 1; --want)
-    for (int k = 0; k < 2; ++k)
-      if ((size_t)want * ws_stage_bytes(ths[k], dil) <= budget) {
-        plan->th = ths[k];
-        plan->stages = want;
-        return true;
-      }
+// Shared memory = weights + ring + stages.  Preference (measured on level 0, 512x640): two stages so that the loads /
+// transform of the next tile overlap this tile's MMAs, and the taller the tile the smaller the share of halo rows
+// that is loaded and transformed twice ((TH + 2 dil) / TH); a four-slot ring costs ~5 % against six slots, far less
+// than a second stage or a taller tile gain at dilation 4 (level 0: 42.5 -> 34.0 us per layer).
+bool plan_for(int dil, int H, int W, int n_img, WsPlan* plan) {
+  // (16-row single-stage tiles at dilation 8 were measured equal to 8-row ones: 54.7 vs 54.2 us per level-0 layer)
+  static const WsPlan prefs[] = {{8, 2, 6}, {8, 2, 4}, {4, 2, 6}, {8, 1, 6}, {4, 2, 4}, {4, 1, 6}};
+  static const int force = getenv("B200MVS_WS_PLAN") ? atoi(getenv("B200MVS_WS_PLAN")) : -1;   // A/B: index into prefs
+  for (int k = 0; k < (int)(sizeof(prefs) / sizeof(prefs[0])); ++k) {
+    const WsPlan& c = prefs[k];
+    if (force >= 0 && k < force && dil >= 4) continue;
+    // worth it only when every SM gets at least one tile; smaller layers are latency bound either way
+    if ((long long)cdiv(W, PW - 2 * dil) * cdiv(H, c.th) * n_img < 148) continue;
+    if (W_BYTES + ring_bytes(c.ring) + (size_t)c.stages * ws_stage_bytes(c.th, dil) <= kSmemBudget) {
+      *plan = c;
+      return true;
+    }
+  }
   return false;
 }
 
@@ -479,10 +497,7 @@ bool conv3x3_ws_supported(const ConvParams& p) {
   if (p.Di != 1 || p.Do != 1 || p.Hi != p.Ho || p.Wi != p.Wo || p.dil < 1 || p.dil > 8) return false;
   if (p.add_src != nullptr || p.out_img_stride != 0 || p.feat.img_div != 1) return false;
   WsPlan plan;
-  if (!plan_for(p.dil, &plan) || encode_fn() == nullptr) return false;
-  // Worth it only when every SM gets at least one tile; smaller layers are latency bound either way.
-  const long long tiles = (long long)cdiv(p.Wo, PW - 2 * p.dil) * cdiv(p.Ho, plan.th) * p.n_img;
-  return tiles >= 148;
+  return plan_for(p.dil, p.Hi, p.Wi, p.n_img, &plan) && encode_fn() != nullptr;
 }
 
 int launch_conv3x3_ws(const ConvParams& p, const uint8_t* w16, cudaStream_t stream) {
@@ -493,7 +508,7 @@ int launch_conv3x3_ws(const ConvParams& p, const uint8_t* w16, cudaStream_t stre
   }
   const bool has_res = p.feat.mode == FEAT_GN_RES;
   WsPlan plan;
-  plan_for(p.dil, &plan);
+  plan_for(p.dil, p.Hi, p.Wi, p.n_img, &plan);
   WsParams q;
   q.x_out = reinterpret_cast<__half*>(p.feat.x_out);
   q.out = reinterpret_cast<__half*>(p.out);
@@ -510,6 +525,7 @@ int launch_conv3x3_ws(const ConvParams& p, const uint8_t* w16, cudaStream_t stre
   q.tiles_x = cdiv(p.Wo, PW - 2 * p.dil);
   q.tiles_y = cdiv(p.Ho, plan.th);
   q.stages = plan.stages;
+  q.ring = plan.ring;
   q.has_res = has_res ? 1 : 0;
   static const bool prof = getenv("B200MVS_WS_PROFILE") != nullptr;
   q.prof = prof ? 1 : 0;
@@ -521,7 +537,7 @@ int launch_conv3x3_ws(const ConvParams& p, const uint8_t* w16, cudaStream_t stre
     set_error("launch_conv3x3_ws: cuTensorMapEncodeTiled failed");
     return -1;
   }
-  const size_t smem = W_BYTES + RING_BYTES + (size_t)plan.stages * ws_stage_bytes(plan.th, p.dil);
+  const size_t smem = W_BYTES + ring_bytes(plan.ring) + (size_t)plan.stages * ws_stage_bytes(plan.th, p.dil);
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;

@@ -37,8 +37,9 @@ __device__ __forceinline__ void accumulate(float est_in, float gt_in, float base
   const float thresh = fmaxf(__fdiv_rn(gt, depth), __fdiv_rn(depth, gt));
   const float diff = __fsub_rn(gt, depth);
   const float sq = __fmul_rn(diff, diff);
-  // float32 logarithms rounded from the float64 value (numpy's float32 log is accurate to < 1 ulp)
-  const float dl = __fsub_rn((float)log((double)gt), (float)log((double)depth));
+  // float32 logarithms as numpy takes them (both implementations are accurate to 1 ulp, neither is correctly
+  // rounded; the float64 route costs 4x the kernel time for no gain in agreement)
+  const float dl = __fsub_rn(logf(gt), logf(depth));
   acc[0] += (double)__fdiv_rn(fabsf(diff), gt);
   acc[1] += (double)__fdiv_rn(sq, gt);
   acc[2] += (double)sq;
