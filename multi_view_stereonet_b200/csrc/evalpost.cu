@@ -147,6 +147,16 @@ int depth_metrics_ctas(long long pixels) {
   return (int)n;
 }
 
+// Per-device scratch for the per-CTA partial sums and the per-image arrival counters, grown on demand and kept
+// (a stream-ordered cudaMallocAsync / cudaFreeAsync pair per call cost ~160 us against a ~15 us kernel).  The
+// counters are zeroed when the buffer is created; the kernel leaves them at zero.  Calls on one device must not
+// overlap on different streams (one process per GPU, one evaluation loop).
+struct EvalScratch {
+  char* base = nullptr;
+  size_t capacity = 0;
+};
+static EvalScratch g_scratch[64];
+
 int launch_depth_metrics(const float* est, const float* baseline, const float* depth_true, bool est_is_depth,
                          float min_depth, float max_depth, int batch, long long pixels, float* idepth_out,
                          float* depth_out, double* metrics, cudaStream_t stream) {
@@ -156,19 +166,36 @@ int launch_depth_metrics(const float* est, const float* baseline, const float* d
   unsigned int* counters = nullptr;
   const bool reduce = metrics != nullptr && depth_true != nullptr;
   if (reduce) {
-    // stream-ordered scratch: per-CTA partial sums and one arrival counter per image
-    const size_t pbytes = (size_t)batch * ctas * kSums * sizeof(double);
-    char* scratch = nullptr;
-    B200MVS_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&scratch), pbytes + (size_t)batch * sizeof(unsigned int), stream));
-    partials = reinterpret_cast<double*>(scratch);
-    counters = reinterpret_cast<unsigned int*>(scratch + pbytes);
-    B200MVS_CUDA_OK(cudaMemsetAsync(counters, 0, (size_t)batch * sizeof(unsigned int), stream));
+    int dev = 0;
+    B200MVS_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) {
+      set_error("b200mvs_depth_metrics: device index out of range");
+      return -1;
+    }
+    EvalScratch& sc = g_scratch[dev];
+    // a fixed 64 KB of counters first (always zero between calls), the partial sums after them
+    constexpr size_t poff = 65536;
+    if ((size_t)batch * sizeof(unsigned int) > poff) {
+      set_error("b200mvs_depth_metrics: at most 16384 images per call");
+      return -1;
+    }
+    const size_t need = poff + (size_t)batch * ctas * kSums * sizeof(double);
+    if (need > sc.capacity) {
+      if (sc.base != nullptr) B200MVS_CUDA_OK(cudaFree(sc.base));   // waits for kernels still using it
+      sc.base = nullptr;
+      sc.capacity = 0;
+      const size_t cap = need < (1u << 20) ? (1u << 20) : need;
+      B200MVS_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&sc.base), cap));
+      B200MVS_CUDA_OK(cudaMemset(sc.base, 0, cap));
+      sc.capacity = cap;
+    }
+    counters = reinterpret_cast<unsigned int*>(sc.base);
+    partials = reinterpret_cast<double*>(sc.base + poff);
   }
   launch_pdl(depth_metrics_kernel, dim3(ctas, batch), dim3(kThreads), (size_t)0, stream, est, baseline, depth_true,
              est_is_depth ? 1 : 0, min_depth, max_depth, pixels, idepth_out, depth_out, reduce ? metrics : (double*)nullptr,
              partials, counters);
   B200MVS_LAUNCH_OK("depth_metrics_kernel");
-  if (reduce) B200MVS_CUDA_OK(cudaFreeAsync(partials, stream));
   return 0;
 }
 
