@@ -97,7 +97,6 @@ __global__ void __launch_bounds__(NT, MINB) conv3x3_tc_kernel(const ConvParams p
   constexpr uint32_t WBLOCK = SPLIT ? 2048u : 1024u;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ float s_a[kC], s_b[kC], s_bias[kC];
-  __shared__ double s_stats[2 * kGroups];
   __shared__ __align__(8) uint64_t s_bar, s_wbar;
   __shared__ uint32_t s_tmem;
 
@@ -134,12 +133,50 @@ __global__ void __launch_bounds__(NT, MINB) conv3x3_tc_kernel(const ConvParams p
     tc::bulk_load_weights(s_w, w16, w_bytes, &s_wbar);
   }
   if (tid < kC) s_bias[tid] = p.bias != nullptr ? __ldg(p.bias + tid) : 0.f;
-  if (tid < 2 * kGroups) s_stats[tid] = 0.0;
   __syncthreads();
   pdl_launch_dependents();   // after the TMEM allocation (see common.cuh)
   TC_STAMP(1);
   pdl_wait();
   TC_STAMP(2);
+  const size_t vol = (size_t)p.Hi * p.Wi;
+  const int rows_in = TH + 2 * d;
+  // ---- stage the transformed 32-channel source ----
+  // The raw loads of a batch do not depend on the GroupNorm coefficients: the first batch is issued before the
+  // coefficients (two statistics loads + float64 math by 32 threads, then a block barrier) are awaited, so the two
+  // memory round trips overlap instead of following each other.
+  const bool hio = p.feat.half_io != 0;
+  const size_t esz = hio ? 2 : 4;   // bytes per stored activation element
+  const uint8_t* fbase = has_feat ? reinterpret_cast<const uint8_t*>(p.feat.ptr) + (size_t)(img / p.feat.img_div) * vol * kC * esz
+                                  : nullptr;
+  const uint8_t* rbase = p.feat.resid != nullptr
+                             ? reinterpret_cast<const uint8_t*>(p.feat.resid) + (size_t)img * vol * kC * esz : nullptr;
+  uint8_t* xbase = p.feat.x_out != nullptr ? reinterpret_cast<uint8_t*>(p.feat.x_out) + (size_t)img * vol * kC * esz
+                                           : nullptr;
+  constexpr int BATCH = MINB >= 3 ? 2 : 4;   // tasks whose global loads are all issued before any is consumed
+  float4 ya[BATCH], yb[BATCH], ra[BATCH], rb[BATCH];   // fp32: two float4; fp16: ya / ra hold 8 halves
+  size_t off[BATCH];
+  bool inb[BATCH];
+  auto issue_loads = [&](int i0) {
+#pragma unroll
+    for (int k = 0; k < BATCH; ++k) {
+      const int i = i0 + k * NT;
+      const int c8 = i & 3;
+      const int L = i >> 2;
+      const int iy = L / PW, ix = L % PW;
+      const int gy = ty0 - d + iy, gx = tx0 - d + ix;
+      inb[k] = i < npos * 4 && iy < rows_in && gy >= 0 && gy < p.Hi && gx >= 0 && gx < p.Wi;
+      off[k] = inb[k] ? (((size_t)gy * p.Wi + gx) * kC + 8 * c8) * esz : 0;
+      if (inb[k]) {
+        ya[k] = __ldg(reinterpret_cast<const float4*>(fbase + off[k]));
+        if (!hio) yb[k] = __ldg(reinterpret_cast<const float4*>(fbase + off[k] + 16));
+        if (mode == FEAT_GN_RES) {
+          ra[k] = __ldg(reinterpret_cast<const float4*>(rbase + off[k]));
+          if (!hio) rb[k] = __ldg(reinterpret_cast<const float4*>(rbase + off[k] + 16));
+        }
+      }
+    }
+  };
+  if (has_feat) issue_loads(tid);
   if (tid < kC && mode >= FEAT_GN) {
     const int grp = tid >> 3;
     const double sum = p.feat.stats[(img * kGroups + grp) * 2 + 0];
@@ -153,40 +190,9 @@ __global__ void __launch_bounds__(NT, MINB) conv3x3_tc_kernel(const ConvParams p
   }
   __syncthreads();
   TC_STAMP(3);
-  const size_t vol = (size_t)p.Hi * p.Wi;
-  const int rows_in = TH + 2 * d;
-  // ---- stage the transformed 32-channel source ----
   if (has_feat) {
-    const bool hio = p.feat.half_io != 0;
-    const size_t esz = hio ? 2 : 4;   // bytes per stored activation element
-    const uint8_t* fbase = reinterpret_cast<const uint8_t*>(p.feat.ptr) + (size_t)(img / p.feat.img_div) * vol * kC * esz;
-    const uint8_t* rbase = p.feat.resid != nullptr
-                               ? reinterpret_cast<const uint8_t*>(p.feat.resid) + (size_t)img * vol * kC * esz : nullptr;
-    uint8_t* xbase = p.feat.x_out != nullptr ? reinterpret_cast<uint8_t*>(p.feat.x_out) + (size_t)img * vol * kC * esz
-                                             : nullptr;
-    constexpr int BATCH = MINB >= 3 ? 2 : 4;   // tasks whose global loads are all issued before any is consumed
     for (int i0 = tid; i0 < npos * 4; i0 += NT * BATCH) {
-      float4 ya[BATCH], yb[BATCH], ra[BATCH], rb[BATCH];   // fp32: two float4; fp16: ya / ra hold 8 halves
-      size_t off[BATCH];
-      bool inb[BATCH];
-#pragma unroll
-      for (int k = 0; k < BATCH; ++k) {
-        const int i = i0 + k * NT;
-        const int c8 = i & 3;
-        const int L = i >> 2;
-        const int iy = L / PW, ix = L % PW;
-        const int gy = ty0 - d + iy, gx = tx0 - d + ix;
-        inb[k] = i < npos * 4 && iy < rows_in && gy >= 0 && gy < p.Hi && gx >= 0 && gx < p.Wi;
-        off[k] = inb[k] ? (((size_t)gy * p.Wi + gx) * kC + 8 * c8) * esz : 0;
-        if (inb[k]) {
-          ya[k] = __ldg(reinterpret_cast<const float4*>(fbase + off[k]));
-          if (!hio) yb[k] = __ldg(reinterpret_cast<const float4*>(fbase + off[k] + 16));
-          if (mode == FEAT_GN_RES) {
-            ra[k] = __ldg(reinterpret_cast<const float4*>(rbase + off[k]));
-            if (!hio) rb[k] = __ldg(reinterpret_cast<const float4*>(rbase + off[k] + 16));
-          }
-        }
-      }
+      if (i0 != tid) issue_loads(i0);
 #pragma unroll
       for (int k = 0; k < BATCH; ++k) {
         const int i = i0 + k * NT;
@@ -373,18 +379,18 @@ __global__ void __launch_bounds__(NT, MINB) conv3x3_tc_kernel(const ConvParams p
         gsq[g] += __shfl_xor_sync(0xffffffffu, gsq[g], o);
       }
     }
-    if (lane == 0) {
+    // every warp adds its totals straight to the layer's statistics (8 reductions in flight per warp, nothing waits
+    // for them but the end of the kernel): lane 2g adds the sum of group g, lane 2g + 1 its sum of squares
+    if (lane < 2 * kGroups) {
+      float v = 0.f;
 #pragma unroll
-      for (int g = 0; g < kGroups; ++g) {
-        atomicAdd(&s_stats[2 * g + 0], (double)gsum[g]);
-        atomicAdd(&s_stats[2 * g + 1], (double)gsq[g]);
-      }
+      for (int g = 0; g < kGroups; ++g)
+        if ((lane >> 1) == g) v = (lane & 1) ? gsq[g] : gsum[g];
+      atomicAdd(p.out_stats + (size_t)img * 2 * kGroups + lane, (double)v);
     }
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (p.out_stats != nullptr && tid < 2 * kGroups)
-    atomicAdd(p.out_stats + (size_t)img * 2 * kGroups + tid, s_stats[tid]);
   TC_STAMP(7);
   if (warp == 0) tc::tmem_dealloc(tmem_base, (uint32_t)TMEM_COLS);
 }
