@@ -76,7 +76,7 @@ struct Shared {
   float delta;
 };
 
-__global__ void __launch_bounds__(128) geometry_kernel(ViewPtrs T, const float* __restrict__ K0p,
+__global__ void __launch_bounds__(640) geometry_kernel(ViewPtrs T, const float* __restrict__ K0p,
                                                        const float* __restrict__ K4p, int D, int rows4, int cols4,
                                                        GeomOut out) {
   pdl_launch_dependents();
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(128) geometry_kernel(ViewPtrs T, const float* 
 
 int launch_geometry(const ViewPtrs& T, const float* K0, const float* K4, int batch, int D, int rows4, int cols4,
                     const GeomOut& out, cudaStream_t stream) {
-  launch_pdl(geometry_kernel, dim3(batch * T.views), dim3(128), (size_t)0, stream, T, K0, K4, D, rows4, cols4, out);
+  launch_pdl(geometry_kernel, dim3(batch * T.views), dim3(640), (size_t)0, stream, T, K0, K4, D, rows4, cols4, out);
   B200MVS_LAUNCH_OK("geometry_kernel");
   return 0;
 }
