@@ -151,6 +151,7 @@ struct b200mvs_net {
   bool use_tensor_cores = true;
   bool half_activations = true;
   bool warp_specialized = true;
+  bool left_late = true;          // left feature network waits for the right one (side stream)
   bool conv0_precompute = true;   // refiner conv0 = precomputed guide part + idepth part (tail.cu)
   int rec_debug = 0;
   // Side stream for the work that does not depend on the comparison views (left feature network) or that
@@ -811,6 +812,9 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
   mark("geometry+warp+right featnet");
   // 3a. FeatureNetwork on the B left images (multi_view_stereonet.py:552): side stream, needed by the cost volume
   //     (enqueued after the critical path's launches)
+  //     and not started before the right feature network is through: its 1-CTA-per-SM kernels would take SMs
+  //     from the critical path, while nothing needs the left features before the sweep (~0.86 ms) has finished
+  if (overlap && net->left_late) B200MVS_CUDA_OK(cudaStreamWaitEvent(net->side, net->ev_right, 0));
   RC(wait_upload(3, left_stream));
   RC(run_featnet(net, L, 0, B, left_pyr[0], tail_stats, ws.feat4, 0, left_stream));
   if (overlap) B200MVS_CUDA_OK(cudaEventRecord(net->ev_left, net->side));
@@ -1168,6 +1172,10 @@ B200MVS_API int b200mvs_set_option(b200mvs_net* net, const char* name, int value
   }
   if (k == "warp_specialized") {
     net->warp_specialized = value != 0;
+    return 0;
+  }
+  if (k == "left_late") {
+    net->left_late = value != 0;
     return 0;
   }
   if (k == "conv0_precompute") {

@@ -228,8 +228,15 @@ __global__ void __launch_bounds__(H_TH * H_TW, 4) refine_head_l0_kernel(const He
         *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + opix * kC + 8 * o8) = make_uint4(h[0], h[1], h[2], h[3]);
       } else {
         float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix * kC + 8 * o8);
-        o[0] = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
-        o[1] = make_float4(acc[k][4], acc[k][5], acc[k][6], acc[k][7]);
+        if (NC == 3) {
+          // the precomputed guide part (42 MB at 512x640) is read ~1.5 ms later: streaming stores, so that it does not
+          // push the depth sweep's working set (feature volume, image half of conv0) out of L2 while the sweep runs
+          __stcs(o, make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]));
+          __stcs(o + 1, make_float4(acc[k][4], acc[k][5], acc[k][6], acc[k][7]));
+        } else {
+          o[0] = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+          o[1] = make_float4(acc[k][4], acc[k][5], acc[k][6], acc[k][7]);
+        }
       }
     }
   }
