@@ -151,13 +151,14 @@ struct b200mvs_net {
   bool use_tensor_cores = true;
   bool half_activations = true;
   bool warp_specialized = true;
+  bool early_d2h = true;          // forward_host: levels 1-4 downloaded on the copy stream next to the level-0 refiner
   bool left_late = true;          // left feature network waits for the right one (side stream)
   bool conv0_precompute = true;   // refiner conv0 = precomputed guide part + idepth part (tail.cu)
   int rec_debug = 0;
   // Side stream for the work that does not depend on the comparison views (left feature network) or that
   // nothing downstream waits for (mask upsampling): forked / joined with events inside one forward.
   cudaStream_t side = nullptr;
-  cudaEvent_t ev_pre = nullptr, ev_right = nullptr;
+  cudaEvent_t ev_pre = nullptr, ev_right = nullptr, ev_coarse = nullptr;
   cudaEvent_t ev_geo = nullptr, ev_imgconv = nullptr, ev_fork = nullptr, ev_left = nullptr, ev_mask_in = nullptr, ev_mask_out = nullptr;
   bool overlap = true;
   // b200mvs_forward_host: uploads run on their own stream in the order the path needs them, compute waits per piece
@@ -713,7 +714,9 @@ int run_featnet(b200mvs_net* net, const Levels& L, int img0, int cnt, const floa
 int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* left_pyr, const float* const* K_pyr,
                  const float* const* Ts, const float* const* right_l0, const float* const* right_l4,
                  float* const* out_idepth, float* const* out_raw, uint8_t* const* out_mask, cudaStream_t stream,
-                 const cudaEvent_t* uploaded = nullptr) {
+                 const cudaEvent_t* uploaded = nullptr, cudaEvent_t coarse_done = nullptr) {
+  // `coarse_done` (b200mvs_forward_host): recorded once the idepth maps of levels 1-4 are final, so that their
+  // download can run next to the level-0 refiner.
   // `uploaded` (b200mvs_forward_host): events after which [0] K/T, [1] right level 0, [2] right level 4, [3] left
   // level 0, [4] left levels 1-4 are resident; null = all inputs already resident.
   auto wait_upload = [&](int which, cudaStream_t on) -> int {
@@ -1046,6 +1049,7 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
     }
     static const char* names[4] = {"upsample+refiner0", "upsample+refiner1", "upsample+refiner2", "upsample+refiner3"};
     mark(names[l]);
+    if (l == 1 && coarse_done != nullptr) B200MVS_CUDA_OK(cudaEventRecord(coarse_done, stream));
   }
   if (overlap && lowest_mask <= 3) B200MVS_CUDA_OK(cudaStreamWaitEvent(stream, net->ev_mask_out, 0));
   if (sprof) {
@@ -1115,6 +1119,7 @@ B200MVS_API int b200mvs_create(int device, int num_tensors, const char* const* n
         cudaEventCreateWithFlags(&net->ev_left, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&net->ev_pre, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&net->ev_right, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&net->ev_coarse, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&net->ev_mask_in, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&net->ev_mask_out, cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithFlags(&net->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -1143,7 +1148,7 @@ B200MVS_API void b200mvs_destroy(b200mvs_net* net) {
   if (net->arena.base != nullptr) cudaFree(net->arena.base);
   if (net->host_stage != nullptr) cudaFree(net->host_stage);
   for (cudaEvent_t e : net->probe.ev) cudaEventDestroy(e);
-  for (cudaEvent_t e : {net->ev_geo, net->ev_imgconv, net->ev_fork, net->ev_left, net->ev_pre, net->ev_right, net->ev_mask_in, net->ev_mask_out})
+  for (cudaEvent_t e : {net->ev_geo, net->ev_imgconv, net->ev_fork, net->ev_left, net->ev_pre, net->ev_right, net->ev_coarse, net->ev_mask_in, net->ev_mask_out})
     if (e != nullptr) cudaEventDestroy(e);
   if (net->side != nullptr) cudaStreamDestroy(net->side);
   for (cudaEvent_t e : net->ev_up)
@@ -1172,6 +1177,10 @@ B200MVS_API int b200mvs_set_option(b200mvs_net* net, const char* name, int value
   }
   if (k == "warp_specialized") {
     net->warp_specialized = value != 0;
+    return 0;
+  }
+  if (k == "early_d2h") {
+    net->early_d2h = value != 0;
     return 0;
   }
   if (k == "left_late") {
@@ -1423,16 +1432,19 @@ B200MVS_API int b200mvs_forward_host(b200mvs_net* net, const b200mvs_shape* shap
     }
   }
   const double t_up = hprof ? now() : 0.0;
-  if (rc == 0) rc = forward_impl(net, s, dl, dk, dT, dr0, dr4, oi, orw, om, stream, net->ev_up);
+  if (rc == 0) rc = forward_impl(net, s, dl, dk, dT, dr0, dr4, oi, orw, om, stream, net->ev_up, net->ev_coarse);
   const double t_enq = hprof ? now() : 0.0;
   if (rc == 0) {
+    // levels 1-4 are final before the level-0 refiner starts: their download runs next to it on the copy stream
+    if (net->early_d2h) cudaStreamWaitEvent(cs, net->ev_coarse, 0);
     for (int l = 0; l < 5; ++l) {
+      cudaStream_t ds = (l == 0 || !net->early_d2h) ? stream : cs;
       if (out_idepth != nullptr && out_idepth[l] != nullptr) {
-        cudaMemcpyAsync(out_idepth[l], oi[l], B * L.px[l] * sizeof(float), cudaMemcpyDeviceToHost, stream);
+        cudaMemcpyAsync(out_idepth[l], oi[l], B * L.px[l] * sizeof(float), cudaMemcpyDeviceToHost, ds);
         d2h += (int64_t)(B * L.px[l] * sizeof(float));
       }
       if (out_idepth_raw != nullptr && out_idepth_raw[l] != nullptr) {
-        cudaMemcpyAsync(out_idepth_raw[l], orw[l], B * L.px[l] * sizeof(float), cudaMemcpyDeviceToHost, stream);
+        cudaMemcpyAsync(out_idepth_raw[l], orw[l], B * L.px[l] * sizeof(float), cudaMemcpyDeviceToHost, ds);
         d2h += (int64_t)(B * L.px[l] * sizeof(float));
       }
       if (out_mask != nullptr && out_mask[l] != nullptr) {
@@ -1440,7 +1452,8 @@ B200MVS_API int b200mvs_forward_host(b200mvs_net* net, const b200mvs_shape* shap
         d2h += (int64_t)(B * D * L.px[l]);
       }
     }
-    cudaError_t e = cudaStreamSynchronize(stream);
+    cudaError_t e = cudaStreamSynchronize(cs);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     if (hprof)
       fprintf(stderr, "forward_host: uploads enqueued %.0f us | kernels enqueued %.0f us | wait for completion %.0f us\n",
               t_up - t_entry, t_enq - t_up, now() - t_enq);
