@@ -188,6 +188,23 @@ class ClockSampler(threading.Thread):
         if self.proc is not None:
             self.proc.terminate()
 
+    def shutdown(self):
+        """Stops the thread, waits for it and releases NVML."""
+        self.stop()
+        if self.is_alive():
+            self.join(timeout=2.0)
+        if self.proc is not None:
+            try:
+                self.proc.wait(timeout=2.0)
+            except Exception:       # noqa: BLE001
+                self.proc.kill()
+        if self.nvml is not None:
+            try:
+                self.nvml.nvmlShutdown()
+            except Exception:       # noqa: BLE001
+                pass
+            self.nvml = None
+
     def summary(self, first=0, last=None):
         window = self.samples[first:last]
         sm = [s[0] for s in window]
@@ -367,7 +384,8 @@ def run_ours(args, rank, world, local_rank):
         t_roof_us = max(byt / (hbm_peak * 1e9), 2 * mac / (0.5 * float(peaks.get("bf16_tflops", 1590.0)) * 1e12)) * 1e6
 
         cpu = None
-        if world >= 1:
+        if world == 1:      # the CPU baseline is timed on rank 0 at N = 1 only (the other ranks would sit in a
+                            # NCCL barrier, spinning on their GPUs, for as long as it runs)
             dmps, ms, cores, runs = cpu_oracle_throughput(state, 20, 1, budget_s=15.0)
             cpu = {"value": dmps, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{runs} full forwards of one cfg2 image group (oracle/mvsnet_oracle.py, torch CPU, "
@@ -408,8 +426,13 @@ def run_ours(args, rank, world, local_rank):
             "cpu_baseline": cpu,
         }
         emit(line)
+    # leave the device idle and every helper stopped before the process goes away
+    sampler.shutdown()
+    net.set_host_outputs(None)
+    torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
+        torch.cuda.synchronize(dev)
         dist.destroy_process_group()
 
 
