@@ -18,3 +18,11 @@ with torch.no_grad():
                                      torch.rand(2, 1, 38, 51, device="cuda") * 3, inputs["right_image_pyr"][0][0])
     torch.cuda.synchronize()
     print("ok", float(pred.mean()))
+    # post-processing row: odd pixel count (scalar path) and a 16-byte aligned one (vector path)
+    from multi_view_stereonet_b200 import evaluation as ev
+    for rows, cols in ((38, 51), (64, 80)):
+        est = torch.rand(2, 1, rows, cols, device="cuda") + 0.05
+        truth = torch.rand(2, 1, rows, cols, device="cuda") * 20
+        _, depth, metrics = ev.evaluate_batch(est, torch.tensor([0.3, 0.5], device="cuda"), truth, "gta_sfm")
+        torch.cuda.synchronize()
+        print("eval", rows, cols, metrics[0]["num_valid"], round(metrics[0]["abs_rel"], 4))
