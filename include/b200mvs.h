@@ -122,7 +122,10 @@ B200MVS_API int b200mvs_get_stage(b200mvs_net* net, const char* name, void* dst,
 B200MVS_API int b200mvs_set_debug(b200mvs_net* net, int keep_stages);
 
 /* Options: "tensor_cores" (default 1) -- run the 3x3 32->32 refiner convolutions of levels 0-2 on the
- * tcgen05 tensor cores with fp16 operands / fp32 accumulation; 0 keeps every layer on the fp32 path. */
+ * tcgen05 tensor cores with fp16 operands / fp32 accumulation; 0 keeps every layer on the fp32 path.
+ * A/B switches of the schedule (all default 1, results unchanged up to float32 rounding): "warp_specialized",
+ * "half_activations", "pdl", "overlap", "conv0_precompute", "left_late", "early_d2h"; debugging: "recurrence_debug",
+ * "recurrence_profile". */
 B200MVS_API int b200mvs_set_option(b200mvs_net* net, const char* name, int value);
 
 /* Stage entry for kernel parity tests: y = conv3x3(x, dilation, padding = dilation) + bias on a
