@@ -76,3 +76,27 @@ def test_synthetic_pyramid_and_intrinsics():
     a = synthetic.make_inputs(64, 80, 1, 4)
     b = synthetic.make_inputs(64, 80, 1, 2, first_item=2)
     assert torch.equal(a[0][0][2:], b[0][0])
+
+
+def test_algorithmic_work_matches_survey_totals():
+    """bench.py's roofline arithmetic (MACs and layerwise-compulsory bytes per depthmap) against the totals SURVEY.md
+    8d states for the BASELINE configurations."""
+    import bench
+    for (rows, cols, views, hyps), (gmac, mbytes) in {
+        (64, 80, 1, 8): (0.455, 14.1),
+        (512, 640, 1, 64): (39.13, 1081.0),
+        (512, 640, 4, 64): (76.58, 1816.0),
+        (1024, 1280, 4, 128): (489.8, 10494.0),
+    }.items():
+        mac, byt, P = bench.algorithmic_work(rows, cols, views, hyps)
+        assert abs(mac / 1e9 - gmac) <= 0.002 * gmac + 0.001, (rows, cols, views, hyps, mac / 1e9)
+        assert abs(byt / 1e6 - mbytes) <= 0.002 * mbytes + 0.05, (rows, cols, views, hyps, byt / 1e6)
+        assert P[0] == rows * cols and len(P) == 5
+
+
+def test_evaluation_has_no_cpu_path():
+    """The post-processing row fails loudly on CPU tensors, like the forward."""
+    import pytest as _pytest
+    from multi_view_stereonet_b200 import evaluation as ev
+    with _pytest.raises(RuntimeError):
+        ev.idepthmap_to_depthmap(torch.rand(1, 1, 4, 4), torch.ones(1))
