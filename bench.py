@@ -238,6 +238,68 @@ def cpu_oracle_throughput(state, steps, warmup, budget_s=25.0):
     return 1e3 / ms, ms, cores, len(times)
 
 
+# BASELINE.json's throughput configurations as one GPU sees them (per-GPU share of the global batch); `value` stays on
+# cfg2 / batch 1, these are reported next to it in the same JSON line ("configs").
+EXTRA_CONFIGS = [
+    ("cfg4_share", dict(rows=512, cols=640, views=1, hyps=64, batch=8),
+     "cfg4: 512x640, 1 comparison view, 64 hypotheses, batch 64 over 8 GPUs = 8 per GPU"),
+    ("cfg3", dict(rows=512, cols=640, views=4, hyps=64, batch=8),
+     "cfg3: 512x640, 4 comparison views, 64 hypotheses, batch 8 on one GPU"),
+    ("cfg5_share", dict(rows=1024, cols=1280, views=4, hyps=128, batch=4),
+     "cfg5: 1024x1280, 4 comparison views, 128 hypotheses, batch 32 over 8 GPUs = 4 per GPU"),
+]
+
+
+def run_extra_configs(net, dev, rank, world, flush, barrier, hbm_peak, tf32_peak_tflops, steps=5, warmup=3):
+    """Times the per-GPU share of cfg4 / cfg3 / cfg5 device-resident (every rank runs its own seeded items, max over
+    ranks) and one profiled forward each for the per-stage breakdown.  Returns {name: {...}} on every rank."""
+    from multi_view_stereonet_b200 import sharding, synthetic
+    out = {}
+    for name, c, what in EXTRA_CONFIGS:
+        B = c["batch"]
+        first_item, _ = sharding.shard_range(world * B, rank, world)
+        inputs = synthetic.to_device(synthetic.make_inputs(c["rows"], c["cols"], c["views"], B, first_item=first_item), dev)
+        flags = (c["hyps"], True, [True] * 5)
+        with torch.no_grad():
+            res = None
+            for _ in range(warmup):
+                flush.zero_()
+                res = net(*inputs, *flags)
+            launches = net.last_launch_count()
+            starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+            ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+            barrier()
+            for i in range(steps):
+                flush.zero_()
+                starts[i].record()
+                res = net(*inputs, *flags)
+                ends[i].record()
+            barrier()
+            step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+            # per-stage breakdown: one extra forward with events at the stage boundaries (not part of the timing above)
+            net.set_option("stage_profile", 1)
+            net(*inputs, *flags)
+            torch.cuda.synchronize(dev)
+            stages = net.last_stage_profile()
+            net.set_option("stage_profile", 0)
+            del res
+        allt = sharding.gather_timings([sum(step_ms)], device=dev)
+        _, worst_ms = sharding.aggregate_throughput(B, steps, allt[:, 0])
+        mac, byt, _ = algorithmic_work(c["rows"], c["cols"], c["views"], c["hyps"])
+        t_roof_us = max(byt / (hbm_peak * 1e9), 2 * mac / (tf32_peak_tflops * 1e12)) * 1e6
+        ms_step = worst_ms / steps
+        out[name] = {
+            "workload": what, "batch_per_gpu": B, "global_batch": world * B, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_step, "depthmaps_per_s": world * B / (ms_step * 1e-3),
+            "roofline_us_per_depthmap": t_roof_us, "frac_of_roofline": t_roof_us / (ms_step / B * 1e3),
+            "gpu_launches_per_step": launches,
+            "stage_us_rank0": {k: round(v, 1) for k, v in stages.items()},
+        }
+        del inputs
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -354,6 +416,15 @@ def run_ours(args, rank, world, local_rank):
     net.set_host_outputs(None)
     h2d, d2h = net.last_h2d_bytes, net.last_d2h_bytes
 
+    # ---- the other BASELINE configurations (per-GPU share), device-resident, every rank ----
+    peaks_all = {}
+    if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")):
+        peaks_all = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    extra = None
+    if not args.no_configs:
+        extra = run_extra_configs(net, dev, rank, world, flush, barrier, float(peaks_all.get("hbm_gbs", 6650.0)),
+                                  0.5 * float(peaks_all.get("bf16_tflops", 1590.0)))
+
     # ---- max over ranks (the path's only collective: one all_gather of per-rank timings) ----
     allt = sharding.gather_timings([total_ms, e2e_s * 1e3], device=dev)
     _, worst_ms = sharding.aggregate_throughput(B, args.steps, allt[:, 0])
@@ -424,6 +495,7 @@ def run_ours(args, rank, world, local_rank):
                            "roofline_us_per_depthmap": t_roof_us,
                            "frac_of_roofline": t_roof_us / (worst_ms / args.steps / B * 1e3)},
             "cpu_baseline": cpu,
+            "configs": extra,
         }
         emit(line)
     # leave the device idle and every helper stopped before the process goes away
@@ -443,6 +515,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch-per-gpu", type=int, default=1)
+    ap.add_argument("--no-configs", action="store_true",
+                    help="skip the cfg3 / cfg4-share / cfg5-share legs (the `configs` block of the JSON line)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -456,7 +530,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"), __file__,
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
-               "--batch-per-gpu", str(args.batch_per_gpu)]
+               "--batch-per-gpu", str(args.batch_per_gpu)] + (["--no-configs"] if args.no_configs else [])
         sys.exit(subprocess.call(cmd))
     run_ours(args, rank, world, local_rank)
 

@@ -108,6 +108,14 @@ B200MVS_API int b200mvs_probe_read(b200mvs_net* net, double* total_ms, int64_t* 
 /* Number of kernels the last b200mvs_forward on this handle launched. */
 B200MVS_API int64_t b200mvs_last_launch_count(const b200mvs_net* net);
 
+/* With option "stage_profile" = 1 every forward records CUDA events at the stage boundaries of its main stream and
+ * synchronises on the last one before returning (measurement mode: it ends the overlap of adjacent kernels at
+ * those boundaries).  Returns "stage=us;...;total=us" of the last such forward (the reference's stages:
+ * multi_view_stereonet.py:552-583 feature networks + warp, :279-290 depth sweep, :586-602 cost / filter /
+ * soft-argmin, :605-627 level-4 refiner + view mean, :629-682 levels 3..0); the string lives until the next
+ * forward on this handle. */
+B200MVS_API const char* b200mvs_last_stage_profile(const b200mvs_net* net);
+
 /* Stage access for parity tests: copies an internal buffer of the LAST forward into `dst` (DEVICE
  * pointer, `capacity` bytes) on `stream`; `*nbytes` receives its size.  Names:
  *   "idepth_samples" (B*V,D)  "baseline" (B*V)  "H0" (B*V,3,3)  "H" (B*V,D,3,3)  "H_inc" (B*V,D,3,3)
@@ -125,7 +133,7 @@ B200MVS_API int b200mvs_set_debug(b200mvs_net* net, int keep_stages);
  * tcgen05 tensor cores with fp16 operands / fp32 accumulation; 0 keeps every layer on the fp32 path.
  * A/B switches of the schedule (all default 1, results unchanged up to float32 rounding): "warp_specialized",
  * "half_activations", "pdl", "overlap", "conv0_precompute", "left_late", "early_d2h"; debugging: "recurrence_debug",
- * "recurrence_profile". */
+ * "recurrence_profile", "stage_profile" (see b200mvs_last_stage_profile). */
 B200MVS_API int b200mvs_set_option(b200mvs_net* net, const char* name, int value);
 
 /* Stage entry for kernel parity tests: y = conv3x3(x, dilation, padding = dilation) + bias on a
@@ -143,6 +151,17 @@ B200MVS_API int b200mvs_conv3x3_c32(const float* x, const float* w_oihw_host, co
  * (multi_view_stereonet.py:230-233). */
 B200MVS_API int b200mvs_homography_warp(const float* H, const float* image, int32_t n, int32_t channels, int32_t rows,
                             int32_t cols, int32_t zero_invalid, float* pred, uint8_t* mask, void* stream);
+
+/* MaskUpsampler.forward (multi_view_stereonet.py:389-396) on DEVICE pointers, no handle: mask (planes, rows, cols)
+ * uint8 0/1 -> float -> bilinear (align_corners=False) to (out_rows, out_cols) -> > 0.5.
+ *   packed == 0: out (planes, out_rows, out_cols) uint8 0/1, as the reference returns it;
+ *   packed != 0: out (planes, out_rows, ceil(out_cols / 8)) bits, bit 7 of a byte = its first pixel
+ *                (numpy.packbits(axis=-1)); with out_rows == rows and out_cols == cols the call only packs.
+ * The forward needs none of the mask volumes below level 4: a caller that passes NULL for
+ * out_mask[0..3] to b200mvs_forward gets the level-4 volume only and produces the finer levels on demand with this
+ * entry, one level at a time (each level is the upsampled *thresholded* coarser level, :630-673). */
+B200MVS_API int b200mvs_upsample_mask(const uint8_t* mask, int64_t planes, int32_t rows, int32_t cols, int32_t out_rows,
+                                      int32_t out_cols, int32_t packed, uint8_t* out, void* stream);
 
 /* The reprojection layers of stereo/image_predictor.py next to the hot path, one fused per-pixel
  * kernel on DEVICE pointers; needs no handle.  K (N,4,4), T_right_in_left (N,4,4), map (N,1,rows,cols):

@@ -38,12 +38,16 @@ SYMBOLS = {
     "b200mvs_probe_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double),
                                           ctypes.POINTER(ctypes.c_int64)]),
     "b200mvs_last_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
+    "b200mvs_last_stage_profile": (ctypes.c_char_p, [ctypes.c_void_p]),
     "b200mvs_get_stage": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64,
                                          ctypes.POINTER(ctypes.c_int64), ctypes.c_void_p]),
     "b200mvs_set_debug": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "b200mvs_homography_warp": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
                                                ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
                                                ctypes.c_void_p, ctypes.c_void_p]),
+    "b200mvs_upsample_mask": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
+                                             ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
+                                             ctypes.c_void_p]),
     "b200mvs_reproject": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
                                          ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                          ctypes.c_int32] + [ctypes.c_void_p] * 7),

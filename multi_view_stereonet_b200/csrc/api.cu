@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -27,6 +28,59 @@ void note_launch() { ++g_launches; }
 static bool g_pdl = true;
 bool pdl_enabled() { return g_pdl; }
 void set_pdl_enabled(bool on) { g_pdl = on; }
+
+namespace {
+std::mutex g_attr_mutex;
+std::map<std::pair<const void*, int>, size_t> g_func_smem;       // (kernel, device) -> opted-in dynamic smem bytes
+std::map<std::pair<const void*, int>, bool> g_func_cluster;      // (kernel, device) -> non-portable clusters allowed
+std::map<int, int> g_sm_count;                                   // device -> SMs
+std::map<std::pair<int, int>, int> g_cluster_size;               // (device, tiles) -> schedulable cluster size
+}  // namespace
+
+int ensure_func_smem(const void* func, size_t bytes) {
+  int dev = 0;
+  B200MVS_CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_attr_mutex);
+  size_t& have = g_func_smem[{func, dev}];
+  if (bytes > have) {
+    B200MVS_CUDA_OK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    have = bytes;
+  }
+  return 0;
+}
+int ensure_func_nonportable_cluster(const void* func) {
+  int dev = 0;
+  B200MVS_CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_attr_mutex);
+  bool& have = g_func_cluster[{func, dev}];
+  if (!have) {
+    B200MVS_CUDA_OK(cudaFuncSetAttribute(func, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    have = true;
+  }
+  return 0;
+}
+int current_device_sm_count(int* sms) {
+  int dev = 0;
+  B200MVS_CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_attr_mutex);
+  int& n = g_sm_count[dev];
+  if (n == 0) B200MVS_CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  *sms = n;
+  return 0;
+}
+int cached_cluster_size(int tiles) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  std::lock_guard<std::mutex> lock(g_attr_mutex);
+  auto it = g_cluster_size.find({dev, tiles});
+  return it == g_cluster_size.end() ? 0 : it->second;
+}
+void remember_cluster_size(int tiles, int cluster) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return;
+  std::lock_guard<std::mutex> lock(g_attr_mutex);
+  g_cluster_size[{dev, tiles}] = cluster;
+}
 
 // Event-pair probe around launches of one kernel class (b200mvs_probe_select).
 struct Probe {
@@ -167,6 +221,8 @@ struct b200mvs_net {
   float* pinned_small = nullptr;
   size_t pinned_small_floats = 0;
   long long* rec_prof = nullptr;  // device [16][12], allocated when option "recurrence_profile" is set
+  bool stage_profile = false;       // option "stage_profile": events at the stage boundaries of the main stream
+  std::string last_stage_profile;   // "name=us;..." of the last profiled forward (b200mvs_last_stage_profile)
   b200mvs_shape last_shape{};
   bool have_last = false;
   int64_t last_launches = 0;
@@ -290,10 +346,13 @@ int build_weights(b200mvs_net* net, const StateDict& sd) {
   const std::string fr = "right_feature_extractor.refiner";
   // input = cat([image(3), features(32)])  (multi_view_stereonet.py:425)
   RC(pack_conv(net, sd, fr + ".conv0", 32, 35, 9, true, 3, {0, 1, 2}, true, &net->fr_conv0));
+  RC(pack_conv_tc(net, sd, fr + ".conv0", 35, true, 3, {0, 1, 2}, &net->fr_conv0));
   RC(pack_gn(net, sd, fr + ".bn0", &net->fr_gn0));
   RC(pack_conv(net, sd, fr + ".res0.conv1", 32, 32, 9, true, 0, {}, true, &net->fr_res0));
+  RC(pack_conv_tc(net, sd, fr + ".res0.conv1", 32, true, 0, {}, &net->fr_res0));
   RC(pack_gn(net, sd, fr + ".res0.bn1", &net->fr_gn1));
   RC(pack_conv(net, sd, fr + ".conv_final", 32, 32, 9, true, 0, {}, true, &net->fr_final));
+  RC(pack_conv_tc(net, sd, fr + ".conv_final", 32, true, 0, {}, &net->fr_final));
 
   {
     const float* w0 = sd.get(fr + ".conv0.weight", 32 * 35 * 9);
@@ -711,21 +770,16 @@ int run_featnet(b200mvs_net* net, const Levels& L, int img0, int cnt, const floa
   return 0;
 }
 
-int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* left_pyr, const float* const* K_pyr,
-                 const float* const* Ts, const float* const* right_l0, const float* const* right_l4,
-                 float* const* out_idepth, float* const* out_raw, uint8_t* const* out_mask, cudaStream_t stream,
-                 const cudaEvent_t* uploaded = nullptr, cudaEvent_t coarse_done = nullptr) {
-  // `coarse_done` (b200mvs_forward_host): recorded once the idepth maps of levels 1-4 are final, so that their
-  // download can run next to the level-0 refiner.
-  // `uploaded` (b200mvs_forward_host): events after which [0] K/T, [1] right level 0, [2] right level 4, [3] left
-  // level 0, [4] left levels 1-4 are resident; null = all inputs already resident.
-  auto wait_upload = [&](int which, cudaStream_t on) -> int {
-    if (uploaded != nullptr) B200MVS_CUDA_OK(cudaStreamWaitEvent(on, uploaded[which], 0));
-    return 0;
-  };
+// Shape and pointer checks shared by both forward entries (before anything is staged or allocated).
+int validate_call(const b200mvs_shape& s, const float* const* left_pyr, const float* const* K_pyr,
+                  const float* const* Ts, const float* const* right_l0, const float* const* right_l4) {
   if (s.batch < 1 || s.views < 1 || s.views > kMaxViews || s.rows < 16 || s.cols < 16 ||
       s.num_idepth_samples < 2 || s.num_idepth_samples > 4096) {
     set_error("b200mvs_forward: bad shape (need batch>=1, 1<=views<=16, rows,cols>=16, 2<=D<=4096)");
+    return B200MVS_EINVAL;
+  }
+  if (left_pyr == nullptr || K_pyr == nullptr || Ts == nullptr || right_l0 == nullptr || right_l4 == nullptr) {
+    set_error("b200mvs_forward: null argument");
     return B200MVS_EINVAL;
   }
   for (int l = 0; l < 5; ++l)
@@ -739,6 +793,22 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
       set_error("b200mvs_forward: missing per-view input");
       return B200MVS_EINVAL;
     }
+  return 0;
+}
+
+int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* left_pyr, const float* const* K_pyr,
+                 const float* const* Ts, const float* const* right_l0, const float* const* right_l4,
+                 float* const* out_idepth, float* const* out_raw, uint8_t* const* out_mask, cudaStream_t stream,
+                 const cudaEvent_t* uploaded = nullptr, cudaEvent_t coarse_done = nullptr) {
+  // `coarse_done` (b200mvs_forward_host): recorded once the idepth maps of levels 1-4 are final, so that their
+  // download can run next to the level-0 refiner.
+  // `uploaded` (b200mvs_forward_host): events after which [0] K/T, [1] right level 0, [2] right level 4, [3] left
+  // level 0, [4] left levels 1-4 are resident; null = all inputs already resident.
+  auto wait_upload = [&](int which, cudaStream_t on) -> int {
+    if (uploaded != nullptr) B200MVS_CUDA_OK(cudaStreamWaitEvent(on, uploaded[which], 0));
+    return 0;
+  };
+  RC(validate_call(s, left_pyr, K_pyr, Ts, right_l0, right_l4));
   B200MVS_CUDA_OK(cudaSetDevice(net->device));
   RC(ensure_workspace(net, s));
   Workspace& ws = net->ws;
@@ -751,7 +821,8 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
   g_probe = net->probe.tag != 0 ? &net->probe : nullptr;
   // Debug hook (B200MVS_STAGE_PROFILE=1): events at the stage boundaries of the main stream, printed to stderr
   // after a synchronise.  Perturbs the pipeline slightly (an event between two kernels ends their PDL overlap).
-  static const bool sprof = getenv("B200MVS_STAGE_PROFILE") != nullptr;
+  static const bool sprof_env = getenv("B200MVS_STAGE_PROFILE") != nullptr;
+  const bool sprof = sprof_env || net->stage_profile;
   std::vector<std::pair<const char*, cudaEvent_t>> marks;
   auto mark = [&](const char* what) {
     if (!sprof) return;
@@ -885,7 +956,7 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
       a.bias = net->fr_conv0.bias;
       a.out = ws.sy0;
       a.out_stats = sc.take(n);
-      RC(launch_conv(CONV_3x3, 32, a, stream));
+      RC(conv3x3_c32(net, a, net->fr_conv0, true, stream));
 
       ConvParams b;  // res0.conv1 on x0 = lrelu(gn0(y0))
       b.n_img = n;
@@ -902,7 +973,7 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
       b.bias = net->fr_res0.bias;
       b.out = ws.sy1;
       b.out_stats = sc.take(n);
-      RC(launch_conv(CONV_3x3, 32, b, stream));
+      RC(conv3x3_c32(net, b, net->fr_res0, true, stream));
 
       ConvParams c;  // conv_final on x1 = lrelu(gn1(y1)) + x0 ; features_d = warped + delta
       c.n_img = n;
@@ -921,7 +992,7 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
       // hypothesis `step` of image i lives at vol + (i * D + step) * P4 * 32
       c.out = ws.vol + (size_t)step * P4 * kC;
       c.out_img_stride = (long long)D * P4 * kC;
-      RC(launch_conv(CONV_3x3, 32, c, stream));
+      RC(conv3x3_c32(net, c, net->fr_final, true, stream));
     }
   }
 
@@ -1057,13 +1128,16 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
     cudaEventSynchronize(marks.back().second);
     float total = 0.f;
     cudaEventElapsedTime(&total, marks.front().second, marks.back().second);
-    fprintf(stderr, "stage profile (us):");
+    if (sprof_env) fprintf(stderr, "stage profile (us):");
+    net->last_stage_profile.clear();
     for (size_t i = 1; i < marks.size(); ++i) {
       float ms = 0.f;
       cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
-      fprintf(stderr, " [%s] %.0f", marks[i].first, ms * 1e3f);
+      if (sprof_env) fprintf(stderr, " [%s] %.0f", marks[i].first, ms * 1e3f);
+      net->last_stage_profile += std::string(marks[i].first) + "=" + std::to_string(ms * 1e3f) + ";";
     }
-    fprintf(stderr, " | total %.0f\n", total * 1e3f);
+    net->last_stage_profile += "total=" + std::to_string(total * 1e3f);
+    if (sprof_env) fprintf(stderr, " | total %.0f\n", total * 1e3f);
     for (auto& m : marks) cudaEventDestroy(m.second);
   }
   if (sc.used > sc.cap) {
@@ -1203,6 +1277,10 @@ B200MVS_API int b200mvs_set_option(b200mvs_net* net, const char* name, int value
     net->overlap = value != 0;
     return 0;
   }
+  if (k == "stage_profile") {
+    net->stage_profile = value != 0;
+    return 0;
+  }
   if (k == "recurrence_debug") {
     net->rec_debug = value;
     return 0;
@@ -1303,6 +1381,10 @@ B200MVS_API int b200mvs_probe_read(b200mvs_net* net, double* total_ms, int64_t* 
 
 B200MVS_API int64_t b200mvs_last_launch_count(const b200mvs_net* net) { return net == nullptr ? 0 : net->last_launches; }
 
+B200MVS_API const char* b200mvs_last_stage_profile(const b200mvs_net* net) {
+  return net == nullptr ? "" : net->last_stage_profile.c_str();
+}
+
 B200MVS_API int b200mvs_forward(b200mvs_net* net, const b200mvs_shape* shape, const float* const* left_image_pyr,
                     const float* const* K_pyr, const float* const* T_right_in_lefts,
                     const float* const* right_image_l0, const float* const* right_image_l4,
@@ -1327,10 +1409,9 @@ B200MVS_API int b200mvs_forward_host(b200mvs_net* net, const b200mvs_shape* shap
     return B200MVS_EINVAL;
   }
   const b200mvs_shape& s = *shape;
-  if (s.batch < 1 || s.views < 1 || s.views > kMaxViews) {
-    set_error("b200mvs_forward_host: bad shape");
-    return B200MVS_EINVAL;
-  }
+  // full validation BEFORE any staging: the pointer arrays are dereferenced and the staging buffer is sized from
+  // the shape below
+  RC(validate_call(s, left_image_pyr, K_pyr, T_right_in_lefts, right_image_l0, right_image_l4));
   B200MVS_CUDA_OK(cudaSetDevice(net->device));
   const Levels L = levels_of(s);
   const size_t B = s.batch, V = s.views, D = s.num_idepth_samples;
@@ -1427,7 +1508,9 @@ B200MVS_API int b200mvs_forward_host(b200mvs_net* net, const b200mvs_shape* shap
       c += B * L.px[l];
       orw[l] = c;
       c += B * L.px[l];
-      om[l] = m;  // masks are always computed (the reference always returns them)
+      // mask volumes: all five when the caller passes no mask list (the reference always computes them); with a
+      // list, only the levels it asks for (and level 4, which the view reduction produces anyway)
+      om[l] = (out_mask == nullptr || out_mask[l] != nullptr || l == 4) ? m : nullptr;
       m += B * D * L.px[l];
     }
   }
@@ -1464,6 +1547,7 @@ B200MVS_API int b200mvs_forward_host(b200mvs_net* net, const b200mvs_shape* shap
   } else {
     cudaStreamSynchronize(cs);
     cudaStreamSynchronize(stream);
+    if (net->side != nullptr) cudaStreamSynchronize(net->side);   // a failed forward may leave it forked
     if (rc == -2 && g_error.empty()) set_error("b200mvs_forward_host: upload failed");
   }
   if (h2d_bytes != nullptr) *h2d_bytes = h2d;
@@ -1535,6 +1619,16 @@ B200MVS_API int b200mvs_homography_warp(const float* H, const float* image, int3
   src.p[0] = image;
   return launch_warp_planar(H, 9, src, n, channels, rows, cols, zero_invalid != 0, pred, mask,
                             static_cast<cudaStream_t>(stream));
+}
+
+B200MVS_API int b200mvs_upsample_mask(const uint8_t* mask, int64_t planes, int32_t rows, int32_t cols, int32_t out_rows,
+                                      int32_t out_cols, int32_t packed, uint8_t* out, void* stream) {
+  if (mask == nullptr || out == nullptr || planes < 0 || rows < 1 || cols < 1 || out_rows < 1 || out_cols < 1) {
+    set_error("b200mvs_upsample_mask: bad argument");
+    return B200MVS_EINVAL;
+  }
+  return launch_upsample_mask(mask, planes, rows, cols, out_rows, out_cols, out, static_cast<cudaStream_t>(stream),
+                              packed != 0);
 }
 
 B200MVS_API int b200mvs_reproject(const float* K, const float* T_right_in_left, const float* map, int32_t map_kind,

@@ -51,6 +51,16 @@ __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 bool pdl_enabled();
 void set_pdl_enabled(bool on);
 
+// cudaFuncSetAttribute applies to the device that is current when it is called, and one process may hold handles
+// on several GPUs (b200mvs_create takes a device index): the opt-ins for > 48 KB of dynamic shared memory and for
+// non-portable cluster sizes are therefore cached per (kernel, device), under a mutex (api.cu).
+int ensure_func_smem(const void* func, size_t bytes);      // raises the limit if it is below `bytes`
+int ensure_func_nonportable_cluster(const void* func);
+int current_device_sm_count(int* sms);
+// Remembers the cluster size that could be scheduled for (device, tiles); 0 = unknown.
+int cached_cluster_size(int tiles);
+void remember_cluster_size(int tiles, int cluster);
+
 #ifdef __CUDACC__
 // L2 residency hints.  The refiner activations ping-pong between four buffers that together fit in the 126 MB L2:
 // stores of tensors the next layer reads are marked evict_last, loads of tensors that are dead after this layer

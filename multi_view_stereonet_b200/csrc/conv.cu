@@ -348,12 +348,9 @@ int launch_cfg(const ConvParams& p, cudaStream_t stream) {
     set_error("conv tile does not fit in shared memory");
     return -1;
   }
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
-    B200MVS_CUDA_OK(cudaFuncSetAttribute(conv_kernel<KD, KH, KW, S, COUT, TD, TH, TW, PXT, CSPLIT>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  if (int rc = ensure_func_smem(reinterpret_cast<const void*>(&conv_kernel<KD, KH, KW, S, COUT, TD, TH, TW, PXT, CSPLIT>),
+                                200 * 1024))
+    return rc;
   dim3 grid(cdiv(p.Wo, TW) * cdiv(p.Ho, TH) * cdiv(p.Do, TD), p.n_img);
   if (p.tag != TAG_NONE) probe_before(p.tag, stream);
   launch_pdl(conv_kernel<KD, KH, KW, S, COUT, TD, TH, TW, PXT, CSPLIT>, grid, dim3(C::NT), smem, stream, p);

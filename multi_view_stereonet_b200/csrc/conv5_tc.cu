@@ -368,11 +368,7 @@ void pack_conv5_c3_weights(const float* w_oihw, std::vector<uint8_t>* out) {
 int launch_conv5x5s2_c32_tc(const float* in, const uint8_t* w16, int n, int Hi, int Wi, float* out,
                             cudaStream_t stream) {
   if (n <= 0) return 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200MVS_CUDA_OK(cudaFuncSetAttribute(conv5x5s2_c32_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A_SMEM));
-    attr_set = true;
-  }
+  if (int rc = ensure_func_smem(reinterpret_cast<const void*>(&conv5x5s2_c32_tc_kernel), A_SMEM)) return rc;
   const int Ho = (Hi + 1) / 2, Wo = (Wi + 1) / 2;
   dim3 grid(cdiv(Wo, A_TW) * cdiv(Ho, A_TH), n);
   launch_pdl(conv5x5s2_c32_tc_kernel, grid, dim3(NT), (size_t)A_SMEM, stream, in, w16, Hi, Wi, Ho, Wo, out);
@@ -382,12 +378,7 @@ int launch_conv5x5s2_c32_tc(const float* in, const uint8_t* w16, int n, int Hi, 
 
 template <int TH, int MINB>
 int launch_c3(const float* in, const uint8_t* w16, int n, int Hi, int Wi, float* out, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200MVS_CUDA_OK(cudaFuncSetAttribute(conv5x5s2_c3_tc_kernel<TH, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)BCfg<TH>::SMEM));
-    attr_set = true;
-  }
+  if (int rc = ensure_func_smem(reinterpret_cast<const void*>(&conv5x5s2_c3_tc_kernel<TH, MINB>), BCfg<TH>::SMEM)) return rc;
   const int Ho = (Hi + 1) / 2, Wo = (Wi + 1) / 2;
   dim3 grid(cdiv(Wo, B_TW) * cdiv(Ho, TH), n);
   launch_pdl(conv5x5s2_c3_tc_kernel<TH, MINB>, grid, dim3(NT), (size_t)BCfg<TH>::SMEM, stream, in, w16, Hi, Wi, Ho, Wo, out);

@@ -404,12 +404,7 @@ size_t tc_smem_bytes(int TH, bool split, const ConvParams& p) {
 template <int TH, bool SPLIT, int MINB = 1>
 int launch_th(const ConvParams& p, const uint8_t* w16, cudaStream_t stream) {
   const size_t smem = tc_smem_bytes(TH, SPLIT, p);
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200MVS_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc_kernel<TH, SPLIT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         220 * 1024));
-    attr_set = true;
-  }
+  if (int rc = ensure_func_smem(reinterpret_cast<const void*>(&conv3x3_tc_kernel<TH, SPLIT, MINB>), 220 * 1024)) return rc;
   const int TW = PW - 2 * p.dil;
   dim3 grid(cdiv(p.Wo, TW) * cdiv(p.Ho, TH), p.n_img);
   if (p.tag != TAG_NONE) probe_before(p.tag, stream);

@@ -465,12 +465,7 @@ bool plan_for(int dil, int H, int W, int n_img, WsPlan* plan) {
 template <int TH>
 int launch_th(const WsParams& q, const uint8_t* w16, const CUtensorMap& tm_y, const CUtensorMap& tm_r, int grid,
               size_t smem, int tag, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200MVS_CUDA_OK(cudaFuncSetAttribute(conv3x3_ws_kernel<TH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kSmemBudget));
-    attr_set = true;
-  }
+  if (int rc = ensure_func_smem(reinterpret_cast<const void*>(&conv3x3_ws_kernel<TH>), kSmemBudget)) return rc;
   if (tag != TAG_NONE) probe_before(tag, stream);
   launch_pdl(conv3x3_ws_kernel<TH>, dim3(grid), dim3(NT), smem, stream, q, w16, tm_y, tm_r);
   if (tag != TAG_NONE) probe_after(tag, stream);
@@ -538,12 +533,8 @@ int launch_conv3x3_ws(const ConvParams& p, const uint8_t* w16, cudaStream_t stre
     return -1;
   }
   const size_t smem = W_BYTES + ring_bytes(plan.ring) + (size_t)plan.stages * ws_stage_bytes(plan.th, p.dil);
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    B200MVS_CUDA_OK(cudaGetDevice(&dev));
-    B200MVS_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int num_sms = 0;
+  if (int rc = current_device_sm_count(&num_sms)) return rc;
   const long long total = (long long)q.tiles_x * q.tiles_y * q.n_img;
   const int grid = (int)(total < num_sms ? total : num_sms);
   if (plan.th == 8) return launch_th<8>(q, w16, tm_y, tm_r, grid, smem, p.tag, stream);

@@ -1,8 +1,9 @@
 // Conv3d 3x3x3 32->32 of the cost-volume filter (CostVolumeFilter.forward, multi_view_stereonet.py:341-353)
 // on tcgen05 tensor cores with split-fp16 operands (fp32-class accuracy, see recurrence.cu).
 //
-// A CTA owns RT output rows (RT * (w+2) <= 128 positions = one UMMA M-tile) of a chunk of depth slices of one
-// volume and streams through depth: every input slice tile ((RT+2) rows, previous layer's GroupNorm + LeakyReLU
+// A CTA owns RT output rows of a column strip of width cw (RT * (cw+2) <= 128 positions = one UMMA M-tile; images
+// wider than 48 pixels are cut into equal strips whose halo columns come from the neighbouring strip) of a chunk of
+// depth slices of one volume and streams through depth: every input slice tile ((RT+2) rows, previous layer's GroupNorm + LeakyReLU
 // applied, split into hi/lo fp16 planes) is staged ONCE into a 4-slot shared-memory ring and used by the three
 // output slices that touch it.  Output slice q = 27 taps x 2 k-steps x 2 MMAs reading ring slots q, q+1, q+2 with
 // the shifted-window descriptors of conv_tc.cu; accumulators are double-buffered in TMEM so the MMAs of slice q
@@ -43,9 +44,13 @@ __host__ __device__ inline Geo make_geo(int w) {
   return g;
 }
 
+constexpr int kMaxStrip = 48;   // widest strip whose 4-slot ring fits next to the weights in shared memory
+__host__ __device__ inline int strip_count(int w) { return (w + kMaxStrip - 1) / kMaxStrip; }
+__host__ __device__ inline int strip_width(int w) { return (w + strip_count(w) - 1) / strip_count(w); }
+
 struct CvfParams {
   CvfArgs a;
-  int DC, row_tiles;
+  int DC, row_tiles, col_tiles, cw;
   int dbg;   // timing ablations (wrong results): 1 no MMAs, 2 no operand staging stores, 4 no output stores, 8 no input loads
 };
 
@@ -60,10 +65,11 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = tc::uniform_warp_index();
   const int n = blockIdx.y;
-  const Geo g = make_geo(p.w);
+  const Geo g = make_geo(P.cw);
   const int PW = g.PW, RT = g.RT, NP = g.NP;
-  const int rt = blockIdx.x % P.row_tiles, dc = blockIdx.x / P.row_tiles;
-  const int y0 = rt * RT;
+  const int ct = blockIdx.x % P.col_tiles;
+  const int rt = (blockIdx.x / P.col_tiles) % P.row_tiles, dc = blockIdx.x / (P.col_tiles * P.row_tiles);
+  const int y0 = rt * RT, x0 = ct * P.cw;
   const int d0 = dc * P.DC;
   const int dcount = min(P.DC, p.D - d0);
   uint8_t* s_w = smem;
@@ -109,7 +115,7 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
     const int i = tid + k * NT;
     t_l[k] = i >> 2;
     const int iy = t_l[k] / PW, ix = t_l[k] % PW;
-    const int gy = y0 - 1 + iy, gx = ix - 1;
+    const int gy = y0 - 1 + iy, gx = x0 + ix - 1;
     t_in[k] = t_l[k] < NP;
     t_real[k] = t_in[k] && iy < RT + 2 && gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;
     t_off[k] = t_real[k] ? ((size_t)gy * p.w + gx) * kC + 8 * t_oct : 0;
@@ -118,8 +124,8 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
   const int wq = warp & 3, chalf = warp >> 2;
   const int jl = wq * 32 + lane;
   const int e_oy = jl / PW, e_ox = jl % PW;
-  const bool e_real = e_oy < RT && e_ox < p.w && (y0 + e_oy) < p.h;
-  const size_t e_off = e_real ? ((size_t)(y0 + e_oy) * p.w + e_ox) * kC + chalf * 16 : 0;
+  const bool e_real = e_oy < RT && e_ox < P.cw && (x0 + e_ox) < p.w && (y0 + e_oy) < p.h;
+  const size_t e_off = e_real ? ((size_t)(y0 + e_oy) * p.w + x0 + e_ox) * kC + chalf * 16 : 0;
   const uint32_t tmem_my = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(chalf * 16);
 
   const uint32_t plane_u16 = g.plane_bytes >> 4, slot_u16 = g.slot_bytes >> 4;
@@ -285,8 +291,8 @@ void pack_cvf_tc_weights(const float* w_oidhw, std::vector<uint8_t>* out) {
 }
 
 bool cvf_tc_supported(int h, int w) {
-  const Geo g = make_geo(w);
-  return g.PW <= 128 && g.RT >= 1 && g.NP * 4 <= MAX_TASKS * NT && g.total + 2048 <= 227 * 1024 && h >= 1;
+  const Geo g = make_geo(strip_width(w));
+  return w >= 1 && g.PW <= 128 && g.RT >= 1 && g.NP * 4 <= MAX_TASKS * NT && g.total + 2048 <= 227 * 1024 && h >= 1;
 }
 
 int launch_cvf_tc(const CvfArgs& a, cudaStream_t stream) {
@@ -295,23 +301,21 @@ int launch_cvf_tc(const CvfArgs& a, cudaStream_t stream) {
     set_error("launch_cvf_tc: shape not supported");
     return -1;
   }
-  const Geo g = make_geo(a.w);
-  static size_t smem_set = 0;
-  if (g.total > smem_set) {
-    B200MVS_CUDA_OK(cudaFuncSetAttribute(cvf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.total));
-    smem_set = g.total;
-  }
+  const Geo g = make_geo(strip_width(a.w));
+  if (int rc = ensure_func_smem(reinterpret_cast<const void*>(&cvf_tc_kernel), g.total)) return rc;
   CvfParams P;
   P.a = a;
   P.row_tiles = cdiv(a.h, g.RT);
+  P.col_tiles = strip_count(a.w);
+  P.cw = strip_width(a.w);
   static const int dbg = getenv("B200MVS_CVF_DEBUG") ? atoi(getenv("B200MVS_CVF_DEBUG")) : 0;
   P.dbg = dbg;
   // One CTA per SM (220 KB of shared memory): split depth into as many chunks as fill the chip once.
-  int chunks = 148 / (P.row_tiles * a.n);
+  int chunks = 148 / (P.row_tiles * P.col_tiles * a.n);
   chunks = chunks < 1 ? 1 : (chunks > a.D ? a.D : chunks);
   P.DC = cdiv(a.D, chunks);
   chunks = cdiv(a.D, P.DC);
-  dim3 grid(P.row_tiles * chunks, a.n);
+  dim3 grid(P.col_tiles * P.row_tiles * chunks, a.n);
   if (a.tag != TAG_NONE) probe_before(a.tag, stream);
   launch_pdl(cvf_tc_kernel, grid, dim3(NT), (size_t)g.total, stream, P);
   if (a.tag != TAG_NONE) probe_after(a.tag, stream);

@@ -72,7 +72,9 @@ int launch_reproject(const float* K, const float* T, const float* map, int kind,
 // F.interpolate(bilinear, align_corners=False) of a (N, planes, h, w) float map, and the
 // float->bilinear->(>0.5) mask variant (multi_view_stereonet.py:372-396).
 int launch_upsample_f32(const float* in, int n_planes, int h, int w, int H, int W, float* out, cudaStream_t stream);
+// packed: `out` is the bit volume (n_planes, H, ceil(W / 8)), numpy.packbits(axis=-1) layout; with h == H and
+// w == W it only packs.
 int launch_upsample_mask(const uint8_t* in, long long n_planes, int h, int w, int H, int W, uint8_t* out,
-                         cudaStream_t stream);
+                         cudaStream_t stream, bool packed = false);
 
 }  // namespace b200mvs

@@ -418,6 +418,55 @@ __global__ void __launch_bounds__(256) upsample_mask_kernel(const uint8_t* __res
   }
 }
 
+// The same upsampling written as a bit volume: out (planes, H, ceil(W / 8)), bit 7 of a byte = its first pixel
+// (numpy.packbits(mask, axis=-1)).  One thread = one output byte.
+__global__ void __launch_bounds__(256) upsample_mask_packed_kernel(const uint8_t* __restrict__ in, int h, int w, int H,
+                                                                   int W, uint8_t* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long plane = blockIdx.y;
+  const int wb = (W + 7) / 8;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * wb) return;
+  const int xb = i % wb, y = i / wb;
+  const Lerp ly = lerp_setup(y, (float)h / (float)H, h);
+  const uint8_t* r0 = in + (size_t)plane * h * w + (size_t)ly.i0 * w;
+  const uint8_t* r1 = in + (size_t)plane * h * w + (size_t)ly.i1 * w;
+  uint32_t bits = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int x = xb * 8 + k;
+    if (x < W) {
+      const Lerp lx = lerp_setup(x, (float)w / (float)W, w);
+      const float v00 = (float)__ldg(r0 + lx.i0), v01 = (float)__ldg(r0 + lx.i1);
+      const float v10 = (float)__ldg(r1 + lx.i0), v11 = (float)__ldg(r1 + lx.i1);
+      const float v = ly.l0 * (lx.l0 * v00 + lx.l1 * v01) + ly.l1 * (lx.l0 * v10 + lx.l1 * v11);
+      bits |= (v > 0.5f ? 1u : 0u) << (7 - k);
+    }
+  }
+  out[(size_t)plane * H * wb + (size_t)y * wb + xb] = (uint8_t)bits;
+}
+
+// Dense (planes, H, W) bytes -> bits, same layout as above (for the level whose dense volume already exists).
+__global__ void __launch_bounds__(256) pack_mask_kernel(const uint8_t* __restrict__ in, int H, int W,
+                                                        uint8_t* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long plane = blockIdx.y;
+  const int wb = (W + 7) / 8;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * wb) return;
+  const int xb = i % wb, y = i / wb;
+  const uint8_t* r = in + (size_t)plane * H * W + (size_t)y * W;
+  uint32_t bits = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int x = xb * 8 + k;
+    if (x < W && __ldg(r + x) != 0) bits |= 1u << (7 - k);
+  }
+  out[(size_t)plane * H * wb + (size_t)y * wb + xb] = (uint8_t)bits;
+}
+
 }  // namespace
 
 int launch_warp_planar(const float* H, int h_stride, const ViewPtrs& src, int n, int channels, int rows, int cols,
@@ -514,8 +563,23 @@ int launch_upsample_f32(const float* in, int n_planes, int h, int w, int H, int 
 }
 
 int launch_upsample_mask(const uint8_t* in, long long n_planes, int h, int w, int H, int W, uint8_t* out,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, bool packed) {
   // gridDim.y is limited to 65535 planes per launch.
+  if (packed) {
+    const int wb = (W + 7) / 8;
+    for (long long p0 = 0; p0 < n_planes; p0 += 65535) {
+      const int np = (int)((n_planes - p0) < 65535 ? (n_planes - p0) : 65535);
+      dim3 grid(cdiv(H * wb, 256), np);
+      if (h == H && w == W)
+        launch_pdl(pack_mask_kernel, grid, dim3(256), (size_t)0, stream, in + (size_t)p0 * h * w, H, W,
+                   out + (size_t)p0 * H * wb);
+      else
+        launch_pdl(upsample_mask_packed_kernel, grid, dim3(256), (size_t)0, stream, in + (size_t)p0 * h * w, h, w, H, W,
+                   out + (size_t)p0 * H * wb);
+      B200MVS_LAUNCH_OK("upsample_mask_packed_kernel");
+    }
+    return 0;
+  }
   const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 3) == 0) && (((long long)H * W) % 4 == 0);
   const bool vec16 = (W % 16 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   for (long long p0 = 0; p0 < n_planes; p0 += 65535) {

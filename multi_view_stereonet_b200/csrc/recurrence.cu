@@ -831,13 +831,10 @@ int launch_recurrence(const RecurrenceArgs& a, cudaStream_t stream) {
     set_error("launch_recurrence: shape not supported by the persistent kernel");
     return -1;
   }
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    B200MVS_CUDA_OK(cudaFuncSetAttribute(recurrence_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B200MVS_CUDA_OK(cudaFuncSetAttribute(recurrence_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    B200MVS_CUDA_OK(cudaFuncSetAttribute(recurrence_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B200MVS_CUDA_OK(cudaFuncSetAttribute(recurrence_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    smem_set = smem;
+  for (const void* f : {reinterpret_cast<const void*>(&recurrence_kernel<false>),
+                        reinterpret_cast<const void*>(&recurrence_kernel<true>)}) {
+    if (int rc = ensure_func_smem(f, smem)) return rc;
+    if (int rc = ensure_func_nonportable_cluster(f)) return rc;
   }
   RecParams p;
   p.vol_in = a.vol;
@@ -861,9 +858,9 @@ int launch_recurrence(const RecurrenceArgs& a, cudaStream_t stream) {
   p.debug = a.debug;
 
   // Cluster size: one CTA per M-tile; if that size cannot be scheduled, pad with idle CTAs.
-  static int good_cluster[17] = {0};
+  const int known_cluster = cached_cluster_size(n_tiles);
   int candidates[3] = {n_tiles, (n_tiles + 1) & ~1, 16};
-  if (good_cluster[n_tiles] != 0) candidates[0] = candidates[1] = candidates[2] = good_cluster[n_tiles];
+  if (known_cluster != 0) candidates[0] = candidates[1] = candidates[2] = known_cluster;
   cudaError_t e = cudaErrorUnknown;
   for (int c = 0; c < 3; ++c) {
     const int cs = candidates[c];
@@ -882,7 +879,7 @@ int launch_recurrence(const RecurrenceArgs& a, cudaStream_t stream) {
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    if (good_cluster[n_tiles] == 0) {
+    if (known_cluster == 0) {
       int max_clusters = 0;
       e = cudaOccupancyMaxActiveClusters(&max_clusters, recurrence_kernel<false>, &cfg);
       if (e != cudaSuccess || max_clusters < 1) {
@@ -894,7 +891,7 @@ int launch_recurrence(const RecurrenceArgs& a, cudaStream_t stream) {
     e = (a.prof != nullptr) ? cudaLaunchKernelEx(&cfg, recurrence_kernel<true>, p)
                             : cudaLaunchKernelEx(&cfg, recurrence_kernel<false>, p);
     if (e == cudaSuccess) {
-      good_cluster[n_tiles] = cs;
+      if (known_cluster == 0) remember_cluster_size(n_tiles, cs);
       break;
     }
     cudaGetLastError();

@@ -6,7 +6,9 @@ key names (so the reference's weights load unchanged); the work is done by the
 hand-written sm_100a kernels behind the C ABI in include/b200mvs.h.  This module
 only holds parameters, validates arguments and passes device pointers.
 """
+import collections.abc
 import ctypes
+import warnings
 from typing import Dict, List, Optional
 
 import torch
@@ -15,6 +17,71 @@ import torch.nn as tnn
 from . import _lib
 
 ListTensor = List[torch.Tensor]
+
+
+class LazyMaskPyramid(collections.abc.Sequence):
+    """`left_idepthmap_mask_pyr` produced on demand (mask_mode = "lazy").
+
+    The reference upsamples the (B, D, h, w) validity volume to every pyramid level inside forward
+    (multi_view_stereonet.py:627-673) although nothing on the path reads it: 28 MB per image group at 512x640 / 64
+    hypotheses, 168 MB at 1024x1280 / 128.  In lazy mode forward produces the level-4 volume only; indexing this
+    sequence runs the MaskUpsampler chain (level 4 -> ... -> requested level, each level from the thresholded
+    coarser one, exactly as the reference) the first time a level is asked for and caches it.  `packed(level)`
+    returns the same volume as bits, (B, D, H, ceil(W / 8)) uint8 in numpy.packbits(axis=-1) layout."""
+
+    def __init__(self, mask4, sizes):
+        self._sizes = [tuple(s) for s in sizes]
+        self._out_device = mask4.device
+        self._dense = {4: mask4}        # uint8 0/1, (B, D, H_l, W_l), on the compute device once needed
+        self._packed = {}
+
+    def __len__(self):
+        return len(self._sizes)
+
+    def _compute_device(self):
+        return self._out_device if self._out_device.type == "cuda" else torch.device("cuda", torch.cuda.current_device())
+
+    def _upsample(self, src, lvl, packed):
+        lib = _lib.load()
+        b, d, h, w = src.shape
+        H, W = self._sizes[lvl]
+        out = torch.empty((b, d, H, (W + 7) // 8 if packed else W), dtype=torch.uint8, device=src.device)
+        with torch.cuda.device(src.device):
+            stream = torch.cuda.current_stream(src.device).cuda_stream
+            _lib.check(lib.b200mvs_upsample_mask(src.data_ptr(), b * d, h, w, H, W, int(packed), out.data_ptr(),
+                                                 ctypes.c_void_p(stream)), "b200mvs_upsample_mask")
+        return out
+
+    def _dense_on_device(self, lvl):
+        """uint8 volume of `lvl` on the compute device, building the chain from the finest level already there."""
+        dev = self._compute_device()
+        have = min(l for l in self._dense if l >= lvl)
+        cur = self._dense[have]
+        if cur.device != dev:
+            cur = cur.to(dev)
+        for l in range(have - 1, lvl - 1, -1):
+            cur = self._upsample(cur, l, False)
+            self._dense[l] = cur
+        return cur
+
+    def __getitem__(self, lvl):
+        if isinstance(lvl, slice):
+            return [self[i] for i in range(*lvl.indices(len(self)))]
+        if lvl < 0:
+            lvl += len(self)
+        if not 0 <= lvl < len(self):
+            raise IndexError(lvl)
+        return self._dense_on_device(lvl).to(self._out_device).view(torch.bool)
+
+    def packed(self, lvl):
+        if lvl not in self._packed:
+            if lvl in self._dense or lvl == len(self) - 1:
+                src, same = self._dense_on_device(lvl), True
+            else:
+                src, same = self._dense_on_device(lvl + 1), False
+            # from the coarser level the bits are written directly; the dense volume of `lvl` is never materialised
+            self._packed[lvl] = self._upsample(src, lvl, True).to(self._out_device)
+        return self._packed[lvl]
 
 
 class _Conv(tnn.Module):
@@ -120,24 +187,46 @@ class MultiViewStereoNet(tnn.Module):
         self._keep_stages = False
         self._host_out = None
         self._options = {}
+        # "dense": the five mask volumes are computed inside forward, as the reference does (default, drop-in);
+        # "lazy":  forward computes level 4 only and returns a LazyMaskPyramid;
+        # "none":  the list holds level 4 only, None elsewhere.
+        self.mask_mode = "dense"
 
     # -- native handle ---------------------------------------------------------------------
-    def _weights_key(self, device_index):
-        return (device_index,) + tuple((id(p), p._version) for p in self.parameters())
+    # The native handle holds a packed copy of the weights; it must follow every change of the parameters, including
+    # the in-place ones no module hook sees: `net.refiner0.load_state_dict(...)`, `torch.nn.init.*`, `p.copy_()`,
+    # `optimizer.step()`.  Each of those bumps the parameter's autograd version counter, so the key -- the parameter
+    # objects plus the sum of their versions -- is re-checked on EVERY forward over a cached parameter list (~20 us;
+    # walking the module tree instead costs ~230 us).  Two edits are invisible to it and need `refresh_weights()`:
+    # writes through `param.data` (PyTorch gives `.data` its own version counter) and re-assigning a submodule's
+    # Parameter object.
+    def _param_list(self):
+        params = getattr(self, "_param_cache", None)
+        if params is None:
+            params = self._param_cache = tuple(self.parameters())
+        return params
 
-    # Walking 226 parameters to build the key costs ~0.1 ms per forward, so the full check only runs when something
-    # may have changed the weights: the standard entry points below mark the native copy stale; code that edits
-    # parameters in place some other way calls `refresh_weights()`.
+    def _weights_key(self, device_index):
+        params = self._param_list()
+        return (device_index, tuple(map(id, params)), sum(p._version for p in params))
+
     def refresh_weights(self):
-        self._weights_stale = True
+        """Forces a re-upload of the weights on the next forward (only needed after `.data` writes or after
+        replacing a submodule's Parameter object; tracked in-place updates are picked up automatically)."""
+        self._param_cache = None
+        self._handle_key = None
 
     def load_state_dict(self, *args, **kwargs):
-        self._weights_stale = True
+        self._param_cache = None
         return super().load_state_dict(*args, **kwargs)
 
     def _apply(self, fn, *args, **kwargs):
-        self._weights_stale = True
+        self._param_cache = None
         return super()._apply(fn, *args, **kwargs)
+
+    def register_parameter(self, name, param):
+        self.__dict__["_param_cache"] = None
+        return super().register_parameter(name, param)
 
     def _release(self):
         if self._handle is not None:
@@ -152,11 +241,7 @@ class MultiViewStereoNet(tnn.Module):
             pass
 
     def _native(self, device_index):
-        if (self._handle is not None and not getattr(self, "_weights_stale", True)
-                and self._handle_key[0] == device_index):
-            return self._handle
         key = self._weights_key(device_index)
-        self._weights_stale = False
         if self._handle is not None and key == self._handle_key:
             return self._handle
         lib = _lib.load()
@@ -213,6 +298,13 @@ class MultiViewStereoNet(tnn.Module):
                    "b200mvs_probe_read")
         return ms.value, n.value
 
+    def last_stage_profile(self):
+        """{stage: microseconds} of the last forward run with set_option("stage_profile", 1)."""
+        if self._handle is None:
+            return {}
+        txt = _lib.load().b200mvs_last_stage_profile(self._handle).decode()
+        return {k: float(v) for k, v in (kv.split("=") for kv in txt.split(";") if kv)}
+
     def last_launch_count(self):
         return int(_lib.load().b200mvs_last_launch_count(self._handle)) if self._handle is not None else 0
 
@@ -261,6 +353,16 @@ class MultiViewStereoNet(tnn.Module):
         tensors are uploaded, processed on cuda:current and downloaded (the
         end-to-end entry `b200mvs_forward_host`)."""
         self._check_args(left_image_pyr, K_pyr, T_right_in_lefts, right_image_pyrs, do_refiners)
+        if torch.is_grad_enabled():
+            # the reference module is trainable; this one implements the inference path only (no backward kernels)
+            if any(t.requires_grad for t in list(left_image_pyr) + [p[0] for p in right_image_pyrs]):
+                raise RuntimeError("MultiViewStereoNet (B200) is inference-only: its outputs carry no grad_fn, so no "
+                                   "gradient can reach inputs that require grad.  Call it under torch.no_grad().")
+            if self.training and not getattr(self, "_warned_training", False):
+                self._warned_training = True
+                warnings.warn("MultiViewStereoNet (B200) is inference-only: called in training mode with autograd "
+                              "enabled, but the outputs carry no grad_fn and the parameters will receive no "
+                              "gradients.  Use .eval() and torch.no_grad() (test.py:191,196).", stacklevel=2)
         lib = _lib.load()
         dev = left_image_pyr[0].device
         shape = self._shape(left_image_pyr, T_right_in_lefts, num_idepth_samples, do_cost_volume_filter, do_refiners)
@@ -295,14 +397,16 @@ class MultiViewStereoNet(tnn.Module):
         else:
             idepth = [torch.empty((b, 1) + s, dtype=torch.float32, device=out_dev) for s in sizes]
             raw = [torch.empty((b, 1) + s, dtype=torch.float32, device=out_dev) for s in sizes]
-            mask = [torch.empty((b, d) + s, dtype=torch.uint8, device=out_dev) for s in sizes]
+            assert self.mask_mode in ("dense", "lazy", "none"), self.mask_mode
+            mask = [torch.empty((b, d) + s, dtype=torch.uint8, device=out_dev)
+                    if (self.mask_mode == "dense" or lvl == 4) else None for lvl, s in enumerate(sizes)]
         null5 = _lib.ptr_array([None] * 5)
         args = [ctypes.byref(shape),
                 _lib.ptr_array([t.data_ptr() for t in left]), _lib.ptr_array([t.data_ptr() for t in Ks]),
                 _lib.ptr_array([t.data_ptr() for t in Ts]), _lib.ptr_array([t.data_ptr() for t in r0]),
                 _lib.ptr_array([t.data_ptr() for t in r4]), _lib.ptr_array([t.data_ptr() for t in idepth]),
                 _lib.ptr_array([t.data_ptr() for t in raw]) if want_raw else null5,
-                _lib.ptr_array([t.data_ptr() for t in mask]) if want_masks else null5]
+                _lib.ptr_array([t.data_ptr() if t is not None else None for t in mask]) if want_masks else null5]
         if on_host:
             h2d, d2h = ctypes.c_int64(), ctypes.c_int64()
             _lib.check(lib.b200mvs_forward_host(handle, *args, ctypes.byref(h2d), ctypes.byref(d2h)),
@@ -316,8 +420,13 @@ class MultiViewStereoNet(tnn.Module):
         outputs: Dict[str, List[Optional[torch.Tensor]]] = {}
         outputs["left_idepthmap_pyr"] = idepth
         outputs["left_idepthmap_raw_pyr"] = raw if want_raw else [None] * 5
-        outputs["left_idepthmap_mask_pyr"] = ([m.view(torch.bool) if m.dtype == torch.uint8 else m for m in mask]
-                                              if want_masks else [None] * 5)
+        if not want_masks:
+            outputs["left_idepthmap_mask_pyr"] = [None] * 5
+        elif mask[0] is None and self.mask_mode == "lazy":
+            outputs["left_idepthmap_mask_pyr"] = LazyMaskPyramid(mask[4], sizes)
+        else:
+            outputs["left_idepthmap_mask_pyr"] = [None if m is None else (m.view(torch.bool) if m.dtype == torch.uint8 else m)
+                                                  for m in mask]
         return outputs
 
     def set_host_outputs(self, out):

@@ -4,6 +4,8 @@
   build_image_pyramid       utils/image_utils.py:111-128      area pyramid, on the device
   multi_view_unpack_batch   :541-641                           pyramids, per-level K, inverse poses, baseline
   multi_view_forward        :643-662                           the timed call of the network
+  unpack_batch, forward     :406-539                           the two-view variants of the same pair (one comparison
+                                                               image, optional right-view estimate)
 
 The pyramids, intrinsics and pose normalisation run in CUDA kernels (b200mvs_area_downsample,
 b200mvs_prepare_cameras); ground-truth depth maps, which only the losses read, are rescaled with plain tensor ops.
@@ -112,3 +114,52 @@ def multi_view_forward(stereo_network, inputs, params):
             "left_idepthmap_raw_pyr": left_outputs["left_idepthmap_raw_pyr"],
             "left_idepthmap_mask_pyr": left_outputs["left_idepthmap_mask_pyr"],
             "stereo_time_ms": tick.elapsed_time(tock)}
+
+
+def unpack_batch(batch, device, num_levels):
+    """Two-view unpack (multi_view_stereonet_utils.py:406-501): `right_image`, `T_right_in_left` (and the right
+    ground truth) are single tensors instead of per-view lists; same kernels as `multi_view_unpack_batch`."""
+    multi = dict(batch)
+    multi["right_image"] = [batch["right_image"]]
+    multi["T_right_in_left"] = [batch["T_right_in_left"]]
+    if "left_depthmap_true" in batch:
+        multi["right_depthmap_true"] = [batch["right_depthmap_true"]]
+    inputs = multi_view_unpack_batch(multi, device, num_levels)
+    for key in ("T_right_in_left", "T_left_in_right", "right_image_pyr", "right_depthmap_true", "right_idepthmap_true"):
+        if key in inputs:
+            inputs[key] = inputs[key][0]
+    if "left_disparity_true" in batch:     # passed through to the device unchanged (:469-474)
+        inputs["left_disparity_true"] = batch["left_disparity_true"].to(device)
+        inputs["right_disparity_true"] = batch["right_disparity_true"].to(device)
+    return inputs
+
+
+def _timed_call(stereo_network, image_pyr, K_pyr, T, other_pyr, params):
+    torch.cuda.synchronize()
+    tick, tock = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tick.record()
+    out = stereo_network(image_pyr, K_pyr, [T], [other_pyr], params["num_idepth_samples"],
+                         params["cost_volume_filter"], params["refiners"])
+    tock.record()
+    torch.cuda.synchronize()
+    return out, tick.elapsed_time(tock)
+
+
+def forward(stereo_network, inputs, params):
+    """Two-view forward (multi_view_stereonet_utils.py:503-539): the left estimate and, if
+    params["estimate_right_idepthmap"], the right one with the roles of the two images swapped
+    (`T_left_in_right`); `stereo_time_ms` is then the mean of the two calls."""
+    left, ms = _timed_call(stereo_network, inputs["left_image_pyr"], inputs["K_pyr"], inputs["T_right_in_left"],
+                           inputs["right_image_pyr"], params)
+    outputs = {"left_idepthmap_pyr": left["left_idepthmap_pyr"],
+               "left_idepthmap_raw_pyr": left["left_idepthmap_raw_pyr"],
+               "left_idepthmap_mask_pyr": left["left_idepthmap_mask_pyr"],
+               "stereo_time_ms": ms}
+    if params["estimate_right_idepthmap"]:
+        right, right_ms = _timed_call(stereo_network, inputs["right_image_pyr"], inputs["K_pyr"],
+                                      inputs["T_left_in_right"], inputs["left_image_pyr"], params)
+        outputs["right_idepthmap_pyr"] = right["left_idepthmap_pyr"]
+        outputs["right_idepthmap_raw_pyr"] = right["left_idepthmap_raw_pyr"]
+        outputs["right_idepthmap_mask_pyr"] = right["left_idepthmap_mask_pyr"]
+        outputs["stereo_time_ms"] = 0.5 * (outputs["stereo_time_ms"] + right_ms)
+    return outputs

@@ -70,7 +70,7 @@ def _rot_x(a):
 PITCH_RAD = 0.01174
 
 
-def make_inputs(rows, cols, views, batch, seed=1234, first_item=0, smooth=False):
+def make_inputs(rows, cols, views, batch, seed=1234, first_item=0, smooth=False, pitch=None):
     """Returns the tensors `MultiViewStereoNet.forward` takes, on the CPU.
 
     Item i of the batch is generated from `seed + first_item + i`, so a rank that
@@ -78,7 +78,10 @@ def make_inputs(rows, cols, views, batch, seed=1234, first_item=0, smooth=False)
 
     smooth=True low-pass filters the images so that neighbouring views correlate
     (uniform noise makes every hypothesis equally bad); parity tests use both.
+    pitch overrides PITCH_RAD (tests also run SURVEY.md's original 0.01 rad, whose geometry has knife-edge mask
+    pixels).
     """
+    pitch = PITCH_RAD if pitch is None else pitch
     lefts, rights = [], [[] for _ in range(views)]
     for i in range(batch):
         g = torch.Generator().manual_seed(seed + first_item + i)
@@ -105,7 +108,7 @@ def make_inputs(rows, cols, views, batch, seed=1234, first_item=0, smooth=False)
     Ts = []
     for v in range(views):
         sgn = (-1.0) ** v
-        R = _rot_y(0.02 * (v + 1) * sgn) @ _rot_x(PITCH_RAD)
+        R = _rot_y(0.02 * (v + 1) * sgn) @ _rot_x(pitch)
         t = torch.tensor([0.30 * (v + 1) * sgn, 0.05, 0.02 * (v + 1)], dtype=torch.float64)
         T = torch.eye(4, dtype=torch.float64)
         T[:3, :3] = R
@@ -155,3 +158,13 @@ def make_raw_batch(B=2, V=2, rows=38, cols=51, seed=99):
              "right_depthmap_true": [torch.rand(B, 1, rows, cols, generator=g) * 10 for _ in range(V)]}
     batch["left_depthmap_true"][:, :, :5] = 0.0                  # invalid (zero) depths stay zero
     return batch
+
+
+def make_raw_batch_two_view(**kw):
+    """The two-view layout of `make_raw_batch(V=1)`: single tensors instead of per-view lists, as the reference's
+    `unpack_batch` takes them (multi_view_stereonet_utils.py:409-415)."""
+    b = make_raw_batch(V=1, **kw)
+    return {"left_image": b["left_image"], "right_image": b["right_image"][0], "K": b["K"],
+            "T_right_in_left": b["T_right_in_left"][0], "left_filename": b["left_filename"],
+            "right_filename": b["right_filename"][0], "left_depthmap_true": b["left_depthmap_true"],
+            "right_depthmap_true": b["right_depthmap_true"][0]}

@@ -42,6 +42,12 @@ def _walk(obj, prefix, out):
                 _walk(v, prefix, out)
 
 
+_ALLOWED_GLOBALS = {("torch._utils", "_rebuild_tensor_v2"), ("torch._utils", "_rebuild_tensor"),
+                    ("torch._utils", "_rebuild_parameter"), ("torch", "device"), ("torch", "Size"),
+                    ("torch.jit._pickle", "build_intlist"), ("torch.jit._pickle", "build_boollist"),
+                    ("torch.jit._pickle", "build_doublelist"), ("torch.jit._pickle", "build_tensorlist")}
+
+
 def load_torchscript_archive_weights(path):
     """Returns {state_dict key: float32 tensor} from a reference `.pt` archive."""
     zf = zipfile.ZipFile(path)
@@ -53,7 +59,11 @@ def load_torchscript_archive_weights(path):
                 return type(name, (_Stub,), {})
             if module == "collections" and name == "OrderedDict":
                 return collections.OrderedDict
-            return super().find_class(module, name)
+            # The archive needs nothing but tensor rebuild helpers and storage types; any other global (os.system,
+            # builtins.eval, ...) in a crafted data.pkl would run code here, so it is refused.
+            if (module, name) in _ALLOWED_GLOBALS or (module == "torch" and name.endswith("Storage")):
+                return super().find_class(module, name)
+            raise pickle.UnpicklingError(f"weight archive references disallowed global {module}.{name}")
 
         def persistent_load(self, pid):
             # ('storage', storage_type, key, location, numel)

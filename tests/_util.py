@@ -34,7 +34,8 @@ def load_case(name):
     z = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
     rows, cols, views, hyps, batch, smooth, cvf = [int(x) for x in z["meta"][:7]]
     refiners = [bool(x) for x in z["meta"][7:12]]
-    inputs = synthetic.make_inputs(rows, cols, views, batch, smooth=bool(smooth))
+    pitch = float(z["pitch"][0]) if "pitch" in z else None
+    inputs = synthetic.make_inputs(rows, cols, views, batch, smooth=bool(smooth), pitch=pitch)
     chk = np.array([float(inputs[0][0].double().sum()), float(inputs[3][-1][0].double().sum()),
                     float(inputs[0][4].double().abs().sum())])
     # The fixtures are only meaningful if this box regenerates identical inputs.

@@ -38,7 +38,12 @@ CASES = {
     "flags_nocvf": (64, 80, 2, 8, 1, True, False, [True, False, True, False, False], False),
     "cfg2": (512, 640, 1, 64, 1, False, True, [True] * 5, False),
     "cfg2_smooth": (512, 640, 1, 64, 1, True, True, [True] * 5, False),
+    # one image group of BASELINE cfg3: 4 comparison views, 64 hypotheses
+    "cfg3_item": (512, 640, 4, 64, 1, False, True, [True] * 5, False),
+    # cfg2 at SURVEY.md 8d's original camera pitch (0.01 rad): the geometry with knife-edge mask pixels
+    "cfg2_pitch001": (512, 640, 1, 64, 1, False, True, [True] * 5, False),
 }
+PITCH = {"cfg2_pitch001": 0.01}
 
 
 def main():
@@ -52,15 +57,19 @@ def main():
     assert sum(v.numel() for v in unique.values()) == 608614       # pretrained/gta_sfm_150epochs/logs.txt:4
     weights.save_state_npz(unique, os.path.join(HERE, "gta_sfm_150epochs_state.npz"))
 
+    only = sys.argv[1:]
     for name, (rows, cols, views, hyps, batch, smooth, cvf, refiners, with_stages) in CASES.items():
-        inp = synthetic.make_inputs(rows, cols, views, batch, smooth=smooth)
+        if only and name not in only:
+            continue
+        inp = synthetic.make_inputs(rows, cols, views, batch, smooth=smooth, pitch=PITCH.get(name))
         left_pyr, K_pyr, Ts, right_pyrs = inp
         with torch.no_grad():
             out = net(left_pyr, K_pyr, Ts, right_pyrs, hyps, cvf, refiners)
         big = rows * cols > 100000
         rec = {"meta": np.array([rows, cols, views, hyps, batch, int(smooth), int(cvf)] + [int(r) for r in refiners]),
                "input_checksum": np.array([float(left_pyr[0].double().sum()), float(right_pyrs[-1][0].double().sum()),
-                                           float(left_pyr[4].double().abs().sum())])}
+                                           float(left_pyr[4].double().abs().sum())]),
+               "pitch": np.array([PITCH.get(name, synthetic.PITCH_RAD)])}
         for lvl in range(5):
             rec[f"idepth{lvl}"] = out["left_idepthmap_pyr"][lvl].numpy()
             m = out["left_idepthmap_mask_pyr"][lvl].numpy()

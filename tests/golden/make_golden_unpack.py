@@ -24,13 +24,27 @@ from multi_view_stereonet_b200 import synthetic  # noqa: E402
 from utils import image_utils  # noqa: E402  (the reference)
 
 
-def reference_unpack():
+def reference_unpack(name="multi_view_unpack_batch"):
     path = os.path.join(REF, "multi_view_stereonet/multi_view_stereonet_utils.py")
     src = open(path).read()
-    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "multi_view_unpack_batch")
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == name)
     ns = {"torch": torch, "image_utils": image_utils}
     exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
-    return ns["multi_view_unpack_batch"]
+    return ns[name]
+
+
+def main_two_view():
+    """Reference `unpack_batch` (:406-501) -> tests/golden/unpack2_small.npz"""
+    out = reference_unpack("unpack_batch")(clone(synthetic.make_raw_batch_two_view()), torch.device("cpu"), 5)
+    flat = {k: out[k] for k in ("baseline", "T_right_in_left", "T_left_in_right", "left_depthmap_true",
+                                "left_idepthmap_true", "right_depthmap_true", "right_idepthmap_true")}
+    for lvl in range(5):
+        flat[f"K_pyr{lvl}"] = out["K_pyr"][lvl]
+        flat[f"left_image_pyr{lvl}"] = out["left_image_pyr"][lvl]
+        flat[f"right_image_pyr{lvl}"] = out["right_image_pyr"][lvl]
+    path = os.path.join(HERE, "unpack2_small.npz")
+    np.savez_compressed(path, **{k: v.numpy() for k, v in flat.items()})
+    print("wrote", path, os.path.getsize(path), "bytes")
 
 
 def clone(batch):
@@ -62,3 +76,4 @@ def main():
 
 if __name__ == "__main__":
     main()
+    main_two_view()

@@ -47,7 +47,10 @@ def test_oracle_matches_reference_small(name, gta_state):
         assert rel_linf(v0["cost_filtered"], z["v0_cost_filtered"]) < ORACLE_TOL
 
 
-@pytest.mark.parametrize("name", ["cfg2", "cfg2_smooth"])
+# cfg3_item: one image group of BASELINE cfg3 (4 comparison views); cfg2_pitch001: cfg2 at SURVEY.md's original
+# camera pitch, the geometry that has knife-edge mask pixels.  Both implementations here are torch on the same CPU
+# and evaluate the mask test with the same float32 operations, so even those pixels must agree.
+@pytest.mark.parametrize("name", ["cfg2", "cfg2_smooth", "cfg3_item", "cfg2_pitch001"])
 def test_oracle_matches_reference_cfg2(name, gta_state):
     z, inputs, hyps, cvf, refiners = load_case(name)
     with torch.no_grad():

@@ -1,0 +1,114 @@
+// Micro-benchmark: cycles per tcgen05.mma (kind::f16, M=128) as a function of N and of the A operand's
+// shared-memory layout / start alignment (no-swizzle K-major planes as the conv kernels use them).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I multi_view_stereonet_b200/csrc tools/mma_bench.cu -o tools/bin/mma_bench
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "tc_common.cuh"
+
+using namespace b200mvs;
+
+namespace b200mvs {
+void set_error(const std::string&) {}
+void note_launch() {}
+bool pdl_enabled() { return false; }
+void set_pdl_enabled(bool) {}
+}
+
+
+// PATTERN: 0 = same A every MMA; 1 = nine taps (ky*PW + kx) of a PW=42 plane, two K-steps, as the conv kernels issue
+// them; 2 = split-precision pairs (N=64 on A_hi, N=32 on A_lo) over the nine taps x two K-steps.
+template <int N, int PATTERN, int COUNT, int BASE, bool INTERLEAVED>
+__global__ void __launch_bounds__(128, 1) bench_kernel(long long* out, int plane_bytes) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t s_tmem;
+  const int warp = tc::uniform_warp_index();
+  for (int i = threadIdx.x; i < 200 * 1024 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (warp == 0) tc::tmem_alloc(&s_tmem, 512u);
+  if (threadIdx.x == 32) {
+    tc::mbar_init(&bar, 1);
+    tc::mbar_init_fence();
+  }
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = s_tmem;
+  const uint32_t plane_u16 = (uint32_t)plane_bytes >> 4;
+  const uint64_t da0 = INTERLEAVED ? tc::umma_desc(tc::smem_u32(smem), 128u, 256u)
+                                   : tc::umma_desc(tc::smem_u32(smem), (uint32_t)plane_bytes, 128u);
+  const uint64_t db0 = tc::umma_desc(tc::smem_u32(smem + 160 * 1024), 1024u, 128u);
+  if (warp == 0) {
+    if (tc::elect_one()) {
+#pragma unroll 1
+      for (int rep = 0; rep < 5; ++rep) {
+        const long long t0 = clock64();
+#pragma unroll
+        for (int i = 0; i < COUNT; ++i) {
+          if (PATTERN == 0) {
+            tc::mma_f16(tmem, da0 + BASE, db0, tc::idesc_f16(N), i ? 1u : 0u);
+          } else {
+            const int tap = (i / 2) % 9, ks = i % 2;
+            const uint32_t pos = (uint32_t)((tap / 3) * 42 + (tap % 3));
+            const uint64_t a = da0 + (uint64_t)(BASE + 2u * ks * plane_u16 + pos);
+            const uint64_t b = db0 + (uint64_t)(((tap * 2 + ks) % 18) * 128);
+            if (PATTERN == 1) {
+              tc::mma_f16(tmem, a, b, tc::idesc_f16(N), i ? 1u : 0u);
+            } else {
+              tc::mma_f16(tmem, a, b, tc::idesc_f16(64), i ? 1u : 0u);
+              tc::mma_f16(tmem, a + 4u * plane_u16, b, tc::idesc_f16(32), 1u);
+            }
+          }
+        }
+        const long long t1 = clock64();
+        tc::mma_commit(&bar);
+        tc::mbar_wait(&bar, (uint32_t)(rep & 1));
+        const long long t2 = clock64();
+        out[rep * 2 + 0] = t1 - t0;
+        out[rep * 2 + 1] = t2 - t0;
+      }
+    }
+    __syncwarp();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512u);
+}
+
+template <int N, int PATTERN, int COUNT, int BASE, bool INTERLEAVED>
+void run(const char* name, long long* d) {
+  auto k = bench_kernel<N, PATTERN, COUNT, BASE, INTERLEAVED>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  k<<<1, 128, 200 * 1024>>>(d, 218 * 16);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long h[10];
+  cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+  const int mmas = COUNT * (PATTERN == 2 ? 2 : 1);
+  printf("%-44s issue %5lld  total %6lld cycles = %6.1f / MMA  (%s)\n", name, h[8], h[9], (double)h[9] / mmas,
+         cudaGetErrorString(e));
+}
+
+int main() {
+  long long* d;
+  cudaMalloc(&d, 10 * sizeof(long long));
+  run<32, 0, 36, 0, false>("N=32 same A aligned", d);
+  run<32, 0, 36, 1, false>("N=32 same A +16 B", d);
+  run<32, 0, 36, 4, false>("N=32 same A +64 B", d);
+  run<64, 0, 36, 0, false>("N=64 same A aligned", d);
+  run<64, 0, 36, 1, false>("N=64 same A +16 B", d);
+  run<128, 0, 36, 0, false>("N=128 same A aligned", d);
+  run<128, 0, 36, 1, false>("N=128 same A +16 B", d);
+  run<256, 0, 36, 0, false>("N=256 same A aligned", d);
+  run<256, 0, 36, 1, false>("N=256 same A +16 B", d);
+  run<8, 0, 36, 0, false>("N=8 same A aligned", d);
+  run<16, 0, 36, 0, false>("N=16 same A aligned", d);
+  run<32, 1, 18, 0, false>("N=32 conv taps x2 ksteps (18)", d);
+  run<64, 1, 18, 0, false>("N=64 conv taps x2 ksteps (18)", d);
+  run<32, 2, 18, 0, false>("split pairs N=64+N=32 (36), one conv", d);
+  run<32, 2, 54, 0, false>("split pairs N=64+N=32 (108), conv3d slice", d);
+  run<32, 0, 36, 0, true>("N=32 interleaved K chunks aligned", d);
+  run<32, 0, 36, 1, true>("N=32 interleaved K chunks +16 B", d);
+  run<32, 0, 36, 2, true>("N=32 interleaved K chunks +32 B", d);
+  run<64, 0, 36, 2, true>("N=64 interleaved K chunks +32 B", d);
+  return 0;
+}
