@@ -197,4 +197,14 @@ __device__ __forceinline__ float upsample_bilinear_at(const float* __restrict__ 
 
 __device__ __forceinline__ float lrelu(float v) { return v > 0.0f ? v : kLreluSlope * v; }
 
+// 1 / sqrt(var + eps) of a GroupNorm from float64 statistics.  Every conv kernel computes this on its critical path
+// (32 threads, then a block barrier): the float32 MUFU estimate refined by one Newton step in float64 (relative
+// error ~1e-13, i.e. the same float32 coefficients after rounding) replaces the float64 library rsqrt, whose
+// software iteration cost ~1 us per layer (measured with B200MVS_TC_PROFILE, "coeffs").
+__device__ __forceinline__ double gn_rstd(double var) {
+  const double x = (var > 0.0 ? var : 0.0) + (double)kGnEps;
+  const double r = (double)rsqrtf((float)x);
+  return r * (1.5 - 0.5 * x * r * r);
+}
+
 }  // namespace b200mvs

@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(NT, MINB) conv3x3_tc_kernel(const ConvParams p
     const double mean = sum * p.feat.inv_count;
     double var = sq * p.feat.inv_count - mean * mean;
     var = var > 0.0 ? var : 0.0;
-    const double rstd = rsqrt(var + (double)kGnEps);
+    const double rstd = gn_rstd(var);
     s_a[tid] = (float)((double)p.feat.gamma[tid] * rstd);
     s_b[tid] = (float)((double)p.feat.beta[tid] - mean * (double)p.feat.gamma[tid] * rstd);
   }

@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(NT, 1) conv3x3_ws_kernel(const WsParams p, con
         const double mean = sum * p.inv_count;
         double var = sq * p.inv_count - mean * mean;
         var = var > 0.0 ? var : 0.0;
-        const double rstd = rsqrt(var + (double)kGnEps);
+        const double rstd = gn_rstd(var);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const double gm = (double)__ldg(p.gamma + 8 * c8 + e);

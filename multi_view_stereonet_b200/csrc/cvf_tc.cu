@@ -6,8 +6,13 @@
 // depth slices of one volume and streams through depth: every input slice tile ((RT+2) rows, previous layer's GroupNorm + LeakyReLU
 // applied, split into hi/lo fp16 planes) is staged ONCE into a 4-slot shared-memory ring and used by the three
 // output slices that touch it.  Output slice q = 27 taps x 2 k-steps x 2 MMAs reading ring slots q, q+1, q+2 with
-// the shifted-window descriptors of conv_tc.cu; accumulators are double-buffered in TMEM so the MMAs of slice q
-// run while the epilogue of slice q-1 stores and the loads of input slice q+3 are in flight.
+// the shifted-window descriptors of conv_tc.cu; accumulators are double-buffered in TMEM.
+// Warp-specialised: eight worker warps stage slices and drain accumulators, a ninth warp only issues MMAs.  One
+// slice's 108 MMAs take ~4.9 k cycles of the tensor pipe and nearly as long to ISSUE (tools/mma_bench.cu: 45 cycles
+// per MMA at N = 64 / 32); with the issue loop on a worker warp every iteration paid issue time plus staging plus
+// epilogue (~9 k cycles, round 1), now the tensor pipe runs back to back and the workers hide under it.  The roles
+// meet only at mbarriers: full[slot] (workers -> issuer), acc_full[buf] (tcgen05.commit -> workers), acc_empty[buf]
+// (workers -> issuer).
 #include <cstdlib>
 #include <vector>
 
@@ -18,7 +23,8 @@
 namespace b200mvs {
 namespace {
 
-constexpr int NT = 256;
+constexpr int NW = 256;            // worker threads (8 warps): staging + epilogue
+constexpr int NT = NW + 32;        // + the MMA-issuing warp
 constexpr int MAX_TASKS = 4;
 constexpr int W_BLOCKS = 27 * 2;
 constexpr int W_BYTES = W_BLOCKS * 2048;
@@ -59,7 +65,7 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ float s_a[kC], s_b[kC], s_bias[kC];
   __shared__ double s_stats[2 * kGroups];
-  __shared__ __align__(8) uint64_t s_bar[2], s_wbar;
+  __shared__ __align__(8) uint64_t s_full[RING], s_acc_full[2], s_acc_empty[2], s_wbar;
   __shared__ uint32_t s_tmem;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -77,8 +83,11 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
 
   if (warp == 0) tc::tmem_alloc(&s_tmem, 128u);
   if (tid == 32) {
-    tc::mbar_init(&s_bar[0], 1);
-    tc::mbar_init(&s_bar[1], 1);
+    for (int i = 0; i < RING; ++i) tc::mbar_init(&s_full[i], NW / 32);   // one arrival per worker warp
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&s_acc_full[i], 1);
+      tc::mbar_init(&s_acc_empty[i], NW / 32);
+    }
     tc::mbar_init(&s_wbar, 1);
     tc::mbar_init_fence();
     tc::bulk_load_weights(s_w, p.w16, (uint32_t)W_BYTES, &s_wbar);   // constant data: before griddepcontrol.wait
@@ -96,7 +105,7 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
     const double mean = sum * p.inv_count;
     double var = sq * p.inv_count - mean * mean;
     var = var > 0.0 ? var : 0.0;
-    const double rstd = rsqrt(var + (double)kGnEps);
+    const double rstd = gn_rstd(var);
     s_a[tid] = (float)((double)p.gamma[tid] * rstd);
     s_b[tid] = (float)((double)p.beta[tid] - mean * (double)p.gamma[tid] * rstd);
   }
@@ -112,7 +121,7 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
   bool t_in[MAX_TASKS], t_real[MAX_TASKS];
 #pragma unroll
   for (int k = 0; k < MAX_TASKS; ++k) {
-    const int i = tid + k * NT;
+    const int i = tid + k * NW;
     t_l[k] = i >> 2;
     const int iy = t_l[k] / PW, ix = t_l[k] % PW;
     const int gy = y0 - 1 + iy, gx = x0 + ix - 1;
@@ -142,122 +151,122 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
   //   issue the MMAs of output slice it - 2 (queued right behind those of slice it - 3: the tensor pipe stays busy)
   //   issue the global loads of input slice it + 1
   //   epilogue of output slice it - 3 (overlaps the MMAs just issued and the loads in flight)
-  float4 ya[MAX_TASKS], yb[MAX_TASKS];
-  bool loaded_valid = false;
-  auto issue_loads = [&](int slice) {
-    const int din = d0 - 1 + slice;
-    loaded_valid = slice <= dcount + 1 && din >= 0 && din < p.D && !(P.dbg & 8);
-    if (loaded_valid) {
-      const float* src = in_n + (size_t)din * slice_elems;
+  if (warp == NW / 32) {
+    // ================= MMA issuer: output slice q once input slices q .. q+2 are staged and its accumulator is free
+    if (tc::elect_one()) {
+      tc::mbar_wait(&s_wbar, 0u);   // the bulk-copied weights have landed
+      for (int q = 0; q < dcount; ++q) {
+        tc::mbar_wait(&s_full[(q + 2) & (RING - 1)], (uint32_t)(((q + 2) / RING) & 1));
+        if (q >= 2) tc::mbar_wait(&s_acc_empty[q & 1], (uint32_t)(((q >> 1) - 1) & 1));
+        tc::fence_after_sync();
+        const uint32_t acc = tmem_base + (uint32_t)((q & 1) * 64);
 #pragma unroll
-      for (int k = 0; k < MAX_TASKS; ++k) {
-        if (t_real[k]) {
-          ya[k] = __ldg(reinterpret_cast<const float4*>(src + t_off[k]));
-          yb[k] = __ldg(reinterpret_cast<const float4*>(src + t_off[k] + 4));
-        }
-      }
-    }
-  };
-  issue_loads(0);
-  for (int it = 0; it <= dcount + 2; ++it) {
-    // ---- transform and stage input slice `it` into ring slot it & 3 (last read by the MMAs of output slice it - 4,
-    //      whose completion the epilogue of slice it - 4 observed one iteration ago) ----
-    if (it <= dcount + 1) {
-      uint8_t* slot = s_ring + (size_t)(it & (RING - 1)) * g.slot_bytes;
+        for (int kz = 0; kz < ((P.dbg & 1) ? 0 : 3); ++kz) {
+          const uint64_t da_slot = da0 + (uint64_t)(((q + kz) & (RING - 1)) * slot_u16);
 #pragma unroll
-      for (int k = 0; k < MAX_TASKS; ++k) {
-        if (t_in[k]) {
-          float v[8];
+          for (int t2 = 0; t2 < 9; ++t2) {
+            const uint32_t pos = (uint32_t)((t2 / 3) * PW + (t2 % 3));
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = 0.f;
-          if (t_real[k] && loaded_valid) {
-            v[0] = ya[k].x; v[1] = ya[k].y; v[2] = ya[k].z; v[3] = ya[k].w;
-            v[4] = yb[k].x; v[5] = yb[k].y; v[6] = yb[k].z; v[7] = yb[k].w;
-            if (p.mode >= FEAT_GN) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = lrelu(fmaf(v[e], s_a[8 * t_oct + e], s_b[8 * t_oct + e]));
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint64_t a_hi = da_slot + (uint64_t)(2 * ks * plane_u16 + pos);
+              const uint64_t a_lo = a_hi + (uint64_t)(4 * plane_u16);
+              const uint64_t b = db0 + (uint64_t)((((kz * 9 + t2) * 2) + ks) * 128);
+              tc::mma_f16(acc, a_hi, b, tc::idesc_f16(64), (kz | t2 | ks) != 0 ? 1u : 0u);
+              tc::mma_f16(acc, a_lo, b, tc::idesc_f16(32), 1u);
             }
           }
-          uint4 hi, lo;
-          tc::split8(v, &hi, &lo);
-          if (!(P.dbg & 2)) {
-            *reinterpret_cast<uint4*>(slot + (size_t)t_oct * g.plane_bytes + (size_t)t_l[k] * 16) = hi;
-            *reinterpret_cast<uint4*>(slot + (size_t)(4 + t_oct) * g.plane_bytes + (size_t)t_l[k] * 16) = lo;
+        }
+        tc::mma_commit(&s_acc_full[q & 1]);   // implies tcgen05.fence::before_thread_sync
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= workers.  Iteration `it`:
+    //   transform + stage input slice it (its global loads were issued one iteration earlier) -> ring slot it & 3,
+    //     last read by the MMAs of output slice it - 4, whose completion this thread observed in its epilogue
+    //   issue the global loads of input slice it + 1
+    //   epilogue of output slice it - 3 (its MMAs were queued behind those of slice it - 4 when slice it - 1 landed)
+    float4 ya[MAX_TASKS], yb[MAX_TASKS];
+    bool loaded_valid = false;
+    auto issue_loads = [&](int slice) {
+      const int din = d0 - 1 + slice;
+      loaded_valid = slice <= dcount + 1 && din >= 0 && din < p.D && !(P.dbg & 8);
+      if (loaded_valid) {
+        const float* src = in_n + (size_t)din * slice_elems;
+#pragma unroll
+        for (int k = 0; k < MAX_TASKS; ++k) {
+          if (t_real[k]) {
+            ya[k] = __ldg(reinterpret_cast<const float4*>(src + t_off[k]));
+            yb[k] = __ldg(reinterpret_cast<const float4*>(src + t_off[k] + 4));
           }
         }
       }
-    }
-    tc::fence_proxy_async();
-    tc::fence_before_sync();
-    __syncthreads();
-
-    // ---- issue the MMAs of output slice q = it - 2 (input slices q, q+1, q+2) ----
-    const int q = it - 2;
-    if (q >= 0 && q < dcount && warp == 0) {
-     if (tc::elect_one()) {
-      if (q == 0) tc::mbar_wait(&s_wbar, 0u);   // the bulk-copied weights have landed
-      tc::fence_after_sync();
-      const uint32_t acc = tmem_base + (uint32_t)((q & 1) * 64);
+    };
+    issue_loads(0);
+    for (int it = 0; it <= dcount + 2; ++it) {
+      if (it <= dcount + 1) {
+        uint8_t* slot = s_ring + (size_t)(it & (RING - 1)) * g.slot_bytes;
 #pragma unroll
-      for (int kz = 0; kz < ((P.dbg & 1) ? 0 : 3); ++kz) {
-        const uint64_t da_slot = da0 + (uint64_t)(((q + kz) & (RING - 1)) * slot_u16);
+        for (int k = 0; k < MAX_TASKS; ++k) {
+          if (t_in[k]) {
+            float v[8];
 #pragma unroll
-        for (int t2 = 0; t2 < 9; ++t2) {
-          const uint32_t pos = (uint32_t)((t2 / 3) * PW + (t2 % 3));
+            for (int e = 0; e < 8; ++e) v[e] = 0.f;
+            if (t_real[k] && loaded_valid) {
+              v[0] = ya[k].x; v[1] = ya[k].y; v[2] = ya[k].z; v[3] = ya[k].w;
+              v[4] = yb[k].x; v[5] = yb[k].y; v[6] = yb[k].z; v[7] = yb[k].w;
+              if (p.mode >= FEAT_GN) {
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            const uint64_t a_hi = da_slot + (uint64_t)(2 * ks * plane_u16 + pos);
-            const uint64_t a_lo = a_hi + (uint64_t)(4 * plane_u16);
-            const uint64_t b = db0 + (uint64_t)((((kz * 9 + t2) * 2) + ks) * 128);
-            tc::mma_f16(acc, a_hi, b, tc::idesc_f16(64), (kz | t2 | ks) != 0 ? 1u : 0u);
-            tc::mma_f16(acc, a_lo, b, tc::idesc_f16(32), 1u);
+                for (int e = 0; e < 8; ++e) v[e] = lrelu(fmaf(v[e], s_a[8 * t_oct + e], s_b[8 * t_oct + e]));
+              }
+            }
+            uint4 hi, lo;
+            tc::split8(v, &hi, &lo);
+            if (!(P.dbg & 2)) {
+              *reinterpret_cast<uint4*>(slot + (size_t)t_oct * g.plane_bytes + (size_t)t_l[k] * 16) = hi;
+              *reinterpret_cast<uint4*>(slot + (size_t)(4 + t_oct) * g.plane_bytes + (size_t)t_l[k] * 16) = lo;
+            }
           }
         }
-      }
-      tc::mma_commit(&s_bar[q & 1]);
-     }
-     __syncwarp();
-    }
-
-    issue_loads(it + 1);
-
-    // ---- epilogue of output slice it - 3 (its MMAs were issued one iteration ago) ----
-    const int qe = it - 3;
-    if (qe >= 0 && qe < dcount) {
-      if (warp == 0) {  // one poller; the other warps park at the hardware barrier
-        if (tc::elect_one()) {
-          tc::mbar_wait(&s_bar[qe & 1], (uint32_t)((qe >> 1) & 1));
-          tc::fence_before_sync();
-        }
+        tc::fence_proxy_async();   // this thread's operand stores -> visible to the tensor core's reads
         __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&s_full[it & (RING - 1)]);
       }
-      __syncthreads();
-      tc::fence_after_sync();
-      float v[16], c[16];
-      const uint32_t acc = tmem_my + (uint32_t)((qe & 1) * 64);
-      tc::tmem_ld16(acc, v);
-      tc::tmem_ld16(acc + 32u, c);
-      if (e_real && !(P.dbg & 4)) {
-        float* dst = out_n + (size_t)(d0 + qe) * slice_elems + e_off;
+
+      issue_loads(it + 1);
+
+      const int qe = it - 3;
+      if (qe >= 0 && qe < dcount) {
+        tc::mbar_wait_warp(&s_acc_full[qe & 1], (uint32_t)((qe >> 1) & 1));
+        tc::fence_after_sync();
+        float v[16], c[16];
+        const uint32_t acc = tmem_my + (uint32_t)((qe & 1) * 64);
+        tc::tmem_ld16(acc, v);
+        tc::tmem_ld16(acc + 32u, c);
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&s_acc_empty[qe & 1]);   // the accumulator may be overwritten
+        if (e_real && !(P.dbg & 4)) {
+          float* dst = out_n + (size_t)(d0 + qe) * slice_elems + e_off;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) v[k] = (v[k] + c[k]) + s_bias[chalf * 16 + k];
+          for (int k = 0; k < 16; ++k) v[k] = (v[k] + c[k]) + s_bias[chalf * 16 + k];
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4)
-          *reinterpret_cast<float4*>(dst + 4 * k4) = make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
+          for (int k4 = 0; k4 < 4; ++k4)
+            *reinterpret_cast<float4*>(dst + 4 * k4) = make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          gs[0] += v[k];
-          gq[0] += v[k] * v[k];
-          gs[1] += v[8 + k];
-          gq[1] += v[8 + k] * v[8 + k];
+          for (int k = 0; k < 8; ++k) {
+            gs[0] += v[k];
+            gq[0] += v[k] * v[k];
+            gs[1] += v[8 + k];
+            gq[1] += v[8 + k] * v[8 + k];
+          }
         }
       }
-      tc::fence_before_sync();
     }
   }
 
   // ---- GroupNorm statistics of what this CTA stored ----
-  if (p.out_stats != nullptr) {
+  if (p.out_stats != nullptr && warp < NW / 32) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       gs[0] += __shfl_xor_sync(0xffffffffu, gs[0], o);
@@ -292,7 +301,7 @@ void pack_cvf_tc_weights(const float* w_oidhw, std::vector<uint8_t>* out) {
 
 bool cvf_tc_supported(int h, int w) {
   const Geo g = make_geo(strip_width(w));
-  return w >= 1 && g.PW <= 128 && g.RT >= 1 && g.NP * 4 <= MAX_TASKS * NT && g.total + 2048 <= 227 * 1024 && h >= 1;
+  return w >= 1 && g.PW <= 128 && g.RT >= 1 && g.NP * 4 <= MAX_TASKS * NW && g.total + 2048 <= 227 * 1024 && h >= 1;
 }
 
 int launch_cvf_tc(const CvfArgs& a, cudaStream_t stream) {

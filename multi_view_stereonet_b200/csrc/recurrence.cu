@@ -28,6 +28,9 @@
 // All weights (hi and lo, three layers, 108 KB) stay resident in shared memory for all steps.
 #include <cuda_fp16.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include <vector>
 
 #include "conv.cuh"
@@ -879,6 +882,25 @@ int launch_recurrence(const RecurrenceArgs& a, cudaStream_t stream) {
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    static const bool occ_dbg = getenv("B200MVS_REC_OCC") != nullptr;
+    if (occ_dbg) {
+      for (int sz = 8; sz <= 16; ++sz) {
+        cudaLaunchConfig_t c2 = cfg;
+        cudaLaunchAttribute a2[1];
+        a2[0].id = cudaLaunchAttributeClusterDimension;
+        a2[0].val.clusterDim.x = sz;
+        a2[0].val.clusterDim.y = 1;
+        a2[0].val.clusterDim.z = 1;
+        c2.attrs = a2;
+        c2.numAttrs = 1;
+        c2.gridDim = dim3(sz, a.n, 1);
+        int mc = -1;
+        cudaError_t ee = cudaOccupancyMaxActiveClusters(&mc, recurrence_kernel<false>, &c2);
+        fprintf(stderr, "recurrence occupancy: cluster %d smem %zu -> max active clusters %d (%s)\n", sz, smem, mc,
+                cudaGetErrorString(ee));
+      }
+      cudaGetLastError();
+    }
     if (known_cluster == 0) {
       int max_clusters = 0;
       e = cudaOccupancyMaxActiveClusters(&max_clusters, recurrence_kernel<false>, &cfg);

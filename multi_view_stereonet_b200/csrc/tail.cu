@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(F_NT) refine_final_kernel(const FinalParams p,
     const double mean = sum * p.inv_count;
     double var = sq * p.inv_count - mean * mean;
     var = var > 0.0 ? var : 0.0;
-    const double rstd = rsqrt(var + (double)kGnEps);
+    const double rstd = gn_rstd(var);
     s_a[tid] = (float)((double)p.gamma[tid] * rstd);
     s_b[tid] = (float)((double)p.beta[tid] - mean * (double)p.gamma[tid] * rstd);
   }
@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(128) cvf_final_partial_kernel(const CvfPartial
     const double mean = sum * p.inv_count;
     double var = sq * p.inv_count - mean * mean;
     var = var > 0.0 ? var : 0.0;
-    const double rstd = rsqrt(var + (double)kGnEps);
+    const double rstd = gn_rstd(var);
     s_a[tid] = (float)((double)p.gamma[tid] * rstd);
     s_b[tid] = (float)((double)p.beta[tid] - mean * (double)p.gamma[tid] * rstd);
   }
