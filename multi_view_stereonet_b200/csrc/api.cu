@@ -59,13 +59,18 @@ int ensure_func_nonportable_cluster(const void* func) {
   }
   return 0;
 }
+// SMs the persistent one-CTA-per-SM kernels (conv_ws, cvf_tc) size their grids for.  While another lane's depth sweep
+// holds clusters, a grid of all SMs cannot be resident at once and its statically assigned tiles would run as two
+// waves; in lane mode the grids are sized for the SMs the sweeps leave free (b200mvs_forward).
+static thread_local int g_sm_reserved = 0;
+void set_reserved_sms(int n) { g_sm_reserved = n; }
 int current_device_sm_count(int* sms) {
   int dev = 0;
   B200MVS_CUDA_OK(cudaGetDevice(&dev));
   std::lock_guard<std::mutex> lock(g_attr_mutex);
   int& n = g_sm_count[dev];
   if (n == 0) B200MVS_CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-  *sms = n;
+  *sms = n - g_sm_reserved > 16 ? n - g_sm_reserved : 16;
   return 0;
 }
 int cached_cluster_size(int tiles) {
@@ -105,6 +110,16 @@ void probe_after(int tag, cudaStream_t stream) {
 }
 
 namespace {
+
+// Debug (B200MVS_LANE_TRACE=1): device timeline of a multi-lane forward, one line per lane with the time of every
+// stage boundary relative to the start of the call.
+struct TraceMark { int lane; const char* what; cudaEvent_t ev; };
+std::vector<TraceMark> g_trace;
+cudaEvent_t g_trace_origin = nullptr;
+bool lane_trace_enabled() {
+  static const bool on = getenv("B200MVS_LANE_TRACE") != nullptr;
+  return on;
+}
 
 struct ConvW {
   float* w = nullptr;
@@ -173,6 +188,25 @@ struct Workspace {
 
 using namespace b200mvs;
 
+// Everything one in-flight forward owns: workspace, side stream, fork / join events.  A call whose pairs need more than
+// one round of the depth sweep's clusters is cut into lanes of whole image groups that run concurrently on their own
+// streams (b200mvs_forward): while the sweep of one lane holds its 11-SM clusters, the other lanes' kernels fill the
+// rest of the chip.
+constexpr int kMaxLanes = 2;   // 3 streams per lane + the caller's: more would exceed the 8 hardware queues of a device
+                               // (CUDA_DEVICE_MAX_CONNECTIONS) and serialise lanes behind each other (measured)
+struct Lane {
+  Arena arena;
+  Workspace ws;
+  b200mvs_shape ws_shape{};
+  bool ws_valid = false;
+  cudaStream_t main = nullptr;   // lanes >= 1 run here (lane 0 runs on the caller's stream)
+  cudaStream_t side = nullptr;
+  cudaStream_t rec = nullptr;    // high priority: the depth sweep's clusters are placed before anything else pending
+  cudaEvent_t ev_pre = nullptr, ev_right = nullptr, ev_geo = nullptr, ev_imgconv = nullptr, ev_fork = nullptr,
+              ev_left = nullptr, ev_mask_in = nullptr, ev_mask_out = nullptr, ev_rec_in = nullptr, ev_rec_out = nullptr,
+              ev_end = nullptr;
+};
+
 struct b200mvs_net {
   int device = 0;
   std::vector<void*> allocs;  // weight allocations
@@ -193,15 +227,23 @@ struct b200mvs_net {
   // IDepthmapRefiner x5 (multi_view_stereonet.py:442-484)
   Refiner refiner[5];
 
-  Arena arena;
-  Workspace ws;
+  Lane lanes[kMaxLanes];
+  Lane* cur = &lanes[0];          // the lane whose kernels are being enqueued (host enqueue is sequential)
+  int lanes_max = 1;              // option "lanes": upper bound on concurrent lanes (1 = never split a call; default:
+                                  // measured slower than one batched call on B200)
+  int last_lanes = 1;
+  cudaEvent_t ev_begin = nullptr;
   Probe probe;
   // device staging of b200mvs_forward_host (inputs, outputs), grown on demand
   char* host_stage = nullptr;
   size_t host_stage_bytes = 0;
-  b200mvs_shape ws_shape{};
-  bool ws_valid = false;
   bool keep_stages = false;
+  // Operand precision of the refiner convolutions at the large levels: fp16 operands cost ~0.05-0.15 px of
+  // disparity-equivalent error on idepth * fx, which is 1e-4 of an idepth range of 63 px (64 hypotheses) but 1-3e-3 of
+  // a range of 11 px (12 hypotheses, the reference's own training configuration) -- beyond the 1e-3 parity bar.
+  // 2 (default) = split fp16 at every level when the sweep has fewer than 48 hypotheses, 1 = always, 0 = never.
+  int precise_refiners = 2;
+  bool precise_now = false;
   bool use_tensor_cores = true;
   bool half_activations = true;
   bool warp_specialized = true;
@@ -211,9 +253,7 @@ struct b200mvs_net {
   int rec_debug = 0;
   // Side stream for the work that does not depend on the comparison views (left feature network) or that
   // nothing downstream waits for (mask upsampling): forked / joined with events inside one forward.
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev_pre = nullptr, ev_right = nullptr, ev_coarse = nullptr;
-  cudaEvent_t ev_geo = nullptr, ev_imgconv = nullptr, ev_fork = nullptr, ev_left = nullptr, ev_mask_in = nullptr, ev_mask_out = nullptr;
+  cudaEvent_t ev_coarse = nullptr;
   bool overlap = true;
   // b200mvs_forward_host: uploads run on their own stream in the order the path needs them, compute waits per piece
   cudaStream_t copy_stream = nullptr, host_stream = nullptr;
@@ -451,8 +491,8 @@ Levels levels_of(const b200mvs_shape& s) {
 
 // Lays the workspace out in the arena (dry run computes the size).
 void layout(b200mvs_net* net, const b200mvs_shape& s, bool dry) {
-  Arena& A = net->arena;
-  Workspace& W = net->ws;
+  Arena& A = net->cur->arena;
+  Workspace& W = net->cur->ws;
   A.used = 0;
   A.dry = dry;
   const Levels L = levels_of(s);
@@ -509,26 +549,26 @@ bool same_shape(const b200mvs_shape& a, const b200mvs_shape& b) {
 }
 
 int ensure_workspace(b200mvs_net* net, const b200mvs_shape& s) {
-  if (net->ws_valid && same_shape(net->ws_shape, s)) return 0;
+  if (net->cur->ws_valid && same_shape(net->cur->ws_shape, s)) return 0;
   layout(net, s, true);
-  const size_t need = net->arena.used;
-  if (need > net->arena.capacity) {
-    if (net->arena.base != nullptr) {
+  const size_t need = net->cur->arena.used;
+  if (need > net->cur->arena.capacity) {
+    if (net->cur->arena.base != nullptr) {
       B200MVS_CUDA_OK(cudaDeviceSynchronize());
-      B200MVS_CUDA_OK(cudaFree(net->arena.base));
-      net->arena.base = nullptr;
-      net->arena.capacity = 0;
+      B200MVS_CUDA_OK(cudaFree(net->cur->arena.base));
+      net->cur->arena.base = nullptr;
+      net->cur->arena.capacity = 0;
     }
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&net->arena.base), need);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&net->cur->arena.base), need);
     if (e != cudaSuccess) {
       set_error("workspace allocation of " + std::to_string(need) + " bytes failed: " + cudaGetErrorString(e));
       return B200MVS_ENOMEM;
     }
-    net->arena.capacity = need;
+    net->cur->arena.capacity = need;
   }
   layout(net, s, false);
-  net->ws_shape = s;
-  net->ws_valid = true;
+  net->cur->ws_shape = s;
+  net->cur->ws_valid = true;
   return 0;
 }
 
@@ -560,11 +600,12 @@ int run_refiner(b200mvs_net* net, const Refiner& R, StatsCursor& sc, int m, int 
                 int guide_div, const float* image, int image_div, const float* prior, const float* Kl, int k_div,
                 float* out, int res_tag, cudaStream_t stream, const float* pre = nullptr,
                 const float* coarse = nullptr, int ch = 0, int cw = 0) {
-  Workspace& ws = net->ws;
+  Workspace& ws = net->cur->ws;
   const size_t P = (size_t)H * W;
   const double inv_count = 1.0 / (8.0 * (double)P);
   double* st_prev = nullptr;
-  const bool precise = (long long)H * W <= 96 * 128;  // levels 3 and 4 of a 512x640 input
+  // levels 3 and 4 of a 512x640 input always; every level when the call asks for it (forward_impl: few hypotheses)
+  const bool precise = (long long)H * W <= 96 * 128 || net->precise_now;
   // Levels 0-2 on the tensor-core path keep the refiner's internal activations (raw conv outputs and the
   // residual stream) in fp16: halves the HBM traffic of 48 % of the network's bytes; measured cost ~1e-4 of
   // the 1e-3 parity budget.  x_out with half storage is only written by the tensor-core kernel.
@@ -680,7 +721,7 @@ int run_refiner_guide(b200mvs_net* net, const Refiner& R, int B, int H, int W, c
 // for all images.
 int run_featnet(b200mvs_net* net, const Levels& L, int img0, int cnt, const float* planar, double* const* tail_stats,
                 float* final_out, long long final_stride, cudaStream_t stream) {
-  Workspace& ws = net->ws;
+  Workspace& ws = net->cur->ws;
   const int h4 = L.h[4], w4 = L.w[4];
   const size_t P4 = L.px[4];
   if (net->use_tensor_cores) {
@@ -796,10 +837,13 @@ int validate_call(const b200mvs_shape& s, const float* const* left_pyr, const fl
   return 0;
 }
 
-int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* left_pyr, const float* const* K_pyr,
-                 const float* const* Ts, const float* const* right_l0, const float* const* right_l4,
-                 float* const* out_idepth, float* const* out_raw, uint8_t* const* out_mask, cudaStream_t stream,
+int forward_impl(b200mvs_net* net, Lane& lane, bool sweep_on_own_stream, const b200mvs_shape& s,
+                 const float* const* left_pyr, const float* const* K_pyr, const float* const* Ts,
+                 const float* const* right_l0, const float* const* right_l4, float* const* out_idepth,
+                 float* const* out_raw, uint8_t* const* out_mask, cudaStream_t stream,
                  const cudaEvent_t* uploaded = nullptr, cudaEvent_t coarse_done = nullptr) {
+  net->cur = &lane;
+  net->precise_now = net->precise_refiners == 1 || (net->precise_refiners == 2 && s.num_idepth_samples < 48);
   // `coarse_done` (b200mvs_forward_host): recorded once the idepth maps of levels 1-4 are final, so that their
   // download can run next to the level-0 refiner.
   // `uploaded` (b200mvs_forward_host): events after which [0] K/T, [1] right level 0, [2] right level 4, [3] left
@@ -811,13 +855,12 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
   RC(validate_call(s, left_pyr, K_pyr, Ts, right_l0, right_l4));
   B200MVS_CUDA_OK(cudaSetDevice(net->device));
   RC(ensure_workspace(net, s));
-  Workspace& ws = net->ws;
+  Workspace& ws = net->cur->ws;
   const Levels L = levels_of(s);
   const int B = s.batch, V = s.views, D = s.num_idepth_samples;
   const int n = B * V, NI = B + n;
   const int h4 = L.h[4], w4 = L.w[4];
   const size_t P4 = L.px[4];
-  g_launches = 0;
   g_probe = net->probe.tag != 0 ? &net->probe : nullptr;
   // Debug hook (B200MVS_STAGE_PROFILE=1): events at the stage boundaries of the main stream, printed to stderr
   // after a synchronise.  Perturbs the pipeline slightly (an event between two kernels ends their PDL overlap).
@@ -825,6 +868,12 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
   const bool sprof = sprof_env || net->stage_profile;
   std::vector<std::pair<const char*, cudaEvent_t>> marks;
   auto mark = [&](const char* what) {
+    if (lane_trace_enabled() && sweep_on_own_stream) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      cudaEventRecord(e, stream);
+      g_trace.push_back({(int)(&lane - net->lanes), what, e});
+    }
     if (!sprof) return;
     cudaEvent_t e;
     cudaEventCreate(&e);
@@ -849,11 +898,11 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
   // cluster's worth of SMs per view and leaves the rest of the chip idle at small batch).
   double* tail_stats[6];
   for (int i = 0; i < 6; ++i) tail_stats[i] = sc.take(NI);
-  const bool overlap = net->overlap && net->side != nullptr;
-  cudaStream_t left_stream = overlap ? net->side : stream;
+  const bool overlap = net->overlap && net->cur->side != nullptr;
+  cudaStream_t left_stream = overlap ? net->cur->side : stream;
   if (overlap) {
-    B200MVS_CUDA_OK(cudaEventRecord(net->ev_fork, stream));
-    B200MVS_CUDA_OK(cudaStreamWaitEvent(net->side, net->ev_fork, 0));
+    B200MVS_CUDA_OK(cudaEventRecord(net->cur->ev_fork, stream));
+    B200MVS_CUDA_OK(cudaStreamWaitEvent(net->cur->side, net->cur->ev_fork, 0));
   }
   // 1. geometry
   RC(wait_upload(0, stream));
@@ -864,13 +913,13 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
   const bool persistent = net->use_tensor_cores && recurrence_supported(h4, w4, nullptr, nullptr);
   if (persistent) {
     if (overlap) {
-      B200MVS_CUDA_OK(cudaEventRecord(net->ev_geo, stream));
-      B200MVS_CUDA_OK(cudaStreamWaitEvent(net->side, net->ev_geo, 0));
+      B200MVS_CUDA_OK(cudaEventRecord(net->cur->ev_geo, stream));
+      B200MVS_CUDA_OK(cudaStreamWaitEvent(net->cur->side, net->cur->ev_geo, 0));
     }
     RC(wait_upload(2, left_stream));
     RC(launch_image_conv(ws.geo.H, R4, net->fr_conv0.w + (size_t)4 * 9 * 8 * 32, net->fr_conv0.bias, n, D, h4, w4,
                          ws.imgconv, left_stream));
-    if (overlap) B200MVS_CUDA_OK(cudaEventRecord(net->ev_imgconv, net->side));
+    if (overlap) B200MVS_CUDA_OK(cudaEventRecord(net->cur->ev_imgconv, net->cur->side));
   }
 
   // 2. full-resolution warp of every comparison image by the idepth-0 homography
@@ -881,17 +930,17 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
   // 3b. FeatureNetwork on the B*V warped right images (shared weights, :507)
   //     conv_final writes hypothesis 0 of every view's feature volume directly (:261, 278)
   RC(run_featnet(net, L, B, n, ws.warped0, tail_stats, ws.vol, (long long)D * (long long)P4 * kC, stream));
-  if (overlap) B200MVS_CUDA_OK(cudaEventRecord(net->ev_right, stream));
+  if (overlap) B200MVS_CUDA_OK(cudaEventRecord(net->cur->ev_right, stream));
 
   mark("geometry+warp+right featnet");
   // 3a. FeatureNetwork on the B left images (multi_view_stereonet.py:552): side stream, needed by the cost volume
   //     (enqueued after the critical path's launches)
   //     and not started before the right feature network is through: its 1-CTA-per-SM kernels would take SMs
   //     from the critical path, while nothing needs the left features before the sweep (~0.86 ms) has finished
-  if (overlap && net->left_late) B200MVS_CUDA_OK(cudaStreamWaitEvent(net->side, net->ev_right, 0));
+  if (overlap && net->left_late) B200MVS_CUDA_OK(cudaStreamWaitEvent(net->cur->side, net->cur->ev_right, 0));
   RC(wait_upload(3, left_stream));
   RC(run_featnet(net, L, 0, B, left_pyr[0], tail_stats, ws.feat4, 0, left_stream));
-  if (overlap) B200MVS_CUDA_OK(cudaEventRecord(net->ev_left, net->side));
+  if (overlap) B200MVS_CUDA_OK(cudaEventRecord(net->cur->ev_left, net->cur->side));
 
   // 3c. every refiner's conv0 is linear in its inputs and all but one of them (image, left features) are known
   //     now: their part is computed here, next to the depth sweep; the idepth channel is added when the coarser
@@ -900,7 +949,7 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
   if (net->conv0_precompute && net->use_tensor_cores) {
     // not before the depth sweep is ready to start: its cluster needs 11 free SMs in one GPC, and a large grid
     // already resident there would hold it back (measured: +29 us on the sweep); smallest level first
-    if (overlap) B200MVS_CUDA_OK(cudaStreamWaitEvent(net->side, net->ev_right, 0));
+    if (overlap) B200MVS_CUDA_OK(cudaStreamWaitEvent(net->cur->side, net->cur->ev_right, 0));
     RC(wait_upload(4, left_stream));
     for (int l = 4; l >= 0; --l) {
       if (!s.do_refiners[l]) continue;
@@ -908,12 +957,12 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
       RC(run_refiner_guide(net, net->refiner[l], B, L.h[l], L.w[l], guide, left_pyr[l], ws.pre[l], left_stream));
       use_pre[l] = true;
     }
-    if (overlap) B200MVS_CUDA_OK(cudaEventRecord(net->ev_pre, net->side));
+    if (overlap) B200MVS_CUDA_OK(cudaEventRecord(net->cur->ev_pre, net->cur->side));
   }
 
   // 5. the depth-sweep recurrence (multi_view_stereonet.py:279-290)
   RC(wait_upload(2, stream));
-  if (overlap && persistent) B200MVS_CUDA_OK(cudaStreamWaitEvent(stream, net->ev_imgconv, 0));
+  if (overlap && persistent) B200MVS_CUDA_OK(cudaStreamWaitEvent(stream, net->cur->ev_imgconv, 0));
   if (persistent) {
     RecurrenceArgs ra;
     ra.imgconv = ws.imgconv;
@@ -934,9 +983,19 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
     ra.cols = w4;
     ra.prof = net->rec_prof;
     ra.debug = net->rec_debug;
-    probe_before(TAG_RECURRENCE, stream);
-    RC(launch_recurrence(ra, stream));
-    probe_after(TAG_RECURRENCE, stream);
+    if (sweep_on_own_stream) {
+      // several lanes in flight: the sweep's cluster launch goes through the lane's high-priority stream, so that
+      // its clusters are placed as soon as a GPC can take them, ahead of the other lanes' pending thread blocks
+      B200MVS_CUDA_OK(cudaEventRecord(lane.ev_rec_in, stream));
+      B200MVS_CUDA_OK(cudaStreamWaitEvent(lane.rec, lane.ev_rec_in, 0));
+      RC(launch_recurrence(ra, lane.rec));
+      B200MVS_CUDA_OK(cudaEventRecord(lane.ev_rec_out, lane.rec));
+      B200MVS_CUDA_OK(cudaStreamWaitEvent(stream, lane.ev_rec_out, 0));
+    } else {
+      probe_before(TAG_RECURRENCE, stream);
+      RC(launch_recurrence(ra, stream));
+      probe_after(TAG_RECURRENCE, stream);
+    }
   } else {
     const double inv_count = 1.0 / (8.0 * (double)P4);
     for (int step = 1; step < D; ++step) {
@@ -998,7 +1057,7 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
 
   mark("recurrence");
   // 6. cost volume |L - R| with invalid voxels zeroed (multi_view_stereonet.py:586-592)
-  if (overlap) B200MVS_CUDA_OK(cudaStreamWaitEvent(stream, net->ev_left, 0));
+  if (overlap) B200MVS_CUDA_OK(cudaStreamWaitEvent(stream, net->cur->ev_left, 0));
   float* cost = net->keep_stages ? ws.cost : ws.vol;
   RC(launch_cost(ws.feat4, ws.vol, ws.geo.H, n, V, D, h4, w4, cost, ws.mask_views, stream));
 
@@ -1074,7 +1133,7 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
   mark("cost+cvf+softargmin");
   // 9. level-4 refiner per view (:605-613)
   RC(wait_upload(4, stream));
-  if (overlap && net->conv0_precompute && net->use_tensor_cores) B200MVS_CUDA_OK(cudaStreamWaitEvent(stream, net->ev_pre, 0));
+  if (overlap && net->conv0_precompute && net->use_tensor_cores) B200MVS_CUDA_OK(cudaStreamWaitEvent(stream, net->cur->ev_pre, 0));
   if (s.do_refiners[4]) {
     RC(run_refiner(net, net->refiner[4], sc, n, h4, w4, ws.feat4, V, left_pyr[4], V, ws.raw_views, K_pyr[4], V,
                    ws.refined_views, TAG_NONE, stream, use_pre[4] ? ws.pre[4] : nullptr));
@@ -1097,15 +1156,15 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
   mark("refiner4+view_reduce");
   // 11. coarse-to-fine: bilinear prior, mask upsample, guided refinement (:629-682).  Nothing on the path reads
   //     the upsampled mask volumes, so their chain runs on the side stream next to the refiners.
-  cudaStream_t mask_stream = overlap ? net->side : stream;
+  cudaStream_t mask_stream = overlap ? net->cur->side : stream;
   if (overlap && lowest_mask <= 3) {
-    B200MVS_CUDA_OK(cudaEventRecord(net->ev_mask_in, stream));
-    B200MVS_CUDA_OK(cudaStreamWaitEvent(net->side, net->ev_mask_in, 0));
+    B200MVS_CUDA_OK(cudaEventRecord(net->cur->ev_mask_in, stream));
+    B200MVS_CUDA_OK(cudaStreamWaitEvent(net->cur->side, net->cur->ev_mask_in, 0));
   }
   for (int l = 3; l >= lowest_mask; --l)
     RC(launch_upsample_mask(mask_l[l + 1], (long long)B * D, L.h[l + 1], L.w[l + 1], L.h[l], L.w[l], mask_l[l],
                             mask_stream));
-  if (overlap && lowest_mask <= 3) B200MVS_CUDA_OK(cudaEventRecord(net->ev_mask_out, net->side));
+  if (overlap && lowest_mask <= 3) B200MVS_CUDA_OK(cudaEventRecord(net->cur->ev_mask_out, net->cur->side));
   for (int l = 3; l >= 0; --l) {
     const bool fused_up = s.do_refiners[l] && use_pre[l];   // the refiner's head upsamples its own prior
     if (!fused_up) RC(launch_upsample_f32(idepth_l[l + 1], B, L.h[l + 1], L.w[l + 1], L.h[l], L.w[l], prior_l[l], stream));
@@ -1122,7 +1181,7 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
     mark(names[l]);
     if (l == 1 && coarse_done != nullptr) B200MVS_CUDA_OK(cudaEventRecord(coarse_done, stream));
   }
-  if (overlap && lowest_mask <= 3) B200MVS_CUDA_OK(cudaStreamWaitEvent(stream, net->ev_mask_out, 0));
+  if (overlap && lowest_mask <= 3) B200MVS_CUDA_OK(cudaStreamWaitEvent(stream, net->cur->ev_mask_out, 0));
   if (sprof) {
     mark("join mask chain");
     cudaEventSynchronize(marks.back().second);
@@ -1144,10 +1203,28 @@ int forward_impl(b200mvs_net* net, const b200mvs_shape& s, const float* const* l
     set_error("internal: GroupNorm statistics arena overflow");
     return B200MVS_EINVAL;
   }
-  net->last_shape = s;
-  net->have_last = true;
-  net->last_launches = g_launches;
   return 0;
+}
+
+// How many lanes a call runs as: 1 unless the depth sweep of its B * V (image group, view) pairs needs more than one
+// round of clusters -- then enough lanes that the first ones are through their sweep while the others still hold
+// clusters (whole image groups per lane, at most lanes_max).
+int plan_lanes(const b200mvs_net* net, const b200mvs_shape& s) {
+  if (net->lanes_max <= 1 || !net->use_tensor_cores || !net->overlap || net->keep_stages || net->stage_profile ||
+      net->probe.tag != 0 || net->rec_prof != nullptr || s.batch < 2)
+    return 1;
+  static const bool sprof_env = getenv("B200MVS_STAGE_PROFILE") != nullptr;
+  if (sprof_env) return 1;
+  const Levels L = levels_of(s);
+  if (!recurrence_supported(L.h[4], L.w[4], nullptr, nullptr)) return 1;
+  const int maxc = recurrence_max_clusters(L.h[4], L.w[4]);
+  const int pairs = s.batch * s.views;
+  if (maxc < 1 || pairs <= maxc) return 1;
+  int want = (pairs + maxc - 1) / maxc;
+  if (want > net->lanes_max) want = net->lanes_max;
+  if (want > s.batch) want = s.batch;
+  const int per = (s.batch + want - 1) / want;   // image groups per lane
+  return (s.batch + per - 1) / per;
 }
 
 }  // namespace
@@ -1184,25 +1261,27 @@ B200MVS_API int b200mvs_create(int device, int num_tensors, const char* const* n
   for (int i = 0; i < num_tensors; ++i) sd.t[names[i]] = {data[i], numels[i]};
   b200mvs_net* net = new b200mvs_net();
   net->device = device;
+  if (const char* env = getenv("B200MVS_LANES")) net->lanes_max = atoi(env) < 1 ? 1 : (atoi(env) > kMaxLanes ? kMaxLanes : atoi(env));
   int rc = build_weights(net, sd);
   if (rc == 0) {
-    if (cudaStreamCreateWithFlags(&net->side, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&net->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&net->ev_geo, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&net->ev_imgconv, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&net->ev_left, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&net->ev_pre, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&net->ev_right, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&net->ev_coarse, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&net->ev_mask_in, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&net->ev_mask_out, cudaEventDisableTiming) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&net->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&net->host_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&net->ev_up[0], cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&net->ev_up[1], cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&net->ev_up[2], cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&net->ev_up[3], cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&net->ev_up[4], cudaEventDisableTiming) != cudaSuccess) {
+    bool ok = true;
+    auto ev = [&](cudaEvent_t* e) { ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
+    int prio_low = 0, prio_high = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high);
+    for (Lane& ln : net->lanes) {
+      ok = ok && cudaStreamCreateWithFlags(&ln.main, cudaStreamNonBlocking) == cudaSuccess;
+      ok = ok && cudaStreamCreateWithFlags(&ln.side, cudaStreamNonBlocking) == cudaSuccess;
+      ok = ok && cudaStreamCreateWithPriority(&ln.rec, cudaStreamNonBlocking, prio_high) == cudaSuccess;
+      for (cudaEvent_t* e : {&ln.ev_fork, &ln.ev_geo, &ln.ev_imgconv, &ln.ev_left, &ln.ev_pre, &ln.ev_right, &ln.ev_mask_in,
+                             &ln.ev_mask_out, &ln.ev_rec_in, &ln.ev_rec_out, &ln.ev_end})
+        ev(e);
+    }
+    ev(&net->ev_coarse);
+    ev(&net->ev_begin);
+    for (cudaEvent_t& e : net->ev_up) ev(&e);
+    ok = ok && cudaStreamCreateWithFlags(&net->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&net->host_stream, cudaStreamNonBlocking) == cudaSuccess;
+    if (!ok) {
       set_error("b200mvs_create: could not create the side stream");
       rc = B200MVS_ECUDA;
     }
@@ -1219,12 +1298,18 @@ B200MVS_API void b200mvs_destroy(b200mvs_net* net) {
   if (net == nullptr) return;
   cudaSetDevice(net->device);
   for (void* p : net->allocs) cudaFree(p);
-  if (net->arena.base != nullptr) cudaFree(net->arena.base);
+  for (Lane& ln : net->lanes) {
+    if (ln.arena.base != nullptr) cudaFree(ln.arena.base);
+    for (cudaEvent_t e : {ln.ev_fork, ln.ev_geo, ln.ev_imgconv, ln.ev_left, ln.ev_pre, ln.ev_right, ln.ev_mask_in,
+                          ln.ev_mask_out, ln.ev_rec_in, ln.ev_rec_out, ln.ev_end})
+      if (e != nullptr) cudaEventDestroy(e);
+    for (cudaStream_t st : {ln.main, ln.side, ln.rec})
+      if (st != nullptr) cudaStreamDestroy(st);
+  }
   if (net->host_stage != nullptr) cudaFree(net->host_stage);
   for (cudaEvent_t e : net->probe.ev) cudaEventDestroy(e);
-  for (cudaEvent_t e : {net->ev_geo, net->ev_imgconv, net->ev_fork, net->ev_left, net->ev_pre, net->ev_right, net->ev_coarse, net->ev_mask_in, net->ev_mask_out})
+  for (cudaEvent_t e : {net->ev_coarse, net->ev_begin})
     if (e != nullptr) cudaEventDestroy(e);
-  if (net->side != nullptr) cudaStreamDestroy(net->side);
   for (cudaEvent_t e : net->ev_up)
     if (e != nullptr) cudaEventDestroy(e);
   if (net->copy_stream != nullptr) cudaStreamDestroy(net->copy_stream);
@@ -1237,7 +1322,7 @@ B200MVS_API int b200mvs_set_debug(b200mvs_net* net, int keep_stages) {
   if (net == nullptr) return B200MVS_EINVAL;
   if (net->keep_stages != (keep_stages != 0)) {
     net->keep_stages = keep_stages != 0;
-    net->ws_valid = false;  // layout changes
+    for (Lane& ln : net->lanes) ln.ws_valid = false;  // layout changes
   }
   return 0;
 }
@@ -1275,6 +1360,14 @@ B200MVS_API int b200mvs_set_option(b200mvs_net* net, const char* name, int value
   }
   if (k == "overlap") {
     net->overlap = value != 0;
+    return 0;
+  }
+  if (k == "precise_refiners") {
+    net->precise_refiners = value;
+    return 0;
+  }
+  if (k == "lanes") {
+    net->lanes_max = value < 1 ? 1 : (value > kMaxLanes ? kMaxLanes : value);
     return 0;
   }
   if (k == "stage_profile") {
@@ -1395,8 +1488,84 @@ B200MVS_API int b200mvs_forward(b200mvs_net* net, const b200mvs_shape* shape, co
     set_error("b200mvs_forward: null argument");
     return B200MVS_EINVAL;
   }
-  return forward_impl(net, *shape, left_image_pyr, K_pyr, T_right_in_lefts, right_image_l0, right_image_l4,
-                      out_idepth, out_idepth_raw, out_mask, static_cast<cudaStream_t>(stream));
+  cudaStream_t caller = static_cast<cudaStream_t>(stream);
+  const b200mvs_shape& s = *shape;
+  RC(validate_call(s, left_image_pyr, K_pyr, T_right_in_lefts, right_image_l0, right_image_l4));
+  g_launches = 0;
+  const int lanes = plan_lanes(net, s);
+  int rc = 0;
+  if (lanes == 1) {
+    rc = forward_impl(net, net->lanes[0], false, s, left_image_pyr, K_pyr, T_right_in_lefts, right_image_l0,
+                      right_image_l4, out_idepth, out_idepth_raw, out_mask, caller);
+  } else {
+    // Lane g owns image groups [g * per, min(B, (g + 1) * per)): every input and output is batch-major, so a lane's
+    // tensors are the caller's pointers advanced by whole image groups.
+    B200MVS_CUDA_OK(cudaSetDevice(net->device));
+    const Levels L = levels_of(s);
+    const int per = (s.batch + lanes - 1) / lanes;
+    B200MVS_CUDA_OK(cudaEventRecord(net->ev_begin, caller));
+    {
+      const int maxc = recurrence_max_clusters(L.h[4], L.w[4]);
+      const int other = per * s.views < maxc ? per * s.views : maxc;   // clusters another lane can hold at once
+      set_reserved_sms(other * 11);
+    }
+    if (lane_trace_enabled()) {
+      cudaEventCreate(&g_trace_origin);
+      cudaEventRecord(g_trace_origin, caller);
+    }
+    for (int g = 0; g < lanes && rc == 0; ++g) {
+      Lane& lane = net->lanes[g];
+      const size_t b0 = (size_t)g * per;
+      b200mvs_shape sub = s;
+      sub.batch = (int)((size_t)s.batch - b0 < (size_t)per ? (size_t)s.batch - b0 : (size_t)per);
+      const float *lp[5], *kp[5], *tp[kMaxViews], *r0[kMaxViews], *r4[kMaxViews];
+      float *oi[5], *orw[5];
+      uint8_t* om[5];
+      for (int l = 0; l < 5; ++l) {
+        lp[l] = left_image_pyr[l] + b0 * 3 * L.px[l];
+        kp[l] = K_pyr[l] + b0 * 16;
+        oi[l] = out_idepth != nullptr && out_idepth[l] != nullptr ? out_idepth[l] + b0 * L.px[l] : nullptr;
+        orw[l] = out_idepth_raw != nullptr && out_idepth_raw[l] != nullptr ? out_idepth_raw[l] + b0 * L.px[l] : nullptr;
+        om[l] = out_mask != nullptr && out_mask[l] != nullptr
+                    ? out_mask[l] + b0 * (size_t)s.num_idepth_samples * L.px[l] : nullptr;
+      }
+      for (int v = 0; v < s.views; ++v) {
+        tp[v] = T_right_in_lefts[v] + b0 * 16;
+        r0[v] = right_image_l0[v] + b0 * 3 * L.px[0];
+        r4[v] = right_image_l4[v] + b0 * 3 * L.px[4];
+      }
+      B200MVS_CUDA_OK(cudaStreamWaitEvent(lane.main, net->ev_begin, 0));
+      rc = forward_impl(net, lane, true, sub, lp, kp, tp, r0, r4, out_idepth != nullptr ? oi : nullptr,
+                        out_idepth_raw != nullptr ? orw : nullptr, out_mask != nullptr ? om : nullptr, lane.main);
+      B200MVS_CUDA_OK(cudaEventRecord(lane.ev_end, lane.main));
+      B200MVS_CUDA_OK(cudaStreamWaitEvent(caller, lane.ev_end, 0));
+    }
+    net->cur = &net->lanes[0];
+    set_reserved_sms(0);
+    if (lane_trace_enabled()) {
+      cudaStreamSynchronize(caller);
+      for (int g = 0; g < lanes; ++g) {
+        fprintf(stderr, "lane %d (us):", g);
+        for (const TraceMark& m : g_trace)
+          if (m.lane == g) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, g_trace_origin, m.ev);
+            fprintf(stderr, " %s@%.0f", m.what, ms * 1e3f);
+          }
+        fprintf(stderr, "\n");
+      }
+      for (const TraceMark& m : g_trace) cudaEventDestroy(m.ev);
+      g_trace.clear();
+      cudaEventDestroy(g_trace_origin);
+    }
+  }
+  if (rc == 0) {
+    net->last_shape = s;
+    net->have_last = true;
+    net->last_launches = g_launches;
+    net->last_lanes = lanes;
+  }
+  return rc;
 }
 
 B200MVS_API int b200mvs_forward_host(b200mvs_net* net, const b200mvs_shape* shape, const float* const* left_image_pyr,
@@ -1515,7 +1684,15 @@ B200MVS_API int b200mvs_forward_host(b200mvs_net* net, const b200mvs_shape* shap
     }
   }
   const double t_up = hprof ? now() : 0.0;
-  if (rc == 0) rc = forward_impl(net, s, dl, dk, dT, dr0, dr4, oi, orw, om, stream, net->ev_up, net->ev_coarse);
+  g_launches = 0;
+  if (rc == 0)
+    rc = forward_impl(net, net->lanes[0], false, s, dl, dk, dT, dr0, dr4, oi, orw, om, stream, net->ev_up, net->ev_coarse);
+  if (rc == 0) {
+    net->last_shape = s;
+    net->have_last = true;
+    net->last_launches = g_launches;
+    net->last_lanes = 1;
+  }
   const double t_enq = hprof ? now() : 0.0;
   if (rc == 0) {
     // levels 1-4 are final before the level-0 refiner starts: their download runs next to it on the copy stream
@@ -1547,7 +1724,7 @@ B200MVS_API int b200mvs_forward_host(b200mvs_net* net, const b200mvs_shape* shap
   } else {
     cudaStreamSynchronize(cs);
     cudaStreamSynchronize(stream);
-    if (net->side != nullptr) cudaStreamSynchronize(net->side);   // a failed forward may leave it forked
+    if (net->cur->side != nullptr) cudaStreamSynchronize(net->cur->side);   // a failed forward may leave it forked
     if (rc == -2 && g_error.empty()) set_error("b200mvs_forward_host: upload failed");
   }
   if (h2d_bytes != nullptr) *h2d_bytes = h2d;
@@ -1563,7 +1740,11 @@ B200MVS_API int b200mvs_get_stage(b200mvs_net* net, const char* name, void* dst,
   }
   const b200mvs_shape& s = net->last_shape;
   const Levels L = levels_of(s);
-  const Workspace& ws = net->ws;
+  if (net->last_lanes != 1) {
+    set_error("b200mvs_get_stage: the last forward was split into lanes; set option \"lanes\" to 1 to inspect stages");
+    return B200MVS_EINVAL;
+  }
+  const Workspace& ws = net->lanes[0].ws;
   const size_t B = s.batch, V = s.views, D = s.num_idepth_samples, n = B * V;
   const std::string k(name);
   const void* src = nullptr;

@@ -13,6 +13,12 @@
 //                           tcgen05.commit frees the stage and publishes the accumulators
 //   epilogue (4 warps)      TMEM -> registers -> bias, GroupNorm statistics of the raw output, fp16 store
 // so the loads of tile i+1, the transform / MMAs of tile i and the stores of tile i-1 overlap.
+//
+// Dilated layers (dilation d = 2, 4, 8) run as d vertical polyphase components: a tile is TH rows of the sub-image
+// made of image rows py, py + d, py + 2d, ... (TMA element stride d along y), on which the vertical taps are +-1
+// row -- a halo of 2 rows instead of 2d (at d = 8 a tile loaded and transformed 24 rows for 8 rows of output, now
+// 10).  Horizontally the dilation stays in the descriptors (tap offset kx * d positions, TW = 64 - 2d valid
+// columns), so loads and stores remain contiguous along x.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -39,11 +45,14 @@ constexpr size_t kSmemBudget = 220 * 1024;
 
 // positions per plane, padded to 2 (mod 8): consecutive planes then start 32 bytes apart modulo 128, so the four
 // octet planes a quarter-warp writes at once fall into distinct banks
-__host__ __device__ inline int ws_npos(int th, int dil) {
-  const int n = (th + 2 * dil) * PW + 2 * dil;
+// vs = vertical tap distance in tile rows (1 in polyphase mode, the dilation otherwise)
+__host__ __device__ inline int ws_npos(int th, int vs, int dil) {
+  const int n = (th + 2 * vs) * PW + 2 * dil;
   return ((n + 5) & ~7) + 2;
 }
-__host__ __device__ inline uint32_t ws_stage_bytes(int th, int dil) { return 4u * (uint32_t)ws_npos(th, dil) * 16u; }
+__host__ __device__ inline uint32_t ws_stage_bytes(int th, int vs, int dil) {
+  return 4u * (uint32_t)ws_npos(th, vs, dil) * 16u;
+}
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
@@ -100,6 +109,7 @@ struct WsParams {
   double inv_count;
   int n_img, H, W, dil;
   int tiles_x, tiles_y, stages, ring, has_res, prof;
+  int poly;   // 1: vertical polyphase (tile rows are image rows py + dil * k); tiles_y counts rows of one component
   int dbg;   // timing ablations (wrong results): 1 transform warps only wait / arrive, 2 no MMAs, 4 no output stores
 };
 
@@ -120,14 +130,31 @@ __global__ void __launch_bounds__(NT, 1) conv3x3_ws_kernel(const WsParams p, con
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = tc::uniform_warp_index();
   const int d = p.dil;
+  const int vs = p.poly ? 1 : d;     // vertical tap distance in tile rows
+  const int rs = p.poly ? d : 1;     // image rows per tile row
   const int TW = PW - 2 * d;
-  const int rows_in = TH + 2 * d;
-  const int npos = ws_npos(TH, d);
+  const int rows_in = TH + 2 * vs;
+  const int npos = ws_npos(TH, vs, d);
   const uint32_t plane_bytes = (uint32_t)npos * 16u;
-  const uint32_t stage_bytes = ws_stage_bytes(TH, d);
+  const uint32_t stage_bytes = ws_stage_bytes(TH, vs, d);
   const int S = p.stages;
-  const int tiles_img = p.tiles_x * p.tiles_y;
+  const int tiles_comp = p.tiles_x * p.tiles_y;            // tiles of one polyphase component (or of the image)
+  const int tiles_img = tiles_comp * (p.poly ? d : 1);
   const int total = tiles_img * p.n_img;
+  // tile t -> image, first image row of tile row 0 (incl. the halo row(s) above), first column, component
+  struct TileAt { int img, tx0, ty0, y_first; };
+  auto tile_at = [&](int t) {
+    TileAt a;
+    a.img = t / tiles_img;
+    int tt = t - a.img * tiles_img;
+    const int py = p.poly ? tt / tiles_comp : 0;
+    tt -= py * tiles_comp;
+    const int tyi = tt / p.tiles_x;
+    a.tx0 = (tt - tyi * p.tiles_x) * TW;
+    a.ty0 = tyi * TH;                                  // first output row, in rows of the component
+    a.y_first = py + rs * (a.ty0 - vs);                // image row of tile row 0
+    return a;
+  };
   uint8_t* s_w = smem;
   uint8_t* s_ring = smem + W_BYTES;            // [slot][y | resid][2 rows][64 positions][32 channels]
   const int RING = p.ring;
@@ -192,9 +219,8 @@ __global__ void __launch_bounds__(NT, 1) conv3x3_ws_kernel(const WsParams p, con
     uint32_t q = 0, qph = 0;   // ring slot of the running chunk counter and the parity of its lap
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
       const int s = it % S;
-      const int img = t / tiles_img, tt = t - img * tiles_img;
-      const int tyi = tt / p.tiles_x;
-      const int tx0 = (tt - tyi * p.tiles_x) * TW, ty0 = tyi * TH;
+      const TileAt ta = tile_at(t);
+      const int img = ta.img, tx0 = ta.tx0;
       if (img != cur_img) {
         cur_img = img;
         const double sum = p.stats[(img * kGroups + c8) * 2 + 0];   // octet == GroupNorm group
@@ -216,14 +242,14 @@ __global__ void __launch_bounds__(NT, 1) conv3x3_ws_kernel(const WsParams p, con
       uint8_t* xpl = s_st + (size_t)s * stage_bytes + (size_t)c8 * plane_bytes + (size_t)ix * 16;
       // x_out address of tile row 0 (may lie above the image; only rows inside it are dereferenced)
       __half* xg = p.x_out != nullptr ? p.x_out + (ptrdiff_t)img * (ptrdiff_t)img_elems +
-                                            ((ptrdiff_t)(ty0 - d) * p.W + (col_ok ? gx : 0)) * kC + 8 * c8
+                                            ((ptrdiff_t)ta.y_first * p.W + (col_ok ? gx : 0)) * kC + 8 * c8
                                       : nullptr;
       tc::mbar_wait_warp(&s_empty[s], (uint32_t)(((it / S) & 1) ^ 1));   // the MMAs that read this stage completed
       for (int c = 0; c < nchunks; ++c) {
         tc::mbar_wait_warp(&s_raw[q], qph);   // this chunk's TMA boxes have landed
         if (c == 0) WS_STAMP(xw == 0 && lane == 0, 1);
         const int r = 2 * c + rr;
-        const int gy = ty0 - d + r;
+        const int gy = ta.y_first + rs * r;
         const uint8_t* raw = s_ring + (size_t)q * 2u * CHUNK_HALF + (size_t)(rr * PW + ix) * 64 + c8 * 16;
         uint4 h = make_uint4(0, 0, 0, 0);
         if (col_ok && gy >= 0 && gy < p.H && !(p.dbg & 1)) {
@@ -238,7 +264,7 @@ __global__ void __launch_bounds__(NT, 1) conv3x3_ws_kernel(const WsParams p, con
             for (int e = 0; e < 8; ++e) v[e] += rs[e];
           }
           h = pack8(v);
-          if (xg != nullptr && col_int && r >= d && r < d + TH) stg_hint(xg + (ptrdiff_t)r * p.W * kC, h, pol_keep);
+          if (xg != nullptr && col_int && r >= vs && r < vs + TH) stg_hint(xg + (ptrdiff_t)r * rs * p.W * kC, h, pol_keep);
         }
         if (!(p.dbg & 1)) *reinterpret_cast<uint4*>(xpl + (size_t)r * (PW * 16)) = h;
         mbar_arrive(&s_rfree[q]);   // this thread is done reading the slot
@@ -259,16 +285,16 @@ __global__ void __launch_bounds__(NT, 1) conv3x3_ws_kernel(const WsParams p, con
       int it = 0;
       uint32_t q = 0, qph = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-        const int img = t / tiles_img, tt = t - img * tiles_img;
-        const int tyi = tt / p.tiles_x;
-        const int tx0 = (tt - tyi * p.tiles_x) * TW, ty0 = tyi * TH;
+        const TileAt ta = tile_at(t);
+        const int img = ta.img, tx0 = ta.tx0;
         for (int c = 0; c < nchunks; ++c) {
           tc::mbar_wait(&s_rfree[q], qph ^ 1u);   // every transform warp has read the slot
           mbar_arrive_tx(&s_raw[q], tx_bytes);
           if (c == 0) WS_STAMP(true, 0);
           uint8_t* slot = s_ring + (size_t)q * 2u * CHUNK_HALF;
-          tma_load_4d(slot, &tm_y, 0, tx0 - d, ty0 - d + 2 * c, img, &s_raw[q]);
-          if (p.has_res) tma_load_4d(slot + CHUNK_HALF, &tm_r, 0, tx0 - d, ty0 - d + 2 * c, img, &s_raw[q]);
+          // (polyphase: the map's element stride along y is the dilation, a box is image rows y, y + dil)
+          tma_load_4d(slot, &tm_y, 0, tx0 - d, ta.y_first + rs * 2 * c, img, &s_raw[q]);
+          if (p.has_res) tma_load_4d(slot + CHUNK_HALF, &tm_r, 0, tx0 - d, ta.y_first + rs * 2 * c, img, &s_raw[q]);
           if (++q == (uint32_t)RING) {
             q = 0;
             qph ^= 1u;
@@ -300,7 +326,7 @@ __global__ void __launch_bounds__(NT, 1) conv3x3_ws_kernel(const WsParams p, con
           const uint32_t dcol = tmem_base + (uint32_t)(a * ACC_COLS + mt * 32);
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            const uint32_t pos = (uint32_t)(mt * 128 + (tap / 3) * d * PW + (tap % 3) * d);
+            const uint32_t pos = (uint32_t)(mt * 128 + (tap / 3) * vs * PW + (tap % 3) * d);
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks)
               tc::mma_f16(dcol, da + (uint64_t)(2u * ks * plane_u16 + pos), db0 + (uint64_t)((tap * 2 + ks) * 64),
@@ -341,9 +367,9 @@ __global__ void __launch_bounds__(NT, 1) conv3x3_ws_kernel(const WsParams p, con
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
       const int a = it & 1;
       const uint32_t aph = (uint32_t)((it >> 1) & 1);
-      const int img = t / tiles_img, tt = t - img * tiles_img;
-      const int tyi = tt / p.tiles_x;
-      const int tx0 = (tt - tyi * p.tiles_x) * TW, ty0 = tyi * TH;
+      const TileAt ta = tile_at(t);
+      const int img = ta.img, tx0 = ta.tx0;
+      const int y_out0 = ta.y_first + rs * vs;   // image row of the tile's first output row
       if (img != cur_img) {
         flush(cur_img);
         cur_img = img;
@@ -354,7 +380,7 @@ __global__ void __launch_bounds__(NT, 1) conv3x3_ws_kernel(const WsParams p, con
 #pragma unroll 1
       for (int mt = mth; mt < MT; mt += N_EPI / 4) {
         const int j = mt * 128 + wq * 32 + lane;
-        const int oy = ty0 + j / PW, ox_t = j % PW, ox = tx0 + ox_t;
+        const int oy = y_out0 + rs * (j / PW), ox_t = j % PW, ox = tx0 + ox_t;
         const bool valid = ox_t < TW && ox < p.W && oy < p.H;
         float v[32];
         const uint32_t ta = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(a * ACC_COLS + mt * 32);
@@ -387,7 +413,7 @@ __global__ void __launch_bounds__(NT, 1) conv3x3_ws_kernel(const WsParams p, con
           hi.z = __shfl_sync(0xffffffffu, ch[2 * (k & 1) + 1].z, src);
           hi.w = __shfl_sync(0xffffffffu, ch[2 * (k & 1) + 1].w, src);
           const int js = mt * 128 + wq * 32 + src;
-          const int oys = ty0 + js / PW, oxts = js % PW, oxs = tx0 + oxts;
+          const int oys = y_out0 + rs * (js / PW), oxts = js % PW, oxs = tx0 + oxts;
           if (oxts < TW && oxs < p.W && oys < p.H && !(p.dbg & 4)) {
             __half* o = p.out + (size_t)img * img_elems + ((size_t)oys * p.W + oxs) * kC + 8 * (2 * (k & 1) + (lane & 1));
             stg_hint(o, (lane & 1) ? hi : lo, pol_keep);
@@ -426,20 +452,21 @@ EncodeTiledFn encode_fn() {
 }
 
 // [n][H][W][32] fp16, box = [1][2][64][32]: two rows of a halo-extended tile, zeros outside the image
-bool make_map(const void* base, int n, int H, int W, CUtensorMap* out) {
+bool make_map(const void* base, int n, int H, int W, int ystride, CUtensorMap* out) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) return false;
   const cuuint64_t dims[4] = {(cuuint64_t)kC, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
   const cuuint64_t strides[3] = {(cuuint64_t)kC * 2, (cuuint64_t)W * kC * 2, (cuuint64_t)H * W * kC * 2};
-  const cuuint32_t box[4] = {(cuuint32_t)kC, (cuuint32_t)PW, 2, 1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  // element stride s along y: the box spans 2 s image rows and delivers every s-th of them, i.e. two rows
+  const cuuint32_t box[4] = {(cuuint32_t)kC, (cuuint32_t)PW, (cuuint32_t)(2 * ystride), 1};
+  const cuuint32_t estr[4] = {1, 1, (cuuint32_t)ystride, 1};
   return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 struct WsPlan {
-  int th, stages, ring;
+  int th, stages, ring, poly;
 };
 // Shared memory = weights + ring + stages.  Preference (measured on level 0, 512x640): two stages so that the loads /
 // transform of the next tile overlap this tile's MMAs, and the taller the tile the smaller the share of halo rows
@@ -447,14 +474,19 @@ struct WsPlan {
 // than a second stage or a taller tile gain at dilation 4 (level 0: 42.5 -> 34.0 us per layer).
 bool plan_for(int dil, int H, int W, int n_img, WsPlan* plan) {
   // (16-row single-stage tiles at dilation 8 were measured equal to 8-row ones: 54.7 vs 54.2 us per level-0 layer)
-  static const WsPlan prefs[] = {{8, 2, 6}, {8, 2, 4}, {4, 2, 6}, {8, 1, 6}, {4, 2, 4}, {4, 1, 6}};
+  static const WsPlan prefs[] = {{8, 2, 6, 0}, {8, 2, 4, 0}, {4, 2, 6, 0}, {8, 1, 6, 0}, {4, 2, 4, 0}, {4, 1, 6, 0}};
   static const int force = getenv("B200MVS_WS_PLAN") ? atoi(getenv("B200MVS_WS_PLAN")) : -1;   // A/B: index into prefs
+  static const bool no_poly = getenv("B200MVS_WS_NOPOLY") != nullptr;                          // A/B: round-1 tiles
+  const bool poly = dil > 1 && !no_poly;
+  const int vs = poly ? 1 : dil;
   for (int k = 0; k < (int)(sizeof(prefs) / sizeof(prefs[0])); ++k) {
-    const WsPlan& c = prefs[k];
+    WsPlan c = prefs[k];
+    c.poly = poly ? 1 : 0;
     if (force >= 0 && k < force && dil >= 4) continue;
     // worth it only when every SM gets at least one tile; smaller layers are latency bound either way
-    if ((long long)cdiv(W, PW - 2 * dil) * cdiv(H, c.th) * n_img < 148) continue;
-    if (W_BYTES + ring_bytes(c.ring) + (size_t)c.stages * ws_stage_bytes(c.th, dil) <= kSmemBudget) {
+    const long long rows_tiles = poly ? (long long)dil * cdiv(cdiv(H, dil), c.th) : cdiv(H, c.th);
+    if ((long long)cdiv(W, PW - 2 * dil) * rows_tiles * n_img < 148) continue;
+    if (W_BYTES + ring_bytes(c.ring) + (size_t)c.stages * ws_stage_bytes(c.th, vs, dil) <= kSmemBudget) {
       *plan = c;
       return true;
     }
@@ -518,7 +550,8 @@ int launch_conv3x3_ws(const ConvParams& p, const uint8_t* w16, cudaStream_t stre
   q.W = p.Wi;
   q.dil = p.dil;
   q.tiles_x = cdiv(p.Wo, PW - 2 * p.dil);
-  q.tiles_y = cdiv(p.Ho, plan.th);
+  q.poly = plan.poly;
+  q.tiles_y = plan.poly ? cdiv(cdiv(p.Ho, p.dil), plan.th) : cdiv(p.Ho, plan.th);
   q.stages = plan.stages;
   q.ring = plan.ring;
   q.has_res = has_res ? 1 : 0;
@@ -527,15 +560,17 @@ int launch_conv3x3_ws(const ConvParams& p, const uint8_t* w16, cudaStream_t stre
   static const int dbg = getenv("B200MVS_WS_DEBUG") ? atoi(getenv("B200MVS_WS_DEBUG")) : 0;
   q.dbg = dbg;
   CUtensorMap tm_y, tm_r;
-  if (!make_map(p.feat.ptr, p.n_img, p.Hi, p.Wi, &tm_y) ||
-      !make_map(has_res ? (const void*)p.feat.resid : (const void*)p.feat.ptr, p.n_img, p.Hi, p.Wi, &tm_r)) {
+  const int ystride = plan.poly ? p.dil : 1;
+  if (!make_map(p.feat.ptr, p.n_img, p.Hi, p.Wi, ystride, &tm_y) ||
+      !make_map(has_res ? (const void*)p.feat.resid : (const void*)p.feat.ptr, p.n_img, p.Hi, p.Wi, ystride, &tm_r)) {
     set_error("launch_conv3x3_ws: cuTensorMapEncodeTiled failed");
     return -1;
   }
-  const size_t smem = W_BYTES + ring_bytes(plan.ring) + (size_t)plan.stages * ws_stage_bytes(plan.th, p.dil);
+  const size_t smem = W_BYTES + ring_bytes(plan.ring) +
+                      (size_t)plan.stages * ws_stage_bytes(plan.th, plan.poly ? 1 : p.dil, p.dil);
   int num_sms = 0;
   if (int rc = current_device_sm_count(&num_sms)) return rc;
-  const long long total = (long long)q.tiles_x * q.tiles_y * q.n_img;
+  const long long total = (long long)q.tiles_x * q.tiles_y * (plan.poly ? p.dil : 1) * q.n_img;
   const int grid = (int)(total < num_sms ? total : num_sms);
   if (plan.th == 8) return launch_th<8>(q, w16, tm_y, tm_r, grid, smem, p.tag, stream);
   return launch_th<4>(q, w16, tm_y, tm_r, grid, smem, p.tag, stream);

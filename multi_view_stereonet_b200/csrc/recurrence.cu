@@ -827,6 +827,39 @@ bool recurrence_supported(int rows, int cols, int* n_tiles, size_t* smem_bytes) 
          L.stage_px >= 1 && L.margin >= cols + 2 && L.total <= kSmemBudget;
 }
 
+int recurrence_max_clusters(int rows, int cols) {
+  int n_tiles = 0;
+  size_t smem = 0;
+  if (!recurrence_supported(rows, cols, &n_tiles, &smem)) return 0;
+  const int cached = cached_cluster_size(1000 + n_tiles);   // (device, key) -> value store of api.cu
+  if (cached != 0) return cached;
+  for (const void* f : {reinterpret_cast<const void*>(&recurrence_kernel<false>)}) {
+    if (ensure_func_smem(f, smem) != 0 || ensure_func_nonportable_cluster(f) != 0) return 0;
+  }
+  int best = 0;
+  const int candidates[3] = {n_tiles, (n_tiles + 1) & ~1, 16};
+  for (int c = 0; c < 3 && best == 0; ++c) {
+    const int cs = candidates[c];
+    if (cs < n_tiles || cs > 16) continue;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(cs, 64, 1);
+    cfg.blockDim = dim3(NT, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int mc = 0;
+    if (cudaOccupancyMaxActiveClusters(&mc, recurrence_kernel<false>, &cfg) == cudaSuccess && mc >= 1) best = mc;
+    cudaGetLastError();
+  }
+  if (best > 0) remember_cluster_size(1000 + n_tiles, best);
+  return best;
+}
+
 int launch_recurrence(const RecurrenceArgs& a, cudaStream_t stream) {
   int n_tiles = 0;
   size_t smem = 0;

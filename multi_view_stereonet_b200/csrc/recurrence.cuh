@@ -23,5 +23,8 @@ void pack_recurrence_weights(const float* w0_oihw35, const float* w1_oihw32, con
                              std::vector<uint8_t>* out);
 bool recurrence_supported(int rows, int cols, int* n_tiles, size_t* smem_bytes);
 int launch_recurrence(const RecurrenceArgs& a, cudaStream_t stream);
+// How many of the kernel's clusters can be resident at once on the current device (cudaOccupancyMaxActiveClusters;
+// B200: 7 clusters of 11 CTAs -- one GPC cannot take an 11-CTA cluster); 0 if the shape is not supported.
+int recurrence_max_clusters(int rows, int cols);
 
 }  // namespace b200mvs

@@ -91,6 +91,25 @@ def test_batch8_matches_single_items(net, gta_state):
         assert int((out8["left_idepthmap_mask_pyr"][lvl][5].cpu() != ref["left_idepthmap_mask_pyr"][lvl][0]).sum()) == 0
 
 
+def test_lanes_option_gives_the_same_results(net):
+    """Option "lanes" = 2 (off by default: measured slower) cuts a call whose depth sweep needs more than
+    one round of clusters into two concurrent lanes of whole image groups; results must not change."""
+    inputs = synthetic.to_device(synthetic.make_inputs(512, 640, 1, 8), "cuda")
+    try:
+        with torch.no_grad():
+            one = net(*inputs, 64, True, [True] * 5)
+            n1 = net.last_launch_count()
+            net.set_option("lanes", 2)
+            two = net(*inputs, 64, True, [True] * 5)
+            n2 = net.last_launch_count()
+    finally:
+        net.set_option("lanes", 1)
+    assert n2 == 2 * n1
+    for lvl in range(5):
+        assert rel_linf(two["left_idepthmap_pyr"][lvl].cpu(), one["left_idepthmap_pyr"][lvl].cpu()) <= REL_LINF_TOL / 2
+        assert bool((two["left_idepthmap_mask_pyr"][lvl] == one["left_idepthmap_mask_pyr"][lvl]).all())
+
+
 def test_lazy_and_packed_mask_volumes(net):
     """mask_mode "lazy": forward produces the level-4 volume only; the finer levels and their bit-packed form come
     from the same MaskUpsampler chain on demand and equal the dense default bit for bit."""
@@ -159,6 +178,8 @@ def test_weights_follow_in_place_updates(gta_state):
     (256, 320, 2, 16, 2, False),
     (512, 640, 1, 64, 1, False),       # cfg2
     (512, 640, 1, 64, 1, True),
+    (500, 636, 1, 64, 1, True),        # rows not a multiple of the dilations: ragged polyphase components at level 0
+    (512, 640, 1, 12, 1, True),        # the reference's own 12 hypotheses: small idepth range, split-fp16 refiners
 ])
 def test_stagewise_vs_oracle(rows, cols, views, hyps, batch, smooth, net, gta_state):
     from tests._gpu_util import run_case
