@@ -320,6 +320,7 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
   __shared__ __align__(8) uint64_t s_tbar;       // TMA staging of the previous hypothesis
   __shared__ uint32_t s_tmem;
   __shared__ float s_H[2][9];    // [step parity] H_inc, fetched one step ahead
+  __shared__ int s_plan[8][MAX_TASKS][9];   // warp 0's gather plan, evaluated by warp 1 (see plan_gathers)
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform
@@ -502,15 +503,33 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
   int g_off[MAX_TASKS][4];
   float g_w[MAX_TASKS][4];
   bool g_ok[MAX_TASKS];
-  auto plan_gathers = [&](int step) {
+  // Warp 0 issues the MMAs of conv0 while the plan is computed, and tcgen05.mma issue blocks at the rate the tensor
+  // pipe drains (~45 cycles per MMA, 1.6 k cycles per conv: tools/mma_bench.cu) -- its own plan used to start that
+  // much later and every other warp waited for it at the barrier (MMA0 phase 4.4 k cycles against 2.4 k of the other
+  // two convs).  Its plan is now evaluated by the lanes of warp 1 that would otherwise repeat their neighbours'
+  // work (lanes 2 / 3 of each quad) and handed over through shared memory.
+  int px_gy = 0, px_gx = 0;
+  bool px_real = false;
+  {
+    const int l = (lane >> 2) + (t_oct & 1) * (NT >> 2);   // warp 0's task (t_oct & 1) of the same quad
+    const int Lg = pos0 + l;
+    px_gy = Lg / PW - 1;
+    px_gx = Lg % PW - 1;
+    px_real = active && l < npl && px_gy >= 0 && px_gy < p.rows && px_gx >= 0 && px_gx < p.cols;
+  }
+  auto plan_gathers = [&](int step, bool first) {
     const float* Hinc = s_H[step & 1];
     int mo[4] = {0, 0, 0, 0};
     float mw[4] = {0.f, 0.f, 0.f, 0.f};
     int mok = 0;
     const int kq = t_oct & 1;   // lanes 0/2 of the quad evaluate task 0, lanes 1/3 task 1 (2 and 3 redundantly)
-    if ((kq == 0 ? t_real[0] : t_real[1]) && !(p.debug & 2)) {
-      const WarpCoord c = homography_coord(Hinc, (float)(kq == 0 ? t_gx[0] : t_gx[1]),
-                                           (float)(kq == 0 ? t_gy[0] : t_gy[1]), p.rows, p.cols);
+    const bool proxy = !first && warp == 1 && (t_oct & 2) != 0;
+    const bool idle = !first && warp == 0;
+    const int ev_gx = proxy ? px_gx : (kq == 0 ? t_gx[0] : t_gx[1]);
+    const int ev_gy = proxy ? px_gy : (kq == 0 ? t_gy[0] : t_gy[1]);
+    const bool ev_real = proxy ? px_real : (kq == 0 ? t_real[0] : t_real[1]);
+    if (!idle && ev_real && !(p.debug & 2)) {
+      const WarpCoord c = homography_coord(Hinc, (float)ev_gx, (float)ev_gy, p.rows, p.cols);
       if (!c.invalid) {
         const Bilinear b = bilinear_setup(c, p.rows, p.cols);
         mok = 1;
@@ -524,6 +543,16 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
         mw[3] = b.w11;
       }
     }
+    if (proxy) {
+      int* d = s_plan[lane >> 2][kq];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        d[t] = mo[t];
+        d[4 + t] = __float_as_int(mw[t]);
+      }
+      d[8] = mok;
+    }
+    if (idle) return;   // warp 0: fetch_plan() after the MMAs
 #pragma unroll
     for (int k = 0; k < MAX_TASKS; ++k) {
       const int srcl = (lane & ~3) + k;
@@ -532,6 +561,20 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
       for (int t = 0; t < 4; ++t) {
         g_off[k][t] = __shfl_sync(0xffffffffu, mo[t], srcl);
         g_w[k][t] = __shfl_sync(0xffffffffu, mw[t], srcl);
+      }
+    }
+  };
+  auto fetch_plan = [&]() {   // warp 0, after a block-wide barrier behind plan_gathers
+    if (warp == 0) {
+#pragma unroll
+      for (int k = 0; k < MAX_TASKS; ++k) {
+        const int* d = s_plan[lane >> 2][k];
+        g_ok[k] = d[8] != 0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          g_off[k][t] = d[t];
+          g_w[k][t] = __int_as_float(d[4 + t]);
+        }
       }
     }
   };
@@ -554,7 +597,7 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
   stage_prev(1);
   fetch_H(1);
   __syncthreads();
-  plan_gathers(1);
+  plan_gathers(1, true);
 
   float x0own[8];
 #pragma unroll
@@ -625,8 +668,9 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
     issue_conv(0);
     // the NEXT step's gather plan, overlapped with conv0's MMAs (this step's plan was consumed above; H_inc of the
     // next step was fetched before the barrier above)
-    if (step + 1 < p.D) plan_gathers(step + 1);
+    if (step + 1 < p.D) plan_gathers(step + 1, false);
     wait_conv();
+    if (step + 1 < p.D) fetch_plan();
     PROF_MARK(1);
 
     // ===== two normalised layers: raw output -> statistics + halo exchange -> wait -> operand -> conv =====
