@@ -192,6 +192,7 @@ using namespace b200mvs;
 // one round of the depth sweep's clusters is cut into lanes of whole image groups that run concurrently on their own
 // streams (b200mvs_forward): while the sweep of one lane holds its 11-SM clusters, the other lanes' kernels fill the
 // rest of the chip.
+constexpr int kRecProfWords = 16 * 12 + 16 * 16 * 32;   // recurrence phase totals + one step's per-warp timeline
 constexpr int kMaxLanes = 2;   // 3 streams per lane + the caller's: more would exceed the 8 hardware queues of a device
                                // (CUDA_DEVICE_MAX_CONNECTIONS) and serialise lanes behind each other (measured)
 struct Lane {
@@ -260,7 +261,8 @@ struct b200mvs_net {
   cudaEvent_t ev_up[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // cameras, right l0, right l4, left l0, rest
   float* pinned_small = nullptr;
   size_t pinned_small_floats = 0;
-  long long* rec_prof = nullptr;  // device [16][12], allocated when option "recurrence_profile" is set
+  long long* rec_prof = nullptr;  // device [16][12] phase totals + [16][16][32] per-warp timeline of one step, allocated
+                                  // when option "recurrence_profile" is set
   bool stage_profile = false;       // option "stage_profile": events at the stage boundaries of the main stream
   std::string last_stage_profile;   // "name=us;..." of the last profiled forward (b200mvs_last_stage_profile)
   b200mvs_shape last_shape{};
@@ -1380,8 +1382,8 @@ B200MVS_API int b200mvs_set_option(b200mvs_net* net, const char* name, int value
   }
   if (k == "recurrence_profile") {
     if (value != 0 && net->rec_prof == nullptr) {
-      B200MVS_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&net->rec_prof), 16 * 12 * sizeof(long long)));
-      B200MVS_CUDA_OK(cudaMemset(net->rec_prof, 0, 16 * 12 * sizeof(long long)));
+      B200MVS_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&net->rec_prof), kRecProfWords * sizeof(long long)));
+      B200MVS_CUDA_OK(cudaMemset(net->rec_prof, 0, kRecProfWords * sizeof(long long)));
       net->allocs.push_back(net->rec_prof);
     }
     return 0;
@@ -1771,6 +1773,7 @@ B200MVS_API int b200mvs_get_stage(b200mvs_net* net, const char* name, void* dst,
   else if (k == "cost_filtered") { src = ws.cost1; bytes = n * D * L.px[4] * 4; }
   else if (k == "idepth4_raw_views") { src = ws.raw_views; bytes = n * L.px[4] * 4; }
   else if (k == "recurrence_profile" && net->rec_prof != nullptr) { src = net->rec_prof; bytes = 16 * 12 * 8; }
+  else if (k == "recurrence_trace" && net->rec_prof != nullptr) { src = net->rec_prof + 16 * 12; bytes = 16 * 16 * 32 * 8; }
   else {
     set_error("b200mvs_get_stage: unknown stage '" + k + "'");
     return B200MVS_EINVAL;

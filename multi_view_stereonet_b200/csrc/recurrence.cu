@@ -195,7 +195,8 @@ struct RecParams {
   const float* imgconv;  // [n][D][rows*cols][32]: image half of conv0 + bias0 (image_conv_kernel)
   int D, rows, cols, n_tiles;
   long long* prof;       // optional [16][12] phase cycle totals (debug)
-  int debug;             // timing ablations (wrong results): 1 skip MMAs, 2 skip gathers
+  int debug;             // timing ablations: 1 skip MMAs, 2 skip gathers (wrong results), 4 mbarrier waits without
+                         // .acquire.cluster (correct), 8 no generic->async proxy fences (may be wrong)
 };
 
 // 8 consecutive fp32 accumulator columns of this thread's TMEM lane.
@@ -269,6 +270,20 @@ __device__ __forceinline__ void st_async_f4(uint32_t raddr, float4 v, uint32_t r
                "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(rbar)
                : "memory");
 }
+__device__ __forceinline__ void st_async_f2(uint32_t raddr, float2 v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(raddr),
+               "f"(v.x), "f"(v.y), "r"(rbar)
+               : "memory");
+}
+// Rows of 32 floats (128 bytes) whose eight 16-byte chunks are XOR-swizzled with the row index: a warp that reads or
+// writes the same chunk of 32 consecutive rows (thread = position, one channel octet) touches every bank group
+// instead of one (a 32-way conflict in the linear layout).
+__device__ __forceinline__ float4* swz_ptr(float* base, int row, int chunk) {
+  return reinterpret_cast<float4*>(base + (size_t)row * 32 + (size_t)((chunk ^ (row & 7)) << 2));
+}
+__device__ __forceinline__ const float4* swz_ptr(const float* base, int row, int chunk) {
+  return reinterpret_cast<const float4*>(base + (size_t)row * 32 + (size_t)((chunk ^ (row & 7)) << 2));
+}
 __device__ __forceinline__ void st_async_f1(uint32_t raddr, float v, uint32_t rbar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(raddr), "f"(v),
                "r"(rbar)
@@ -276,6 +291,23 @@ __device__ __forceinline__ void st_async_f1(uint32_t raddr, float v, uint32_t rb
 }
 __device__ __forceinline__ void mbar_arm_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Default (.acquire.cta) wait: enough for bytes that st.async / cp.async.bulk completed on this CTA's own barrier (the
+// data is in shared memory); an .acquire.cluster wait makes ptxas add CCTL.IVALL (an L1 invalidation) to every poll.
+__device__ __forceinline__ void mbar_wait_cta(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  }
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
@@ -312,9 +344,10 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, ui
 template <bool PROF>
 __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  // GroupNorm partial (sum, sumsq) of [layer][source CTA][group][warp quarter]
-  __shared__ __align__(16) float s_part[2][16][kGroups][4][2];
-  __shared__ float s_bias[2][kC], s_gamma[2][kC], s_beta[2][kC];   // biases of conv1, conv2 (conv0's is in imgconv)
+  // GroupNorm partial (sum, sumsq) of [layer][source CTA][group], pushed by the source CTA
+  __shared__ __align__(16) float2 s_part[2][16][kGroups];
+  __shared__ __align__(16) float2 s_loc[kGroups][4];   // this CTA's warp partials [group][warp quarter]
+  __shared__ __align__(16) float s_bias[2][kC], s_gamma[2][kC], s_beta[2][kC];   // biases of conv1, conv2 (conv0's is in imgconv)
   __shared__ __align__(8) uint64_t s_bar;        // MMA completion
   __shared__ __align__(8) uint64_t s_xbar[2];    // per layer: bytes pushed into this CTA by the cluster
   __shared__ __align__(8) uint64_t s_tbar;       // TMA staging of the previous hypothesis
@@ -460,9 +493,9 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
     const int gy = Lg / PW - 1, gx = Lg % PW - 1;
     h_real = h_in && gy >= 0 && gy < p.rows && gx >= 0 && gx < p.cols;
   }
-  // bytes the cluster pushes into this CTA per layer: every active CTA's 16 warp partials (sum, sumsq) and the
+  // bytes the cluster pushes into this CTA per layer: every active CTA's (sum, sumsq) of the four groups and the
   // boundary rows of the two neighbours
-  const uint32_t xbytes = (uint32_t)p.n_tiles * 16u * 2u * 4u +
+  const uint32_t xbytes = (uint32_t)p.n_tiles * (uint32_t)kGroups * 8u +
                           (rank > 0 ? (uint32_t)halo * kC * 4u : 0u) +
                           ((int)rank + 1 < p.n_tiles ? (uint32_t)halo * kC * 4u : 0u);
   // staged pixel range of the previous hypothesis: the pixels under the own + halo positions, plus a margin
@@ -494,6 +527,17 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
       acc_t[k] += _t - t_prev;                \
       t_prev = _t;                            \
     }                                         \
+  } while (0)
+
+  // Per-warp timeline of one step (PROF only): clock64 of lane 0 of every warp at ~30 points, [rank][warp][32]
+  // behind the [16][12] phase totals.  All CTAs leave the cluster barrier within a few cycles of each other, so
+  // point 0 (taken right behind it) is the common origin across CTAs.
+  long long* const trace = (PROF && p.prof != nullptr && blockIdx.y == 0) ? p.prof + 16 * 12 + ((size_t)rank * 16 + warp) * 32 : nullptr;
+  const int trace_step = p.D / 2;
+  int cur_step = 0;
+#define TRACE(k)                                                                   \
+  do {                                                                             \
+    if (PROF && trace != nullptr && cur_step == trace_step && lane == 0) trace[k] = clock64(); \
   } while (0)
 
   pdl_wait();  // everything above ran under the previous kernel's tail; from here on its outputs are read
@@ -585,7 +629,13 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
   auto stage_prev = [&](int step) {
     if (warp == 1) {
       if (active && elect_one()) {
-        asm volatile("fence.proxy.async;" ::: "memory");   // other CTAs' generic-proxy stores -> this async-proxy read
+        // other CTAs' generic-proxy stores -> this async-proxy read
+        if (p.debug & 32) {
+        } else if (p.debug & 16) {
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+        } else {
+          asm volatile("fence.proxy.async;" ::: "memory");
+        }
         mbar_arm_tx(&s_tbar, (uint32_t)st_n * 4u);
         tma_load_1d(smem + L.off_stage, p.vol_in + ((size_t)n * p.D + (step - 1)) * pixels * kC + st_lo,
                     (uint32_t)st_n * 4u, &s_tbar);
@@ -604,6 +654,8 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
   for (int k = 0; k < 8; ++k) x0own[k] = 0.f;
 
   for (int step = 1; step < p.D; ++step) {
+    cur_step = step;
+    TRACE(0);
     if (active && tid == 0) {
       mbar_arm_tx(&s_xbar[0], xbytes);
       mbar_arm_tx(&s_xbar[1], xbytes);
@@ -618,16 +670,22 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
     }
     fetch_H(step + 1);   // read after several block-wide barriers
     // ================= W: warp previous features into the conv0 operand ============================
-    if (active) mbar_wait_cluster(&s_tbar, (uint32_t)((step - 1) & 1));
+    if (active) {
+      if (p.debug & 4) mbar_wait_cta(&s_tbar, (uint32_t)((step - 1) & 1));
+      else mbar_wait_cluster(&s_tbar, (uint32_t)((step - 1) & 1));
+    }
+    TRACE(1);
     {
       const float* prev = p.vol_in + ((size_t)n * p.D + (step - 1)) * pixels * kC + 8 * t_oct;
       const float* stg = s_stage + 8 * t_oct;
 #pragma unroll
       for (int k = 0; k < MAX_TASKS; ++k) {
         if (active && t_l[k] < npl) {
-          float v[8];
+          // u[0..3] accumulate the 16-byte half read first (half `sw` of the octet), u[4..7] the other half:
+          // neighbouring quads start on different halves, so one warp-wide load touches all 32 banks
+          float u[8], v[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = 0.f;
+          for (int e = 0; e < 8; ++e) u[e] = 0.f;
           if (g_ok[k]) {
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
@@ -635,24 +693,28 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
               float4 a, b;
               if ((unsigned)loc < (unsigned)st_n) {
                 const float4* sp = reinterpret_cast<const float4*>(stg + loc);
-                const float4 f = sp[sw], s2 = sp[sw ^ 1];
-                a = sw ? s2 : f;
-                b = sw ? f : s2;
+                a = sp[sw];
+                b = sp[sw ^ 1];
               } else {   // tap outside the staged range (large incremental motion): global memory
                 const float4* gp = reinterpret_cast<const float4*>(prev + g_off[k][t]);
-                a = __ldcg(gp);
-                b = __ldcg(gp + 1);
+                a = __ldcg(gp + sw);
+                b = __ldcg(gp + (sw ^ 1));
               }
               const float wt = g_w[k][t];
-              v[0] = fmaf(a.x, wt, v[0]); v[1] = fmaf(a.y, wt, v[1]); v[2] = fmaf(a.z, wt, v[2]); v[3] = fmaf(a.w, wt, v[3]);
-              v[4] = fmaf(b.x, wt, v[4]); v[5] = fmaf(b.y, wt, v[5]); v[6] = fmaf(b.z, wt, v[6]); v[7] = fmaf(b.w, wt, v[7]);
+              u[0] = fmaf(a.x, wt, u[0]); u[1] = fmaf(a.y, wt, u[1]); u[2] = fmaf(a.z, wt, u[2]); u[3] = fmaf(a.w, wt, u[3]);
+              u[4] = fmaf(b.x, wt, u[4]); u[5] = fmaf(b.y, wt, u[5]); u[6] = fmaf(b.z, wt, u[6]); u[7] = fmaf(b.w, wt, u[7]);
             }
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            v[e] = sw ? u[4 + e] : u[e];
+            v[4 + e] = sw ? u[e] : u[4 + e];
           }
           const int l = t_l[k];
           if (l >= halo && l < halo + MTILE) {
-            float4* wfp = reinterpret_cast<float4*>(s_wf + (l - halo) * kC + 8 * t_oct);
-            wfp[0] = make_float4(v[0], v[1], v[2], v[3]);
-            wfp[1] = make_float4(v[4], v[5], v[6], v[7]);
+            const int jo = l - halo;
+            *swz_ptr(s_wf, jo, 2 * t_oct) = make_float4(v[0], v[1], v[2], v[3]);
+            *swz_ptr(s_wf, jo, 2 * t_oct + 1) = make_float4(v[4], v[5], v[6], v[7]);
           }
           uint4 hi, lo;
           split8(v, &hi, &lo);
@@ -661,17 +723,21 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
         }
       }
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    TRACE(2);
+    if (!(p.debug & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     PROF_MARK(0);
+    TRACE(3);
     issue_conv(0);
     // the NEXT step's gather plan, overlapped with conv0's MMAs (this step's plan was consumed above; H_inc of the
     // next step was fetched before the barrier above)
     if (step + 1 < p.D) plan_gathers(step + 1, false);
+    TRACE(4);
     wait_conv();
     if (step + 1 < p.D) fetch_plan();
     PROF_MARK(1);
+    TRACE(5);
 
     // ===== two normalised layers: raw output -> statistics + halo exchange -> wait -> operand -> conv =====
 #pragma unroll 1
@@ -681,27 +747,33 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
       if (active) {
         float c[8];
         tmem_ld8x2(tmem_my, tmem_my + 32u, y, c);
+        TRACE(6 + 8 * layer);
         if (layer == 0) {
           const float add[8] = {ic0.x, ic0.y, ic0.z, ic0.w, ic1.x, ic1.y, ic1.z, ic1.w};
 #pragma unroll
           for (int k = 0; k < 8; ++k) y[k] = (y[k] + c[k]) + add[k];
         } else {
+          const float4 b0 = *reinterpret_cast<const float4*>(&s_bias[0][oct_e * 8]);
+          const float4 b1 = *reinterpret_cast<const float4*>(&s_bias[0][oct_e * 8 + 4]);
+          const float add[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-          for (int k = 0; k < 8; ++k) y[k] = (y[k] + c[k]) + s_bias[0][oct_e * 8 + k];
+          for (int k = 0; k < 8; ++k) y[k] = (y[k] + c[k]) + add[k];
         }
         // the neighbour indexes its halo buffer [layer][side][i][32]
-        if (jl < halo && rank > 0) {  // upper halo (side 1) of rank-1, index jl
-          const uint32_t ra = map_to_rank(smem_u32(s_halo + (((layer * 2 + 1) * halo) + jl) * kC + oct_e * 8), rank - 1);
+        // halo rows of a layer: [2 * halo][32] fp32, lower halo then upper halo, 16-byte chunks XOR-swizzled with the
+        // row index (the receiver reads one octet of 32 consecutive rows per instruction)
+        if (jl < halo && rank > 0) {  // upper halo of rank-1, row halo + jl
+          float* hb = s_halo + (size_t)layer * 2 * halo * kC;
           const uint32_t rb = map_to_rank(smem_u32(&s_xbar[layer]), rank - 1);
-          st_async_f4(ra, make_float4(y[0], y[1], y[2], y[3]), rb);
-          st_async_f4(ra + 16u, make_float4(y[4], y[5], y[6], y[7]), rb);
+          st_async_f4(map_to_rank(smem_u32(swz_ptr(hb, halo + jl, 2 * oct_e)), rank - 1), make_float4(y[0], y[1], y[2], y[3]), rb);
+          st_async_f4(map_to_rank(smem_u32(swz_ptr(hb, halo + jl, 2 * oct_e + 1)), rank - 1), make_float4(y[4], y[5], y[6], y[7]), rb);
         }
-        if (jl >= MTILE - halo && (int)rank + 1 < p.n_tiles) {  // lower halo (side 0) of rank+1
+        if (jl >= MTILE - halo && (int)rank + 1 < p.n_tiles) {  // lower halo of rank+1
           const int idx = jl - (MTILE - halo);
-          const uint32_t ra = map_to_rank(smem_u32(s_halo + (((layer * 2 + 0) * halo) + idx) * kC + oct_e * 8), rank + 1);
+          float* hb = s_halo + (size_t)layer * 2 * halo * kC;
           const uint32_t rb = map_to_rank(smem_u32(&s_xbar[layer]), rank + 1);
-          st_async_f4(ra, make_float4(y[0], y[1], y[2], y[3]), rb);
-          st_async_f4(ra + 16u, make_float4(y[4], y[5], y[6], y[7]), rb);
+          st_async_f4(map_to_rank(smem_u32(swz_ptr(hb, idx, 2 * oct_e)), rank + 1), make_float4(y[0], y[1], y[2], y[3]), rb);
+          st_async_f4(map_to_rank(smem_u32(swz_ptr(hb, idx, 2 * oct_e + 1)), rank + 1), make_float4(y[4], y[5], y[6], y[7]), rb);
         }
         float gs = 0.f, gq = 0.f;
         if (real_out) {
@@ -716,45 +788,61 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
           gs += __shfl_xor_sync(0xffffffffu, gs, o);
           gq += __shfl_xor_sync(0xffffffffu, gq, o);
         }
-        // lane 2d + m pushes this warp's (sum | sumsq) to CTA d
-        if (lane < 2 * p.n_tiles) {
-          const uint32_t dst = (uint32_t)(lane >> 1);
-          const int m = lane & 1;
-          st_async_f1(map_to_rank(smem_u32(&s_part[layer][rank][oct_e][wq][m]), dst), m ? gq : gs,
-                      map_to_rank(smem_u32(&s_xbar[layer]), dst));
+        // The four warps of a group add up inside the CTA (fixed order), then lane d of the group's first warp pushes
+        // the CTA's (sum, sumsq) to CTA d: 4 * n_tiles remote stores per CTA instead of one per warp and value (a
+        // remote store costs ~2 cycles of issue whatever its size; 352 of them were ~700 cycles of every epilogue).
+        if (lane == 0) s_loc[oct_e][wq] = make_float2(gs, gq);
+        if (wq != 0) {
+          asm volatile("bar.arrive %0, 128;" ::"r"(1 + oct_e) : "memory");
+        } else {
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + oct_e) : "memory");
+          if (lane < p.n_tiles) {
+            const float4 u = *reinterpret_cast<const float4*>(&s_loc[oct_e][0]);
+            const float4 w = *reinterpret_cast<const float4*>(&s_loc[oct_e][2]);
+            st_async_f2(map_to_rank(smem_u32(&s_part[layer][rank][oct_e]), (uint32_t)lane),
+                        make_float2((u.x + u.z) + (w.x + w.z), (u.y + u.w) + (w.y + w.w)),
+                        map_to_rank(smem_u32(&s_xbar[layer]), (uint32_t)lane));
+          }
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       PROF_MARK(2 + 4 * layer);
-      if (active) mbar_wait_cluster(&s_xbar[layer], (uint32_t)((step - 1) & 1));
+      TRACE(7 + 8 * layer);
+      if (active) {
+        if (p.debug & 4) mbar_wait_cta(&s_xbar[layer], (uint32_t)((step - 1) & 1));
+        else mbar_wait_cluster(&s_xbar[layer], (uint32_t)((step - 1) & 1));
+      }
       PROF_MARK(3 + 4 * layer);
+      TRACE(8 + 8 * layer);
 
       if (active) {
         // ---- GroupNorm coefficients of the own octet's group: lane r sums CTA r's four warp partials, then a
         //      butterfly over the lanes (every lane ends with the same bits: deterministic) ----
         float ca[8], cb[8];
         {
+          // every thread adds the CTAs' partials in rank order (broadcast loads; same bits everywhere)
           float ts = 0.f, tq = 0.f;
-          if (lane < p.n_tiles) {
-            const float4 u = *reinterpret_cast<const float4*>(&s_part[layer][lane][oct_e][0][0]);
-            const float4 w = *reinterpret_cast<const float4*>(&s_part[layer][lane][oct_e][2][0]);
-            ts = (u.x + u.z) + (w.x + w.z);
-            tq = (u.y + u.w) + (w.y + w.w);
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            ts += __shfl_xor_sync(0xffffffffu, ts, o);
-            tq += __shfl_xor_sync(0xffffffffu, tq, o);
+          for (int src = 0; src < p.n_tiles; ++src) {
+            const float2 u = s_part[layer][src][oct_e];
+            ts += u.x;
+            tq += u.y;
           }
           const double mean = (double)ts * (double)inv_count;
           const double var = (double)tq * (double)inv_count - mean * mean;  // cancellation in double
           const float rstd = rsqrtf(fmaxf((float)var, 0.f) + kGnEps);
+          const float4 g0 = *reinterpret_cast<const float4*>(&s_gamma[layer][8 * oct_e]);
+          const float4 g1 = *reinterpret_cast<const float4*>(&s_gamma[layer][8 * oct_e + 4]);
+          const float4 e0 = *reinterpret_cast<const float4*>(&s_beta[layer][8 * oct_e]);
+          const float4 e1 = *reinterpret_cast<const float4*>(&s_beta[layer][8 * oct_e + 4]);
+          const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          const float bt[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            ca[k] = s_gamma[layer][8 * oct_e + k] * rstd;
-            cb[k] = s_beta[layer][8 * oct_e + k] - (float)mean * ca[k];
+            ca[k] = gm[k] * rstd;
+            cb[k] = bt[k] - (float)mean * ca[k];
           }
         }
+        TRACE(9 + 8 * layer);
         // ---- next operand: x = lrelu(GN(y)) (+ x0 for the residual block) over own + halo positions ----
         {
           float x[8];
@@ -769,6 +857,7 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
           *plane_ptr(PLANE_HI + oct_e, own_l) = hi;
           *plane_ptr(PLANE_LO + oct_e, own_l) = lo;
         }
+        TRACE(10 + 8 * layer);
         if (h_in) {
           float v[8];
 #pragma unroll
@@ -776,8 +865,8 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
           uint4* ph = plane_ptr(PLANE_HI + oct_e, h_l);
           uint4* plo = plane_ptr(PLANE_LO + oct_e, h_l);
           if (h_real) {
-            const float4* src = reinterpret_cast<const float4*>(s_halo + ((layer * 2) * halo + h_idx) * kC + 8 * oct_e);
-            const float4 a = src[0], b = src[1];
+            const float* hb = s_halo + (size_t)layer * 2 * halo * kC;
+            const float4 a = *swz_ptr(hb, h_idx, 2 * oct_e), b = *swz_ptr(hb, h_idx, 2 * oct_e + 1);
             const float yy[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
             float xprev[8];
             if (layer == 1) unsplit8(*ph, *plo, xprev);
@@ -793,38 +882,46 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
           *plo = lo;
         }
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      TRACE(11 + 8 * layer);
+      if (!(p.debug & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();
       PROF_MARK(4 + 4 * layer);
+      TRACE(12 + 8 * layer);
       issue_conv(1 + layer);
       wait_conv();
       PROF_MARK(5 + 4 * layer);
+      TRACE(13 + 8 * layer);
     }
 
     // ================= E2: features_step = wf + delta -> global =====================================
     if (active) {
       float v[8], c[8];
       tmem_ld8x2(tmem_my, tmem_my + 32u, v, c);
+      TRACE(22);
       if (real_out) {
         float* dst = p.vol + (((size_t)n * p.D + step) * pixels + own_pix) * kC + oct_e * 8;
-        const float* wfp = s_wf + jl * kC + oct_e * 8;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
+          const float4 wv = *swz_ptr(s_wf, jl, 2 * oct_e + q);
+          const float4 bv = *reinterpret_cast<const float4*>(&s_bias[1][oct_e * 8 + 4 * q]);
           float4 r;
-          r.x = wfp[4 * q + 0] + ((v[4 * q + 0] + c[4 * q + 0]) + s_bias[1][oct_e * 8 + 4 * q + 0]);
-          r.y = wfp[4 * q + 1] + ((v[4 * q + 1] + c[4 * q + 1]) + s_bias[1][oct_e * 8 + 4 * q + 1]);
-          r.z = wfp[4 * q + 2] + ((v[4 * q + 2] + c[4 * q + 2]) + s_bias[1][oct_e * 8 + 4 * q + 2]);
-          r.w = wfp[4 * q + 3] + ((v[4 * q + 3] + c[4 * q + 3]) + s_bias[1][oct_e * 8 + 4 * q + 3]);
+          r.x = wv.x + ((v[4 * q + 0] + c[4 * q + 0]) + bv.x);
+          r.y = wv.y + ((v[4 * q + 1] + c[4 * q + 1]) + bv.y);
+          r.z = wv.z + ((v[4 * q + 2] + c[4 * q + 2]) + bv.z);
+          r.w = wv.w + ((v[4 * q + 3] + c[4 * q + 3]) + bv.w);
           __stcg(reinterpret_cast<float4*>(dst) + q, r);
         }
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     PROF_MARK(10);
+    TRACE(23);
     cluster_sync_all();  // hypothesis `step` is visible to every CTA; exchange buffers are free again
+    TRACE(24);
     if (step + 1 < p.D) stage_prev(step + 1);
     PROF_MARK(11);
+    TRACE(25);
   }
   if (PROF && p.prof != nullptr && tid == 0 && blockIdx.y == 0) {
     for (int k = 0; k < 12; ++k) p.prof[rank * 12 + k] = acc_t[PROF ? k : 0];
