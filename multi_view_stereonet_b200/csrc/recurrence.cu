@@ -193,10 +193,12 @@ struct RecParams {
   const float* gamma1;
   const float* beta1;
   const float* imgconv;  // [n][D][rows*cols][32]: image half of conv0 + bias0 (image_conv_kernel)
+  const float4* plan;    // [n][D][plan_stride]: gather plan of every step (gather_plan_kernel)
+  int plan_stride;
   int D, rows, cols, n_tiles;
   long long* prof;       // optional [16][12] phase cycle totals (debug)
-  int debug;             // timing ablations: 1 skip MMAs, 2 skip gathers (wrong results), 4 mbarrier waits without
-                         // .acquire.cluster (correct), 8 no generic->async proxy fences (may be wrong)
+  int debug;             // timing ablations (wrong results): 1 skip MMAs, 2 skip gathers, 8 no generic->async proxy
+                         // fences before the MMAs
 };
 
 // 8 consecutive fp32 accumulator columns of this thread's TMEM lane.
@@ -344,16 +346,14 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, ui
 template <bool PROF>
 __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  // GroupNorm partial (sum, sumsq) of [layer][source CTA][group], pushed by the source CTA
-  __shared__ __align__(16) float2 s_part[2][16][kGroups];
+  // GroupNorm partial (sum, sumsq) of [layer][group][source CTA], pushed by the source CTA; unused slots stay zero
+  __shared__ __align__(16) float2 s_part[2][kGroups][16];
   __shared__ __align__(16) float2 s_loc[kGroups][4];   // this CTA's warp partials [group][warp quarter]
   __shared__ __align__(16) float s_bias[2][kC], s_gamma[2][kC], s_beta[2][kC];   // biases of conv1, conv2 (conv0's is in imgconv)
   __shared__ __align__(8) uint64_t s_bar;        // MMA completion
   __shared__ __align__(8) uint64_t s_xbar[2];    // per layer: bytes pushed into this CTA by the cluster
   __shared__ __align__(8) uint64_t s_tbar;       // TMA staging of the previous hypothesis
   __shared__ uint32_t s_tmem;
-  __shared__ float s_H[2][9];    // [step parity] H_inc, fetched one step ahead
-  __shared__ int s_plan[8][MAX_TASKS][9];   // warp 0's gather plan, evaluated by warp 1 (see plan_gathers)
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform
@@ -385,6 +385,7 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_tbar)), "r"(1) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (tid < 2 * kGroups * 16) (&s_part[0][0][0])[tid] = make_float2(0.f, 0.f);
   if (tid < kC) {
     s_bias[0][tid] = __ldg(p.bias1 + tid);
     s_bias[1][tid] = __ldg(p.bias2 + tid);
@@ -417,8 +418,8 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
   const uint64_t da_lo0 = umma_desc(smem_u32(s_planes) + (uint32_t)PLANE_LO * L.plane_bytes, L.plane_bytes, 128u);
   const uint64_t db_c0 = umma_desc(smem_u32(s_w), 1024u, 128u);
 
-  // Tensor-core conv: an elected lane of warp 0 issues and commits; later the same lane polls the completion
-  // mbarrier while everyone else parks at the hardware barrier.  Work placed between the two overlaps the MMAs.
+  // Tensor-core conv: an elected lane of warp 0 issues and commits.  Work placed between issue and wait overlaps the
+  // MMAs.
   auto issue_conv = [&](int layer) {
     if (warp == 0) {
       if (active && elect_one()) {
@@ -433,28 +434,11 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
       __syncwarp();
     }
   };
+  // every thread waits on the completion barrier itself (a hardware sleep, ~60 cycles from arrive to wake-up): no
+  // block-wide barrier between the tensor core and the epilogue
   auto wait_conv = [&]() {
-    if (warp == 0) {
-      if (active && elect_one()) {
-        const uint32_t bar = smem_u32(&s_bar);
-        uint32_t done = 0;
-        while (!done) {
-          asm volatile(
-              "{\n\t"
-              ".reg .pred q;\n\t"
-              "mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
-              "selp.u32 %0, 1, 0, q;\n\t"
-              "}\n"
-              : "=r"(done)
-              : "r"(bar), "r"(bar_phase)
-              : "memory");
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      }
-      __syncwarp();
-    }
+    if (active) mbar_wait_cta(&s_bar, bar_phase);
     bar_phase ^= 1u;
-    __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   };
 
@@ -472,17 +456,9 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
   // a quad share the position and take one octet each.
   const int t_oct = tid & 3;  // NT % 4 == 0: the octet is the same for every task of a thread
   const int sw = (tid >> 2) & 1;   // which 16-byte half of the octet is read first (shared-memory bank spread)
-  int t_l[MAX_TASKS], t_gy[MAX_TASKS], t_gx[MAX_TASKS];
-  bool t_real[MAX_TASKS];
+  int t_l[MAX_TASKS];
 #pragma unroll
-  for (int k = 0; k < MAX_TASKS; ++k) {
-    const int i = tid + k * NT;
-    t_l[k] = i >> 2;
-    const int Lg = pos0 + t_l[k];
-    t_gy[k] = Lg / PW - 1;
-    t_gx[k] = Lg % PW - 1;
-    t_real[k] = active && t_l[k] < npl && t_gy[k] >= 0 && t_gy[k] < p.rows && t_gx[k] >= 0 && t_gx[k] < p.cols;
-  }
+  for (int k = 0; k < MAX_TASKS; ++k) t_l[k] = (tid + k * NT) >> 2;
   // halo staging task: halo position (tid & 127) of the thread's own octet; 2 * halo <= 128
   const int h_idx = tid & 127;                              // lower halo then upper halo, as laid out in s_halo
   const bool h_in = active && h_idx < 2 * halo;
@@ -511,6 +487,29 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
     q_cnt = L.stage_px;
   }
   const int st_lo = q_lo * kC, st_n = q_cnt * kC;   // in floats, relative to the hypothesis base
+  // The real pixels of the own tile are one contiguous pixel range of the image (rows of the tile follow each other in
+  // memory).  The last epilogue leaves the new features in shared memory and the tile goes out as 16-byte chunks
+  // in pixel order: 32 lanes = 512 contiguous bytes.  (One thread = one position stored 32 bytes at a 128-byte
+  // stride: 32 sectors per warp instruction, ~1 k cycles of store issue per step.)
+  int co_src[2], co_dst[2];   // float offsets into s_wf (swizzled) and into the hypothesis; -1: nothing
+  {
+    int first = pos0 % PW < p.cols ? pos0 : (pos0 / PW + 1) * PW;
+    int last = pos0 + MTILE - 1 < p.rows * PW - 1 ? pos0 + MTILE - 1 : p.rows * PW - 1;
+    if (last % PW >= p.cols) last = (last / PW) * PW + p.cols - 1;
+    const bool any = active && first <= last;
+    const int px_lo = any ? (first / PW) * p.cols + first % PW : 0;
+    const int px_hi = any ? (last / PW) * p.cols + last % PW : -1;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int i = tid + k * NT, px = px_lo + (i >> 3), chunk = i & 7;
+      co_src[k] = co_dst[k] = -1;
+      if (px <= px_hi) {
+        const int row = (px / p.cols) * PW + px % p.cols - pos0;   // local output position
+        co_src[k] = row * 32 + ((chunk ^ (row & 7)) << 2);
+        co_dst[k] = px * kC + chunk * 4;
+      }
+    }
+  }
 
   auto plane_ptr = [&](int plane, int l) -> uint4* {
     return reinterpret_cast<uint4*>(s_planes + (size_t)plane * L.plane_bytes + (size_t)l * 16);
@@ -542,100 +541,25 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
 
   pdl_wait();  // everything above ran under the previous kernel's tail; from here on its outputs are read
 
-  // Gather plan of the coming step (element offsets of the four bilinear taps and their weights), computed one
-  // step ahead while the tensor core runs: quad lane k evaluates task k's homography and broadcasts it.
-  int g_off[MAX_TASKS][4];
-  float g_w[MAX_TASKS][4];
-  bool g_ok[MAX_TASKS];
-  // Warp 0 issues the MMAs of conv0 while the plan is computed, and tcgen05.mma issue blocks at the rate the tensor
-  // pipe drains (~45 cycles per MMA, 1.6 k cycles per conv: tools/mma_bench.cu) -- its own plan used to start that
-  // much later and every other warp waited for it at the barrier (MMA0 phase 4.4 k cycles against 2.4 k of the other
-  // two convs).  Its plan is now evaluated by the lanes of warp 1 that would otherwise repeat their neighbours'
-  // work (lanes 2 / 3 of each quad) and handed over through shared memory.
-  int px_gy = 0, px_gx = 0;
-  bool px_real = false;
-  {
-    const int l = (lane >> 2) + (t_oct & 1) * (NT >> 2);   // warp 0's task (t_oct & 1) of the same quad
-    const int Lg = pos0 + l;
-    px_gy = Lg / PW - 1;
-    px_gx = Lg % PW - 1;
-    px_real = active && l < npl && px_gy >= 0 && px_gy < p.rows && px_gx >= 0 && px_gx < p.cols;
-  }
-  auto plan_gathers = [&](int step, bool first) {
-    const float* Hinc = s_H[step & 1];
-    int mo[4] = {0, 0, 0, 0};
-    float mw[4] = {0.f, 0.f, 0.f, 0.f};
-    int mok = 0;
-    const int kq = t_oct & 1;   // lanes 0/2 of the quad evaluate task 0, lanes 1/3 task 1 (2 and 3 redundantly)
-    const bool proxy = !first && warp == 1 && (t_oct & 2) != 0;
-    const bool idle = !first && warp == 0;
-    const int ev_gx = proxy ? px_gx : (kq == 0 ? t_gx[0] : t_gx[1]);
-    const int ev_gy = proxy ? px_gy : (kq == 0 ? t_gy[0] : t_gy[1]);
-    const bool ev_real = proxy ? px_real : (kq == 0 ? t_real[0] : t_real[1]);
-    if (!idle && ev_real && !(p.debug & 2)) {
-      const WarpCoord c = homography_coord(Hinc, (float)ev_gx, (float)ev_gy, p.rows, p.cols);
-      if (!c.invalid) {
-        const Bilinear b = bilinear_setup(c, p.rows, p.cols);
-        mok = 1;
-        mo[0] = (b.y0 * p.cols + b.x0) * kC;
-        mo[1] = (b.y0 * p.cols + b.x1) * kC;
-        mo[2] = (b.y1 * p.cols + b.x0) * kC;
-        mo[3] = (b.y1 * p.cols + b.x1) * kC;
-        mw[0] = b.w00;
-        mw[1] = b.w01;
-        mw[2] = b.w10;
-        mw[3] = b.w11;
-      }
-    }
-    if (proxy) {
-      int* d = s_plan[lane >> 2][kq];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        d[t] = mo[t];
-        d[4 + t] = __float_as_int(mw[t]);
-      }
-      d[8] = mok;
-    }
-    if (idle) return;   // warp 0: fetch_plan() after the MMAs
+  // Gather plan of the coming step: one float4 per (step, padded input position) -- first tap's pixel index, east and
+  // south weights, flags -- precomputed for all steps by gather_plan_kernel (it depends on the homographies only).
+  // Loaded one step ahead, under conv0's MMAs.
+  const float4* const plan_base = p.plan + (size_t)n * p.D * p.plan_stride + pos0;
+  float4 g_plan[MAX_TASKS];
+  auto load_plan = [&](int step) {
 #pragma unroll
     for (int k = 0; k < MAX_TASKS; ++k) {
-      const int srcl = (lane & ~3) + k;
-      g_ok[k] = __shfl_sync(0xffffffffu, mok, srcl) != 0;
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        g_off[k][t] = __shfl_sync(0xffffffffu, mo[t], srcl);
-        g_w[k][t] = __shfl_sync(0xffffffffu, mw[t], srcl);
-      }
+      g_plan[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (active && t_l[k] < npl && !(p.debug & 2)) g_plan[k] = __ldg(plan_base + (size_t)step * p.plan_stride + t_l[k]);
     }
-  };
-  auto fetch_plan = [&]() {   // warp 0, after a block-wide barrier behind plan_gathers
-    if (warp == 0) {
-#pragma unroll
-      for (int k = 0; k < MAX_TASKS; ++k) {
-        const int* d = s_plan[lane >> 2][k];
-        g_ok[k] = d[8] != 0;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          g_off[k][t] = d[t];
-          g_w[k][t] = __int_as_float(d[4 + t]);
-        }
-      }
-    }
-  };
-  auto fetch_H = [&](int step) {
-    if (step < p.D && tid < 9) s_H[step & 1][tid] = __ldg(p.geo.Hinc + ((size_t)n * p.D + step) * 9 + tid);
   };
   // one lane: bulk copy of hypothesis `step - 1`, pixels [q_lo, q_lo + q_cnt), into the staging buffer
   auto stage_prev = [&](int step) {
     if (warp == 1) {
       if (active && elect_one()) {
-        // other CTAs' generic-proxy stores -> this async-proxy read
-        if (p.debug & 32) {
-        } else if (p.debug & 16) {
-          asm volatile("fence.proxy.async.global;" ::: "memory");
-        } else {
-          asm volatile("fence.proxy.async;" ::: "memory");
-        }
+        // other CTAs' generic-proxy stores to global memory -> this async-proxy read (the all-state-spaces form of
+        // the fence cost ~1.1 k cycles here, the .global form ~0.3 k)
+        asm volatile("fence.proxy.async.global;" ::: "memory");
         mbar_arm_tx(&s_tbar, (uint32_t)st_n * 4u);
         tma_load_1d(smem + L.off_stage, p.vol_in + ((size_t)n * p.D + (step - 1)) * pixels * kC + st_lo,
                     (uint32_t)st_n * 4u, &s_tbar);
@@ -645,9 +569,7 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
   };
 
   stage_prev(1);
-  fetch_H(1);
-  __syncthreads();
-  plan_gathers(1, true);
+  load_plan(1);
 
   float x0own[8];
 #pragma unroll
@@ -668,12 +590,8 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
       ic0 = __ldg(icp);
       ic1 = __ldg(icp + 1);
     }
-    fetch_H(step + 1);   // read after several block-wide barriers
     // ================= W: warp previous features into the conv0 operand ============================
-    if (active) {
-      if (p.debug & 4) mbar_wait_cta(&s_tbar, (uint32_t)((step - 1) & 1));
-      else mbar_wait_cluster(&s_tbar, (uint32_t)((step - 1) & 1));
-    }
+    if (active) mbar_wait_cta(&s_tbar, (uint32_t)((step - 1) & 1));
     TRACE(1);
     {
       const float* prev = p.vol_in + ((size_t)n * p.D + (step - 1)) * pixels * kC + 8 * t_oct;
@@ -686,23 +604,31 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
           float u[8], v[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) u[e] = 0.f;
-          if (g_ok[k]) {
+          const int fl = __float_as_int(g_plan[k].w);
+          if (fl & 1) {
+            const float we = g_plan[k].y, ws = g_plan[k].z;
+            const float ww = 1.0f - we, wn = 1.0f - ws;
+            const float wt[4] = {wn * ww, wn * we, ws * ww, ws * we};
+            const int dxo = (fl & 2) ? kC : 0, dyo = (fl & 4) ? p.cols * kC : 0;
+            const int o00 = __float_as_int(g_plan[k].x) * kC;
+            const int off[4] = {0, dxo, dyo, dyo + dxo};
+            const int loc = o00 - st_lo;
+            if (loc >= 0 && loc + dyo + dxo < st_n) {
+              const float4* sp = reinterpret_cast<const float4*>(stg + loc);
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const int loc = g_off[k][t] - st_lo;
-              float4 a, b;
-              if ((unsigned)loc < (unsigned)st_n) {
-                const float4* sp = reinterpret_cast<const float4*>(stg + loc);
-                a = sp[sw];
-                b = sp[sw ^ 1];
-              } else {   // tap outside the staged range (large incremental motion): global memory
-                const float4* gp = reinterpret_cast<const float4*>(prev + g_off[k][t]);
-                a = __ldcg(gp + sw);
-                b = __ldcg(gp + (sw ^ 1));
+              for (int t = 0; t < 4; ++t) {
+                const float4 a = sp[(off[t] >> 2) + sw], b = sp[(off[t] >> 2) + (sw ^ 1)];
+                u[0] = fmaf(a.x, wt[t], u[0]); u[1] = fmaf(a.y, wt[t], u[1]); u[2] = fmaf(a.z, wt[t], u[2]); u[3] = fmaf(a.w, wt[t], u[3]);
+                u[4] = fmaf(b.x, wt[t], u[4]); u[5] = fmaf(b.y, wt[t], u[5]); u[6] = fmaf(b.z, wt[t], u[6]); u[7] = fmaf(b.w, wt[t], u[7]);
               }
-              const float wt = g_w[k][t];
-              u[0] = fmaf(a.x, wt, u[0]); u[1] = fmaf(a.y, wt, u[1]); u[2] = fmaf(a.z, wt, u[2]); u[3] = fmaf(a.w, wt, u[3]);
-              u[4] = fmaf(b.x, wt, u[4]); u[5] = fmaf(b.y, wt, u[5]); u[6] = fmaf(b.z, wt, u[6]); u[7] = fmaf(b.w, wt, u[7]);
+            } else {   // a tap outside the staged range (large incremental motion): global memory
+              const float4* gp = reinterpret_cast<const float4*>(prev + o00);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float4 a = __ldcg(gp + (off[t] >> 2) + sw), b = __ldcg(gp + (off[t] >> 2) + (sw ^ 1));
+                u[0] = fmaf(a.x, wt[t], u[0]); u[1] = fmaf(a.y, wt[t], u[1]); u[2] = fmaf(a.z, wt[t], u[2]); u[3] = fmaf(a.w, wt[t], u[3]);
+                u[4] = fmaf(b.x, wt[t], u[4]); u[5] = fmaf(b.y, wt[t], u[5]); u[6] = fmaf(b.z, wt[t], u[6]); u[7] = fmaf(b.w, wt[t], u[7]);
+              }
             }
           }
 #pragma unroll
@@ -730,12 +656,10 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
     PROF_MARK(0);
     TRACE(3);
     issue_conv(0);
-    // the NEXT step's gather plan, overlapped with conv0's MMAs (this step's plan was consumed above; H_inc of the
-    // next step was fetched before the barrier above)
-    if (step + 1 < p.D) plan_gathers(step + 1, false);
+    // the NEXT step's gather plan, in flight under conv0's MMAs (this step's plan was consumed above)
+    if (step + 1 < p.D) load_plan(step + 1);
     TRACE(4);
     wait_conv();
-    if (step + 1 < p.D) fetch_plan();
     PROF_MARK(1);
     TRACE(5);
 
@@ -799,7 +723,7 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
           if (lane < p.n_tiles) {
             const float4 u = *reinterpret_cast<const float4*>(&s_loc[oct_e][0]);
             const float4 w = *reinterpret_cast<const float4*>(&s_loc[oct_e][2]);
-            st_async_f2(map_to_rank(smem_u32(&s_part[layer][rank][oct_e]), (uint32_t)lane),
+            st_async_f2(map_to_rank(smem_u32(&s_part[layer][oct_e][rank]), (uint32_t)lane),
                         make_float2((u.x + u.z) + (w.x + w.z), (u.y + u.w) + (w.y + w.w)),
                         map_to_rank(smem_u32(&s_xbar[layer]), (uint32_t)lane));
           }
@@ -808,10 +732,7 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       PROF_MARK(2 + 4 * layer);
       TRACE(7 + 8 * layer);
-      if (active) {
-        if (p.debug & 4) mbar_wait_cta(&s_xbar[layer], (uint32_t)((step - 1) & 1));
-        else mbar_wait_cluster(&s_xbar[layer], (uint32_t)((step - 1) & 1));
-      }
+      if (active) mbar_wait_cta(&s_xbar[layer], (uint32_t)((step - 1) & 1));
       PROF_MARK(3 + 4 * layer);
       TRACE(8 + 8 * layer);
 
@@ -820,12 +741,28 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
         //      butterfly over the lanes (every lane ends with the same bits: deterministic) ----
         float ca[8], cb[8];
         {
-          // every thread adds the CTAs' partials in rank order (broadcast loads; same bits everywhere)
-          float ts = 0.f, tq = 0.f;
-          for (int src = 0; src < p.n_tiles; ++src) {
-            const float2 u = s_part[layer][src][oct_e];
-            ts += u.x;
-            tq += u.y;
+          // every thread adds the 16 CTA slots of its group in one fixed tree (broadcast loads, unused slots are
+          // zero; the same bits in every thread of the cluster)
+          float ts, tq;
+          {
+            const float4* sp = reinterpret_cast<const float4*>(&s_part[layer][oct_e][0]);
+            float4 q[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) q[i] = sp[i];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              q[i].x += q[i].z;
+              q[i].y += q[i].w;
+            }
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1)
+#pragma unroll
+              for (int i = 0; i < 8; i += 2 * o) {
+                q[i].x += q[i + o].x;
+                q[i].y += q[i + o].y;
+              }
+            ts = q[0].x;
+            tq = q[0].y;
           }
           const double mean = (double)ts * (double)inv_count;
           const double var = (double)tq * (double)inv_count - mean * mean;  // cancellation in double
@@ -894,25 +831,33 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
       TRACE(13 + 8 * layer);
     }
 
-    // ================= E2: features_step = wf + delta -> global =====================================
+    // ================= E2: features_step = wf + delta, in place in shared memory, then out in pixel order ========
     if (active) {
       float v[8], c[8];
       tmem_ld8x2(tmem_my, tmem_my + 32u, v, c);
       TRACE(22);
       if (real_out) {
-        float* dst = p.vol + (((size_t)n * p.D + step) * pixels + own_pix) * kC + oct_e * 8;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          const float4 wv = *swz_ptr(s_wf, jl, 2 * oct_e + q);
+          float4* wp = swz_ptr(s_wf, jl, 2 * oct_e + q);
+          const float4 wv = *wp;
           const float4 bv = *reinterpret_cast<const float4*>(&s_bias[1][oct_e * 8 + 4 * q]);
           float4 r;
           r.x = wv.x + ((v[4 * q + 0] + c[4 * q + 0]) + bv.x);
           r.y = wv.y + ((v[4 * q + 1] + c[4 * q + 1]) + bv.y);
           r.z = wv.z + ((v[4 * q + 2] + c[4 * q + 2]) + bv.z);
           r.w = wv.w + ((v[4 * q + 3] + c[4 * q + 3]) + bv.w);
-          __stcg(reinterpret_cast<float4*>(dst) + q, r);
+          *wp = r;
         }
       }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    {
+      float* dst = p.vol + ((size_t)n * p.D + step) * pixels * kC;
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        if (co_src[k] >= 0) __stcg(reinterpret_cast<float4*>(dst + co_dst[k]), *reinterpret_cast<const float4*>(s_wf + co_src[k]));
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     PROF_MARK(10);
@@ -933,7 +878,57 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
   }
 }
 
+// Gather plan of the sweep: for every step and every padded input position Lg (image pixel (Lg / PW - 1, Lg % PW - 1);
+// CTA r gathers positions [128 r, 128 r + 128 + 2 halo)), where the incremental homography H_{d-1}^-1 H_d
+// (multi_view_stereonet.py:280-282) sends the pixel: {pixel index of the north-west tap, east weight, south weight,
+// flags (1 valid, 2 east tap exists, 4 south tap exists)}.  It depends on the cameras only, so it is computed for all
+// steps next to the sweep's other inputs instead of inside its dependent chain (there it was ~250 instructions per
+// thread and step, longer than the MMAs it was hidden under).
+__global__ void __launch_bounds__(256) gather_plan_kernel(const float* __restrict__ Hinc, int D, int rows, int cols,
+                                                          int PW, int plan_stride, float4* __restrict__ plan) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int Lg = blockIdx.x * blockDim.x + threadIdx.x;
+  const int step = blockIdx.y + 1, n = blockIdx.z;
+  if (Lg >= plan_stride) return;
+  float H[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) H[i] = __ldg(Hinc + ((size_t)n * D + step) * 9 + i);
+  const int gy = Lg / PW - 1, gx = Lg % PW - 1;
+  float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (gy >= 0 && gy < rows && gx >= 0 && gx < cols) {
+    const WarpCoord c = homography_coord(H, (float)gx, (float)gy, rows, cols);
+    if (!c.invalid) {
+      const float fx0 = floorf(c.ix), fy0 = floorf(c.iy);   // bilinear_setup (common.cuh), kept as (tap, weights)
+      const int x0 = (int)fx0, y0 = (int)fy0;
+      int fl = 1;
+      if (x0 + 1 <= cols - 1) fl |= 2;   // otherwise the east tap is clamped onto x0 (and carries weight 0)
+      if (y0 + 1 <= rows - 1) fl |= 4;
+      out.x = __int_as_float(y0 * cols + x0);
+      out.y = c.ix - fx0;
+      out.z = c.iy - fy0;
+      out.w = __int_as_float(fl);
+    }
+  }
+  plan[((size_t)n * D + step) * plan_stride + Lg] = out;
+}
+
 }  // namespace
+
+int recurrence_plan_stride(int rows, int cols) {
+  const Layout L = make_layout(rows, cols);
+  return cdiv(rows * L.PW, MTILE) * MTILE + 2 * L.halo;
+}
+
+int launch_gather_plan(const float* Hinc, int n, int D, int rows, int cols, float* plan, cudaStream_t stream) {
+  if (D < 2 || n <= 0) return 0;
+  const Layout L = make_layout(rows, cols);
+  const int stride = recurrence_plan_stride(rows, cols);
+  launch_pdl(gather_plan_kernel, dim3(cdiv(stride, 256), D - 1, n), dim3(256), (size_t)0, stream, Hinc, D, rows, cols,
+             L.PW, stride, reinterpret_cast<float4*>(plan));
+  B200MVS_LAUNCH_OK("gather_plan_kernel");
+  return 0;
+}
 
 // Weight blocks of 2 KB = one N=64 B operand [k half (2)][n (64)][8 fp16] (UMMA K-major, no swizzle) whose
 // rows 0..31 hold W_hi and rows 32..63 hold W_lo; an N=32 descriptor on the same block reads W_hi only.
@@ -1027,6 +1022,8 @@ int launch_recurrence(const RecurrenceArgs& a, cudaStream_t stream) {
   p.gamma1 = a.gamma1;
   p.beta1 = a.beta1;
   p.imgconv = a.imgconv;
+  p.plan = reinterpret_cast<const float4*>(a.plan);
+  p.plan_stride = recurrence_plan_stride(a.rows, a.cols);
   p.D = a.D;
   p.rows = a.rows;
   p.cols = a.cols;
