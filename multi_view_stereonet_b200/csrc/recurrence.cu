@@ -198,7 +198,7 @@ struct RecParams {
   int D, rows, cols, n_tiles;
   long long* prof;       // optional [16][12] phase cycle totals (debug)
   int debug;             // timing ablations (wrong results): 1 skip MMAs, 2 skip gathers, 8 no generic->async proxy
-                         // fences before the MMAs
+                         // fences before the MMAs, 16 no halo exchange
 };
 
 // 8 consecutive fp32 accumulator columns of this thread's TMEM lane.
@@ -327,6 +327,13 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
   }
 }
 
+// shared::cta -> another CTA's shared memory, bytes counted on an mbarrier of the destination CTA
+__device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t rbar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   dst_cluster),
+               "r"(src_cta), "r"(bytes), "r"(rbar)
+               : "memory");
+}
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(smem_dst)),
@@ -472,8 +479,8 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
   // bytes the cluster pushes into this CTA per layer: every active CTA's (sum, sumsq) of the four groups and the
   // boundary rows of the two neighbours
   const uint32_t xbytes = (uint32_t)p.n_tiles * (uint32_t)kGroups * 8u +
-                          (rank > 0 ? (uint32_t)halo * kC * 4u : 0u) +
-                          ((int)rank + 1 < p.n_tiles ? (uint32_t)halo * kC * 4u : 0u);
+                          (rank > 0 && !(p.debug & 16) ? (uint32_t)halo * kC * 4u : 0u) +
+                          ((int)rank + 1 < p.n_tiles && !(p.debug & 16) ? (uint32_t)halo * kC * 4u : 0u);
   // staged pixel range of the previous hypothesis: the pixels under the own + halo positions, plus a margin
   int q_lo, q_cnt;
   {
@@ -683,22 +690,57 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) y[k] = (y[k] + c[k]) + add[k];
         }
-        // the neighbour indexes its halo buffer [layer][side][i][32]
-        // halo rows of a layer: [2 * halo][32] fp32, lower halo then upper halo, 16-byte chunks XOR-swizzled with the
-        // row index (the receiver reads one octet of 32 consecutive rows per instruction)
-        if (jl < halo && rank > 0) {  // upper halo of rank-1, row halo + jl
-          float* hb = s_halo + (size_t)layer * 2 * halo * kC;
-          const uint32_t rb = map_to_rank(smem_u32(&s_xbar[layer]), rank - 1);
-          st_async_f4(map_to_rank(smem_u32(swz_ptr(hb, halo + jl, 2 * oct_e)), rank - 1), make_float4(y[0], y[1], y[2], y[3]), rb);
-          st_async_f4(map_to_rank(smem_u32(swz_ptr(hb, halo + jl, 2 * oct_e + 1)), rank - 1), make_float4(y[4], y[5], y[6], y[7]), rb);
+        // Halo rows of a layer at the receiver: [2 * halo][32] fp32, lower halo then upper halo, 16-byte chunks
+        // XOR-swizzled with the row index (the receiver reads one octet of 32 consecutive rows per instruction).
+        // The boundary rows are written into a local image of the receiver's rows -- in the staging buffer of the
+        // previous hypothesis, which is dead between the gather and the next step's bulk load -- and go out as ONE
+        // bulk copy per neighbour (shared::cta -> shared::cluster, bytes counted on the receiver's mbarrier): a remote
+        // store costs ~2 cycles of issue whatever its size, and 2 x 344 of them were ~1.2 k cycles of every epilogue.
+        float* hout = reinterpret_cast<float*>(smem + L.off_stage) + (size_t)layer * 2 * halo * kC;   // [to prev | to next]
+        if (jl < halo && rank > 0) {  // -> upper halo of rank-1, its row halo + jl
+          const int key = (halo + jl) & 7;
+          float* row = hout + (size_t)jl * kC;
+          *reinterpret_cast<float4*>(row + (((2 * oct_e) ^ key) << 2)) = make_float4(y[0], y[1], y[2], y[3]);
+          *reinterpret_cast<float4*>(row + (((2 * oct_e + 1) ^ key) << 2)) = make_float4(y[4], y[5], y[6], y[7]);
         }
-        if (jl >= MTILE - halo && (int)rank + 1 < p.n_tiles) {  // lower halo of rank+1
+        if (jl >= MTILE - halo && (int)rank + 1 < p.n_tiles) {  // -> lower halo of rank+1, its row idx
           const int idx = jl - (MTILE - halo);
-          float* hb = s_halo + (size_t)layer * 2 * halo * kC;
-          const uint32_t rb = map_to_rank(smem_u32(&s_xbar[layer]), rank + 1);
-          st_async_f4(map_to_rank(smem_u32(swz_ptr(hb, idx, 2 * oct_e)), rank + 1), make_float4(y[0], y[1], y[2], y[3]), rb);
-          st_async_f4(map_to_rank(smem_u32(swz_ptr(hb, idx, 2 * oct_e + 1)), rank + 1), make_float4(y[4], y[5], y[6], y[7]), rb);
+          *swz_ptr(hout + (size_t)halo * kC, idx, 2 * oct_e) = make_float4(y[0], y[1], y[2], y[3]);
+          *swz_ptr(hout + (size_t)halo * kC, idx, 2 * oct_e + 1) = make_float4(y[4], y[5], y[6], y[7]);
         }
+        if (layer == 0) TRACE(26);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // these rows -> readable by the copy engine
+        if (layer == 0) TRACE(27);
+        if (wq < 2) {          // positions [0, 64): the writers of the rows for rank-1 (8 warps)
+          if (rank > 0) {
+            if (warp == 0) {
+              asm volatile("bar.sync 5, 256;" ::: "memory");
+              if (!(p.debug & 16) && elect_one()) {
+                float* hb = s_halo + ((size_t)layer * 2 + 1) * halo * kC;
+                dsmem_bulk_copy(map_to_rank(smem_u32(hb), rank - 1), smem_u32(hout), (uint32_t)halo * kC * 4u,
+                                map_to_rank(smem_u32(&s_xbar[layer]), rank - 1));
+              }
+              __syncwarp();
+            } else {
+              asm volatile("bar.arrive 5, 256;" ::: "memory");
+            }
+          }
+        } else {               // positions [64, 128): the writers of the rows for rank+1
+          if ((int)rank + 1 < p.n_tiles) {
+            if (warp == 2) {
+              asm volatile("bar.sync 6, 256;" ::: "memory");
+              if (!(p.debug & 16) && elect_one()) {
+                float* hb = s_halo + (size_t)layer * 2 * halo * kC;
+                dsmem_bulk_copy(map_to_rank(smem_u32(hb), rank + 1), smem_u32(hout + (size_t)halo * kC),
+                                (uint32_t)halo * kC * 4u, map_to_rank(smem_u32(&s_xbar[layer]), rank + 1));
+              }
+              __syncwarp();
+            } else {
+              asm volatile("bar.arrive 6, 256;" ::: "memory");
+            }
+          }
+        }
+        if (layer == 0) TRACE(28);
         float gs = 0.f, gq = 0.f;
         if (real_out) {
 #pragma unroll
@@ -715,6 +757,7 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
         // The four warps of a group add up inside the CTA (fixed order), then lane d of the group's first warp pushes
         // the CTA's (sum, sumsq) to CTA d: 4 * n_tiles remote stores per CTA instead of one per warp and value (a
         // remote store costs ~2 cycles of issue whatever its size; 352 of them were ~700 cycles of every epilogue).
+        if (layer == 0) TRACE(29);
         if (lane == 0) s_loc[oct_e][wq] = make_float2(gs, gq);
         if (wq != 0) {
           asm volatile("bar.arrive %0, 128;" ::"r"(1 + oct_e) : "memory");
@@ -960,7 +1003,7 @@ bool recurrence_supported(int rows, int cols, int* n_tiles, size_t* smem_bytes) 
   if (n_tiles != nullptr) *n_tiles = tiles;
   if (smem_bytes != nullptr) *smem_bytes = L.total;
   return tiles <= 16 && L.halo <= MTILE && L.npl * 4 <= MAX_TASKS * NT && 2 * L.halo <= 128 &&
-         L.stage_px >= 1 && L.margin >= cols + 2 && L.total <= kSmemBudget;
+         L.stage_px >= 4 * L.halo && L.margin >= cols + 2 && L.total <= kSmemBudget;   // (stage also holds 4 halo blocks)
 }
 
 int recurrence_max_clusters(int rows, int cols) {

@@ -12,7 +12,7 @@ from multi_view_stereonet_b200 import MultiViewStereoNet, synthetic
 
 POINTS = ["start", "tma_done", "gathered", "sync_W", "plan/issue0", "conv0_done", "E0_ld", "E0_sent", "barA",
           "coef1", "own1", "halo1", "sync_S1", "conv1_done", "E1_ld", "E1_sent", "barC", "coef2", "own2", "halo2",
-          "sync_S2", "conv2_done", "E2_ld", "E2_stored", "cl_barrier", "tma_issued"]
+          "sync_S2", "conv2_done", "E2_ld", "E2_stored", "cl_barrier", "tma_issued", "E0_sts", "E0_fence", "E0_bulk", "E0_shfl"]
 
 
 def main():
@@ -46,7 +46,7 @@ def main():
             cols.append(f"{flat.max().item():6d} ({idx // 16},{idx % 16})")
             print(f"{name:>12} | " + " | ".join(cols))
         # per-warp detail of rank 5 at the points where warps diverge
-        for k in (1, 2, 4, 6, 7, 8, 9, 10, 11, 22, 23):
+        for k in (1, 2, 4, 6, 26, 27, 28, 29, 7, 8, 9, 10, 11, 12, 22, 23):
             print(f"rank5 {POINTS[k]:>10}:", " ".join(f"{rel[5, w, k].item():5d}" for w in range(16)))
     net.set_option("recurrence_debug", 0)
 
