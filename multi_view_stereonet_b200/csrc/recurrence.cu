@@ -39,7 +39,9 @@
 namespace b200mvs {
 namespace {
 
-constexpr int NT = 512;
+constexpr int NT = 512;            // worker threads: 16 warps = (4 lane quarters of the M-tile) x (4 channel octets)
+constexpr bool kMmaWarp = false;   // a 17th warp that only issues the MMAs (caps the kernel at 96 registers: 5 warps on one SMSP)
+constexpr int NT_ALL = NT + (kMmaWarp ? 32 : 0);
 constexpr int MTILE = 128;
 constexpr int W0_BLOCKS = 9 * 2;   // taps x k-steps (32 input channels)
 constexpr int W1_BLOCKS = 9 * 2;
@@ -351,7 +353,7 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, ui
 //   E1 / wait / S2 | MMA2 | E2: features = warped + delta -> global
 //   one cluster barrier: hypothesis `step` is published, exchange buffers are free again
 template <bool PROF>
-__global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
+__global__ void __launch_bounds__(NT_ALL, 1) recurrence_kernel(const RecParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   // GroupNorm partial (sum, sumsq) of [layer][group][source CTA], pushed by the source CTA; unused slots stay zero
   __shared__ __align__(16) float2 s_part[2][kGroups][16];
@@ -404,12 +406,12 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.w16);
     uint4* dst = reinterpret_cast<uint4*>(s_w);
-    for (int i = tid; i < W_TOTAL_BYTES / 16; i += NT) dst[i] = __ldg(src + i);
+    for (int i = tid; i < W_TOTAL_BYTES / 16; i += NT_ALL) dst[i] = __ldg(src + i);
     // zero every plane once: padding lanes stay zero
     uint4* pl = reinterpret_cast<uint4*>(s_planes);
-    for (int i = tid; i < NUM_PLANES * L.npl_pad; i += NT) pl[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < NUM_PLANES * L.npl_pad; i += NT_ALL) pl[i] = make_uint4(0, 0, 0, 0);
     float4* hz = reinterpret_cast<float4*>(s_halo);
-    for (int i = tid; i < 2 * 2 * halo * kC / 4; i += NT) hz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < 2 * 2 * halo * kC / 4; i += NT_ALL) hz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -425,20 +427,42 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
   const uint64_t da_lo0 = umma_desc(smem_u32(s_planes) + (uint32_t)PLANE_LO * L.plane_bytes, L.plane_bytes, 128u);
   const uint64_t db_c0 = umma_desc(smem_u32(s_w), 1024u, 128u);
 
-  // Tensor-core conv: an elected lane of warp 0 issues and commits.  Work placed between issue and wait overlaps the
-  // MMAs.
-  auto issue_conv = [&](int layer) {
-    if (warp == 0) {
-      if (active && elect_one()) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (!(p.debug & 1))
-          issue_conv_mmas(da_hi0, da_lo0, db_c0 + (uint64_t)(layer * W1_BLOCKS * (2048 / 16)), plane_u16, (uint32_t)PW,
-                          tmem_base);
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                         smem_u32(&s_bar))
-                     : "memory");
+  // Tensor-core conv.  Warp 16 does nothing but issue: it sleeps at named barrier 7 until the 512 workers have staged
+  // an operand (they only ARRIVE there and go on to wait for the MMAs' completion barrier), issues the 36 MMAs of the
+  // conv from one elected lane and commits them to s_bar.  (tcgen05.mma issue blocks at the rate the tensor pipe
+  // drains; issued from a worker warp, that warp entered every epilogue ~400 cycles behind the other fifteen, and
+  // the cluster waited for it.)
+  auto issue_conv = [&](int layer) {   // warp-uniform caller
+    if (active && elect_one()) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (!(p.debug & 1))
+        issue_conv_mmas(da_hi0, da_lo0, db_c0 + (uint64_t)(layer * W1_BLOCKS * (2048 / 16)), plane_u16, (uint32_t)PW,
+                        tmem_base);
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                       smem_u32(&s_bar))
+                   : "memory");
+    }
+    __syncwarp();
+  };
+  if (kMmaWarp && warp == 16) {
+    for (int step = 1; step < p.D; ++step) {
+#pragma unroll 1
+      for (int layer = 0; layer < 3; ++layer) {
+        asm volatile("bar.sync 7, %0;" ::"n"(NT_ALL) : "memory");
+        issue_conv(layer);
       }
-      __syncwarp();
+      cluster_sync_all();   // the per-step cluster barrier counts every thread
+    }
+    return;   // (TMEM is freed by warp 0 behind a barrier of the worker warps only)
+  }
+  // workers: operand staged (generic-proxy writes fenced by the caller) -> wake the MMA warp, do not wait
+  // (without the extra warp: warp 0 waits for the others' arrival and issues; nobody else waits)
+  auto operands_ready = [&](int layer) {
+    if (!kMmaWarp && warp == 0) {
+      asm volatile("bar.sync 7, %0;" ::"n"(NT_ALL) : "memory");
+      issue_conv(layer);
+    } else {
+      asm volatile("bar.arrive 7, %0;" ::"n"(NT_ALL) : "memory");
     }
   };
   // every thread waits on the completion barrier itself (a hardware sleep, ~60 cycles from arrive to wake-up): no
@@ -589,14 +613,6 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
       mbar_arm_tx(&s_xbar[0], xbytes);
       mbar_arm_tx(&s_xbar[1], xbytes);
     }
-    // image half of conv0 (+ bias) at this thread's output position, consumed in the first epilogue
-    float4 ic0 = make_float4(0.f, 0.f, 0.f, 0.f), ic1 = ic0;
-    if (real_out) {
-      const float4* icp =
-          reinterpret_cast<const float4*>(p.imgconv + (((size_t)n * p.D + step) * pixels + own_pix) * kC + oct_e * 8);
-      ic0 = __ldg(icp);
-      ic1 = __ldg(icp + 1);
-    }
     // ================= W: warp previous features into the conv0 operand ============================
     if (active) mbar_wait_cta(&s_tbar, (uint32_t)((step - 1) & 1));
     TRACE(1);
@@ -659,12 +675,18 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
     TRACE(2);
     if (!(p.debug & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    operands_ready(0);
     PROF_MARK(0);
     TRACE(3);
-    issue_conv(0);
-    // the NEXT step's gather plan, in flight under conv0's MMAs (this step's plan was consumed above)
-    if (step + 1 < p.D) load_plan(step + 1);
+    // image half of conv0 (+ bias) at this thread's output position, consumed in the first epilogue: in flight under
+    // conv0's MMAs
+    float4 ic0 = make_float4(0.f, 0.f, 0.f, 0.f), ic1 = ic0;
+    if (real_out) {
+      const float4* icp =
+          reinterpret_cast<const float4*>(p.imgconv + (((size_t)n * p.D + step) * pixels + own_pix) * kC + oct_e * 8);
+      ic0 = __ldg(icp);
+      ic1 = __ldg(icp + 1);
+    }
     TRACE(4);
     wait_conv();
     PROF_MARK(1);
@@ -865,10 +887,9 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
       TRACE(11 + 8 * layer);
       if (!(p.debug & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncthreads();
+      operands_ready(1 + layer);
       PROF_MARK(4 + 4 * layer);
       TRACE(12 + 8 * layer);
-      issue_conv(1 + layer);
       wait_conv();
       PROF_MARK(5 + 4 * layer);
       TRACE(13 + 8 * layer);
@@ -895,13 +916,15 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    asm volatile("bar.sync 8, %0;" ::"n"(NT) : "memory");   // the 512 workers
     {
       float* dst = p.vol + ((size_t)n * p.D + step) * pixels * kC;
 #pragma unroll
       for (int k = 0; k < 2; ++k)
         if (co_src[k] >= 0) __stcg(reinterpret_cast<float4*>(dst + co_dst[k]), *reinterpret_cast<const float4*>(s_wf + co_src[k]));
     }
+    // the NEXT step's gather plan, in flight under the cluster barrier and the bulk load behind it
+    if (step + 1 < p.D) load_plan(step + 1);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     PROF_MARK(10);
     TRACE(23);
@@ -915,7 +938,7 @@ __global__ void __launch_bounds__(NT, 1) recurrence_kernel(const RecParams p) {
     for (int k = 0; k < 12; ++k) p.prof[rank * 12 + k] = acc_t[PROF ? k : 0];
   }
 
-  __syncthreads();
+  asm volatile("bar.sync 8, %0;" ::"n"(NT) : "memory");   // the workers (the MMA warp has left)
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64u) : "memory");
   }
@@ -1022,7 +1045,7 @@ int recurrence_max_clusters(int rows, int cols) {
     if (cs < n_tiles || cs > 16) continue;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(cs, 64, 1);
-    cfg.blockDim = dim3(NT, 1, 1);
+    cfg.blockDim = dim3(NT_ALL, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1084,7 +1107,7 @@ int launch_recurrence(const RecurrenceArgs& a, cudaStream_t stream) {
     if (cs < n_tiles || cs > 16) continue;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(cs, a.n, 1);
-    cfg.blockDim = dim3(NT, 1, 1);
+    cfg.blockDim = dim3(NT_ALL, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
