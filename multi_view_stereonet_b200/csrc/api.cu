@@ -166,6 +166,7 @@ struct Workspace {
   // recurrence
   float* imgconv = nullptr;
   float* rec_plan = nullptr;   // gather plan of the persistent sweep, [n][D][recurrence_plan_stride][4]
+  int* rec_flags = nullptr;    // [n][17] progress / out-of-window flags of the persistent sweep
   float *vol = nullptr, *wf = nullptr, *wimg = nullptr, *sy0 = nullptr, *sx0 = nullptr, *sy1 = nullptr;
   // cost volume
   float *cost = nullptr, *cvfA = nullptr, *cost1 = nullptr;
@@ -520,6 +521,7 @@ void layout(b200mvs_net* net, const b200mvs_shape& s, bool dry) {
   W.imgconv = A.take<float>(n * D * L.px[4] * kC);
   if (recurrence_supported(L.h[4], L.w[4], nullptr, nullptr))
     W.rec_plan = A.take<float>(n * D * (size_t)recurrence_plan_stride(L.h[4], L.w[4]) * 4);
+  W.rec_flags = A.take<int>(n * 17);
   W.wf = A.take<float>(n * L.px[4] * kC);
   W.wimg = A.take<float>(n * 3 * L.px[4]);
   W.sy0 = A.take<float>(n * L.px[4] * kC);
@@ -924,7 +926,7 @@ int forward_impl(b200mvs_net* net, Lane& lane, bool sweep_on_own_stream, const b
     RC(wait_upload(2, left_stream));
     RC(launch_image_conv(ws.geo.H, R4, net->fr_conv0.w + (size_t)4 * 9 * 8 * 32, net->fr_conv0.bias, n, D, h4, w4,
                          ws.imgconv, left_stream));
-    RC(launch_gather_plan(ws.geo.Hinc, n, D, h4, w4, ws.rec_plan, left_stream));
+    RC(launch_gather_plan(ws.geo.Hinc, n, D, h4, w4, ws.rec_plan, ws.rec_flags, left_stream));
     if (overlap) B200MVS_CUDA_OK(cudaEventRecord(net->cur->ev_imgconv, net->cur->side));
   }
 
@@ -973,6 +975,7 @@ int forward_impl(b200mvs_net* net, Lane& lane, bool sweep_on_own_stream, const b
     RecurrenceArgs ra;
     ra.imgconv = ws.imgconv;
     ra.plan = ws.rec_plan;
+    ra.flags = ws.rec_flags;
     ra.vol = ws.vol;
     ra.geo = ws.geo;
     ra.right_l4 = R4;

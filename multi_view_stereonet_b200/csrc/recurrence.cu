@@ -137,8 +137,10 @@ __device__ __forceinline__ void unsplit8(const uint4& hi, const uint4& lo, float
 
 struct Layout {
   int PW, halo, npl, npl_pad;
-  int stage_px;            // pixels of the previous hypothesis staged per step (own + halo + margin)
-  int margin;              // pixels staged before / after the own + halo range
+  // Window of the previous hypothesis kept in shared memory: output positions [pos0 - wm, pos0 + MTILE + wm), one
+  // 128-byte row (fp32 [32]) per position.  wm = halo + one image row + 2: the taps of the own + halo positions under an
+  // incremental motion of up to one row / two columns.
+  int wm, win_rows;
   uint32_t plane_bytes;
   // byte offsets into dynamic shared memory
   uint32_t off_w, off_planes, off_halo, off_wf, off_stage, total;
@@ -158,27 +160,27 @@ __host__ __device__ inline Layout make_layout(int rows, int cols) {
   // the lanes of a quad write at once fall into distinct shared-memory banks
   L.npl_pad = ((L.npl + 5) & ~7) + 2;
   L.plane_bytes = (uint32_t)L.npl_pad * 16u;
+  L.wm = L.halo + L.PW + 2;
+  L.win_rows = MTILE + 2 * L.wm;
   uint32_t o = 0;
   L.off_w = o;
   o += W_TOTAL_BYTES;
   L.off_planes = o;
   o += NUM_PLANES * L.plane_bytes;
-  L.off_halo = o;          // [layer 2][side 2][halo][32] fp32, written by the neighbour CTAs
+  L.off_halo = o;          // [layer 2][lower, upper][halo][32] fp32, written by the neighbour CTAs
   o += 2 * 2 * (uint32_t)L.halo * kC * 4;
   L.off_wf = o;            // warped features of the own positions, fp32 [128][32]
   o += MTILE * kC * 4;
-  L.off_stage = o;         // previous hypothesis, pixels [q_lo, q_lo + stage_px), fp32 [px][32]
-  // own + halo positions cover at most this many consecutive pixels; the rest of the budget is margin
-  const int span = ((L.npl - 1) / L.PW + 2) * cols;
-  int cap = o < kSmemBudget ? (int)((kSmemBudget - o) / (kC * 4)) : 0;
-  const int want = span + 2 * (2 * cols + 4);
-  if (cap > want) cap = want;
-  if (cap > rows * cols) cap = rows * cols;
-  L.stage_px = cap;
-  L.margin = (cap - span) / 2;
-  o += (uint32_t)(cap > 0 ? cap : 0) * kC * 4;
+  L.off_stage = o;         // the window
+  o += (uint32_t)L.win_rows * kC * 4;
   L.total = o;
   return L;
+}
+
+// Do the taps of a gather (north-west tap at output position P00, flags as in the plan) lie in the window of CTA r?
+__host__ __device__ inline bool taps_in_window(int P00, int fl, int r, const Layout& L) {
+  const int w00 = P00 - (r * MTILE - L.wm);
+  return w00 >= 0 && w00 + ((fl & 4) ? L.PW : 0) + ((fl >> 1) & 1) < L.win_rows;
 }
 
 struct RecParams {
@@ -197,6 +199,8 @@ struct RecParams {
   const float* imgconv;  // [n][D][rows*cols][32]: image half of conv0 + bias0 (image_conv_kernel)
   const float4* plan;    // [n][D][plan_stride]: gather plan of every step (gather_plan_kernel)
   int plan_stride;
+  int* flags;            // [n][17]: [rank] = last hypothesis CTA `rank` has made visible in global memory (only kept up
+                         // to date when [16] != 0); [16] != 0: some tap of the sweep lies outside its CTA's window
   int D, rows, cols, n_tiles;
   long long* prof;       // optional [16][12] phase cycle totals (debug)
   int debug;             // timing ablations (wrong results): 1 skip MMAs, 2 skip gathers, 8 no generic->async proxy
@@ -361,7 +365,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) recurrence_kernel(const RecParams p
   __shared__ __align__(16) float s_bias[2][kC], s_gamma[2][kC], s_beta[2][kC];   // biases of conv1, conv2 (conv0's is in imgconv)
   __shared__ __align__(8) uint64_t s_bar;        // MMA completion
   __shared__ __align__(8) uint64_t s_xbar[2];    // per layer: bytes pushed into this CTA by the cluster
-  __shared__ __align__(8) uint64_t s_tbar;       // TMA staging of the previous hypothesis
+  __shared__ __align__(8) uint64_t s_tbar;       // bytes the neighbours copied into this CTA's window
   __shared__ uint32_t s_tmem;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -378,7 +382,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) recurrence_kernel(const RecParams p
   uint8_t* s_planes = smem + L.off_planes;
   float* s_halo = reinterpret_cast<float*>(smem + L.off_halo);
   float* s_wf = reinterpret_cast<float*>(smem + L.off_wf);
-  const float* s_stage = reinterpret_cast<const float*>(smem + L.off_stage);
+  uint8_t* const s_win = smem + L.off_stage;   // window rows [pos0 - wm, pos0 + MTILE + wm), see Layout
 
   // ---- one-time setup ----
   if (warp == 0) {
@@ -451,8 +455,8 @@ __global__ void __launch_bounds__(NT_ALL, 1) recurrence_kernel(const RecParams p
         asm volatile("bar.sync 7, %0;" ::"n"(NT_ALL) : "memory");
         issue_conv(layer);
       }
-      cluster_sync_all();   // the per-step cluster barrier counts every thread
     }
+    cluster_sync_all();   // the final cluster barrier counts every thread
     return;   // (TMEM is freed by warp 0 behind a barrier of the worker warps only)
   }
   // workers: operand staged (generic-proxy writes fenced by the caller) -> wake the MMA warp, do not wait
@@ -505,24 +509,20 @@ __global__ void __launch_bounds__(NT_ALL, 1) recurrence_kernel(const RecParams p
   const uint32_t xbytes = (uint32_t)p.n_tiles * (uint32_t)kGroups * 8u +
                           (rank > 0 && !(p.debug & 16) ? (uint32_t)halo * kC * 4u : 0u) +
                           ((int)rank + 1 < p.n_tiles && !(p.debug & 16) ? (uint32_t)halo * kC * 4u : 0u);
-  // staged pixel range of the previous hypothesis: the pixels under the own + halo positions, plus a margin
-  int q_lo, q_cnt;
-  {
-    const int gy0 = pos0 / PW - 1;
-    int gx0 = pos0 % PW - 1;
-    gx0 = gx0 < 0 ? 0 : (gx0 > p.cols - 1 ? p.cols - 1 : gx0);
-    int first = gy0 * p.cols + gx0 - L.margin;
-    first = first < 0 ? 0 : first;
-    if (first > pixels - L.stage_px) first = pixels - L.stage_px;   // stage_px <= pixels
-    q_lo = first;
-    q_cnt = L.stage_px;
-  }
-  const int st_lo = q_lo * kC, st_n = q_cnt * kC;   // in floats, relative to the hypothesis base
+  // Window of the previous hypothesis (Layout): filled where the data is produced -- the own rows by this CTA's last
+  // epilogue, the wm rows on either side by the two neighbours' bulk copies.  A window row is 128 bytes whose eight
+  // 16-byte chunks are XOR-swizzled with the (global) output position, so rows copy verbatim between CTAs, the last
+  // epilogue (thread = position) writes without bank conflicts and the gather (quad = position) reads without.
+  const int Wm = L.wm;
+  const int win_lo = pos0 - Wm;   // output position of window row 0
+  const bool has_prev = active && rank > 0, has_next = active && (int)rank + 1 < p.n_tiles;
+  const uint32_t wbytes = ((has_prev ? 1u : 0u) + (has_next ? 1u : 0u)) * (uint32_t)Wm * kC * 4u;
+  int* const gflags = p.flags + (size_t)n * 17;
   // The real pixels of the own tile are one contiguous pixel range of the image (rows of the tile follow each other in
   // memory).  The last epilogue leaves the new features in shared memory and the tile goes out as 16-byte chunks
   // in pixel order: 32 lanes = 512 contiguous bytes.  (One thread = one position stored 32 bytes at a 128-byte
   // stride: 32 sectors per warp instruction, ~1 k cycles of store issue per step.)
-  int co_src[2], co_dst[2];   // float offsets into s_wf (swizzled) and into the hypothesis; -1: nothing
+  int co_src[2], co_dst[2];   // byte offset into the window (swizzled) / float offset into the hypothesis; -1: nothing
   {
     int first = pos0 % PW < p.cols ? pos0 : (pos0 / PW + 1) * PW;
     int last = pos0 + MTILE - 1 < p.rows * PW - 1 ? pos0 + MTILE - 1 : p.rows * PW - 1;
@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) recurrence_kernel(const RecParams p
       co_src[k] = co_dst[k] = -1;
       if (px <= px_hi) {
         const int row = (px / p.cols) * PW + px % p.cols - pos0;   // local output position
-        co_src[k] = row * 32 + ((chunk ^ (row & 7)) << 2);
+        co_src[k] = (Wm + row) * 128 + ((chunk ^ (row & 7)) << 4);
         co_dst[k] = px * kC + chunk * 4;
       }
     }
@@ -584,22 +584,21 @@ __global__ void __launch_bounds__(NT_ALL, 1) recurrence_kernel(const RecParams p
       if (active && t_l[k] < npl && !(p.debug & 2)) g_plan[k] = __ldg(plan_base + (size_t)step * p.plan_stride + t_l[k]);
     }
   };
-  // one lane: bulk copy of hypothesis `step - 1`, pixels [q_lo, q_lo + q_cnt), into the staging buffer
-  auto stage_prev = [&](int step) {
-    if (warp == 1) {
-      if (active && elect_one()) {
-        // other CTAs' generic-proxy stores to global memory -> this async-proxy read (the all-state-spaces form of
-        // the fence cost ~1.1 k cycles here, the .global form ~0.3 k)
-        asm volatile("fence.proxy.async.global;" ::: "memory");
-        mbar_arm_tx(&s_tbar, (uint32_t)st_n * 4u);
-        tma_load_1d(smem + L.off_stage, p.vol_in + ((size_t)n * p.D + (step - 1)) * pixels * kC + st_lo,
-                    (uint32_t)st_n * 4u, &s_tbar);
+  // hypothesis 0 (written by the feature network): the whole window from global memory, once
+  if (active) {
+    const float4* src0 = reinterpret_cast<const float4*>(p.vol_in + (size_t)n * p.D * pixels * kC);
+    for (int i = tid; i < L.win_rows * 8; i += NT) {
+      const int w = i >> 3, chunk = i & 7, P = win_lo + w;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (P >= 0) {
+        const int y = P / PW, x = P - y * PW;
+        if (y < p.rows && x < p.cols) v = __ldg(src0 + ((size_t)y * p.cols + x) * 8 + chunk);
       }
-      __syncwarp();
+      *reinterpret_cast<float4*>(s_win + (size_t)w * 128 + ((chunk ^ (P & 7)) << 4)) = v;
     }
-  };
-
-  stage_prev(1);
+  }
+  const bool slow = __ldg(gflags + 16) != 0;   // some tap lies outside its window: global memory + progress flags
+  asm volatile("bar.sync 8, %0;" ::"n"(NT) : "memory");
   load_plan(1);
 
   float x0own[8];
@@ -612,52 +611,58 @@ __global__ void __launch_bounds__(NT_ALL, 1) recurrence_kernel(const RecParams p
     if (active && tid == 0) {
       mbar_arm_tx(&s_xbar[0], xbytes);
       mbar_arm_tx(&s_xbar[1], xbytes);
+      if (step >= 2 && wbytes != 0) mbar_arm_tx(&s_tbar, wbytes);   // (bytes that are already here count ahead)
     }
     // ================= W: warp previous features into the conv0 operand ============================
-    if (active) mbar_wait_cta(&s_tbar, (uint32_t)((step - 1) & 1));
+    if (active && step >= 2 && wbytes != 0) mbar_wait_cta(&s_tbar, (uint32_t)(step & 1));
     TRACE(1);
     {
       const float* prev = p.vol_in + ((size_t)n * p.D + (step - 1)) * pixels * kC + 8 * t_oct;
-      const float* stg = s_stage + 8 * t_oct;
 #pragma unroll
       for (int k = 0; k < MAX_TASKS; ++k) {
         if (active && t_l[k] < npl) {
-          // u[0..3] accumulate the 16-byte half read first (half `sw` of the octet), u[4..7] the other half:
-          // neighbouring quads start on different halves, so one warp-wide load touches all 32 banks
-          float u[8], v[8];
+          float v[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) u[e] = 0.f;
+          for (int e = 0; e < 8; ++e) v[e] = 0.f;
           const int fl = __float_as_int(g_plan[k].w);
           if (fl & 1) {
             const float we = g_plan[k].y, ws = g_plan[k].z;
             const float ww = 1.0f - we, wn = 1.0f - ws;
             const float wt[4] = {wn * ww, wn * we, ws * ww, ws * we};
-            const int dxo = (fl & 2) ? kC : 0, dyo = (fl & 4) ? p.cols * kC : 0;
-            const int o00 = __float_as_int(g_plan[k].x) * kC;
-            const int off[4] = {0, dxo, dyo, dyo + dxo};
-            const int loc = o00 - st_lo;
-            if (loc >= 0 && loc + dyo + dxo < st_n) {
-              const float4* sp = reinterpret_cast<const float4*>(stg + loc);
+            const int P00 = __float_as_int(g_plan[k].x);   // output position of the north-west tap
+            const int dx = (fl >> 1) & 1, dyP = (fl & 4) ? PW : 0;
+            const int offP[4] = {0, dx, dyP, dyP + dx};
+            if (taps_in_window(P00, fl, (int)rank, L)) {
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
-                const float4 a = sp[(off[t] >> 2) + sw], b = sp[(off[t] >> 2) + (sw ^ 1)];
-                u[0] = fmaf(a.x, wt[t], u[0]); u[1] = fmaf(a.y, wt[t], u[1]); u[2] = fmaf(a.z, wt[t], u[2]); u[3] = fmaf(a.w, wt[t], u[3]);
-                u[4] = fmaf(b.x, wt[t], u[4]); u[5] = fmaf(b.y, wt[t], u[5]); u[6] = fmaf(b.z, wt[t], u[6]); u[7] = fmaf(b.w, wt[t], u[7]);
+                const int Pt = P00 + offP[t];
+                const uint8_t* rowp = s_win + (size_t)(Pt - win_lo) * 128;
+                const uint32_t ca = (uint32_t)(((2 * t_oct) ^ (Pt & 7)) << 4);
+                const float4 a = *reinterpret_cast<const float4*>(rowp + ca);
+                const float4 b = *reinterpret_cast<const float4*>(rowp + (ca ^ 16u));
+                v[0] = fmaf(a.x, wt[t], v[0]); v[1] = fmaf(a.y, wt[t], v[1]); v[2] = fmaf(a.z, wt[t], v[2]); v[3] = fmaf(a.w, wt[t], v[3]);
+                v[4] = fmaf(b.x, wt[t], v[4]); v[5] = fmaf(b.y, wt[t], v[5]); v[6] = fmaf(b.z, wt[t], v[6]); v[7] = fmaf(b.w, wt[t], v[7]);
               }
-            } else {   // a tap outside the staged range (large incremental motion): global memory
-              const float4* gp = reinterpret_cast<const float4*>(prev + o00);
+            } else {
+              // a tap outside the window (incremental motion beyond one row): global memory, once the CTA that owns the
+              // pixel has published the previous hypothesis (gather_plan_kernel found such taps: `slow` is set and
+              // every CTA keeps its progress flag up to date)
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
-                const float4 a = __ldcg(gp + (off[t] >> 2) + sw), b = __ldcg(gp + (off[t] >> 2) + (sw ^ 1));
-                u[0] = fmaf(a.x, wt[t], u[0]); u[1] = fmaf(a.y, wt[t], u[1]); u[2] = fmaf(a.z, wt[t], u[2]); u[3] = fmaf(a.w, wt[t], u[3]);
-                u[4] = fmaf(b.x, wt[t], u[4]); u[5] = fmaf(b.y, wt[t], u[5]); u[6] = fmaf(b.z, wt[t], u[6]); u[7] = fmaf(b.w, wt[t], u[7]);
+                const int Pt = P00 + offP[t];
+                if (step >= 2) {
+                  int seen;
+                  do {
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(gflags + Pt / MTILE) : "memory");
+                  } while (seen < step - 1);
+                }
+                const int y = Pt / PW, x = Pt - y * PW;
+                const float4* gp = reinterpret_cast<const float4*>(prev + ((size_t)y * p.cols + x) * kC);
+                const float4 a = __ldcg(gp), b = __ldcg(gp + 1);
+                v[0] = fmaf(a.x, wt[t], v[0]); v[1] = fmaf(a.y, wt[t], v[1]); v[2] = fmaf(a.z, wt[t], v[2]); v[3] = fmaf(a.w, wt[t], v[3]);
+                v[4] = fmaf(b.x, wt[t], v[4]); v[5] = fmaf(b.y, wt[t], v[5]); v[6] = fmaf(b.z, wt[t], v[6]); v[7] = fmaf(b.w, wt[t], v[7]);
               }
             }
-          }
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            v[e] = sw ? u[4 + e] : u[e];
-            v[4 + e] = sw ? u[e] : u[4 + e];
           }
           const int l = t_l[k];
           if (l >= halo && l < halo + MTILE) {
@@ -718,17 +723,20 @@ __global__ void __launch_bounds__(NT_ALL, 1) recurrence_kernel(const RecParams p
         // previous hypothesis, which is dead between the gather and the next step's bulk load -- and go out as ONE
         // bulk copy per neighbour (shared::cta -> shared::cluster, bytes counted on the receiver's mbarrier): a remote
         // store costs ~2 cycles of issue whatever its size, and 2 x 344 of them were ~1.2 k cycles of every epilogue.
-        float* hout = reinterpret_cast<float*>(smem + L.off_stage) + (size_t)layer * 2 * halo * kC;   // [to prev | to next]
+        // (rows for rank-1 in the window's lower side rows, rows for rank+1 in its upper side rows: dead from the end of
+        //  the gather until that neighbour's last epilogue of this step, by which time it has received them)
+        float* hout_prev = reinterpret_cast<float*>(s_win) + (size_t)layer * halo * kC;
+        float* hout_next = reinterpret_cast<float*>(s_win) + (size_t)(Wm + MTILE) * kC + (size_t)layer * halo * kC;
         if (jl < halo && rank > 0) {  // -> upper halo of rank-1, its row halo + jl
           const int key = (halo + jl) & 7;
-          float* row = hout + (size_t)jl * kC;
+          float* row = hout_prev + (size_t)jl * kC;
           *reinterpret_cast<float4*>(row + (((2 * oct_e) ^ key) << 2)) = make_float4(y[0], y[1], y[2], y[3]);
           *reinterpret_cast<float4*>(row + (((2 * oct_e + 1) ^ key) << 2)) = make_float4(y[4], y[5], y[6], y[7]);
         }
         if (jl >= MTILE - halo && (int)rank + 1 < p.n_tiles) {  // -> lower halo of rank+1, its row idx
           const int idx = jl - (MTILE - halo);
-          *swz_ptr(hout + (size_t)halo * kC, idx, 2 * oct_e) = make_float4(y[0], y[1], y[2], y[3]);
-          *swz_ptr(hout + (size_t)halo * kC, idx, 2 * oct_e + 1) = make_float4(y[4], y[5], y[6], y[7]);
+          *swz_ptr(hout_next, idx, 2 * oct_e) = make_float4(y[0], y[1], y[2], y[3]);
+          *swz_ptr(hout_next, idx, 2 * oct_e + 1) = make_float4(y[4], y[5], y[6], y[7]);
         }
         if (layer == 0) TRACE(26);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // these rows -> readable by the copy engine
@@ -739,7 +747,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) recurrence_kernel(const RecParams p
               asm volatile("bar.sync 5, 256;" ::: "memory");
               if (!(p.debug & 16) && elect_one()) {
                 float* hb = s_halo + ((size_t)layer * 2 + 1) * halo * kC;
-                dsmem_bulk_copy(map_to_rank(smem_u32(hb), rank - 1), smem_u32(hout), (uint32_t)halo * kC * 4u,
+                dsmem_bulk_copy(map_to_rank(smem_u32(hb), rank - 1), smem_u32(hout_prev), (uint32_t)halo * kC * 4u,
                                 map_to_rank(smem_u32(&s_xbar[layer]), rank - 1));
               }
               __syncwarp();
@@ -753,7 +761,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) recurrence_kernel(const RecParams p
               asm volatile("bar.sync 6, 256;" ::: "memory");
               if (!(p.debug & 16) && elect_one()) {
                 float* hb = s_halo + (size_t)layer * 2 * halo * kC;
-                dsmem_bulk_copy(map_to_rank(smem_u32(hb), rank + 1), smem_u32(hout + (size_t)halo * kC),
+                dsmem_bulk_copy(map_to_rank(smem_u32(hb), rank + 1), smem_u32(hout_next),
                                 (uint32_t)halo * kC * 4u, map_to_rank(smem_u32(&s_xbar[layer]), rank + 1));
               }
               __syncwarp();
@@ -895,45 +903,64 @@ __global__ void __launch_bounds__(NT_ALL, 1) recurrence_kernel(const RecParams p
       TRACE(13 + 8 * layer);
     }
 
-    // ================= E2: features_step = wf + delta, in place in shared memory, then out in pixel order ========
+    // ===== E2: features_step = wf + delta -> own rows of the window; boundary rows -> the neighbours' windows
+    //           (their gather source of the next step); the tile -> global memory in pixel order =====
+    const bool more = step + 1 < p.D;
     if (active) {
       float v[8], c[8];
       tmem_ld8x2(tmem_my, tmem_my + 32u, v, c);
       TRACE(22);
       if (real_out) {
+        uint8_t* rowp = s_win + (size_t)(Wm + jl) * 128;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          float4* wp = swz_ptr(s_wf, jl, 2 * oct_e + q);
-          const float4 wv = *wp;
+          const float4 wv = *swz_ptr(s_wf, jl, 2 * oct_e + q);
           const float4 bv = *reinterpret_cast<const float4*>(&s_bias[1][oct_e * 8 + 4 * q]);
           float4 r;
           r.x = wv.x + ((v[4 * q + 0] + c[4 * q + 0]) + bv.x);
           r.y = wv.y + ((v[4 * q + 1] + c[4 * q + 1]) + bv.y);
           r.z = wv.z + ((v[4 * q + 2] + c[4 * q + 2]) + bv.z);
           r.w = wv.w + ((v[4 * q + 3] + c[4 * q + 3]) + bv.w);
-          *wp = r;
+          *reinterpret_cast<float4*>(rowp + (((2 * oct_e + q) ^ (jl & 7)) << 4)) = r;
         }
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (more) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // own rows -> readable by the copy engine
     asm volatile("bar.sync 8, %0;" ::"n"(NT) : "memory");   // the 512 workers
+    // The first / last wm own rows are the upper / lower side rows of the neighbours' windows.  They are past this
+    // step's gather (they sent the statistics this CTA waited for after it), so their side rows are free.
+    if (more && warp == 1) {
+      if (has_prev && elect_one())
+        dsmem_bulk_copy(map_to_rank(smem_u32(s_win + (size_t)(Wm + MTILE) * 128), rank - 1), smem_u32(s_win + (size_t)Wm * 128),
+                        (uint32_t)Wm * 128u, map_to_rank(smem_u32(&s_tbar), rank - 1));
+      __syncwarp();
+    }
+    if (more && warp == 2) {
+      if (has_next && elect_one())
+        dsmem_bulk_copy(map_to_rank(smem_u32(s_win), rank + 1), smem_u32(s_win + (size_t)MTILE * 128), (uint32_t)Wm * 128u,
+                        map_to_rank(smem_u32(&s_tbar), rank + 1));
+      __syncwarp();
+    }
+    TRACE(24);
     {
       float* dst = p.vol + ((size_t)n * p.D + step) * pixels * kC;
 #pragma unroll
       for (int k = 0; k < 2; ++k)
-        if (co_src[k] >= 0) __stcg(reinterpret_cast<float4*>(dst + co_dst[k]), *reinterpret_cast<const float4*>(s_wf + co_src[k]));
+        if (co_src[k] >= 0) __stcg(reinterpret_cast<float4*>(dst + co_dst[k]), *reinterpret_cast<const float4*>(s_win + co_src[k]));
     }
-    // the NEXT step's gather plan, in flight under the cluster barrier and the bulk load behind it
-    if (step + 1 < p.D) load_plan(step + 1);
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (slow && more) {   // out-of-window taps of other CTAs read this tile from global memory
+      asm volatile("bar.sync 8, %0;" ::"n"(NT) : "memory");
+      if (active && tid == 32) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(gflags + rank), "r"(step) : "memory");
+    }
+    // the NEXT step's gather plan, in flight while the neighbours' rows arrive
+    if (more) load_plan(step + 1);
     PROF_MARK(10);
     TRACE(23);
-    cluster_sync_all();  // hypothesis `step` is visible to every CTA; exchange buffers are free again
-    TRACE(24);
-    if (step + 1 < p.D) stage_prev(step + 1);
     PROF_MARK(11);
     TRACE(25);
   }
+  cluster_sync_all();   // no CTA leaves while a peer may still read from or write into its shared memory
   if (PROF && p.prof != nullptr && tid == 0 && blockIdx.y == 0) {
     for (int k = 0; k < 12; ++k) p.prof[rank * 12 + k] = acc_t[PROF ? k : 0];
   }
@@ -946,12 +973,14 @@ __global__ void __launch_bounds__(NT_ALL, 1) recurrence_kernel(const RecParams p
 
 // Gather plan of the sweep: for every step and every padded input position Lg (image pixel (Lg / PW - 1, Lg % PW - 1);
 // CTA r gathers positions [128 r, 128 r + 128 + 2 halo)), where the incremental homography H_{d-1}^-1 H_d
-// (multi_view_stereonet.py:280-282) sends the pixel: {pixel index of the north-west tap, east weight, south weight,
-// flags (1 valid, 2 east tap exists, 4 south tap exists)}.  It depends on the cameras only, so it is computed for all
+// (multi_view_stereonet.py:280-282) sends the pixel: {output position y0 * PW + x0 of the north-west tap, east weight,
+// south weight, flags (1 valid, 2 east tap exists, 4 south tap exists)}; flags[n][16] is raised when a tap lies
+// outside the shared-memory window of a CTA that gathers it (the sweep then keeps progress flags in global memory).  It depends on the cameras only, so it is computed for all
 // steps next to the sweep's other inputs instead of inside its dependent chain (there it was ~250 instructions per
 // thread and step, longer than the MMAs it was hidden under).
 __global__ void __launch_bounds__(256) gather_plan_kernel(const float* __restrict__ Hinc, int D, int rows, int cols,
-                                                          int PW, int plan_stride, float4* __restrict__ plan) {
+                                                          int plan_stride, int n_tiles, float4* __restrict__ plan,
+                                                          int* __restrict__ flags) {
   pdl_wait();
   pdl_launch_dependents();
   const int Lg = blockIdx.x * blockDim.x + threadIdx.x;
@@ -960,6 +989,8 @@ __global__ void __launch_bounds__(256) gather_plan_kernel(const float* __restric
   float H[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) H[i] = __ldg(Hinc + ((size_t)n * D + step) * 9 + i);
+  const Layout L = make_layout(rows, cols);
+  const int PW = L.PW;
   const int gy = Lg / PW - 1, gx = Lg % PW - 1;
   float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
   if (gy >= 0 && gy < rows && gx >= 0 && gx < cols) {
@@ -970,10 +1001,18 @@ __global__ void __launch_bounds__(256) gather_plan_kernel(const float* __restric
       int fl = 1;
       if (x0 + 1 <= cols - 1) fl |= 2;   // otherwise the east tap is clamped onto x0 (and carries weight 0)
       if (y0 + 1 <= rows - 1) fl |= 4;
-      out.x = __int_as_float(y0 * cols + x0);
+      const int P00 = y0 * PW + x0;
+      out.x = __int_as_float(P00);
       out.y = c.ix - fx0;
       out.z = c.iy - fy0;
       out.w = __int_as_float(fl);
+      // every CTA that gathers this position (as an own or a halo position) must find the taps in its window
+      int r_lo = (Lg - L.npl + MTILE) / MTILE, r_hi = Lg / MTILE;
+      r_lo = r_lo < 0 ? 0 : r_lo;
+      r_hi = r_hi > n_tiles - 1 ? n_tiles - 1 : r_hi;
+      bool inside = true;
+      for (int r = r_lo; r <= r_hi; ++r) inside = inside && taps_in_window(P00, fl, r, L);
+      if (!inside) atomicOr(flags + (size_t)n * 17 + 16, 1);
     }
   }
   plan[((size_t)n * D + step) * plan_stride + Lg] = out;
@@ -986,12 +1025,17 @@ int recurrence_plan_stride(int rows, int cols) {
   return cdiv(rows * L.PW, MTILE) * MTILE + 2 * L.halo;
 }
 
-int launch_gather_plan(const float* Hinc, int n, int D, int rows, int cols, float* plan, cudaStream_t stream) {
+int launch_gather_plan(const float* Hinc, int n, int D, int rows, int cols, float* plan, int* flags,
+                       cudaStream_t stream) {
   if (D < 2 || n <= 0) return 0;
   const Layout L = make_layout(rows, cols);
   const int stride = recurrence_plan_stride(rows, cols);
+  if (cudaMemsetAsync(flags, 0, (size_t)n * 17 * sizeof(int), stream) != cudaSuccess) {
+    set_error("launch_gather_plan: memset failed");
+    return -1;
+  }
   launch_pdl(gather_plan_kernel, dim3(cdiv(stride, 256), D - 1, n), dim3(256), (size_t)0, stream, Hinc, D, rows, cols,
-             L.PW, stride, reinterpret_cast<float4*>(plan));
+             stride, cdiv(rows * L.PW, MTILE), reinterpret_cast<float4*>(plan), flags);
   B200MVS_LAUNCH_OK("gather_plan_kernel");
   return 0;
 }
@@ -1026,7 +1070,7 @@ bool recurrence_supported(int rows, int cols, int* n_tiles, size_t* smem_bytes) 
   if (n_tiles != nullptr) *n_tiles = tiles;
   if (smem_bytes != nullptr) *smem_bytes = L.total;
   return tiles <= 16 && L.halo <= MTILE && L.npl * 4 <= MAX_TASKS * NT && 2 * L.halo <= 128 &&
-         L.stage_px >= 4 * L.halo && L.margin >= cols + 2 && L.total <= kSmemBudget;   // (stage also holds 4 halo blocks)
+         L.wm <= MTILE && 2 * L.halo <= L.wm && L.total <= kSmemBudget;   // (window side rows also stage 2 halo blocks)
 }
 
 int recurrence_max_clusters(int rows, int cols) {
@@ -1090,6 +1134,7 @@ int launch_recurrence(const RecurrenceArgs& a, cudaStream_t stream) {
   p.imgconv = a.imgconv;
   p.plan = reinterpret_cast<const float4*>(a.plan);
   p.plan_stride = recurrence_plan_stride(a.rows, a.cols);
+  p.flags = a.flags;
   p.D = a.D;
   p.rows = a.rows;
   p.cols = a.cols;

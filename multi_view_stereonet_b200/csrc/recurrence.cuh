@@ -15,6 +15,7 @@ struct RecurrenceArgs {
   const float *gamma0, *beta0, *gamma1, *beta1;
   const float* imgconv;  // [n][D][rows*cols][32] image half of conv0 + bias0 (launch_image_conv)
   const float* plan;     // [n][D][recurrence_plan_stride][4] gather plan of every step (launch_gather_plan)
+  int* flags;            // [n][17] progress flags + "taps outside the window" flag (launch_gather_plan zeroes / sets)
   int n, D, rows, cols;
   int debug = 0;              // timing ablations, see recurrence.cu
   long long* prof = nullptr;  // optional [16 ranks][12 phases] cycle totals (debug builds of the tests)
@@ -24,7 +25,8 @@ void pack_recurrence_weights(const float* w0_oihw35, const float* w1_oihw32, con
                              std::vector<uint8_t>* out);
 // Gather plan of all steps (needs only the incremental homographies): floats per (image, hypothesis) = 4 * stride.
 int recurrence_plan_stride(int rows, int cols);
-int launch_gather_plan(const float* Hinc, int n, int D, int rows, int cols, float* plan, cudaStream_t stream);
+int launch_gather_plan(const float* Hinc, int n, int D, int rows, int cols, float* plan, int* flags,
+                       cudaStream_t stream);
 bool recurrence_supported(int rows, int cols, int* n_tiles, size_t* smem_bytes);
 int launch_recurrence(const RecurrenceArgs& a, cudaStream_t stream);
 // How many of the kernel's clusters can be resident at once on the current device (cudaOccupancyMaxActiveClusters;
