@@ -261,21 +261,22 @@ def run_extra_configs(net, dev, rank, world, flush, barrier, hbm_peak, tf32_peak
         inputs = synthetic.to_device(synthetic.make_inputs(c["rows"], c["cols"], c["views"], B, first_item=first_item), dev)
         flags = (c["hyps"], True, [True] * 5)
         with torch.no_grad():
+            # warm-up and timed steps run in ONE loop with the same event / output-lifetime pattern (a first timed step
+            # that allocates differently from the warm-up stalled in cudaMalloc for ~30 ms once); the last `steps`
+            # iterations are the timed ones
             res = None
-            for _ in range(warmup):
-                flush.zero_()
-                res = net(*inputs, *flags)
-            launches = net.last_launch_count()
-            starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
-            ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
-            barrier()
-            for i in range(steps):
+            starts = [torch.cuda.Event(enable_timing=True) for _ in range(warmup + steps)]
+            ends = [torch.cuda.Event(enable_timing=True) for _ in range(warmup + steps)]
+            for i in range(warmup + steps):
+                if i == warmup:
+                    barrier()
                 flush.zero_()
                 starts[i].record()
                 res = net(*inputs, *flags)
                 ends[i].record()
             barrier()
-            step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+            launches = net.last_launch_count()
+            step_ms = [s.elapsed_time(e) for s, e in zip(starts[warmup:], ends[warmup:])]
             # per-stage breakdown: one extra forward with events at the stage boundaries (not part of the timing above)
             net.set_option("stage_profile", 1)
             net(*inputs, *flags)
@@ -292,7 +293,7 @@ def run_extra_configs(net, dev, rank, world, flush, barrier, hbm_peak, tf32_peak
             "workload": what, "batch_per_gpu": B, "global_batch": world * B, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_step, "depthmaps_per_s": world * B / (ms_step * 1e-3),
             "roofline_us_per_depthmap": t_roof_us, "frac_of_roofline": t_roof_us / (ms_step / B * 1e3),
-            "gpu_launches_per_step": launches,
+            "gpu_launches_per_step": launches, "step_ms_rank0": [round(t, 3) for t in step_ms],
             "stage_us_rank0": {k: round(v, 1) for k, v in stages.items()},
         }
         del inputs

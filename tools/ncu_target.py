@@ -14,7 +14,7 @@ sd, _ = bench.load_state()
 net = MultiViewStereoNet()
 net.load_state_dict(sd)
 net = net.cuda().eval()
-inp = synthetic.to_device(synthetic.make_inputs(512, 640, 1, 1), "cuda")
+inp = synthetic.to_device(synthetic.make_inputs(512, 640, int(os.environ.get("VIEWS", "1")), int(os.environ.get("BATCH", "1"))), "cuda")
 with torch.no_grad():
     for _ in range(int(os.environ.get("FORWARDS", "2"))):
         net(*inp, 64, True, [True] * 5)
