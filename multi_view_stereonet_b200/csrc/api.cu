@@ -265,6 +265,7 @@ struct b200mvs_net {
   size_t pinned_small_floats = 0;
   long long* rec_prof = nullptr;  // device [16][12] phase totals + [16][16][32] per-warp timeline of one step, allocated
                                   // when option "recurrence_profile" is set
+  bool prio_main = false;           // option "prio_main": single-lane forwards run on a high-priority stream
   bool stage_profile = false;       // option "stage_profile": events at the stage boundaries of the main stream
   std::string last_stage_profile;   // "name=us;..." of the last profiled forward (b200mvs_last_stage_profile)
   b200mvs_shape last_shape{};
@@ -968,6 +969,29 @@ int forward_impl(b200mvs_net* net, Lane& lane, bool sweep_on_own_stream, const b
     if (overlap) B200MVS_CUDA_OK(cudaEventRecord(net->cur->ev_pre, net->cur->side));
   }
 
+  // Output buffers, and the mask volumes: they depend on the cameras only (a voxel is masked where the views'
+  // homographies leave the image, :293-298, voted over the views :623-627, then upsampled level by level :389-396), so
+  // their whole chain runs on the side stream next to the depth sweep.  (Run next to the refiners, its large grids
+  // held back the small kernels of refiners 3 and 2: 32 us per forward at batch 1, 330 us at batch 8.)
+  float* idepth_l[5];
+  float* prior_l[5];
+  uint8_t* mask_l[5];
+  int lowest_mask = 5;
+  for (int l = 0; l < 5; ++l) {
+    idepth_l[l] = out_idepth != nullptr && out_idepth[l] != nullptr ? out_idepth[l] : ws.idepth[l];
+    prior_l[l] = out_raw != nullptr && out_raw[l] != nullptr ? out_raw[l] : ws.prior[l];
+    mask_l[l] = out_mask != nullptr && out_mask[l] != nullptr ? out_mask[l] : ws.mask[l];
+    if (out_mask != nullptr && out_mask[l] != nullptr && l < lowest_mask) lowest_mask = l;
+  }
+  const bool early_masks = overlap;
+  if (early_masks) {
+    RC(launch_mask_vote(ws.geo.H, B, V, D, h4, w4, mask_l[4], net->cur->side));
+    for (int l = 3; l >= lowest_mask; --l)
+      RC(launch_upsample_mask(mask_l[l + 1], (long long)B * D, L.h[l + 1], L.w[l + 1], L.h[l], L.w[l], mask_l[l],
+                              net->cur->side));
+    B200MVS_CUDA_OK(cudaEventRecord(net->cur->ev_mask_out, net->cur->side));
+  }
+
   // 5. the depth-sweep recurrence (multi_view_stereonet.py:279-290)
   RC(wait_upload(2, stream));
   if (overlap && persistent) B200MVS_CUDA_OK(cudaStreamWaitEvent(stream, net->cur->ev_imgconv, 0));
@@ -1150,31 +1174,15 @@ int forward_impl(b200mvs_net* net, Lane& lane, bool sweep_on_own_stream, const b
   }
 
   // 10. baseline un-normalisation, mean over views, mask vote (:616-627)
-  float* idepth_l[5];
-  float* prior_l[5];
-  uint8_t* mask_l[5];
-  int lowest_mask = 5;
-  for (int l = 0; l < 5; ++l) {
-    idepth_l[l] = out_idepth != nullptr && out_idepth[l] != nullptr ? out_idepth[l] : ws.idepth[l];
-    prior_l[l] = out_raw != nullptr && out_raw[l] != nullptr ? out_raw[l] : ws.prior[l];
-    mask_l[l] = out_mask != nullptr && out_mask[l] != nullptr ? out_mask[l] : ws.mask[l];
-    if (out_mask != nullptr && out_mask[l] != nullptr && l < lowest_mask) lowest_mask = l;
-  }
   RC(launch_view_reduce(ws.raw_views, ws.refined_views, ws.mask_views, ws.geo.baseline, B, V, D, (int)P4,
-                        !s.do_refiners[4], prior_l[4], idepth_l[4], mask_l[4], stream));
+                        !s.do_refiners[4], prior_l[4], idepth_l[4], early_masks ? nullptr : mask_l[4], stream));
 
   mark("refiner4+view_reduce");
-  // 11. coarse-to-fine: bilinear prior, mask upsample, guided refinement (:629-682).  Nothing on the path reads
-  //     the upsampled mask volumes, so their chain runs on the side stream next to the refiners.
-  cudaStream_t mask_stream = overlap ? net->cur->side : stream;
-  if (overlap && lowest_mask <= 3) {
-    B200MVS_CUDA_OK(cudaEventRecord(net->cur->ev_mask_in, stream));
-    B200MVS_CUDA_OK(cudaStreamWaitEvent(net->cur->side, net->cur->ev_mask_in, 0));
-  }
-  for (int l = 3; l >= lowest_mask; --l)
-    RC(launch_upsample_mask(mask_l[l + 1], (long long)B * D, L.h[l + 1], L.w[l + 1], L.h[l], L.w[l], mask_l[l],
-                            mask_stream));
-  if (overlap && lowest_mask <= 3) B200MVS_CUDA_OK(cudaEventRecord(net->cur->ev_mask_out, net->cur->side));
+  // 11. coarse-to-fine: bilinear prior, mask upsample, guided refinement (:629-682).  (The mask volumes were
+  //     produced next to the depth sweep unless the side stream is off.)
+  if (!early_masks)
+    for (int l = 3; l >= lowest_mask; --l)
+      RC(launch_upsample_mask(mask_l[l + 1], (long long)B * D, L.h[l + 1], L.w[l + 1], L.h[l], L.w[l], mask_l[l], stream));
   for (int l = 3; l >= 0; --l) {
     const bool fused_up = s.do_refiners[l] && use_pre[l];   // the refiner's head upsamples its own prior
     if (!fused_up) RC(launch_upsample_f32(idepth_l[l + 1], B, L.h[l + 1], L.w[l + 1], L.h[l], L.w[l], prior_l[l], stream));
@@ -1191,7 +1199,7 @@ int forward_impl(b200mvs_net* net, Lane& lane, bool sweep_on_own_stream, const b
     mark(names[l]);
     if (l == 1 && coarse_done != nullptr) B200MVS_CUDA_OK(cudaEventRecord(coarse_done, stream));
   }
-  if (overlap && lowest_mask <= 3) B200MVS_CUDA_OK(cudaStreamWaitEvent(stream, net->cur->ev_mask_out, 0));
+  if (early_masks) B200MVS_CUDA_OK(cudaStreamWaitEvent(stream, net->cur->ev_mask_out, 0));
   if (sprof) {
     mark("join mask chain");
     cudaEventSynchronize(marks.back().second);
@@ -1384,6 +1392,10 @@ B200MVS_API int b200mvs_set_option(b200mvs_net* net, const char* name, int value
     net->stage_profile = value != 0;
     return 0;
   }
+  if (k == "prio_main") {
+    net->prio_main = value != 0;
+    return 0;
+  }
   if (k == "recurrence_debug") {
     net->rec_debug = value;
     return 0;
@@ -1504,7 +1516,18 @@ B200MVS_API int b200mvs_forward(b200mvs_net* net, const b200mvs_shape* shape, co
   g_launches = 0;
   const int lanes = plan_lanes(net, s);
   int rc = 0;
-  if (lanes == 1) {
+  if (lanes == 1 && net->prio_main && net->overlap) {
+    // experiment: the critical path on a high-priority stream of our own, so that the side stream's grids only get
+    // the SMs it leaves idle
+    Lane& l0 = net->lanes[0];
+    B200MVS_CUDA_OK(cudaSetDevice(net->device));
+    B200MVS_CUDA_OK(cudaEventRecord(net->ev_begin, caller));
+    B200MVS_CUDA_OK(cudaStreamWaitEvent(l0.rec, net->ev_begin, 0));
+    rc = forward_impl(net, l0, false, s, left_image_pyr, K_pyr, T_right_in_lefts, right_image_l0, right_image_l4,
+                      out_idepth, out_idepth_raw, out_mask, l0.rec);
+    B200MVS_CUDA_OK(cudaEventRecord(l0.ev_end, l0.rec));
+    B200MVS_CUDA_OK(cudaStreamWaitEvent(caller, l0.ev_end, 0));
+  } else if (lanes == 1) {
     rc = forward_impl(net, net->lanes[0], false, s, left_image_pyr, K_pyr, T_right_in_lefts, right_image_l0,
                       right_image_l4, out_idepth, out_idepth_raw, out_mask, caller);
   } else {

@@ -52,6 +52,8 @@ int launch_softargmin(const float* cost, const float* samples, int n, int D, int
                       cudaStream_t stream);
 
 // Per-view baseline un-normalisation and the mean over views (multi_view_stereonet.py:616-627).
+int launch_mask_vote(const float* H, int batch, int views, int D, int rows, int cols, uint8_t* mask4,
+                     cudaStream_t stream);
 int launch_view_reduce(const float* raw_views, const float* refined_views, const uint8_t* mask_views,
                        const float* baseline, int batch, int views, int D, int pixels, bool refined_is_alias,
                        float* raw4, float* idepth4, uint8_t* mask4, cudaStream_t stream);

@@ -371,6 +371,25 @@ __global__ void __launch_bounds__(128) view_reduce_kernel(const float* __restric
   }
 }
 
+// The same vote straight from the plane-sweep homographies (the mask of a view is where its homography leaves the
+// image, multi_view_stereonet.py:293-298): the mask volumes depend on the cameras only, so their whole chain can run
+// next to the depth sweep instead of next to the refiners.
+__global__ void __launch_bounds__(128) mask_vote_kernel(const float* __restrict__ H, int views, int D, int rows, int cols,
+                                                        uint8_t* __restrict__ mask4) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.y, d = blockIdx.z;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pixels = rows * cols;
+  if (p >= pixels) return;
+  float ms = 0.f;
+  for (int v = 0; v < views; ++v) {
+    const WarpCoord c = homography_coord(H + ((size_t)(b * views + v) * D + d) * 9, (float)(p % cols), (float)(p / cols), rows, cols);
+    ms += c.invalid ? 1.f : 0.f;
+  }
+  mask4[((size_t)b * D + d) * pixels + p] = (__fdiv_rn(ms, (float)views) > 0.5f) ? 1 : 0;
+}
+
 __global__ void __launch_bounds__(256) upsample_f32_kernel(const float* __restrict__ in, int h, int w, int H, int W,
                                                            float* __restrict__ out) {
   pdl_launch_dependents();
@@ -545,10 +564,18 @@ int launch_softargmin(const float* cost, const float* samples, int n, int D, int
   return 0;
 }
 
+int launch_mask_vote(const float* H, int batch, int views, int D, int rows, int cols, uint8_t* mask4,
+                     cudaStream_t stream) {
+  launch_pdl(mask_vote_kernel, dim3(cdiv(rows * cols, 128), batch, D), dim3(128), (size_t)0, stream, H, views, D, rows, cols,
+             mask4);
+  B200MVS_LAUNCH_OK("mask_vote_kernel");
+  return 0;
+}
+
 int launch_view_reduce(const float* raw_views, const float* refined_views, const uint8_t* mask_views,
                        const float* baseline, int batch, int views, int D, int pixels, bool refined_is_alias,
                        float* raw4, float* idepth4, uint8_t* mask4, cudaStream_t stream) {
-  dim3 grid(cdiv(pixels, 128), batch, 1 + D);
+  dim3 grid(cdiv(pixels, 128), batch, mask4 != nullptr ? 1 + D : 1);   // (mask4 == nullptr: the vote ran elsewhere)
   launch_pdl(view_reduce_kernel, grid, dim3(128), (size_t)0, stream, raw_views, refined_views, mask_views, baseline, views, D, pixels,
                                                refined_is_alias ? 1 : 0, raw4, idepth4, mask4);
   B200MVS_LAUNCH_OK("view_reduce_kernel");

@@ -19,6 +19,7 @@ sd, _ = bench.load_state()
 net = MultiViewStereoNet()
 net.load_state_dict(sd)
 net = net.cuda().eval()
+net.mask_mode = os.environ.get("MASK_MODE", "dense")
 for kv in filter(None, (sys.argv[6] if len(sys.argv) > 6 else "").split(",")):
     k, v = kv.split("=")
     net.set_option(k, int(v))
