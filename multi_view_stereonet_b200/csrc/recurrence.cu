@@ -364,7 +364,8 @@ __global__ void __launch_bounds__(NT_ALL, 1) recurrence_kernel(const RecParams p
   __shared__ __align__(16) float2 s_loc[kGroups][4];   // this CTA's warp partials [group][warp quarter]
   __shared__ __align__(16) float s_bias[2][kC], s_gamma[2][kC], s_beta[2][kC];   // biases of conv1, conv2 (conv0's is in imgconv)
   __shared__ __align__(8) uint64_t s_bar;        // MMA completion
-  __shared__ __align__(8) uint64_t s_xbar[2];    // per layer: bytes pushed into this CTA by the cluster
+  __shared__ __align__(8) uint64_t s_sbar[2];    // per layer: GroupNorm partials pushed into this CTA by the cluster
+  __shared__ __align__(8) uint64_t s_hbar[2];    // per layer: boundary rows copied into this CTA by its neighbours
   __shared__ __align__(8) uint64_t s_tbar;       // bytes the neighbours copied into this CTA's window
   __shared__ uint32_t s_tmem;
 
@@ -393,8 +394,10 @@ __global__ void __launch_bounds__(NT_ALL, 1) recurrence_kernel(const RecParams p
   }
   if (tid == 32) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_bar)), "r"(1) : "memory");
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_xbar[0])), "r"(1) : "memory");
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_xbar[1])), "r"(1) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_sbar[0])), "r"(1) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_sbar[1])), "r"(1) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_hbar[0])), "r"(1) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_hbar[1])), "r"(1) : "memory");
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_tbar)), "r"(1) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -506,8 +509,8 @@ __global__ void __launch_bounds__(NT_ALL, 1) recurrence_kernel(const RecParams p
   }
   // bytes the cluster pushes into this CTA per layer: every active CTA's (sum, sumsq) of the four groups and the
   // boundary rows of the two neighbours
-  const uint32_t xbytes = (uint32_t)p.n_tiles * (uint32_t)kGroups * 8u +
-                          (rank > 0 && !(p.debug & 16) ? (uint32_t)halo * kC * 4u : 0u) +
+  const uint32_t sbytes = (uint32_t)p.n_tiles * (uint32_t)kGroups * 8u;
+  const uint32_t hbytes = (rank > 0 && !(p.debug & 16) ? (uint32_t)halo * kC * 4u : 0u) +
                           ((int)rank + 1 < p.n_tiles && !(p.debug & 16) ? (uint32_t)halo * kC * 4u : 0u);
   // Window of the previous hypothesis (Layout): filled where the data is produced -- the own rows by this CTA's last
   // epilogue, the wm rows on either side by the two neighbours' bulk copies.  A window row is 128 bytes whose eight
@@ -609,8 +612,12 @@ __global__ void __launch_bounds__(NT_ALL, 1) recurrence_kernel(const RecParams p
     cur_step = step;
     TRACE(0);
     if (active && tid == 0) {
-      mbar_arm_tx(&s_xbar[0], xbytes);
-      mbar_arm_tx(&s_xbar[1], xbytes);
+      mbar_arm_tx(&s_sbar[0], sbytes);
+      mbar_arm_tx(&s_sbar[1], sbytes);
+      if (hbytes != 0) {
+        mbar_arm_tx(&s_hbar[0], hbytes);
+        mbar_arm_tx(&s_hbar[1], hbytes);
+      }
       if (step >= 2 && wbytes != 0) mbar_arm_tx(&s_tbar, wbytes);   // (bytes that are already here count ahead)
     }
     // ================= W: warp previous features into the conv0 operand ============================
@@ -717,6 +724,38 @@ __global__ void __launch_bounds__(NT_ALL, 1) recurrence_kernel(const RecParams p
 #pragma unroll
           for (int k = 0; k < 8; ++k) y[k] = (y[k] + c[k]) + add[k];
         }
+        // ---- statistics first: every CTA of the cluster waits for every other CTA's push ----
+        float gs = 0.f, gq = 0.f;
+        if (real_out) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            gs += y[k];
+            gq += y[k] * y[k];
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          gs += __shfl_xor_sync(0xffffffffu, gs, o);
+          gq += __shfl_xor_sync(0xffffffffu, gq, o);
+        }
+        // The four warps of a group add up inside the CTA (fixed order), then lane d of the group's first warp pushes
+        // the CTA's (sum, sumsq) to CTA d: 4 * n_tiles remote stores per CTA instead of one per warp and value (a
+        // remote store costs ~2 cycles of issue whatever its size; 352 of them were ~700 cycles of every epilogue).
+        if (layer == 0) TRACE(28);
+        if (lane == 0) s_loc[oct_e][wq] = make_float2(gs, gq);
+        if (wq != 0) {
+          asm volatile("bar.arrive %0, 128;" ::"r"(1 + oct_e) : "memory");
+        } else {
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + oct_e) : "memory");
+          if (lane < p.n_tiles) {
+            const float4 u = *reinterpret_cast<const float4*>(&s_loc[oct_e][0]);
+            const float4 w = *reinterpret_cast<const float4*>(&s_loc[oct_e][2]);
+            st_async_f2(map_to_rank(smem_u32(&s_part[layer][oct_e][rank]), (uint32_t)lane),
+                        make_float2((u.x + u.z) + (w.x + w.z), (u.y + u.w) + (w.y + w.w)),
+                        map_to_rank(smem_u32(&s_sbar[layer]), (uint32_t)lane));
+          }
+        }
+        if (layer == 0) TRACE(29);
         // Halo rows of a layer at the receiver: [2 * halo][32] fp32, lower halo then upper halo, 16-byte chunks
         // XOR-swizzled with the row index (the receiver reads one octet of 32 consecutive rows per instruction).
         // The boundary rows are written into a local image of the receiver's rows -- in the staging buffer of the
@@ -738,9 +777,8 @@ __global__ void __launch_bounds__(NT_ALL, 1) recurrence_kernel(const RecParams p
           *swz_ptr(hout_next, idx, 2 * oct_e) = make_float4(y[0], y[1], y[2], y[3]);
           *swz_ptr(hout_next, idx, 2 * oct_e + 1) = make_float4(y[4], y[5], y[6], y[7]);
         }
-        if (layer == 0) TRACE(26);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // these rows -> readable by the copy engine
-        if (layer == 0) TRACE(27);
+        if (layer == 0) TRACE(26);
         if (wq < 2) {          // positions [0, 64): the writers of the rows for rank-1 (8 warps)
           if (rank > 0) {
             if (warp == 0) {
@@ -748,7 +786,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) recurrence_kernel(const RecParams p
               if (!(p.debug & 16) && elect_one()) {
                 float* hb = s_halo + ((size_t)layer * 2 + 1) * halo * kC;
                 dsmem_bulk_copy(map_to_rank(smem_u32(hb), rank - 1), smem_u32(hout_prev), (uint32_t)halo * kC * 4u,
-                                map_to_rank(smem_u32(&s_xbar[layer]), rank - 1));
+                                map_to_rank(smem_u32(&s_hbar[layer]), rank - 1));
               }
               __syncwarp();
             } else {
@@ -762,7 +800,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) recurrence_kernel(const RecParams p
               if (!(p.debug & 16) && elect_one()) {
                 float* hb = s_halo + (size_t)layer * 2 * halo * kC;
                 dsmem_bulk_copy(map_to_rank(smem_u32(hb), rank + 1), smem_u32(hout_next),
-                                (uint32_t)halo * kC * 4u, map_to_rank(smem_u32(&s_xbar[layer]), rank + 1));
+                                (uint32_t)halo * kC * 4u, map_to_rank(smem_u32(&s_hbar[layer]), rank + 1));
               }
               __syncwarp();
             } else {
@@ -770,42 +808,11 @@ __global__ void __launch_bounds__(NT_ALL, 1) recurrence_kernel(const RecParams p
             }
           }
         }
-        if (layer == 0) TRACE(28);
-        float gs = 0.f, gq = 0.f;
-        if (real_out) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            gs += y[k];
-            gq += y[k] * y[k];
-          }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          gs += __shfl_xor_sync(0xffffffffu, gs, o);
-          gq += __shfl_xor_sync(0xffffffffu, gq, o);
-        }
-        // The four warps of a group add up inside the CTA (fixed order), then lane d of the group's first warp pushes
-        // the CTA's (sum, sumsq) to CTA d: 4 * n_tiles remote stores per CTA instead of one per warp and value (a
-        // remote store costs ~2 cycles of issue whatever its size; 352 of them were ~700 cycles of every epilogue).
-        if (layer == 0) TRACE(29);
-        if (lane == 0) s_loc[oct_e][wq] = make_float2(gs, gq);
-        if (wq != 0) {
-          asm volatile("bar.arrive %0, 128;" ::"r"(1 + oct_e) : "memory");
-        } else {
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + oct_e) : "memory");
-          if (lane < p.n_tiles) {
-            const float4 u = *reinterpret_cast<const float4*>(&s_loc[oct_e][0]);
-            const float4 w = *reinterpret_cast<const float4*>(&s_loc[oct_e][2]);
-            st_async_f2(map_to_rank(smem_u32(&s_part[layer][oct_e][rank]), (uint32_t)lane),
-                        make_float2((u.x + u.z) + (w.x + w.z), (u.y + u.w) + (w.y + w.w)),
-                        map_to_rank(smem_u32(&s_xbar[layer]), (uint32_t)lane));
-          }
-        }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       PROF_MARK(2 + 4 * layer);
       TRACE(7 + 8 * layer);
-      if (active) mbar_wait_cta(&s_xbar[layer], (uint32_t)((step - 1) & 1));
+      if (active) mbar_wait_cta(&s_sbar[layer], (uint32_t)((step - 1) & 1));
       PROF_MARK(3 + 4 * layer);
       TRACE(8 + 8 * layer);
 
@@ -868,6 +875,8 @@ __global__ void __launch_bounds__(NT_ALL, 1) recurrence_kernel(const RecParams p
           *plane_ptr(PLANE_LO + oct_e, own_l) = lo;
         }
         TRACE(10 + 8 * layer);
+        // the neighbours' boundary rows have had the coefficient and own-row work to arrive
+        if (hbytes != 0) mbar_wait_cta(&s_hbar[layer], (uint32_t)((step - 1) & 1));
         if (h_in) {
           float v[8];
 #pragma unroll
