@@ -265,6 +265,7 @@ struct b200mvs_net {
   size_t pinned_small_floats = 0;
   long long* rec_prof = nullptr;  // device [16][12] phase totals + [16][16][32] per-warp timeline of one step, allocated
                                   // when option "recurrence_profile" is set
+  bool l4_chain = true;             // option "l4_chain": the level-4 tail of the feature network as one cluster kernel
   bool prio_main = false;           // option "prio_main": single-lane forwards run on a high-priority stream
   bool stage_profile = false;       // option "stage_profile": events at the stage boundaries of the main stream
   std::string last_stage_profile;   // "name=us;..." of the last profiled forward (b200mvs_last_stage_profile)
@@ -774,7 +775,26 @@ int run_featnet(b200mvs_net* net, const Levels& L, int img0, int cnt, const floa
       RC(launch_conv(CONV_5x5_S2, 32, p, stream));
     }
   }
-  {
+  if (net->use_tensor_cores && net->l4_chain && !net->keep_stages && l4_tail_supported(h4, w4) &&
+      net->feat_res[0].w16s != nullptr && net->feat_final.w16s != nullptr) {
+    // six residual blocks + conv_final at level 4 (multi_view_stereonet.py:119-127) in one cluster kernel per image
+    L4TailArgs ta;
+    ta.x0 = ws.l4x[0] + (size_t)img0 * P4 * kC;
+    ta.out = final_out;
+    ta.out_stride = final_stride != 0 ? final_stride : (long long)P4 * kC;
+    for (int i = 0; i < 6; ++i) {
+      ta.w[i] = net->feat_res[i].w16s;
+      ta.bias[i] = net->feat_res[i].bias;
+      ta.gamma[i] = net->feat_gn[i].gamma;
+      ta.beta[i] = net->feat_gn[i].beta;
+    }
+    ta.w[6] = net->feat_final.w16s;
+    ta.bias[6] = net->feat_final.bias;
+    ta.n = cnt;
+    ta.rows = h4;
+    ta.cols = w4;
+    RC(launch_l4_tail(ta, stream));
+  } else {
     // six residual blocks + conv_final at level 4 (multi_view_stereonet.py:119-127)
     const double inv_count = 1.0 / (8.0 * (double)P4);
     const size_t ioff = (size_t)img0 * P4 * kC;
@@ -1394,6 +1414,10 @@ B200MVS_API int b200mvs_set_option(b200mvs_net* net, const char* name, int value
   }
   if (k == "prio_main") {
     net->prio_main = value != 0;
+    return 0;
+  }
+  if (k == "l4_chain") {
+    net->l4_chain = value != 0;
     return 0;
   }
   if (k == "recurrence_debug") {

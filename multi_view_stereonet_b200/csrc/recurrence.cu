@@ -1027,6 +1027,377 @@ __global__ void __launch_bounds__(256) gather_plan_kernel(const float* __restric
   plan[((size_t)n * D + step) * plan_stride + Lg] = out;
 }
 
+
+// =================================================================================================================
+// The level-4 tail of FeatureNetwork -- six residual blocks x_{i+1} = lrelu(GN(conv_i(x_i))) + x_i and conv_final
+// (multi_view_stereonet.py:96-105, 119-127; utils/resnet.py:93-109) -- as ONE cluster kernel per image with the
+// activations, the GroupNorm statistics and the tile boundaries exchanged on chip, exactly as in the sweep above:
+// seven 3x3 32->32 layers on a 32 x 40 image are seven ~3 us layers here against seven ~8 us kernels (each of those
+// is statistics round trip + staging + 36 MMAs + epilogue + store flush + launch boundary).  The weights of a layer
+// (36 KB, split fp16, the same 2 KB blocks as conv_tc.cu uses) stream through two buffers one layer ahead.
+// =================================================================================================================
+constexpr int TAIL_LAYERS = 7;
+constexpr uint32_t TAIL_W_BYTES = W1_BLOCKS * 2u * 1024u;   // one layer: 18 blocks of [W_hi | W_lo]
+
+struct TailLayout {
+  uint32_t off_w, off_planes, off_halo, off_hout, total;
+};
+__host__ __device__ inline TailLayout make_tail_layout(const Layout& L) {
+  TailLayout T;
+  uint32_t o = 0;
+  T.off_w = o;
+  o += 2 * TAIL_W_BYTES;
+  T.off_planes = o;
+  o += NUM_PLANES * L.plane_bytes;
+  T.off_halo = o;          // [layer parity 2][lower, upper][halo][32] fp32, written by the neighbour CTAs
+  o += 2 * 2 * (uint32_t)L.halo * kC * 4;
+  T.off_hout = o;          // [layer parity 2][to prev, to next][halo][32] fp32, the bulk copies' sources
+  o += 2 * 2 * (uint32_t)L.halo * kC * 4;
+  T.total = o;
+  return T;
+}
+
+struct TailParams {
+  const float* x0;         // [images][rows*cols][32] output of FeatureNetwork.conv3
+  float* out;              // image i at out + i * out_stride, [rows*cols][32]
+  long long out_stride;
+  const uint8_t* w[TAIL_LAYERS];
+  const float* bias[TAIL_LAYERS];
+  const float* gamma[TAIL_LAYERS - 1];
+  const float* beta[TAIL_LAYERS - 1];
+  int rows, cols, n_tiles;
+};
+
+__global__ void __launch_bounds__(NT, 1) l4_tail_kernel(const TailParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(16) float2 s_part[2][kGroups][16];
+  __shared__ __align__(16) float2 s_loc[kGroups][4];
+  __shared__ __align__(16) float s_bias[TAIL_LAYERS][kC], s_gamma[TAIL_LAYERS - 1][kC], s_beta[TAIL_LAYERS - 1][kC];
+  __shared__ __align__(8) uint64_t s_bar, s_sbar[2], s_hbar[2], s_wbar[2];
+  __shared__ uint32_t s_tmem;
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const uint32_t rank = cluster_ctarank();
+  const int img = blockIdx.y;
+  const Layout L = make_layout(p.rows, p.cols);
+  const TailLayout T = make_tail_layout(L);
+  const int PW = L.PW, halo = L.halo;
+  const int pixels = p.rows * p.cols;
+  const bool active = (int)rank < p.n_tiles;
+  const int pos0 = (int)rank * MTILE;
+  uint8_t* s_w = smem + T.off_w;
+  uint8_t* s_planes = smem + T.off_planes;
+  float* s_halo = reinterpret_cast<float*>(smem + T.off_halo);
+  float* s_hout = reinterpret_cast<float*>(smem + T.off_hout);
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(64u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    for (uint64_t* b : {&s_bar, &s_sbar[0], &s_sbar[1], &s_hbar[0], &s_hbar[1], &s_wbar[0], &s_wbar[1]})
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 2 * kGroups * 16) (&s_part[0][0][0])[tid] = make_float2(0.f, 0.f);
+  for (int i = tid; i < TAIL_LAYERS * kC; i += NT) {
+    const int l = i / kC, c = i % kC;
+    s_bias[l][c] = p.bias[l] != nullptr ? __ldg(p.bias[l] + c) : 0.f;
+    if (l < TAIL_LAYERS - 1) {
+      s_gamma[l][c] = __ldg(p.gamma[l] + c);
+      s_beta[l][c] = __ldg(p.beta[l] + c);
+    }
+  }
+  {
+    uint4* pl = reinterpret_cast<uint4*>(s_planes);
+    for (int i = tid; i < NUM_PLANES * L.npl_pad; i += NT) pl[i] = make_uint4(0, 0, 0, 0);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = s_tmem;
+  uint32_t bar_phase = 0;
+  pdl_launch_dependents();
+  // weights are parameters, not outputs of an earlier kernel: layer 0's go in flight before the dependency wait
+  auto load_weights = [&](int layer) {
+    if (warp == 1) {
+      if (active && elect_one()) {
+        uint64_t* bar = &s_wbar[layer & 1];
+        mbar_arm_tx(bar, TAIL_W_BYTES);
+        uint8_t* dst = s_w + (size_t)(layer & 1) * TAIL_W_BYTES;
+        tma_load_1d(dst, p.w[layer], 32768u, bar);
+        tma_load_1d(dst + 32768u, p.w[layer] + 32768u, TAIL_W_BYTES - 32768u, bar);
+      }
+      __syncwarp();
+    }
+  };
+  load_weights(0);
+  cluster_sync_all();
+
+  const float inv_count = 1.0f / (8.0f * (float)pixels);
+  const uint32_t plane_u16 = L.plane_bytes >> 4;
+  const uint64_t da_hi0 = umma_desc(smem_u32(s_planes) + (uint32_t)PLANE_HI * L.plane_bytes, L.plane_bytes, 128u);
+  const uint64_t da_lo0 = umma_desc(smem_u32(s_planes) + (uint32_t)PLANE_LO * L.plane_bytes, L.plane_bytes, 128u);
+  const uint64_t db0 = umma_desc(smem_u32(s_w), 1024u, 128u);
+  auto operands_ready = [&](int layer) {   // warp 0 waits for everyone's operand rows and the weights, then issues
+    if (warp == 0) {
+      asm volatile("bar.sync 7, %0;" ::"n"(NT) : "memory");
+      if (active && elect_one()) {
+        mbar_wait_cta(&s_wbar[layer & 1], (uint32_t)((layer >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        issue_conv_mmas(da_hi0, da_lo0, db0 + (uint64_t)((layer & 1) * (TAIL_W_BYTES / 16)), plane_u16, (uint32_t)PW,
+                        tmem_base);
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                         smem_u32(&s_bar))
+                     : "memory");
+      }
+      __syncwarp();
+    } else {
+      asm volatile("bar.arrive 7, %0;" ::"n"(NT) : "memory");
+    }
+  };
+  auto wait_conv = [&]() {
+    if (active) mbar_wait_cta(&s_bar, bar_phase);
+    bar_phase ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  };
+  auto plane_ptr = [&](int plane, int l) -> uint4* {
+    return reinterpret_cast<uint4*>(s_planes + (size_t)plane * L.plane_bytes + (size_t)l * 16);
+  };
+
+  // thread = (output position, channel octet) as in the sweep
+  const int wq = warp & 3, oct_e = warp >> 2;
+  const int jl = wq * 32 + lane, jg = pos0 + jl;
+  const int oy = jg / PW, ox = jg % PW;
+  const bool real_out = active && ox < p.cols && oy < p.rows;
+  const uint32_t tmem_my = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(oct_e * 8);
+  const int own_l = jl + halo;
+  const size_t own_pix = real_out ? (size_t)oy * p.cols + ox : 0;
+  const int h_idx = tid & 127;
+  const bool h_in = active && h_idx < 2 * halo;
+  const int h_l = h_idx < halo ? h_idx : h_idx + MTILE;
+  bool h_real;
+  size_t h_pix = 0;
+  {
+    const int Lg = pos0 + h_l;
+    const int gy = Lg / PW - 1, gx = Lg % PW - 1;
+    h_real = h_in && gy >= 0 && gy < p.rows && gx >= 0 && gx < p.cols;
+    if (h_real) h_pix = (size_t)gy * p.cols + gx;
+  }
+  const bool has_prev = active && rank > 0, has_next = active && (int)rank + 1 < p.n_tiles;
+  const uint32_t sbytes = (uint32_t)p.n_tiles * (uint32_t)kGroups * 8u;
+  const uint32_t hbytes = ((has_prev ? 1u : 0u) + (has_next ? 1u : 0u)) * (uint32_t)halo * kC * 4u;
+
+  pdl_wait();
+  // ---- x_0 (raw conv3 output) of the own and halo positions: every position is in global memory ----
+  float xres[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) xres[k] = 0.f;
+  if (active) {
+    const float* xin = p.x0 + (size_t)img * pixels * kC + oct_e * 8;
+    if (real_out) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(xin + own_pix * kC));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(xin + own_pix * kC) + 1);
+      xres[0] = a.x; xres[1] = a.y; xres[2] = a.z; xres[3] = a.w;
+      xres[4] = b.x; xres[5] = b.y; xres[6] = b.z; xres[7] = b.w;
+    }
+    uint4 hi, lo;
+    split8(xres, &hi, &lo);
+    *plane_ptr(PLANE_HI + oct_e, own_l) = hi;
+    *plane_ptr(PLANE_LO + oct_e, own_l) = lo;
+    if (h_in) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = 0.f;
+      if (h_real) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(xin + h_pix * kC));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(xin + h_pix * kC) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      }
+      split8(v, &hi, &lo);
+      *plane_ptr(PLANE_HI + oct_e, h_l) = hi;
+      *plane_ptr(PLANE_LO + oct_e, h_l) = lo;
+    }
+  }
+
+#pragma unroll 1
+  for (int layer = 0; layer < TAIL_LAYERS; ++layer) {
+    const int pb = layer & 1;
+    const uint32_t par = (uint32_t)((layer >> 1) & 1);
+    const bool last = layer == TAIL_LAYERS - 1;
+    if (active && tid == 0 && !last) {
+      mbar_arm_tx(&s_sbar[pb], sbytes);
+      if (hbytes != 0) mbar_arm_tx(&s_hbar[pb], hbytes);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    operands_ready(layer);
+    // the other weight buffer was last read by layer - 1's MMAs, which everyone has seen complete
+    if (!last) load_weights(layer + 1);
+    wait_conv();
+
+    float y[8];
+    if (active) {
+      float c[8];
+      tmem_ld8x2(tmem_my, tmem_my + 32u, y, c);
+      const float4 b0 = *reinterpret_cast<const float4*>(&s_bias[layer][oct_e * 8]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&s_bias[layer][oct_e * 8 + 4]);
+      const float add[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) y[k] = (y[k] + c[k]) + add[k];
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (last) {   // conv_final: no normalisation, no activation
+      if (real_out) {
+        float* dst = p.out + (size_t)img * p.out_stride + own_pix * kC + oct_e * 8;
+        __stcg(reinterpret_cast<float4*>(dst), make_float4(y[0], y[1], y[2], y[3]));
+        __stcg(reinterpret_cast<float4*>(dst) + 1, make_float4(y[4], y[5], y[6], y[7]));
+      }
+      break;
+    }
+    if (active) {
+      // ---- statistics to every CTA, boundary rows to the neighbours (see the sweep's epilogue) ----
+      float gs = 0.f, gq = 0.f;
+      if (real_out) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          gs += y[k];
+          gq += y[k] * y[k];
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        gs += __shfl_xor_sync(0xffffffffu, gs, o);
+        gq += __shfl_xor_sync(0xffffffffu, gq, o);
+      }
+      if (lane == 0) s_loc[oct_e][wq] = make_float2(gs, gq);
+      if (wq != 0) {
+        asm volatile("bar.arrive %0, 128;" ::"r"(1 + oct_e) : "memory");
+      } else {
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + oct_e) : "memory");
+        if (lane < p.n_tiles) {
+          const float4 u = *reinterpret_cast<const float4*>(&s_loc[oct_e][0]);
+          const float4 w = *reinterpret_cast<const float4*>(&s_loc[oct_e][2]);
+          st_async_f2(map_to_rank(smem_u32(&s_part[pb][oct_e][rank]), (uint32_t)lane),
+                      make_float2((u.x + u.z) + (w.x + w.z), (u.y + u.w) + (w.y + w.w)),
+                      map_to_rank(smem_u32(&s_sbar[pb]), (uint32_t)lane));
+        }
+      }
+      float* hout_prev = s_hout + (size_t)(pb * 2) * halo * kC;
+      float* hout_next = s_hout + (size_t)(pb * 2 + 1) * halo * kC;
+      if (jl < halo && has_prev) {
+        const int key = (halo + jl) & 7;
+        float* row = hout_prev + (size_t)jl * kC;
+        *reinterpret_cast<float4*>(row + (((2 * oct_e) ^ key) << 2)) = make_float4(y[0], y[1], y[2], y[3]);
+        *reinterpret_cast<float4*>(row + (((2 * oct_e + 1) ^ key) << 2)) = make_float4(y[4], y[5], y[6], y[7]);
+      }
+      if (jl >= MTILE - halo && has_next) {
+        const int idx = jl - (MTILE - halo);
+        *swz_ptr(hout_next, idx, 2 * oct_e) = make_float4(y[0], y[1], y[2], y[3]);
+        *swz_ptr(hout_next, idx, 2 * oct_e + 1) = make_float4(y[4], y[5], y[6], y[7]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (wq < 2) {
+        if (has_prev) {
+          if (warp == 0) {
+            asm volatile("bar.sync 5, 256;" ::: "memory");
+            if (elect_one())
+              dsmem_bulk_copy(map_to_rank(smem_u32(s_halo + (size_t)(pb * 2 + 1) * halo * kC), rank - 1), smem_u32(hout_prev),
+                              (uint32_t)halo * kC * 4u, map_to_rank(smem_u32(&s_hbar[pb]), rank - 1));
+            __syncwarp();
+          } else {
+            asm volatile("bar.arrive 5, 256;" ::: "memory");
+          }
+        }
+      } else {
+        if (has_next) {
+          if (warp == 2) {
+            asm volatile("bar.sync 6, 256;" ::: "memory");
+            if (elect_one())
+              dsmem_bulk_copy(map_to_rank(smem_u32(s_halo + (size_t)(pb * 2) * halo * kC), rank + 1), smem_u32(hout_next),
+                              (uint32_t)halo * kC * 4u, map_to_rank(smem_u32(&s_hbar[pb]), rank + 1));
+            __syncwarp();
+          } else {
+            asm volatile("bar.arrive 6, 256;" ::: "memory");
+          }
+        }
+      }
+      mbar_wait_cta(&s_sbar[pb], par);
+
+      // ---- GroupNorm coefficients, then x_{i+1} = lrelu(GN(y)) + x_i over the own and halo positions ----
+      float ca[8], cb[8];
+      {
+        const float4* sp = reinterpret_cast<const float4*>(&s_part[pb][oct_e][0]);
+        float4 q[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q[i] = sp[i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          q[i].x += q[i].z;
+          q[i].y += q[i].w;
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1)
+#pragma unroll
+          for (int i = 0; i < 8; i += 2 * o) {
+            q[i].x += q[i + o].x;
+            q[i].y += q[i + o].y;
+          }
+        const double mean = (double)q[0].x * (double)inv_count;
+        const double var = (double)q[0].y * (double)inv_count - mean * mean;
+        const float rstd = rsqrtf(fmaxf((float)var, 0.f) + kGnEps);
+        const float4 g0 = *reinterpret_cast<const float4*>(&s_gamma[layer][8 * oct_e]);
+        const float4 g1 = *reinterpret_cast<const float4*>(&s_gamma[layer][8 * oct_e + 4]);
+        const float4 e0 = *reinterpret_cast<const float4*>(&s_beta[layer][8 * oct_e]);
+        const float4 e1 = *reinterpret_cast<const float4*>(&s_beta[layer][8 * oct_e + 4]);
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bt[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          ca[k] = gm[k] * rstd;
+          cb[k] = bt[k] - (float)mean * ca[k];
+        }
+      }
+      {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) xres[k] = real_out ? lrelu(fmaf(y[k], ca[k], cb[k])) + xres[k] : 0.f;
+        uint4 hi, lo;
+        split8(xres, &hi, &lo);
+        *plane_ptr(PLANE_HI + oct_e, own_l) = hi;
+        *plane_ptr(PLANE_LO + oct_e, own_l) = lo;
+      }
+      if (hbytes != 0) mbar_wait_cta(&s_hbar[pb], par);
+      if (h_in) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        uint4* ph = plane_ptr(PLANE_HI + oct_e, h_l);
+        uint4* plo = plane_ptr(PLANE_LO + oct_e, h_l);
+        if (h_real) {
+          const float* hb = s_halo + (size_t)pb * 2 * halo * kC;
+          const float4 a = *swz_ptr(hb, h_idx, 2 * oct_e), b = *swz_ptr(hb, h_idx, 2 * oct_e + 1);
+          const float yy[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+          float xprev[8];
+          unsplit8(*ph, *plo, xprev);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = lrelu(fmaf(yy[e], ca[e], cb[e])) + xprev[e];
+        }
+        uint4 hi, lo;
+        split8(v, &hi, &lo);
+        *ph = hi;
+        *plo = lo;
+      }
+    }
+  }
+  cluster_sync_all();   // no CTA leaves while a peer may still read from or write into its shared memory
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64u) : "memory");
+  }
+}
+
 }  // namespace
 
 int recurrence_plan_stride(int rows, int cols) {
@@ -1113,6 +1484,85 @@ int recurrence_max_clusters(int rows, int cols) {
   }
   if (best > 0) remember_cluster_size(1000 + n_tiles, best);
   return best;
+}
+
+bool l4_tail_supported(int rows, int cols) {
+  int n_tiles = 0;
+  if (!recurrence_supported(rows, cols, &n_tiles, nullptr)) return false;
+  const Layout L = make_layout(rows, cols);
+  return make_tail_layout(L).total <= kSmemBudget;
+}
+
+int launch_l4_tail(const L4TailArgs& a, cudaStream_t stream) {
+  if (a.n <= 0) return 0;
+  int n_tiles = 0;
+  if (!l4_tail_supported(a.rows, a.cols) || !recurrence_supported(a.rows, a.cols, &n_tiles, nullptr)) {
+    set_error("launch_l4_tail: shape not supported");
+    return -1;
+  }
+  const Layout L = make_layout(a.rows, a.cols);
+  const size_t smem = make_tail_layout(L).total;
+  const void* f = reinterpret_cast<const void*>(&l4_tail_kernel);
+  if (int rc = ensure_func_smem(f, smem)) return rc;
+  if (int rc = ensure_func_nonportable_cluster(f)) return rc;
+  TailParams p;
+  p.x0 = a.x0;
+  p.out = a.out;
+  p.out_stride = a.out_stride;
+  for (int i = 0; i < TAIL_LAYERS; ++i) {
+    p.w[i] = a.w[i];
+    p.bias[i] = a.bias[i];
+    if (i < TAIL_LAYERS - 1) {
+      p.gamma[i] = a.gamma[i];
+      p.beta[i] = a.beta[i];
+    }
+  }
+  p.rows = a.rows;
+  p.cols = a.cols;
+  p.n_tiles = n_tiles;
+  const int known = cached_cluster_size(2000 + n_tiles);
+  int candidates[3] = {n_tiles, (n_tiles + 1) & ~1, 16};
+  if (known != 0) candidates[0] = candidates[1] = candidates[2] = known;
+  cudaError_t e = cudaErrorUnknown;
+  for (int c = 0; c < 3; ++c) {
+    const int cs = candidates[c];
+    if (cs < n_tiles || cs > 16) continue;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(cs, a.n, 1);
+    cfg.blockDim = dim3(NT, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    if (known == 0) {
+      int max_clusters = 0;
+      e = cudaOccupancyMaxActiveClusters(&max_clusters, l4_tail_kernel, &cfg);
+      if (e != cudaSuccess || max_clusters < 1) {
+        cudaGetLastError();
+        e = cudaErrorLaunchOutOfResources;
+        continue;
+      }
+    }
+    e = cudaLaunchKernelEx(&cfg, l4_tail_kernel, p);
+    if (e == cudaSuccess) {
+      if (known == 0) remember_cluster_size(2000 + n_tiles, cs);
+      break;
+    }
+    cudaGetLastError();
+  }
+  if (e != cudaSuccess) {
+    set_error(std::string("l4_tail_kernel launch: ") + cudaGetErrorString(e));
+    return -2;
+  }
+  note_launch();
+  return 0;
 }
 
 int launch_recurrence(const RecurrenceArgs& a, cudaStream_t stream) {

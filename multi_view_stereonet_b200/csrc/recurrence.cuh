@@ -21,6 +21,21 @@ struct RecurrenceArgs {
   long long* prof = nullptr;  // optional [16 ranks][12 phases] cycle totals (debug builds of the tests)
 };
 
+// The level-4 tail of FeatureNetwork (six residual blocks + conv_final, multi_view_stereonet.py:119-127) as one
+// cluster kernel per image (recurrence.cu: l4_tail_kernel); weights in the split-fp16 block format of conv_tc.cu.
+struct L4TailArgs {
+  const float* x0;        // [n][rows*cols][32]: conv3 output
+  float* out;             // image i at out + i * out_stride
+  long long out_stride;
+  const uint8_t* w[7];    // res0..res5, conv_final
+  const float* bias[7];
+  const float* gamma[6];
+  const float* beta[6];
+  int n, rows, cols;
+};
+bool l4_tail_supported(int rows, int cols);
+int launch_l4_tail(const L4TailArgs& a, cudaStream_t stream);
+
 void pack_recurrence_weights(const float* w0_oihw35, const float* w1_oihw32, const float* w2_oihw32,
                              std::vector<uint8_t>* out);
 // Gather plan of all steps (needs only the incremental homographies): floats per (image, hypothesis) = 4 * stride.
