@@ -132,8 +132,12 @@ B200MVS_API int b200mvs_set_debug(b200mvs_net* net, int keep_stages);
 /* Options: "tensor_cores" (default 1) -- run the 3x3 32->32 refiner convolutions of levels 0-2 on the
  * tcgen05 tensor cores with fp16 operands / fp32 accumulation; 0 keeps every layer on the fp32 path.
  * A/B switches of the schedule (all default 1, results unchanged up to float32 rounding): "warp_specialized",
- * "half_activations", "pdl", "overlap", "conv0_precompute", "left_late", "early_d2h"; debugging: "recurrence_debug",
- * "recurrence_profile", "stage_profile" (see b200mvs_last_stage_profile). */
+ * "half_activations", "pdl", "overlap", "conv0_precompute", "left_late", "early_d2h", "l4_chain" (the level-4 tail of
+ * the feature network as one cluster kernel per image); "lanes" (upper bound on concurrent sub-batches, default 1),
+ * "precise_refiners", "prio_main" (default 0: single-lane forwards on a high-priority stream of the library's own);
+ * debugging: "recurrence_debug", "recurrence_profile" (phase totals and a per-warp timeline of one step, read back
+ * with b200mvs_get_stage "recurrence_profile" / "recurrence_trace"), "stage_profile" (see
+ * b200mvs_last_stage_profile). */
 B200MVS_API int b200mvs_set_option(b200mvs_net* net, const char* name, int value);
 
 /* Stage entry for kernel parity tests: y = conv3x3(x, dilation, padding = dilation) + bias on a
