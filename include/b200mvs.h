@@ -123,6 +123,8 @@ B200MVS_API const char* b200mvs_last_stage_profile(const b200mvs_net* net);
  *   "left_feature1".."left_feature4" (B,H_l,W_l,32 channels-last)
  *   "right_feature_volume" (B*V,D,h4,w4,32 channels-last, unmasked; only valid if kept, see
  *    b200mvs_set_debug)      "cost_filtered" (B*V,D,h4,w4)    "idepth4_raw_views" (B*V,h4,w4)
+ *   "recurrence_flags" (B*V,17) i32: [16] != 0 when some tap of the sweep's incremental warp lies outside the shared-
+ *    memory window of the CTA that gathers it (those taps are read from global memory behind the progress flags [0..15])
  * Image index n = b*V + v. */
 B200MVS_API int b200mvs_get_stage(b200mvs_net* net, const char* name, void* dst, int64_t capacity, int64_t* nbytes,
                       void* stream);

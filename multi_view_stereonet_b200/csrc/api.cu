@@ -1828,6 +1828,7 @@ B200MVS_API int b200mvs_get_stage(b200mvs_net* net, const char* name, void* dst,
   else if (k == "cost_filtered") { src = ws.cost1; bytes = n * D * L.px[4] * 4; }
   else if (k == "idepth4_raw_views") { src = ws.raw_views; bytes = n * L.px[4] * 4; }
   else if (k == "recurrence_profile" && net->rec_prof != nullptr) { src = net->rec_prof; bytes = 16 * 12 * 8; }
+  else if (k == "recurrence_flags" && ws.rec_flags != nullptr) { src = ws.rec_flags; bytes = n * 17 * 4; }
   else if (k == "recurrence_trace" && net->rec_prof != nullptr) { src = net->rec_prof + 16 * 12; bytes = 16 * 16 * 32 * 8; }
   else {
     set_error("b200mvs_get_stage: unknown stage '" + k + "'");

@@ -70,7 +70,7 @@ def _rot_x(a):
 PITCH_RAD = 0.01174
 
 
-def make_inputs(rows, cols, views, batch, seed=1234, first_item=0, smooth=False, pitch=None):
+def make_inputs(rows, cols, views, batch, seed=1234, first_item=0, smooth=False, pitch=None, translation=None):
     """Returns the tensors `MultiViewStereoNet.forward` takes, on the CPU.
 
     Item i of the batch is generated from `seed + first_item + i`, so a rank that
@@ -79,7 +79,8 @@ def make_inputs(rows, cols, views, batch, seed=1234, first_item=0, smooth=False,
     smooth=True low-pass filters the images so that neighbouring views correlate
     (uniform noise makes every hypothesis equally bad); parity tests use both.
     pitch overrides PITCH_RAD (tests also run SURVEY.md's original 0.01 rad, whose geometry has knife-edge mask
-    pixels).
+    pixels).  translation overrides the first comparison view's (0.30, 0.05, 0.02), e.g. a forward / vertical motion whose
+    incremental warp between consecutive hypotheses moves corner pixels by more than one row at 1/16 scale.
     """
     pitch = PITCH_RAD if pitch is None else pitch
     lefts, rights = [], [[] for _ in range(views)]
@@ -110,6 +111,8 @@ def make_inputs(rows, cols, views, batch, seed=1234, first_item=0, smooth=False,
         sgn = (-1.0) ** v
         R = _rot_y(0.02 * (v + 1) * sgn) @ _rot_x(pitch)
         t = torch.tensor([0.30 * (v + 1) * sgn, 0.05, 0.02 * (v + 1)], dtype=torch.float64)
+        if translation is not None:
+            t = torch.tensor(translation, dtype=torch.float64) * (v + 1) * torch.tensor([sgn, 1.0, 1.0], dtype=torch.float64)
         T = torch.eye(4, dtype=torch.float64)
         T[:3, :3] = R
         T[:3, 3] = t

@@ -200,6 +200,43 @@ def test_flag_variants(net, gta_state):
         _assert_report(rep)
 
 
+def test_large_incremental_motion_leaves_the_sweep_window(net, gta_state):
+    """Forward + vertical camera motion: between consecutive hypotheses the corner pixels of the 1/16-scale image move
+    by more than one row, so some taps of the depth sweep's warp lie outside the CTA's shared-memory window
+    (recurrence.cu).  gather_plan_kernel must raise the per-(group, view) flag and the sweep must read those taps
+    from global memory behind the progress flags; the ordinary geometry must not raise it."""
+    from tests._gpu_util import run_case
+    inputs = synthetic.make_inputs(512, 640, 2, 1, smooth=True, translation=(0.02, 0.22, 0.30))
+    rep, _, _ = run_case(net, gta_state, inputs, 24, stages=False)
+    _assert_report(rep)
+    flags = net.get_stage("recurrence_flags", torch.int32).view(-1, 17).cpu()
+    assert int(flags[:, 16].max()) == 1, flags
+    assert int(flags[:, :11].min()) >= 22          # every CTA published up to the second-to-last hypothesis
+    with torch.no_grad():
+        net(*synthetic.to_device(synthetic.make_inputs(512, 640, 1, 1), "cuda"), 64, True, [True] * 5)
+    flags = net.get_stage("recurrence_flags", torch.int32).view(-1, 17).cpu()
+    assert int(flags[:, 16].max()) == 0 and int(flags[:, :16].max()) == 0, flags
+
+
+def test_l4_chain_matches_per_layer_kernels(net):
+    """The level-4 tail of the feature network as one cluster kernel (option l4_chain, default) against the seven
+    per-layer launches: same arithmetic (split-fp16 MMAs, fp32 accumulation), different statistics summation order."""
+    inputs = synthetic.to_device(synthetic.make_inputs(512, 640, 2, 2, smooth=True), "cuda")
+    with torch.no_grad():
+        a = net(*inputs, 64, True, [True] * 5)
+        na = net.last_launch_count()
+        net.set_option("l4_chain", 0)
+        try:
+            b = net(*inputs, 64, True, [True] * 5)
+            nb = net.last_launch_count()
+        finally:
+            net.set_option("l4_chain", 1)
+    assert nb - na == 12, (na, nb)                 # two feature networks x (7 launches -> 1)
+    for lvl in range(5):
+        assert rel_linf(a["left_idepthmap_pyr"][lvl].cpu(), b["left_idepthmap_pyr"][lvl].cpu()) <= REL_LINF_TOL / 4
+        assert bool((a["left_idepthmap_mask_pyr"][lvl] == b["left_idepthmap_mask_pyr"][lvl]).all())
+
+
 def test_cfg3_item_multiview(net, gta_state):
     """One image group of BASELINE cfg3 (4 comparison views, 64 hypotheses) against the oracle, and a batch of
     two groups: items are independent, so item 0 of the batch must reproduce the batch-1 run of the same item.
