@@ -322,8 +322,10 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
           atomicAdd(p.out_stats + (size_t)n * 2 * kGroups + tid, s_stats[tid]);
           s_stats[tid] = 0.0;
         }
-        // (no warp can reach the next segment's statistics before these threads are through: every staged slice of
-        //  that segment needs an arrival of this warp, which comes after the lines above in program order)
+        // No warp can reach the next segment's statistics before these threads are through (every staged slice of that
+        // segment needs an arrival of this warp, which comes after the lines above in program order); the barrier makes
+        // that explicit for compute-sanitizer's racecheck, once per segment.
+        worker_barrier();
       }
       sc += (uint32_t)dcount + 2u;
       oc += (uint32_t)dcount;
