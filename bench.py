@@ -445,7 +445,7 @@ def run_ours(args, rank, world, local_rank):
         # = one fp32 read + one fp32 write of a (B, 512, 640, 32) activation
         k_bytes = B * P[0] * 64 * 4
         traffic = None
-        tpath = os.path.join(REPO, "profiles", "r1_traffic.json")
+        tpath = os.path.join(REPO, "profiles", "r2_traffic.json")
         if os.path.exists(tpath) and B == 1:
             # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel from the committed ncu --set full capture
             traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")
