@@ -233,7 +233,8 @@ def test_l4_chain_matches_per_layer_kernels(net):
             net.set_option("l4_chain", 1)
     assert nb - na == 12, (na, nb)                 # two feature networks x (7 launches -> 1)
     for lvl in range(5):
-        assert rel_linf(a["left_idepthmap_pyr"][lvl].cpu(), b["left_idepthmap_pyr"][lvl].cpu()) <= REL_LINF_TOL / 4
+        # (float32 statistics summed in a fixed tree vs float64 atomics: ~1e-6 per layer, amplified by the 63-step sweep)
+        assert rel_linf(a["left_idepthmap_pyr"][lvl].cpu(), b["left_idepthmap_pyr"][lvl].cpu()) <= REL_LINF_TOL / 2
         assert bool((a["left_idepthmap_mask_pyr"][lvl] == b["left_idepthmap_mask_pyr"][lvl]).all())
 
 
