@@ -19,13 +19,16 @@
 // conv_tc.cu).  The 1/16-scale stages need ~fp32 operand accuracy, so every
 // operand is split x = hi + lo into two fp16 values and each k-step issues the three products
 // (hi*hi + lo*hi + hi*lo) as two MMAs, fp32 accumulation in TMEM: ~22 significant bits.
-// GroupNorm needs whole-image statistics twice per step: every warp pushes its partial sums into every CTA's
-// shared memory and the raw conv outputs of the PW+1 positions next to a tile boundary into the neighbour CTA's
-// halo buffer with st.async, which completes bytes on the RECEIVER's mbarrier; each CTA waits for its own expected
-// byte count (no cluster-wide barrier) and normalises its tile plus halo locally.  One cluster barrier per step
-// publishes the new hypothesis; the next step's gather source (own tile + halo + margin, a contiguous pixel
-// range) is then pulled into shared memory by one 1-D TMA bulk copy and gathered from there.
-// All weights (hi and lo, three layers, 108 KB) stay resident in shared memory for all steps.
+// GroupNorm needs whole-image statistics twice per step: every CTA pushes its (sum, sumsq) per channel group into
+// every CTA's shared memory with st.async, and the raw conv outputs of the PW + 1 positions next to a tile boundary go to
+// the neighbour CTA as one bulk shared::cta -> shared::cluster copy; both complete BYTES ON THE RECEIVER'S mbarrier,
+// so each CTA waits for its own expected byte count (no cluster-wide barrier) and normalises its tile plus halo
+// locally.  The previous hypothesis -- the gather source of the next step -- lives in a position-indexed shared-memory
+// window that is filled where the data is produced: own rows by the CTA's last epilogue, side rows by the neighbours'
+// bulk copies; global memory only receives the result (and serves taps that leave the window, behind progress flags).
+// The gather plan of every step (taps, bilinear weights) depends on the cameras only and is precomputed
+// (gather_plan_kernel).  All weights (hi and lo, three layers, 108 KB) stay resident in shared memory for all steps.
+// The level-4 tail of the feature network (l4_tail_kernel, below) reuses the same decomposition.
 #include <cuda_fp16.h>
 
 #include <cstdio>
@@ -73,19 +76,6 @@ __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_
       : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
 
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
@@ -100,14 +90,6 @@ __device__ __forceinline__ uint32_t map_to_rank(uint32_t local_saddr, uint32_t r
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_saddr), "r"(rank));
   return r;
-}
-__device__ __forceinline__ void st_cluster_f4(uint32_t raddr, float4 v) {
-  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "f"(v.x), "f"(v.y), "f"(v.z),
-               "f"(v.w)
-               : "memory");
-}
-__device__ __forceinline__ void st_cluster_f1(uint32_t raddr, float v) {
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(raddr), "f"(v) : "memory");
 }
 
 // x = hi + lo with both halves fp16 (round to nearest): ~22 significant bits.
@@ -207,17 +189,6 @@ struct RecParams {
                          // fences before the MMAs, 16 no halo exchange
 };
 
-// 8 consecutive fp32 accumulator columns of this thread's TMEM lane.
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
-  uint32_t r[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr)
-               : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
 
 // Two 8-column slices of this thread's TMEM lane (the hi*hi+lo*hi and hi*lo accumulators): both loads in flight,
 // one wait.
@@ -271,13 +242,6 @@ __device__ __forceinline__ void issue_conv_mmas(uint64_t da_hi0, uint64_t da_lo0
   }
 }
 
-// Remote shared-memory store that signals `bytes stored` on an mbarrier of the destination CTA: the receiver
-// waits for its expected byte count instead of the whole cluster meeting at a barrier.
-__device__ __forceinline__ void st_async_f4(uint32_t raddr, float4 v, uint32_t rbar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
-               "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(rbar)
-               : "memory");
-}
 __device__ __forceinline__ void st_async_f2(uint32_t raddr, float2 v, uint32_t rbar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(raddr),
                "f"(v.x), "f"(v.y), "r"(rbar)
@@ -292,11 +256,6 @@ __device__ __forceinline__ float4* swz_ptr(float* base, int row, int chunk) {
 __device__ __forceinline__ const float4* swz_ptr(const float* base, int row, int chunk) {
   return reinterpret_cast<const float4*>(base + (size_t)row * 32 + (size_t)((chunk ^ (row & 7)) << 2));
 }
-__device__ __forceinline__ void st_async_f1(uint32_t raddr, float v, uint32_t rbar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(raddr), "f"(v),
-               "r"(rbar)
-               : "memory");
-}
 __device__ __forceinline__ void mbar_arm_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -310,21 +269,6 @@ __device__ __forceinline__ void mbar_wait_cta(uint64_t* bar, uint32_t parity) {
         "{\n\t"
         ".reg .pred q;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, q;\n\t"
-        "}\n"
-        : "=r"(done)
-        : "r"(a), "r"(parity)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  const uint32_t a = smem_u32(bar);
-  uint32_t done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred q;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 q, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, q;\n\t"
         "}\n"
         : "=r"(done)
@@ -348,14 +292,16 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, ui
 }
 
 // Per-step schedule of one CTA (one 128-position M-tile of one view):
-//   T   one lane: TMA bulk copy of the previous hypothesis' pixels [q_lo, q_lo + count) into shared memory
-//   W   gather-warp from shared memory (plan computed during the previous step; taps outside the staged range
-//       fall back to global memory) -> split-fp16 conv0 operand
-//   MMA0 | E0: raw output + image half -> st.async pushes of boundary rows to the neighbours and of the GroupNorm
-//             partial sums to every CTA, each completing bytes on the receiver's mbarrier
-//   wait own mbarrier | S1: normalise own + halo -> operand | MMA1 (meanwhile: next step's gather plan)
-//   E1 / wait / S2 | MMA2 | E2: features = warped + delta -> global
-//   one cluster barrier: hypothesis `step` is published, exchange buffers are free again
+//   W    wait for the neighbours' rows of the previous hypothesis (bulk copies into the window's side rows), gather
+//        own + halo positions from the window (plan loaded during the previous step; taps outside the window: global
+//        memory) -> split-fp16 conv0 operand
+//   MMA0 | E0: raw output + image half -> (sum, sumsq) per group to every CTA (st.async), boundary rows to the two
+//        neighbours (one bulk copy each), each completing bytes on the receiver's mbarriers
+//   wait for the statistics | S1: coefficients, normalise own rows, wait for the boundary rows, normalise the halo
+//        -> operand | MMA1 | E1 / wait / S2 | MMA2
+//   E2   features = warped + delta -> own rows of the window; first / last wm rows -> the neighbours' windows (bulk
+//        copies); the tile -> global memory as coalesced 16-byte chunks; next step's plan loads
+// No cluster-wide barrier inside the loop: every wait is on bytes that land in this CTA's own shared memory.
 template <bool PROF>
 __global__ void __launch_bounds__(NT_ALL, 1) recurrence_kernel(const RecParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -493,7 +439,6 @@ __global__ void __launch_bounds__(NT_ALL, 1) recurrence_kernel(const RecParams p
   // Gather tasks of this thread, fixed for all steps: (local input position l, channel octet).  The four lanes of
   // a quad share the position and take one octet each.
   const int t_oct = tid & 3;  // NT % 4 == 0: the octet is the same for every task of a thread
-  const int sw = (tid >> 2) & 1;   // which 16-byte half of the octet is read first (shared-memory bank spread)
   int t_l[MAX_TASKS];
 #pragma unroll
   for (int k = 0; k < MAX_TASKS; ++k) t_l[k] = (tid + k * NT) >> 2;
