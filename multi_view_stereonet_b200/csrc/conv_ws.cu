@@ -121,8 +121,13 @@ __global__ void __launch_bounds__(NT, 1) conv3x3_ws_kernel(const WsParams p, con
   constexpr int ACC_COLS = MT * 32;      // TMEM columns of one accumulator set
   constexpr uint32_t TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t s_raw[MAX_RING], s_rfree[MAX_RING], s_full[MAX_STAGES], s_empty[MAX_STAGES], s_tfull[2],
-      s_tempty[2];
+  // s_full / s_tfull are per M-tile: an M-tile's MMAs start when the chunks under its three tap rows are transformed
+  // (not the whole tile), and its epilogue when ITS MMAs have completed -- the tile's pipeline fill shrinks from
+  // (transform + MMA + epilogue) of a tile to roughly that of one M-tile
+  constexpr int MAX_MT = 4;
+  static_assert(MT <= MAX_MT, "tile height");
+  __shared__ __align__(8) uint64_t s_raw[MAX_RING], s_rfree[MAX_RING], s_full[MAX_STAGES][MAX_MT], s_empty[MAX_STAGES],
+      s_tfull[2][MAX_MT], s_tempty[2];
   __shared__ __align__(8) uint64_t s_wbar;   // bulk copy of the weights
   __shared__ float s_bias[kC];
   __shared__ uint32_t s_tmem;
@@ -168,11 +173,11 @@ __global__ void __launch_bounds__(NT, 1) conv3x3_ws_kernel(const WsParams p, con
       tc::mbar_init(&s_rfree[q], NXF_T);
     }
     for (int s = 0; s < MAX_STAGES; ++s) {
-      tc::mbar_init(&s_full[s], NXF_T);
+      for (int m = 0; m < MAX_MT; ++m) tc::mbar_init(&s_full[s][m], NXF_T);
       tc::mbar_init(&s_empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
-      tc::mbar_init(&s_tfull[a], 1);
+      for (int m = 0; m < MAX_MT; ++m) tc::mbar_init(&s_tfull[a][m], 1);
       tc::mbar_init(&s_tempty[a], N_EPI * 32);
     }
     tc::mbar_init(&s_wbar, 1);
@@ -272,9 +277,12 @@ __global__ void __launch_bounds__(NT, 1) conv3x3_ws_kernel(const WsParams p, con
           q = 0;
           qph ^= 1u;
         }
+        // M-tile mt reads tile rows 2 mt .. 2 mt + 1 + 2 vs, i.e. chunks up to mt + vs: complete with this chunk
+        if (c >= vs) {
+          tc::fence_proxy_async();
+          mbar_arrive(&s_full[s][c - vs]);
+        }
       }
-      tc::fence_proxy_async();
-      mbar_arrive(&s_full[s]);
       WS_STAMP(xw == 0 && lane == 0, 2);
     }
   } else if (warp == N_EPI + 1) {
@@ -317,24 +325,26 @@ __global__ void __launch_bounds__(NT, 1) conv3x3_ws_kernel(const WsParams p, con
         const int a = it & 1;
         const uint32_t aph = (uint32_t)((it >> 1) & 1);
         tc::mbar_wait(&s_tempty[a], aph ^ 1u);   // the epilogue has drained this accumulator set
-        tc::mbar_wait(&s_full[s], ph);           // the transform warps have finished this stage
-        WS_STAMP(true, 3);
-        tc::fence_after_sync();
         const uint64_t da = da0 + (uint64_t)(s * (stage_bytes >> 4));
 #pragma unroll 1
-        for (int mt = 0; mt < ((p.dbg & 2) ? 0 : MT); ++mt) {
+        for (int mt = 0; mt < MT; ++mt) {
+          tc::mbar_wait(&s_full[s][mt], ph);     // the transform warps have finished the rows under this M-tile
+          if (mt == 0) WS_STAMP(true, 3);
+          tc::fence_after_sync();
           const uint32_t dcol = tmem_base + (uint32_t)(a * ACC_COLS + mt * 32);
+          if (!(p.dbg & 2)) {
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const uint32_t pos = (uint32_t)(mt * 128 + (tap / 3) * vs * PW + (tap % 3) * d);
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint32_t pos = (uint32_t)(mt * 128 + (tap / 3) * vs * PW + (tap % 3) * d);
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks)
-              tc::mma_f16(dcol, da + (uint64_t)(2u * ks * plane_u16 + pos), db0 + (uint64_t)((tap * 2 + ks) * 64),
-                          tc::idesc_f16(32), (tap | ks) != 0 ? 1u : 0u);
+              for (int ks = 0; ks < 2; ++ks)
+                tc::mma_f16(dcol, da + (uint64_t)(2u * ks * plane_u16 + pos), db0 + (uint64_t)((tap * 2 + ks) * 64),
+                            tc::idesc_f16(32), (tap | ks) != 0 ? 1u : 0u);
+            }
           }
+          tc::mma_commit(&s_tfull[a][mt]);       // this M-tile's accumulators are complete
         }
         tc::mma_commit(&s_empty[s]);
-        tc::mma_commit(&s_tfull[a]);
         WS_STAMP(true, 4);
       }
     }
@@ -374,11 +384,11 @@ __global__ void __launch_bounds__(NT, 1) conv3x3_ws_kernel(const WsParams p, con
         flush(cur_img);
         cur_img = img;
       }
-      tc::mbar_wait_warp(&s_tfull[a], aph);
-      tc::fence_after_sync();
-      WS_STAMP(tid == 0, 5);
 #pragma unroll 1
       for (int mt = mth; mt < MT; mt += N_EPI / 4) {
+        tc::mbar_wait_warp(&s_tfull[a][mt], aph);
+        tc::fence_after_sync();
+        if (mt == mth) WS_STAMP(tid == 0, 5);
         const int j = mt * 128 + wq * 32 + lane;
         const int oy = y_out0 + rs * (j / PW), ox_t = j % PW, ox = tx0 + ox_t;
         const bool valid = ox_t < TW && ox < p.W && oy < p.H;
