@@ -495,7 +495,8 @@ bool plan_for(int dil, int H, int W, int n_img, WsPlan* plan) {
     if (force >= 0 && k < force && dil >= 4) continue;
     // worth it only when every SM gets at least one tile; smaller layers are latency bound either way
     const long long rows_tiles = poly ? (long long)dil * cdiv(cdiv(H, dil), c.th) : cdiv(H, c.th);
-    if ((long long)cdiv(W, PW - 2 * dil) * rows_tiles * n_img < 148) continue;
+    static const int min_tiles = getenv("B200MVS_WS_MIN_TILES") ? atoi(getenv("B200MVS_WS_MIN_TILES")) : 148;   // A/B
+    if ((long long)cdiv(W, PW - 2 * dil) * rows_tiles * n_img < min_tiles) continue;
     if (W_BYTES + ring_bytes(c.ring) + (size_t)c.stages * ws_stage_bytes(c.th, vs, dil) <= kSmemBudget) {
       *plan = c;
       return true;
