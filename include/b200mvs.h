@@ -135,7 +135,8 @@ B200MVS_API int b200mvs_set_debug(b200mvs_net* net, int keep_stages);
  * tcgen05 tensor cores with fp16 operands / fp32 accumulation; 0 keeps every layer on the fp32 path.
  * A/B switches of the schedule (all default 1, results unchanged up to float32 rounding): "warp_specialized",
  * "half_activations", "pdl", "overlap", "conv0_precompute", "left_late", "early_d2h", "l4_chain" (the level-4 tail of
- * the feature network as one cluster kernel per image); "lanes" (upper bound on concurrent sub-batches, default 1),
+ * the feature network as one cluster kernel per image); "lanes" (0 = automatic, the default: a call is split into two concurrent sub-batches when the last
+ * round of the depth sweep's clusters would be nearly empty; 1 = never; 2 = whenever the sweep needs more than one round),
  * "precise_refiners", "prio_main" (default 0: single-lane forwards on a high-priority stream of the library's own);
  * debugging: "recurrence_debug", "recurrence_profile" (phase totals and a per-warp timeline of one step, read back
  * with b200mvs_get_stage "recurrence_profile" / "recurrence_trace"), "stage_profile" (see

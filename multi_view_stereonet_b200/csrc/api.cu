@@ -232,8 +232,8 @@ struct b200mvs_net {
 
   Lane lanes[kMaxLanes];
   Lane* cur = &lanes[0];          // the lane whose kernels are being enqueued (host enqueue is sequential)
-  int lanes_max = 1;              // option "lanes": upper bound on concurrent lanes (1 = never split a call; default:
-                                  // measured slower than one batched call on B200)
+  int lanes_max = 0;              // option "lanes": 0 = automatic (plan_lanes), 1 = never split a call, 2 = up to two
+                                  // concurrent lanes whenever the sweep needs more than one round of clusters
   int last_lanes = 1;
   cudaEvent_t ev_begin = nullptr;
   Probe probe;
@@ -1247,9 +1247,14 @@ int forward_impl(b200mvs_net* net, Lane& lane, bool sweep_on_own_stream, const b
 // How many lanes a call runs as: 1 unless the depth sweep of its B * V (image group, view) pairs needs more than one
 // round of clusters -- then enough lanes that the first ones are through their sweep while the others still hold
 // clusters (whole image groups per lane, at most lanes_max).
+// lanes_max = 0 (default) decides by measurement: two lanes exactly when the sweep's last round would hold one or two
+// clusters (batch 8 with one view on B200: 7 clusters are co-resident, the 8th ran alone for 0.6 ms; as two lanes of
+// four groups the lonely cluster overlaps the other lane's cost filter and refiners: 5.15 -> 5.01 ms).  With fuller
+// rounds two lanes lose (batch 8 with 2 / 4 views: 6.76 -> 7.42 ms, 9.94 -> 11.2 ms; batch 16: 9.64 -> 10.2 ms).
 int plan_lanes(const b200mvs_net* net, const b200mvs_shape& s) {
-  if (net->lanes_max <= 1 || !net->use_tensor_cores || !net->overlap || net->keep_stages || net->stage_profile ||
-      net->probe.tag != 0 || net->rec_prof != nullptr || s.batch < 2)
+  const bool automatic = net->lanes_max == 0;
+  if ((!automatic && net->lanes_max <= 1) || !net->use_tensor_cores || !net->overlap || net->keep_stages ||
+      net->stage_profile || net->probe.tag != 0 || net->rec_prof != nullptr || s.batch < 2)
     return 1;
   static const bool sprof_env = getenv("B200MVS_STAGE_PROFILE") != nullptr;
   if (sprof_env) return 1;
@@ -1258,6 +1263,7 @@ int plan_lanes(const b200mvs_net* net, const b200mvs_shape& s) {
   const int maxc = recurrence_max_clusters(L.h[4], L.w[4]);
   const int pairs = s.batch * s.views;
   if (maxc < 1 || pairs <= maxc) return 1;
+  if (automatic) return (pairs - maxc <= 2 && pairs <= 2 * maxc) ? 2 : 1;
   int want = (pairs + maxc - 1) / maxc;
   if (want > net->lanes_max) want = net->lanes_max;
   if (want > s.batch) want = s.batch;
@@ -1299,7 +1305,7 @@ B200MVS_API int b200mvs_create(int device, int num_tensors, const char* const* n
   for (int i = 0; i < num_tensors; ++i) sd.t[names[i]] = {data[i], numels[i]};
   b200mvs_net* net = new b200mvs_net();
   net->device = device;
-  if (const char* env = getenv("B200MVS_LANES")) net->lanes_max = atoi(env) < 1 ? 1 : (atoi(env) > kMaxLanes ? kMaxLanes : atoi(env));
+  if (const char* env = getenv("B200MVS_LANES")) net->lanes_max = atoi(env) < 0 ? 0 : (atoi(env) > kMaxLanes ? kMaxLanes : atoi(env));
   int rc = build_weights(net, sd);
   if (rc == 0) {
     bool ok = true;
@@ -1405,7 +1411,7 @@ B200MVS_API int b200mvs_set_option(b200mvs_net* net, const char* name, int value
     return 0;
   }
   if (k == "lanes") {
-    net->lanes_max = value < 1 ? 1 : (value > kMaxLanes ? kMaxLanes : value);
+    net->lanes_max = value < 0 ? 0 : (value > kMaxLanes ? kMaxLanes : value);
     return 0;
   }
   if (k == "stage_profile") {

@@ -92,18 +92,24 @@ def test_batch8_matches_single_items(net, gta_state):
 
 
 def test_lanes_option_gives_the_same_results(net):
-    """Option "lanes" = 2 (off by default: measured slower) cuts a call whose depth sweep needs more than
-    one round of clusters into two concurrent lanes of whole image groups; results must not change."""
+    """Option "lanes" = 2 cuts a call whose depth sweep needs more than one round of clusters into two concurrent lanes
+    of whole image groups (1 = never; 0 = automatic, the default: two lanes when the last round would hold one or two
+    clusters, e.g. batch 8 with one view); results must not change."""
     inputs = synthetic.to_device(synthetic.make_inputs(512, 640, 1, 8), "cuda")
     try:
         with torch.no_grad():
+            net.set_option("lanes", 1)
             one = net(*inputs, 64, True, [True] * 5)
             n1 = net.last_launch_count()
             net.set_option("lanes", 2)
             two = net(*inputs, 64, True, [True] * 5)
             n2 = net.last_launch_count()
+            net.set_option("lanes", 0)
+            auto = net(*inputs, 64, True, [True] * 5)
+            assert net.last_launch_count() == n2        # 8 pairs, 7 co-resident clusters: the automatic rule splits
+            assert rel_linf(auto["left_idepthmap_pyr"][0].cpu(), two["left_idepthmap_pyr"][0].cpu()) <= REL_LINF_TOL / 2
     finally:
-        net.set_option("lanes", 1)
+        net.set_option("lanes", 0)
     assert n2 == 2 * n1
     for lvl in range(5):
         assert rel_linf(two["left_idepthmap_pyr"][lvl].cpu(), one["left_idepthmap_pyr"][lvl].cpu()) <= REL_LINF_TOL / 2
