@@ -196,6 +196,15 @@ def test_stagewise_vs_oracle(rows, cols, views, hyps, batch, smooth, net, gta_st
     assert rep["left_feature4"] <= 1e-4
 
 
+@pytest.mark.parametrize("rows,cols,hyps", [(64, 80, 2), (96, 128, 3), (256, 320, 2)])
+def test_minimal_hypothesis_counts(rows, cols, hyps, net, gta_state):
+    """Two hypotheses are the smallest sweep the reference supports (one step: no hand-off between CTAs ever happens,
+    the last-step paths of the persistent kernel run first); three add exactly one hand-off."""
+    from tests._gpu_util import run_case
+    rep, _, _ = run_case(net, gta_state, synthetic.make_inputs(rows, cols, 1, 1, smooth=True), hyps, stages=False)
+    _assert_report(rep)
+
+
 def test_flag_variants(net, gta_state):
     """do_cost_volume_filter=False and partially disabled refiners, including the
     reference's double baseline division when do_refiners[4] is False."""
