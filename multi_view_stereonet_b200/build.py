@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libb200mvs.so")
-SOURCES = ["api.cu", "conv.cu", "conv_tc.cu", "conv_ws.cu", "conv5_tc.cu", "cvf_tc.cu", "geom.cu", "recurrence.cu", "misc.cu", "tail.cu", "reproject.cu", "evalpost.cu"]
+SOURCES = ["api.cu", "conv.cu", "conv_tc.cu", "conv_ws.cu", "conv5_tc.cu", "cvf_tc.cu", "geom.cu", "recurrence.cu", "sweep_wide.cu", "misc.cu", "tail.cu", "reproject.cu", "evalpost.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

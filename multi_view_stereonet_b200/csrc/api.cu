@@ -167,6 +167,7 @@ struct Workspace {
   float* imgconv = nullptr;
   float* rec_plan = nullptr;   // gather plan of the persistent sweep, [n][D][recurrence_plan_stride][4]
   int* rec_flags = nullptr;    // [n][17] progress / out-of-window flags of the persistent sweep
+  WideScratch wide{nullptr, nullptr, nullptr, nullptr};   // scratch of the wide sweep (sweep_wide.cu)
   float *vol = nullptr, *wf = nullptr, *wimg = nullptr, *sy0 = nullptr, *sx0 = nullptr, *sy1 = nullptr;
   // cost volume
   float *cost = nullptr, *cvfA = nullptr, *cost1 = nullptr;
@@ -254,6 +255,8 @@ struct b200mvs_net {
   bool left_late = true;          // left feature network waits for the right one (side stream)
   bool conv0_precompute = true;   // refiner conv0 = precomputed guide part + idepth part (tail.cu)
   int rec_debug = 0;
+  int sweep_mode = 0;             // option "sweep": 0 = cluster kernel where the image fits one cluster, else the wide
+                                  // kernel; 1 = wide kernel wherever it is supported; 2 = step by step (a launch per layer)
   // Side stream for the work that does not depend on the comparison views (left feature network) or that
   // nothing downstream waits for (mask upsampling): forked / joined with events inside one forward.
   cudaEvent_t ev_coarse = nullptr;
@@ -521,9 +524,17 @@ void layout(b200mvs_net* net, const b200mvs_shape& s, bool dry) {
   }
   W.vol = A.take<float>(n * D * L.px[4] * kC);
   W.imgconv = A.take<float>(n * D * L.px[4] * kC);
-  if (recurrence_supported(L.h[4], L.w[4], nullptr, nullptr))
+  if (recurrence_supported(L.h[4], L.w[4], nullptr, nullptr) || sweep_wide_supported(L.h[4], L.w[4]))
     W.rec_plan = A.take<float>(n * D * (size_t)recurrence_plan_stride(L.h[4], L.w[4]) * 4);
   W.rec_flags = A.take<int>(n * 17);
+  if (sweep_wide_supported(L.h[4], L.w[4])) {
+    size_t wf = 0, y = 0, part = 0, ctr = 0;
+    sweep_wide_scratch(L.h[4], L.w[4], (int)n, &wf, &y, &part, &ctr);
+    W.wide.wf = A.take<float>(wf);
+    W.wide.y = A.take<float>(y);
+    W.wide.part = A.take<float>(2 * part);
+    W.wide.ctr = A.take<unsigned>(ctr);
+  }
   W.wf = A.take<float>(n * L.px[4] * kC);
   W.wimg = A.take<float>(n * 3 * L.px[4]);
   W.sy0 = A.take<float>(n * L.px[4] * kC);
@@ -938,7 +949,9 @@ int forward_impl(b200mvs_net* net, Lane& lane, bool sweep_on_own_stream, const b
 
   // 1b. image half of FeatureRefiner.conv0 for every hypothesis (needs only the homographies and the 1/16-scale
   //     comparison images): first thing on the side stream, the recurrence waits for it
-  const bool persistent = net->use_tensor_cores && recurrence_supported(h4, w4, nullptr, nullptr);
+  const bool cluster_sweep = net->use_tensor_cores && net->sweep_mode == 0 && recurrence_supported(h4, w4, nullptr, nullptr);
+  const bool wide_sweep = net->use_tensor_cores && !cluster_sweep && net->sweep_mode != 2 && sweep_wide_supported(h4, w4);
+  const bool persistent = cluster_sweep || wide_sweep;
   if (persistent) {
     if (overlap) {
       B200MVS_CUDA_OK(cudaEventRecord(net->cur->ev_geo, stream));
@@ -1037,7 +1050,11 @@ int forward_impl(b200mvs_net* net, Lane& lane, bool sweep_on_own_stream, const b
     ra.cols = w4;
     ra.prof = net->rec_prof;
     ra.debug = net->rec_debug;
-    if (sweep_on_own_stream) {
+    if (wide_sweep) {
+      probe_before(TAG_RECURRENCE, stream);
+      RC(launch_sweep_wide(ra, ws.wide, stream));
+      probe_after(TAG_RECURRENCE, stream);
+    } else if (sweep_on_own_stream) {
       // several lanes in flight: the sweep's cluster launch goes through the lane's high-priority stream, so that
       // its clusters are placed as soon as a GPC can take them, ahead of the other lanes' pending thread blocks
       B200MVS_CUDA_OK(cudaEventRecord(lane.ev_rec_in, stream));
@@ -1254,8 +1271,8 @@ int forward_impl(b200mvs_net* net, Lane& lane, bool sweep_on_own_stream, const b
 int plan_lanes(const b200mvs_net* net, const b200mvs_shape& s) {
   const bool automatic = net->lanes_max == 0;
   if ((!automatic && net->lanes_max <= 1) || !net->use_tensor_cores || !net->overlap || net->keep_stages ||
-      net->stage_profile || net->probe.tag != 0 || net->rec_prof != nullptr || s.batch < 2)
-    return 1;
+      net->stage_profile || net->probe.tag != 0 || net->rec_prof != nullptr || s.batch < 2 || net->sweep_mode != 0)
+    return 1;   // (the wide sweep is a cooperative grid: never two of them in flight)
   static const bool sprof_env = getenv("B200MVS_STAGE_PROFILE") != nullptr;
   if (sprof_env) return 1;
   const Levels L = levels_of(s);
@@ -1424,6 +1441,10 @@ B200MVS_API int b200mvs_set_option(b200mvs_net* net, const char* name, int value
   }
   if (k == "l4_chain") {
     net->l4_chain = value != 0;
+    return 0;
+  }
+  if (k == "sweep") {
+    net->sweep_mode = value < 0 || value > 2 ? 0 : value;
     return 0;
   }
   if (k == "recurrence_debug") {

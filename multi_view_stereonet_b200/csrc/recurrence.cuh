@@ -44,6 +44,19 @@ int launch_gather_plan(const float* Hinc, int n, int D, int rows, int cols, floa
                        cudaStream_t stream);
 bool recurrence_supported(int rows, int cols, int* n_tiles, size_t* smem_bytes);
 int launch_recurrence(const RecurrenceArgs& a, cudaStream_t stream);
+// The same recurrence for images beyond one cluster (sweep_wide.cu): one cooperative launch, up to five M-tiles per CTA,
+// the chain's CTAs exchange statistics and boundary rows through L2 behind a counter barrier.  Uses the same
+// weights, image half and gather plan as launch_recurrence.
+struct WideScratch {
+  float* wf;       // sizes from sweep_wide_scratch
+  float* y;
+  float* part;     // float2 pairs
+  unsigned* ctr;
+};
+bool sweep_wide_supported(int rows, int cols);
+void sweep_wide_scratch(int rows, int cols, int n, size_t* wf_floats, size_t* y_floats, size_t* part_float2,
+                        size_t* counters);
+int launch_sweep_wide(const RecurrenceArgs& a, const WideScratch& s, cudaStream_t stream);
 // How many of the kernel's clusters can be resident at once on the current device (cudaOccupancyMaxActiveClusters;
 // B200: 7 clusters of 11 CTAs -- one GPC cannot take an 11-CTA cluster); 0 if the shape is not supported.
 int recurrence_max_clusters(int rows, int cols);

@@ -205,6 +205,37 @@ def test_minimal_hypothesis_counts(rows, cols, hyps, net, gta_state):
     _assert_report(rep)
 
 
+@pytest.mark.parametrize("rows,cols,views,hyps,batch", [
+    (512, 640, 1, 16, 1),    # 11 CTAs of one tile each
+    (512, 640, 2, 8, 3),     # 6 chains
+    (96, 128, 1, 5, 1),      # a single CTA
+    (272, 400, 2, 6, 2),     # odd 1/16-scale image (17 x 25)
+])
+def test_wide_sweep_vs_oracle(rows, cols, views, hyps, batch, net, gta_state):
+    """The wide sweep (sweep_wide.cu: one cooperative launch, chain barriers through L2) forced onto shapes the
+    cluster kernel normally takes: same parity bar, and its feature volume agrees with the cluster kernel's far
+    inside that bar (same split-fp16 arithmetic; only the order of the GroupNorm partial sums differs)."""
+    from tests._gpu_util import run_case
+    inputs = synthetic.make_inputs(rows, cols, views, batch, smooth=True)
+    net.keep_stages(True)
+    with torch.no_grad():
+        net(*synthetic.to_device(inputs, torch.device("cuda")), hyps, True, [True] * 5)
+        torch.cuda.synchronize()
+        vol_cluster = net.get_stage("right_feature_volume", torch.float32).clone()
+    net.set_option("sweep", 1)
+    try:
+        rep, _, _ = run_case(net, gta_state, inputs, hyps, stages=True)
+        vol_wide = net.get_stage("right_feature_volume", torch.float32)
+        scale = float(vol_cluster.abs().max())
+        assert float((vol_wide - vol_cluster).abs().max()) <= 2e-4 * scale
+    finally:
+        net.set_option("sweep", 0)
+        net.keep_stages(False)
+    _assert_report(rep)
+    for v in range(views):
+        assert rep[f"v{v}/right_feature_volume"] <= 1e-3
+
+
 def test_flag_variants(net, gta_state):
     """do_cost_volume_filter=False and partially disabled refiners, including the
     reference's double baseline division when do_refiners[4] is False."""
@@ -279,8 +310,8 @@ def test_cfg3_item_multiview(net, gta_state):
 
 def test_cfg5_item_large_image(net, gta_state):
     """One image group of BASELINE cfg5 (1024x1280, 4 comparison views, 128 hypotheses): the 1/16-scale image
-    (64x80 = 41 M-tiles) is beyond the persistent recurrence kernel's cluster, so this exercises the multi-launch
-    fallback of the depth sweep, and the full-resolution warp has a knife-edge mask pixel on these inputs
+    (64x80 = 41 M-tiles) is beyond the persistent recurrence kernel's cluster, so this exercises the wide sweep
+    (sweep_wide.cu; 4 chains of 21 two-tile CTAs), and the full-resolution warp has a knife-edge mask pixel on these inputs
     (tests/_gpu_util.py re-runs the oracle with the CUDA path's tie-break after checking it is one)."""
     from tests._gpu_util import run_case
     rep, _, _ = run_case(net, gta_state, synthetic.make_inputs(1024, 1280, 4, 1), 128, stages=False)

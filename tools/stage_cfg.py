@@ -44,3 +44,12 @@ mac, byt, _ = bench.algorithmic_work(rows, cols, views, hyps)
 print(f"{rows}x{cols} V={views} D={hyps} B={batch}: event mean {sum(ms) / steps:.3f} ms (min {min(ms):.3f}), "
       f"wall/step {1e3 * wall / steps:.3f} ms, {batch / (sum(ms) / steps) * 1e3:.1f} depthmaps/s, "
       f"launches {net.last_launch_count()}, mem {torch.cuda.max_memory_allocated() / 2**30:.2f} GiB torch", flush=True)
+if os.environ.get("SWEEP_PROF"):
+    # per-phase cycle totals of CTA (0, 0) of the wide sweep (sweep_wide.cu) or rank 0 of the cluster kernel
+    net.set_option("recurrence_profile", 1)
+    with torch.no_grad():
+        net(*inp, *flags)
+    torch.cuda.synchronize()
+    prof = net.get_stage("recurrence_profile", torch.int64).cpu()[:12].tolist()
+    print("sweep phases (cycles per step): " + " ".join(f"{v / max(1, hyps - 1):.0f}" for v in prof)
+          + f" | total {sum(prof[:10]) / max(1, hyps - 1):.0f}", flush=True)
