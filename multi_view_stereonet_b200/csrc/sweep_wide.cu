@@ -117,6 +117,25 @@ __device__ __forceinline__ void tmem_ld8x2(uint32_t taddr0, uint32_t taddr1, flo
   }
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+// registers -> this thread's TMEM lane (the caller issues tcgen05.wait::st before it reads them back)
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr),
+               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+               "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+               "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+
 // The 36 MMAs of one M-tile of a 3x3 conv (see recurrence.cu: issue_conv_mmas).
 __device__ __forceinline__ void issue_tile_mmas(uint64_t da_hi, uint64_t da_lo, uint64_t db, uint32_t plane_u16,
                                                 uint32_t PW, uint32_t d_tmem) {
@@ -187,10 +206,6 @@ __global__ void __launch_bounds__(NT, 1) sweep_wide_kernel(const WideParams p) {
   const uint32_t tmem_base = s_tmem;
 
   const float inv_count = 1.0f / (8.0f * (float)pixels);
-  const uint32_t plane_u16 = L.plane_bytes >> 4;
-  const uint64_t da_hi0 = tc::umma_desc(tc::smem_u32(s_planes) + (uint32_t)PLANE_HI * L.plane_bytes, L.plane_bytes, 128u);
-  const uint64_t da_lo0 = tc::umma_desc(tc::smem_u32(s_planes) + (uint32_t)PLANE_LO * L.plane_bytes, L.plane_bytes, 128u);
-  const uint64_t db0 = tc::umma_desc(tc::smem_u32(s_w), 1024u, 128u);
 
   uint32_t conv_phase = 0;
   bool weights_seen = false;
@@ -204,7 +219,10 @@ __global__ void __launch_bounds__(NT, 1) sweep_wide_kernel(const WideParams p) {
       if (!weights_seen) tc::mbar_wait(&s_wbar, 0);
       if (tc::elect_one()) {
         tc::fence_after_sync();
-        const uint64_t db = db0 + (uint64_t)(layer * W_BLOCKS * (2048 / 16));
+        const uint32_t plane_u16 = L.plane_bytes >> 4;
+        const uint64_t da_hi0 = tc::umma_desc(tc::smem_u32(s_planes) + (uint32_t)PLANE_HI * L.plane_bytes, L.plane_bytes, 128u);
+        const uint64_t da_lo0 = tc::umma_desc(tc::smem_u32(s_planes) + (uint32_t)PLANE_LO * L.plane_bytes, L.plane_bytes, 128u);
+        const uint64_t db = tc::umma_desc(tc::smem_u32(s_w), 1024u, 128u) + (uint64_t)(layer * W_BLOCKS * (2048 / 16));
 #pragma unroll 1
         for (int t = 0; t < nmy; ++t) {
           issue_tile_mmas(da_hi0 + (uint64_t)(t * MTILE), da_lo0 + (uint64_t)(t * MTILE), db, plane_u16, (uint32_t)PW,
@@ -239,17 +257,30 @@ __global__ void __launch_bounds__(NT, 1) sweep_wide_kernel(const WideParams p) {
     return reinterpret_cast<uint4*>(s_planes + (size_t)plane * L.plane_bytes + (size_t)l * 16);
   };
 
-  // gather tasks: (local input position l, channel octet); the four lanes of a quad share a position
+  // gather tasks: (local input position l, channel octet); the four lanes of a quad share a position; lane j of the
+  // quad keeps the plan entries of iterations k = j, j + 4 and hands them out by shuffle
   const int t_oct = tid & 3;
+  constexpr int PLAN_REGS = (ITERS + 3) / 4;
   const float4* const plan_base = p.plan + (size_t)chain * p.D * p.plan_stride + pos0;
-  float4 g_plan[ITERS];
+  float4 g_plan[PLAN_REGS];
   auto load_plan = [&](int step) {
 #pragma unroll
-    for (int k = 0; k < ITERS; ++k) {
+    for (int i = 0; i < PLAN_REGS; ++i) {
+      const int k = t_oct + 4 * i;
       const int l = (tid + k * NT) >> 2;
-      g_plan[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (l < npl_my) g_plan[k] = __ldg(plan_base + (size_t)step * p.plan_stride + l);
+      g_plan[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < ITERS && l < npl_my) g_plan[i] = __ldg(plan_base + (size_t)step * p.plan_stride + l);
     }
+  };
+  auto plan_of = [&](int k) -> float4 {   // k is a compile-time constant after unrolling
+    const float4 src = g_plan[k >> 2];
+    const int from = (lane & ~3) | (k & 3);
+    float4 r;
+    r.x = __shfl_sync(0xffffffffu, src.x, from);
+    r.y = __shfl_sync(0xffffffffu, src.y, from);
+    r.z = __shfl_sync(0xffffffffu, src.z, from);
+    r.w = __shfl_sync(0xffffffffu, src.w, from);
+    return r;
   };
 
   float* const wf_chain = p.wfbuf + (size_t)chain * p.npos * kC;
@@ -286,21 +317,22 @@ __global__ void __launch_bounds__(NT, 1) sweep_wide_kernel(const WideParams p) {
 #pragma unroll
       for (int k = 0; k < ITERS; ++k) {
         const int l = (tid + k * NT) >> 2;
+        const float4 e = plan_of(k);
         if (l < npl_my) {
           float v[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = 0.f;
-          const int fl = __float_as_int(g_plan[k].w);
+          for (int i = 0; i < 8; ++i) v[i] = 0.f;
+          const int fl = __float_as_int(e.w);
           if (fl & 1) {
-            const float we = g_plan[k].y, ws = g_plan[k].z;
+            const float we = e.y, ws = e.z;
             const float ww = 1.0f - we, wn = 1.0f - ws;
             const float wt[4] = {wn * ww, wn * we, ws * ww, ws * we};
-            const int P00 = __float_as_int(g_plan[k].x);   // output position of the north-west tap
+            const int P00 = __float_as_int(e.x);   // output position of the north-west tap
             const int y0 = P00 / PW, x0 = P00 - y0 * PW;
             const int dx = (fl >> 1) & 1, dy = (fl >> 2) & 1;
             const float* p00 = prev + ((size_t)y0 * p.cols + x0) * kC;
-            const float* tp[4] = {p00, p00 + dx * kC, p00 + (size_t)dy * p.cols * kC,
-                                  p00 + ((size_t)dy * p.cols + dx) * kC};
+            const float* p10 = p00 + (size_t)dy * p.cols * kC;
+            const float* tp[4] = {p00, p00 + dx * kC, p10, p10 + dx * kC};
             float4 a[4], b[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
@@ -331,50 +363,56 @@ __global__ void __launch_bounds__(NT, 1) sweep_wide_kernel(const WideParams p) {
     WIDE_MARK(1);
 
     // ===== two normalised layers: raw output -> statistics + boundary rows -> chain barrier -> operand -> conv =====
-    float y[MT][8];
 #pragma unroll 1
     for (int layer = 0; layer < 2; ++layer) {
       float gs = 0.f, gq = 0.f;
       float* const y_layer = y_chain + (size_t)layer * p.npos * kC;
+      // what is added to the accumulators (image half of conv0 + bias0, or bias1), loaded one tile ahead; the raw
+      // output goes back into the tile's first accumulator columns (tcgen05.st) and is read again behind the chain
+      // barrier, so that nothing per tile stays in registers across it
+      auto load_add = [&](int t, float4* i0, float4* i1) {
+        *i0 = *i1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (layer == 0) {
+          if (own_pix[t] >= 0) {
+            const float4* icp = reinterpret_cast<const float4*>(
+                p.imgconv + (((size_t)chain * p.D + step) * pixels + own_pix[t]) * kC + oct_e * 8);
+            *i0 = __ldg(icp);
+            *i1 = __ldg(icp + 1);
+          }
+        } else {
+          *i0 = *reinterpret_cast<const float4*>(&s_bias[0][oct_e * 8]);
+          *i1 = *reinterpret_cast<const float4*>(&s_bias[0][oct_e * 8 + 4]);
+        }
+      };
+      float4 n0, n1;
+      load_add(0, &n0, &n1);
 #pragma unroll
       for (int t = 0; t < MT; ++t) {
         if (t < nmy) {
-          float c[8], add[8];
-          if (layer == 0) {   // image half of conv0 + bias0
-            float4 i0 = make_float4(0.f, 0.f, 0.f, 0.f), i1 = i0;
-            if (own_pix[t] >= 0) {
-              const float4* icp = reinterpret_cast<const float4*>(
-                  p.imgconv + (((size_t)chain * p.D + step) * pixels + own_pix[t]) * kC + oct_e * 8);
-              i0 = __ldg(icp);
-              i1 = __ldg(icp + 1);
-            }
-            add[0] = i0.x; add[1] = i0.y; add[2] = i0.z; add[3] = i0.w;
-            add[4] = i1.x; add[5] = i1.y; add[6] = i1.z; add[7] = i1.w;
-          } else {
-            const float4 b0 = *reinterpret_cast<const float4*>(&s_bias[0][oct_e * 8]);
-            const float4 b1 = *reinterpret_cast<const float4*>(&s_bias[0][oct_e * 8 + 4]);
-            add[0] = b0.x; add[1] = b0.y; add[2] = b0.z; add[3] = b0.w;
-            add[4] = b1.x; add[5] = b1.y; add[6] = b1.z; add[7] = b1.w;
-          }
+          const float add[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
+          if (t + 1 < MT) load_add(t + 1, &n0, &n1);
+          float y[8], c[8];
           tc::mbar_wait(&s_bar[t], conv_phase);
           tc::fence_after_sync();
-          tmem_ld8x2(tmem_my + (uint32_t)(t * 64), tmem_my + (uint32_t)(t * 64) + 32u, y[t], c);
+          tmem_ld8x2(tmem_my + (uint32_t)(t * 64), tmem_my + (uint32_t)(t * 64) + 32u, y, c);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) y[t][k] = (y[t][k] + c[k]) + add[k];
+          for (int k = 0; k < 8; ++k) y[k] = (y[k] + c[k]) + add[k];
+          tmem_st8(tmem_my + (uint32_t)(t * 64), y);
           if (own_pix[t] >= 0) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-              gs += y[t][k];
-              gq += y[t][k] * y[t][k];
+              gs += y[k];
+              gq += y[k] * y[k];
             }
           }
           if (own_bnd[t]) {
             float4* dst = reinterpret_cast<float4*>(y_layer + (size_t)(pos0 + t * MTILE + wq * 32 + lane) * kC + oct_e * 8);
-            __stcg(dst, make_float4(y[t][0], y[t][1], y[t][2], y[t][3]));
-            __stcg(dst + 1, make_float4(y[t][4], y[t][5], y[t][6], y[t][7]));
+            __stcg(dst, make_float4(y[0], y[1], y[2], y[3]));
+            __stcg(dst + 1, make_float4(y[4], y[5], y[6], y[7]));
           }
         }
       }
+      asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
       conv_phase ^= 1u;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -400,6 +438,20 @@ __global__ void __launch_bounds__(NT, 1) sweep_wide_kernel(const WideParams p) {
       }
       __syncthreads();
       WIDE_MARK(3 + 3 * layer);
+      // the neighbours' boundary rows this thread normalises (two tasks at most: 2 halo * 4 <= 2 * NT): in flight under
+      // the coefficients and the own rows
+      float4 hy[2][2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int h = (tid + i * NT) >> 2;
+        const int q = pos0 + (h < halo ? h : h + own_n) - halo;   // the output position the halo position mirrors
+        hy[i][0] = hy[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (h < 2 * halo && q >= 0 && q < npos_img && q % PW < p.cols) {
+          const float4* src = reinterpret_cast<const float4*>(y_layer + (size_t)q * kC + t_oct * 8);
+          hy[i][0] = __ldcg(src);
+          hy[i][1] = __ldcg(src + 1);
+        }
+      }
       // ---- GroupNorm coefficients: warp g adds the chain's slots of group g in one fixed order ----
       if (warp < kGroups) {
         float ts = 0.f, tq = 0.f;
@@ -440,12 +492,14 @@ __global__ void __launch_bounds__(NT, 1) sweep_wide_kernel(const WideParams p) {
             float x[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) x[k] = 0.f;
+            float y[8];
+            tmem_ld8(tmem_my + (uint32_t)(t * 64), y);   // (.sync.aligned: the whole warp, outside the per-lane branch)
             if (own_pix[t] >= 0) {
               float xprev[8];
               if (layer == 1) unsplit8(*ph, *plo, xprev);
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
-                x[k] = lrelu(fmaf(y[t][k], ca[k], cb[k]));
+                x[k] = lrelu(fmaf(y[k], ca[k], cb[k]));
                 if (layer == 1) x[k] += xprev[k];
               }
             }
@@ -461,31 +515,32 @@ __global__ void __launch_bounds__(NT, 1) sweep_wide_kernel(const WideParams p) {
         const float4 c0 = *reinterpret_cast<const float4*>(&s_cb[t_oct * 8]), c1 = *reinterpret_cast<const float4*>(&s_cb[t_oct * 8 + 4]);
         const float ca[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
         const float cb[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-        for (int task = tid; task < 2 * halo * 4; task += NT) {
-          const int h = task >> 2;
-          const int l = h < halo ? h : h + own_n;   // lower halo, then upper halo
-          const int q = pos0 + l - halo;            // the output position it mirrors
-          uint4* ph = plane_ptr(PLANE_HI + t_oct, l);
-          uint4* plo = plane_ptr(PLANE_LO + t_oct, l);
-          float v[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = 0.f;
-          if (q >= 0 && q < npos_img && q % PW < p.cols) {
-            const float4* src = reinterpret_cast<const float4*>(y_layer + (size_t)q * kC + t_oct * 8);
-            const float4 u0 = __ldcg(src), u1 = __ldcg(src + 1);
-            const float yy[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-            float xprev[8];
-            if (layer == 1) unsplit8(*ph, *plo, xprev);
+        for (int i = 0; i < 2; ++i) {
+          const int h = (tid + i * NT) >> 2;
+          if (h < 2 * halo) {
+            const int l = h < halo ? h : h + own_n;   // lower halo, then upper halo
+            const int q = pos0 + l - halo;
+            uint4* ph = plane_ptr(PLANE_HI + t_oct, l);
+            uint4* plo = plane_ptr(PLANE_LO + t_oct, l);
+            float v[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              v[e] = lrelu(fmaf(yy[e], ca[e], cb[e]));
-              if (layer == 1) v[e] += xprev[e];
+            for (int e = 0; e < 8; ++e) v[e] = 0.f;
+            if (q >= 0 && q < npos_img && q % PW < p.cols) {
+              const float yy[8] = {hy[i][0].x, hy[i][0].y, hy[i][0].z, hy[i][0].w, hy[i][1].x, hy[i][1].y, hy[i][1].z, hy[i][1].w};
+              float xprev[8];
+              if (layer == 1) unsplit8(*ph, *plo, xprev);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                v[e] = lrelu(fmaf(yy[e], ca[e], cb[e]));
+                if (layer == 1) v[e] += xprev[e];
+              }
             }
+            uint4 hi, lo;
+            tc::split8(v, &hi, &lo);
+            *ph = hi;
+            *plo = lo;
           }
-          uint4 hi, lo;
-          tc::split8(v, &hi, &lo);
-          *ph = hi;
-          *plo = lo;
         }
       }
       issue_conv(1 + layer);
@@ -498,15 +553,22 @@ __global__ void __launch_bounds__(NT, 1) sweep_wide_kernel(const WideParams p) {
       float* dst_h = p.vol + ((size_t)chain * p.D + step) * pixels * kC + oct_e * 8;
       const float4 b0 = *reinterpret_cast<const float4*>(&s_bias[1][oct_e * 8]);
       const float4 b1 = *reinterpret_cast<const float4*>(&s_bias[1][oct_e * 8 + 4]);
+      auto load_wf = [&](int t, float4* w0, float4* w1) {
+        *w0 = *w1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (own_pix[t] >= 0) {
+          const float4* wp = reinterpret_cast<const float4*>(wf_chain + (size_t)(pos0 + t * MTILE + wq * 32 + lane) * kC + oct_e * 8);
+          *w0 = __ldcg(wp);
+          *w1 = __ldcg(wp + 1);
+        }
+      };
+      float4 n0[2], n1[2];   // two tiles ahead
+      load_wf(0, &n0[0], &n1[0]);
+      if (MT > 1) load_wf(MT > 1 ? 1 : 0, &n0[1], &n1[1]);
 #pragma unroll
       for (int t = 0; t < MT; ++t) {
         if (t < nmy) {
-          float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
-          if (own_pix[t] >= 0) {
-            const float4* wp = reinterpret_cast<const float4*>(wf_chain + (size_t)(pos0 + t * MTILE + wq * 32 + lane) * kC + oct_e * 8);
-            w0 = __ldcg(wp);
-            w1 = __ldcg(wp + 1);
-          }
+          const float4 w0 = n0[t & 1], w1 = n1[t & 1];
+          if (t + 2 < MT) load_wf(t + 2 < MT ? t + 2 : 0, &n0[t & 1], &n1[t & 1]);
           tc::mbar_wait(&s_bar[t], conv_phase);
           tc::fence_after_sync();
           float v[8], c[8];
