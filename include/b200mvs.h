@@ -137,6 +137,11 @@ B200MVS_API int b200mvs_set_debug(b200mvs_net* net, int keep_stages);
  * "half_activations", "pdl", "overlap", "conv0_precompute", "left_late", "early_d2h", "l4_chain" (the level-4 tail of
  * the feature network as one cluster kernel per image); "lanes" (0 = automatic, the default: a call is split into two concurrent sub-batches when the last
  * round of the depth sweep's clusters would be nearly empty; 1 = never; 2 = whenever the sweep needs more than one round),
+ * "sweep" (which kernel runs the depth sweep, multi_view_stereonet.py:279-290: 0 = automatic, the default -- the cluster
+ * kernel while the chains of a call need at most two rounds of clusters, the wide kernel (one co-resident cooperative
+ * grid for all chains, sweep_wide.cu) beyond that and for 1/16-scale images larger than one cluster, e.g. 1024x1280;
+ * 1 = the wide kernel wherever it is supported; 2 = step by step, one launch per layer.  The wide kernel's CTAs wait
+ * for each other: do not run two forwards that use it concurrently on one GPU),
  * "precise_refiners", "prio_main" (default 0: single-lane forwards on a high-priority stream of the library's own);
  * debugging: "recurrence_debug", "recurrence_profile" (phase totals and a per-warp timeline of one step, read back
  * with b200mvs_get_stage "recurrence_profile" / "recurrence_trace"), "stage_profile" (see

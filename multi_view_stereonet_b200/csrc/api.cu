@@ -949,8 +949,26 @@ int forward_impl(b200mvs_net* net, Lane& lane, bool sweep_on_own_stream, const b
 
   // 1b. image half of FeatureRefiner.conv0 for every hypothesis (needs only the homographies and the 1/16-scale
   //     comparison images): first thing on the side stream, the recurrence waits for it
-  const bool cluster_sweep = net->use_tensor_cores && net->sweep_mode == 0 && recurrence_supported(h4, w4, nullptr, nullptr);
-  const bool wide_sweep = net->use_tensor_cores && !cluster_sweep && net->sweep_mode != 2 && sweep_wide_supported(h4, w4);
+  // Which sweep kernel: the cluster kernel (recurrence.cu) runs one chain per cluster, recurrence_max_clusters (7 on
+  // B200) of them at a time, at ~9 us per dependent step; the wide kernel (sweep_wide.cu) takes every chain of the call
+  // in one co-resident grid at ~25-40 us per step.  Measured at 512x640 / 64 hypotheses (cluster -> wide): 8 chains
+  // 5.03 -> 5.25 ms, 12 chains 4.31 -> 4.39, 16 chains 6.75 -> 6.50 and 9.64 -> 9.31, 32 chains 9.95 -> 8.97, 64
+  // chains 19.4 -> 17.4: the wide kernel from the third round of clusters on.  Never next to another lane's sweep
+  // (two cooperative grids in flight could each hold SMs the other waits for).
+  const bool cluster_ok = recurrence_supported(h4, w4, nullptr, nullptr);
+  const bool wide_ok = sweep_wide_supported(h4, w4) && !sweep_on_own_stream;
+  bool cluster_sweep = false, wide_sweep = false;
+  if (net->use_tensor_cores && net->sweep_mode != 2) {
+    if (net->sweep_mode == 1 && wide_ok) {
+      wide_sweep = true;
+    } else if (cluster_ok) {
+      const int maxc = recurrence_max_clusters(h4, w4);
+      wide_sweep = wide_ok && net->sweep_mode == 0 && maxc > 0 && n > 2 * maxc && net->rec_prof == nullptr;
+      cluster_sweep = !wide_sweep;
+    } else {
+      wide_sweep = wide_ok;
+    }
+  }
   const bool persistent = cluster_sweep || wide_sweep;
   if (persistent) {
     if (overlap) {

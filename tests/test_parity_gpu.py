@@ -91,6 +91,31 @@ def test_batch8_matches_single_items(net, gta_state):
         assert int((out8["left_idepthmap_mask_pyr"][lvl][5].cpu() != ref["left_idepthmap_mask_pyr"][lvl][0]).sum()) == 0
 
 
+def test_many_chains_take_the_wide_sweep(net):
+    """From the third round of clusters on (more than 14 (image group, view) chains on B200) the automatic rule hands
+    the depth sweep to the wide kernel (one co-resident grid for all chains).  Batch 8 with two views = 16 chains:
+    same results as the cluster kernel (option sweep = 0 with lanes = 1 and a forced "sweep" = 2 step-by-step run are
+    the two references), and a forced two-lane call never starts two cooperative grids (it falls back to clusters)."""
+    inputs = synthetic.to_device(synthetic.make_inputs(512, 640, 2, 8), "cuda")
+    try:
+        with torch.no_grad():
+            auto = net(*inputs, 16, True, [True] * 5)
+            net.set_option("sweep", 2)
+            steps = net(*inputs, 16, True, [True] * 5)
+            n_steps = net.last_launch_count()
+            net.set_option("sweep", 0)
+            net.set_option("lanes", 2)
+            lanes = net(*inputs, 16, True, [True] * 5)
+        assert n_steps > net.last_launch_count() / 2 + 15 * 3      # 15 steps x (warp + three convs) instead of one launch
+        for lvl in range(5):
+            for other in (steps, lanes):
+                assert rel_linf(auto["left_idepthmap_pyr"][lvl].cpu(), other["left_idepthmap_pyr"][lvl].cpu()) <= REL_LINF_TOL / 2
+                assert bool((auto["left_idepthmap_mask_pyr"][lvl] == other["left_idepthmap_mask_pyr"][lvl]).all())
+    finally:
+        net.set_option("sweep", 0)
+        net.set_option("lanes", 0)
+
+
 def test_lanes_option_gives_the_same_results(net):
     """Option "lanes" = 2 cuts a call whose depth sweep needs more than one round of clusters into two concurrent lanes
     of whole image groups (1 = never; 0 = automatic, the default: two lanes when the last round would hold one or two
