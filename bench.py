@@ -250,7 +250,7 @@ EXTRA_CONFIGS = [
 ]
 
 
-def run_extra_configs(net, dev, rank, world, flush, barrier, hbm_peak, tf32_peak_tflops, steps=5, warmup=3):
+def run_extra_configs(net, dev, rank, world, flush, barrier, hbm_peak, tf32_peak_tflops, steps=5, warmup=4):
     """Times the per-GPU share of cfg4 / cfg3 / cfg5 device-resident (every rank runs its own seeded items, max over
     ranks) and one profiled forward each for the per-stage breakdown.  Returns {name: {...}} on every rank."""
     from multi_view_stereonet_b200 import sharding, synthetic
@@ -267,9 +267,9 @@ def run_extra_configs(net, dev, rank, world, flush, barrier, hbm_peak, tf32_peak
             res = None
             starts = [torch.cuda.Event(enable_timing=True) for _ in range(warmup + steps)]
             ends = [torch.cuda.Event(enable_timing=True) for _ in range(warmup + steps)]
+            barrier()   # ranks start together; no host synchronisation between the warm-up and the timed steps (the
+            #             first forward behind a synchronise ran 1-9 ms long in the two-lane configuration)
             for i in range(warmup + steps):
-                if i == warmup:
-                    barrier()
                 flush.zero_()
                 starts[i].record()
                 res = net(*inputs, *flags)
