@@ -1,12 +1,12 @@
 // 3x3 (dilated) 32->32 convolution on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
 //
 // Implicit GEMM without an im2col copy.  One CTA owns a TH x TW tile of output pixels of one image:
-//   * the halo-extended input tile ((TH+2d) rows of PW = 64 positions, TW = PW - 2d of them valid
-//     outputs) is staged ONCE in shared memory, previous layer's GroupNorm + LeakyReLU (+ residual)
+//   * the halo-extended input tile ((TH+2) rows of PW = 64 positions of one vertical polyphase component, see
+//     tc_npos; TW = PW - 2d of the positions of a row are valid outputs) is staged ONCE in shared memory, previous layer's GroupNorm + LeakyReLU (+ residual)
 //     applied on the way, converted to fp16 and laid out as four planes of [position][8 channels]
 //     (16 bytes per position).  With the UMMA "no swizzle, K-major" canonical layout (core matrix =
 //     8 rows x 16 bytes, contiguous) a plane IS a valid A operand whose row m is position m, and
-//     the A operand of filter tap (ky, kx) is the same plane started (ky*d*PW + kx*d) positions
+//     the A operand of filter tap (ky, kx) is the same plane started (ky*PW + kx*d) positions
 //     later -- the nine taps are nine descriptors into one buffer;
 //   * per M-tile of 128 consecutive positions (two output rows) 9 taps x 2 k-steps of
 //     tcgen05.mma.kind::f16 (M=128, N=32, K=16) accumulate in fp32 into 32 TMEM columns;
@@ -33,8 +33,11 @@ namespace {
 constexpr int PW = 64;        // positions per tile row (valid outputs: PW - 2*dil)
 constexpr int NT = 256;       // threads per CTA
 
+// Dilated layers run as `dil` vertical polyphase components (as in conv_ws.cu): a tile is TH rows of the sub-image made
+// of image rows py, py + dil, py + 2 dil, ..., on which the vertical taps are +-1 tile row -- a halo of 2 rows instead
+// of 2 dil (at dilation 8 a two-row tile staged 18 rows).  Horizontally the dilation stays in the tap offsets.
 __host__ __device__ inline int tc_npos(int TH, int dil) {
-  int n = (TH + 2 * dil) * PW + 2 * dil;
+  int n = (TH + 2) * PW + 2 * dil;
   return ((n + 5) & ~7) + 2;   // 2 (mod 8): the four octet planes a lane quad writes start in distinct banks
 }
 
@@ -107,8 +110,10 @@ __global__ void __launch_bounds__(NT, MINB) conv3x3_tc_kernel(const ConvParams p
   const int d = p.dil;
   const int TW = PW - 2 * d;
   const int tiles_x = cdiv(p.Wo, TW);
+  const int sub_tiles = cdiv(cdiv(p.Ho, d), TH);   // row tiles per vertical phase
   const int tx0 = (blockIdx.x % tiles_x) * TW;
-  const int ty0 = (blockIdx.x / tiles_x) * TH;
+  const int py = (blockIdx.x / tiles_x) / sub_tiles;            // vertical phase: image rows py, py + d, ...
+  const int sy0 = ((blockIdx.x / tiles_x) % sub_tiles) * TH;    // first sub-image row of the tile
   const int npos = tc_npos(TH, d);
   const uint32_t plane_bytes = (uint32_t)npos * 16u;
   const int mode = p.feat.mode;
@@ -139,7 +144,7 @@ __global__ void __launch_bounds__(NT, MINB) conv3x3_tc_kernel(const ConvParams p
   pdl_wait();
   TC_STAMP(2);
   const size_t vol = (size_t)p.Hi * p.Wi;
-  const int rows_in = TH + 2 * d;
+  const int rows_in = TH + 2;
   // ---- stage the transformed 32-channel source ----
   // The raw loads of a batch do not depend on the GroupNorm coefficients: the first batch is issued before the
   // coefficients (two statistics loads + float64 math by 32 threads, then a block barrier) are awaited, so the two
@@ -163,8 +168,9 @@ __global__ void __launch_bounds__(NT, MINB) conv3x3_tc_kernel(const ConvParams p
       const int c8 = i & 3;
       const int L = i >> 2;
       const int iy = L / PW, ix = L % PW;
-      const int gy = ty0 - d + iy, gx = tx0 - d + ix;
-      inb[k] = i < npos * 4 && iy < rows_in && gy >= 0 && gy < p.Hi && gx >= 0 && gx < p.Wi;
+      const int sy = sy0 - 1 + iy;
+      const int gy = py + d * sy, gx = tx0 - d + ix;
+      inb[k] = i < npos * 4 && iy < rows_in && sy >= 0 && gy < p.Hi && gx >= 0 && gx < p.Wi;
       off[k] = inb[k] ? (((size_t)gy * p.Wi + gx) * kC + 8 * c8) * esz : 0;
       if (inb[k]) {
         ya[k] = __ldg(reinterpret_cast<const float4*>(fbase + off[k]));
@@ -224,7 +230,7 @@ __global__ void __launch_bounds__(NT, MINB) conv3x3_tc_kernel(const ConvParams p
               for (int e = 0; e < 8; ++e) v[e] += r[e];
             }
             const int iy = L / PW, ix = L % PW;
-            if (xbase != nullptr && iy >= d && iy < d + TH && ix >= d && ix < d + TW) {
+            if (xbase != nullptr && iy >= 1 && iy < 1 + TH && ix >= d && ix < d + TW) {
               if (hio) {
                 *reinterpret_cast<uint4*>(xbase + off[k]) = pack8(v);
               } else {
@@ -243,11 +249,12 @@ __global__ void __launch_bounds__(NT, MINB) conv3x3_tc_kernel(const ConvParams p
     uint8_t* xplane = s_in + (size_t)fplanes * plane_bytes;
     for (int L = tid; L < npos; L += NT) {
       const int iy = L / PW, ix = L % PW;
-      const int gy = ty0 - d + iy, gx = tx0 - d + ix;
+      const int sy = sy0 - 1 + iy;
+      const int gy = py + d * sy, gx = tx0 - d + ix;
       float v[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] = 0.f;
-      if (iy < rows_in && gy >= 0 && gy < p.Hi && gx >= 0 && gx < p.Wi) {
+      if (iy < rows_in && sy >= 0 && gy < p.Hi && gx >= 0 && gx < p.Wi) {
         const size_t pix = (size_t)gy * p.Wi + gx;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -285,7 +292,7 @@ __global__ void __launch_bounds__(NT, MINB) conv3x3_tc_kernel(const ConvParams p
       const uint32_t dcol = tmem_base + (uint32_t)(mt * ACC_COLS);
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
-        const uint32_t pos = (uint32_t)(mt * 128 + (tap / 3) * d * PW + (tap % 3) * d);
+        const uint32_t pos = (uint32_t)(mt * 128 + (tap / 3) * PW + (tap % 3) * d);
 #pragma unroll
         for (int ks = 0; ks < 3; ++ks) {
           if (ks < KS) {
@@ -321,7 +328,7 @@ __global__ void __launch_bounds__(NT, MINB) conv3x3_tc_kernel(const ConvParams p
   const size_t ostride = p.out_img_stride != 0 ? (size_t)p.out_img_stride : ovol * kC;
   for (int mt = warp >> 2; mt < MT; mt += NT / 128) {
     const int j = mt * 128 + wq * 32 + lane;
-    const int oy = ty0 + j / PW, ox_t = j % PW;
+    const int oy = py + d * (sy0 + j / PW), ox_t = j % PW;
     const int ox = tx0 + ox_t;
     const bool valid = ox_t < TW && ox < p.Wo && oy < p.Ho;
     const size_t opix = valid ? (size_t)oy * p.Wo + ox : 0;
@@ -406,7 +413,7 @@ int launch_th(const ConvParams& p, const uint8_t* w16, cudaStream_t stream) {
   const size_t smem = tc_smem_bytes(TH, SPLIT, p);
   if (int rc = ensure_func_smem(reinterpret_cast<const void*>(&conv3x3_tc_kernel<TH, SPLIT, MINB>), 220 * 1024)) return rc;
   const int TW = PW - 2 * p.dil;
-  dim3 grid(cdiv(p.Wo, TW) * cdiv(p.Ho, TH), p.n_img);
+  dim3 grid(cdiv(p.Wo, TW) * p.dil * cdiv(cdiv(p.Ho, p.dil), TH), p.n_img);
   if (p.tag != TAG_NONE) probe_before(p.tag, stream);
   static const bool prof = getenv("B200MVS_TC_PROFILE") != nullptr;
   if (prof) {
@@ -470,7 +477,7 @@ int launch_conv3x3_tc(const ConvParams& p, const uint8_t* w16, bool split, cudaS
   for (int k = 0; k < 3; ++k) {
     const int th = ths[k];
     if (split && th == 16) continue;  // 8 M-tiles x 64 columns would exceed TMEM
-    const long long tiles = (long long)cdiv(p.Wo, TW) * cdiv(p.Ho, th) * p.n_img;
+    const long long tiles = (long long)cdiv(p.Wo, TW) * p.dil * cdiv(cdiv(p.Ho, p.dil), th) * p.n_img;
     const size_t smem = tc_smem_bytes(th, split, p);
     if (smem > 210 * 1024) continue;
     if (tiles >= 296 && (smem <= 110 * 1024 || p.dil >= 8)) { pick = th; break; }  // big halo: amortise it
@@ -484,7 +491,7 @@ int launch_conv3x3_tc(const ConvParams& p, const uint8_t* w16, bool split, cudaS
   // Small images (a few dozen tiles at most): the layer is one dependent latency chain, so halve the chain of every
   // CTA -- two-row tiles = one M-tile each -- rather than amortise the halo.
   static const int small_th = getenv("B200MVS_TC_SMALL_TH") ? atoi(getenv("B200MVS_TC_SMALL_TH")) : 2;
-  const bool tiny = pick == 4 && (long long)cdiv(p.Wo, TW) * cdiv(p.Ho, 4) * p.n_img < 74 && small_th == 2;
+  const bool tiny = pick == 4 && (long long)cdiv(p.Wo, TW) * p.dil * cdiv(cdiv(p.Ho, p.dil), 4) * p.n_img < 74 && small_th == 2;
   if (split) {
     if (pick == 8) return launch_th<8, true>(p, w16, stream);
     if (tiny) return launch_th<2, true>(p, w16, stream);

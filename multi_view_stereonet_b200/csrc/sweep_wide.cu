@@ -80,6 +80,11 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// arrival at a chain counter: one release reduction (everything this thread wrote, and what the block barrier in front
+// of it made it observe, is ordered before the increment)
+__device__ __forceinline__ void red_release_add(unsigned* p) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
 // weak global load that may be served by L1 (never the non-coherent path)
 __device__ __forceinline__ float4 ld_f4(const float* p) {
   float4 v;
@@ -431,8 +436,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_wide_kernel(const WideParams p) {
           const float2 u0 = s_loc[g][0], u1 = s_loc[g][1], u2 = s_loc[g][2], u3 = s_loc[g][3];
           __stcg(slot + g, make_float2((u0.x + u1.x) + (u2.x + u3.x), (u0.y + u1.y) + (u2.y + u3.y)));
         }
-        __threadfence();
-        atomicAdd(ctr, 1u);
+        red_release_add(ctr);
         const unsigned target = T * sync_k;
         while (ld_acquire_u32(ctr) < target) {}
       }
@@ -595,8 +599,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_wide_kernel(const WideParams p) {
     tc::fence_before_sync();
     __syncthreads();
     if (more && tid == 0) {
-      __threadfence();
-      atomicAdd(ctr, 1u);
+      red_release_add(ctr);
     }
     WIDE_MARK(8);
   }
