@@ -977,7 +977,7 @@ int forward_impl(b200mvs_net* net, Lane& lane, bool sweep_on_own_stream, const b
     }
     RC(wait_upload(2, left_stream));
     RC(launch_image_conv(ws.geo.H, R4, net->fr_conv0.w + (size_t)4 * 9 * 8 * 32, net->fr_conv0.bias, n, D, h4, w4,
-                         ws.imgconv, left_stream));
+                         ws.imgconv, left_stream, /*oct_major=*/wide_sweep));
     RC(launch_gather_plan(ws.geo.Hinc, n, D, h4, w4, ws.rec_plan, ws.rec_flags, left_stream));
     if (overlap) B200MVS_CUDA_OK(cudaEventRecord(net->cur->ev_imgconv, net->cur->side));
   }

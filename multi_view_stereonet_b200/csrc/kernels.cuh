@@ -35,9 +35,10 @@ int launch_warp_planar(const float* H, int h_stride, const ViewPtrs& src, int n,
 int launch_step_warp(const float* vol, const GeomOut& geo, const ViewPtrs& right_l4, int n, int D, int step,
                      int rows, int cols, float* wf, float* wimg, cudaStream_t stream);
 
-// Image half of FeatureRefiner.conv0 (+ bias) for hypotheses 1..D-1 (see misc.cu): out [n][D][rows*cols][32].
+// Image half of FeatureRefiner.conv0 (+ bias) for hypotheses 1..D-1 (see misc.cu): out [n][D][rows*cols][32], or
+// [n][D][4 octets][rows*cols][8] with oct_major (what the wide sweep reads).
 int launch_image_conv(const float* H, const ViewPtrs& right_l4, const float* w_tap8x32, const float* bias, int n,
-                      int D, int rows, int cols, float* out, cudaStream_t stream);
+                      int D, int rows, int cols, float* out, cudaStream_t stream, bool oct_major = false);
 
 // cost = |L - R| where valid, 0 elsewhere; also emits the validity mask volume
 // (multi_view_stereonet.py:293-298, 586-592).  `cost` may alias `vol`.

@@ -45,7 +45,8 @@ __global__ void __launch_bounds__(256) warp_planar_kernel(const float* __restric
 constexpr int kIcRows = 8;
 __global__ void __launch_bounds__(256) image_conv_kernel(const float* __restrict__ H, ViewPtrs right_l4,
                                                          const float* __restrict__ w, const float* __restrict__ bias,
-                                                         int D, int rows, int cols, float* __restrict__ out) {
+                                                         int D, int rows, int cols, int oct_major,
+                                                         float* __restrict__ out) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float s_ic[];
@@ -100,7 +101,11 @@ __global__ void __launch_bounds__(256) image_conv_kernel(const float* __restrict
         for (int k = 0; k < 8; ++k) acc[k] = fmaf(a, wr[k], acc[k]);
       }
     }
-    float4* o = reinterpret_cast<float4*>(out + (((size_t)n * D + d) * pixels + (size_t)(y0 + y) * cols + x) * kC + oct * 8);
+    // oct_major: [n][D][octet][pixel][8] -- the wide sweep's epilogue warps (lane = position, warp = octet) then read
+    // 1 KB contiguous per 32 positions instead of 32 bytes from each of 32 lines
+    const size_t opix = (size_t)(y0 + y) * cols + x;
+    float4* o = reinterpret_cast<float4*>(
+        out + (oct_major ? ((((size_t)n * D + d) * 4 + oct) * pixels + opix) * 8 : (((size_t)n * D + d) * pixels + opix) * kC + oct * 8));
     o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
     o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
   }
@@ -499,7 +504,7 @@ int launch_warp_planar(const float* H, int h_stride, const ViewPtrs& src, int n,
 }
 
 int launch_image_conv(const float* H, const ViewPtrs& right_l4, const float* w_tap8x32, const float* bias, int n,
-                      int D, int rows, int cols, float* out, cudaStream_t stream) {
+                      int D, int rows, int cols, float* out, cudaStream_t stream, bool oct_major) {
   if (D < 2) return 0;
   dim3 grid(cdiv(rows, kIcRows), D - 1, n);
   const size_t smem = ((size_t)3 * (kIcRows + 2) * (cols + 2) + 27 * 32 + 32) * sizeof(float);
@@ -507,7 +512,8 @@ int launch_image_conv(const float* H, const ViewPtrs& right_l4, const float* w_t
     set_error("launch_image_conv: image too wide");
     return -1;
   }
-  launch_pdl(image_conv_kernel, grid, dim3(256), smem, stream, H, right_l4, w_tap8x32, bias, D, rows, cols, out);
+  launch_pdl(image_conv_kernel, grid, dim3(256), smem, stream, H, right_l4, w_tap8x32, bias, D, rows, cols,
+             oct_major ? 1 : 0, out);
   B200MVS_LAUNCH_OK("image_conv_kernel");
   return 0;
 }

@@ -30,7 +30,10 @@
 namespace b200mvs {
 namespace {
 
-constexpr int NT = 512;          // 16 warps = (4 lane quarters of an M-tile) x (4 channel octets)
+constexpr int NT = 512;          // worker threads: 16 warps = (4 lane quarters of an M-tile) x (4 channel octets)
+constexpr int NT_ALL = NT + 32;  // + a warp that only issues the MMAs (tcgen05.mma issue blocks at the rate the tensor pipe
+                                 //   drains: issued from worker warp 0, that warp started every epilogue ~9 k cycles late
+                                 //   and the other fifteen waited for it at the next block barrier, ~3 k cycles per conv)
 constexpr int MTILE = 128;
 constexpr int MAX_MT = 5;        // M-tiles per CTA: 5 x 64 accumulator columns <= 512 TMEM columns, planes <= 117 KB
 constexpr int W_BLOCKS = 9 * 2;  // taps x k-steps of one layer
@@ -61,10 +64,11 @@ struct WideParams {
   float* vol;            // same buffer
   const uint8_t* w16;    // pack_recurrence_weights
   const float *bias1, *bias2, *gamma0, *beta0, *gamma1, *beta1;
-  const float* imgconv;  // [n][D][rows*cols][32]: image half of conv0 + bias0
+  const float* imgconv;  // [n][D][4 octets][rows*cols][8]: image half of conv0 + bias0 (octet-major)
   const float4* plan;    // [n][D][plan_stride]
   int plan_stride;
-  float* wfbuf;          // [n][npos][32] warped features of the current step
+  float* wfbuf;          // [n][4 octets][npos][8] warped features of the current step (octet-major: an epilogue warp
+                         // reads 32 positions x 32 B contiguously)
   float* ybuf;           // [n][2][npos][32] raw layer outputs next to the CTA boundaries
   float2* part;          // [n][2][T_max][4] GroupNorm partials per CTA
   unsigned* ctr;         // [n] arrivals at the chain barrier (zeroed before the launch)
@@ -159,7 +163,7 @@ __device__ __forceinline__ void issue_tile_mmas(uint64_t da_hi, uint64_t da_lo, 
 }
 
 template <int MT>
-__global__ void __launch_bounds__(NT, 1) sweep_wide_kernel(const WideParams p) {
+__global__ void __launch_bounds__(NT_ALL, 1) sweep_wide_kernel(const WideParams p) {
   constexpr int ITERS = MT + 2;   // gather tasks per thread: (MT * 128 + 2 halo) * 4 / 512, halo <= 128
   constexpr uint32_t TMEM_COLS = MT == 1 ? 64u : (MT == 2 ? 128u : (MT <= 4 ? 256u : 512u));
   extern __shared__ __align__(128) uint8_t smem[];
@@ -202,7 +206,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_wide_kernel(const WideParams p) {
   }
   {
     uint4* pl = reinterpret_cast<uint4*>(s_planes);   // padding positions stay zero
-    for (int i = tid; i < NUM_PLANES * L.npl_pad; i += NT) pl[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < NUM_PLANES * L.npl_pad; i += NT_ALL) pl[i] = make_uint4(0, 0, 0, 0);
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -213,32 +217,42 @@ __global__ void __launch_bounds__(NT, 1) sweep_wide_kernel(const WideParams p) {
   const float inv_count = 1.0f / (8.0f * (float)pixels);
 
   uint32_t conv_phase = 0;
-  bool weights_seen = false;
-  // all threads have staged the operand (generic-proxy writes fenced by the caller): warp 0 issues every tile's MMAs,
-  // one commit per tile so that a tile's epilogue runs under the following tiles' MMAs
-  auto issue_conv = [&](int layer) {
+  // ---- the issuing warp: sleeps at named barrier 2 until the 512 workers have staged an operand (they only ARRIVE
+  //      there and go on to the tiles' completion barriers), issues every tile's MMAs from one elected lane, one
+  //      commit per tile so that a tile's epilogue runs under the following tiles' MMAs
+  if (warp == NT / 32) {
+    tc::mbar_wait(&s_wbar, 0);   // the bulk-copied weights have landed
+    for (int step = 1; step < p.D; ++step) {
+#pragma unroll 1
+      for (int layer = 0; layer < 3; ++layer) {
+        asm volatile("bar.sync 2, %0;" ::"n"(NT_ALL) : "memory");
+        if (tc::elect_one()) {
+          tc::fence_after_sync();
+          const uint32_t plane_u16 = L.plane_bytes >> 4;
+          const uint64_t da_hi0 = tc::umma_desc(tc::smem_u32(s_planes) + (uint32_t)PLANE_HI * L.plane_bytes, L.plane_bytes, 128u);
+          const uint64_t da_lo0 = tc::umma_desc(tc::smem_u32(s_planes) + (uint32_t)PLANE_LO * L.plane_bytes, L.plane_bytes, 128u);
+          const uint64_t db = tc::umma_desc(tc::smem_u32(s_w), 1024u, 128u) + (uint64_t)(layer * W_BLOCKS * (2048 / 16));
+#pragma unroll 1
+          for (int t = 0; t < nmy; ++t) {
+            issue_tile_mmas(da_hi0 + (uint64_t)(t * MTILE), da_lo0 + (uint64_t)(t * MTILE), db, plane_u16, (uint32_t)PW,
+                            tmem_base + (uint32_t)(t * 64));
+            tc::mma_commit(&s_bar[t]);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    tc::fence_before_sync();
+    __syncthreads();   // the kernel's last block barrier (TMEM is freed behind it)
+    return;
+  }
+  // workers: the operand is staged (generic-proxy writes fenced here) -> wake the issuing warp, do not wait
+  auto issue_conv = [&](int) {
     tc::fence_proxy_async();
     tc::fence_before_sync();
-    __syncthreads();
-    if (warp == 0) {
-      if (!weights_seen) tc::mbar_wait(&s_wbar, 0);
-      if (tc::elect_one()) {
-        tc::fence_after_sync();
-        const uint32_t plane_u16 = L.plane_bytes >> 4;
-        const uint64_t da_hi0 = tc::umma_desc(tc::smem_u32(s_planes) + (uint32_t)PLANE_HI * L.plane_bytes, L.plane_bytes, 128u);
-        const uint64_t da_lo0 = tc::umma_desc(tc::smem_u32(s_planes) + (uint32_t)PLANE_LO * L.plane_bytes, L.plane_bytes, 128u);
-        const uint64_t db = tc::umma_desc(tc::smem_u32(s_w), 1024u, 128u) + (uint64_t)(layer * W_BLOCKS * (2048 / 16));
-#pragma unroll 1
-        for (int t = 0; t < nmy; ++t) {
-          issue_tile_mmas(da_hi0 + (uint64_t)(t * MTILE), da_lo0 + (uint64_t)(t * MTILE), db, plane_u16, (uint32_t)PW,
-                          tmem_base + (uint32_t)(t * 64));
-          tc::mma_commit(&s_bar[t]);
-        }
-      }
-      __syncwarp();
-    }
-    weights_seen = true;
+    asm volatile("bar.arrive 2, %0;" ::"n"(NT_ALL) : "memory");
   };
+  auto sync_workers = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); };
 
   // ---- chain barrier: arrivals counted in global memory, one polling thread per CTA ----
   unsigned* const ctr = p.ctr + chain;
@@ -314,7 +328,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_wide_kernel(const WideParams p) {
         const unsigned target = T * sync_k;
         while (ld_acquire_u32(ctr) < target) {}
       }
-      __syncthreads();
+      sync_workers();
     }
     WIDE_MARK(0);
     {
@@ -353,7 +367,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_wide_kernel(const WideParams p) {
             }
           }
           if (l >= halo && l < halo + own_n) {
-            float4* dst = reinterpret_cast<float4*>(wf_chain + (size_t)(pos0 + l - halo) * kC + 8 * t_oct);
+            float4* dst = reinterpret_cast<float4*>(wf_chain + ((size_t)t_oct * p.npos + (size_t)(pos0 + l - halo)) * 8);
             __stcg(dst, make_float4(v[0], v[1], v[2], v[3]));
             __stcg(dst + 1, make_float4(v[4], v[5], v[6], v[7]));
           }
@@ -379,8 +393,8 @@ __global__ void __launch_bounds__(NT, 1) sweep_wide_kernel(const WideParams p) {
         *i0 = *i1 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (layer == 0) {
           if (own_pix[t] >= 0) {
-            const float4* icp = reinterpret_cast<const float4*>(
-                p.imgconv + (((size_t)chain * p.D + step) * pixels + own_pix[t]) * kC + oct_e * 8);
+            const float4* icp = reinterpret_cast<const float4*>(   // [n][D][octet][pixel][8] (launch_image_conv, oct_major)
+                p.imgconv + ((((size_t)chain * p.D + step) * 4 + oct_e) * pixels + own_pix[t]) * 8);
             *i0 = __ldg(icp);
             *i1 = __ldg(icp + 1);
           }
@@ -426,7 +440,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_wide_kernel(const WideParams p) {
       }
       if (lane == 0) s_loc[oct_e][wq] = make_float2(gs, gq);
       tc::fence_before_sync();
-      __syncthreads();
+      sync_workers();
       WIDE_MARK(2 + 3 * layer);
       ++sync_k;
       if (tid == 0) {
@@ -440,7 +454,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_wide_kernel(const WideParams p) {
         const unsigned target = T * sync_k;
         while (ld_acquire_u32(ctr) < target) {}
       }
-      __syncthreads();
+      sync_workers();
       WIDE_MARK(3 + 3 * layer);
       // the neighbours' boundary rows this thread normalises (two tasks at most: 2 halo * 4 <= 2 * NT): in flight under
       // the coefficients and the own rows
@@ -480,7 +494,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_wide_kernel(const WideParams p) {
           s_cb[ch] = s_beta[layer][ch] - (float)mean * ca;
         }
       }
-      __syncthreads();
+      sync_workers();
       // ---- next operand: x = lrelu(GN(y)) (+ x0 in the residual block) over own + halo positions ----
       {
         const float4 a0 = *reinterpret_cast<const float4*>(&s_ca[oct_e * 8]), a1 = *reinterpret_cast<const float4*>(&s_ca[oct_e * 8 + 4]);
@@ -560,7 +574,7 @@ __global__ void __launch_bounds__(NT, 1) sweep_wide_kernel(const WideParams p) {
       auto load_wf = [&](int t, float4* w0, float4* w1) {
         *w0 = *w1 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (own_pix[t] >= 0) {
-          const float4* wp = reinterpret_cast<const float4*>(wf_chain + (size_t)(pos0 + t * MTILE + wq * 32 + lane) * kC + oct_e * 8);
+          const float4* wp = reinterpret_cast<const float4*>(wf_chain + ((size_t)oct_e * p.npos + (size_t)(pos0 + t * MTILE + wq * 32 + lane)) * 8);
           *w0 = __ldcg(wp);
           *w1 = __ldcg(wp + 1);
         }
@@ -595,13 +609,14 @@ __global__ void __launch_bounds__(NT, 1) sweep_wide_kernel(const WideParams p) {
       }
       conv_phase ^= 1u;
     }
+    WIDE_MARK(8);
     if (more) load_plan(step + 1);
     tc::fence_before_sync();
-    __syncthreads();
+    sync_workers();
     if (more && tid == 0) {
       red_release_add(ctr);
     }
-    WIDE_MARK(8);
+    WIDE_MARK(9);
   }
   if (prof) {
     for (int k = 0; k < 10; ++k) p.prof[k] = s_prof[k];
@@ -648,7 +663,7 @@ int launch_mt(const WideParams& p, int chains, size_t smem, cudaStream_t stream)
   if (int rc = ensure_func_smem(f, smem)) return rc;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(p.T, chains, 1);
-  cfg.blockDim = dim3(NT, 1, 1);
+  cfg.blockDim = dim3(NT_ALL, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
