@@ -89,12 +89,29 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 __device__ __forceinline__ void red_release_add(unsigned* p) {
   asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
-// weak global load that may be served by L1 (never the non-coherent path)
-__device__ __forceinline__ float4 ld_f4(const float* p) {
-  float4 v;
-  asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-  return v;
-}
+// 256-bit global accesses (sm_100: LDG / STG .256): a thread's 8 channels of one position in ONE instruction -- the
+// L1 processes a warp instruction once per 128-byte line it touches, so two 16-byte halves cost twice the wavefronts.
+// ld8: weak load that may be served by L1 (never the non-coherent path); _cg: L2 only; _nc: read-only data.
+#define B200MVS_LD8(name, op)                                                                                        \
+  __device__ __forceinline__ void name(const float* p, float* v) {                                                  \
+    asm volatile(op " {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"                                                       \
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])    \
+                 : "l"(p)                                                                                            \
+                 : "memory");                                                                                        \
+  }
+B200MVS_LD8(ld8, "ld.global.v8.f32")
+B200MVS_LD8(ld8_cg, "ld.global.cg.v8.f32")
+B200MVS_LD8(ld8_nc, "ld.global.nc.v8.f32")
+#undef B200MVS_LD8
+#define B200MVS_ST8(name, op)                                                                                        \
+  __device__ __forceinline__ void name(float* p, const float* v) {                                                  \
+    asm volatile(op " [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), \
+                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])                                                          \
+                 : "memory");                                                                                        \
+  }
+B200MVS_ST8(st8, "st.global.v8.f32")
+B200MVS_ST8(st8_cg, "st.global.cg.v8.f32")
+#undef B200MVS_ST8
 
 __device__ __forceinline__ void unsplit8(const uint4& hi, const uint4& lo, float* v) {
   const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
@@ -352,24 +369,16 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_wide_kernel(const WideParams 
             const float* p00 = prev + ((size_t)y0 * p.cols + x0) * kC;
             const float* p10 = p00 + (size_t)dy * p.cols * kC;
             const float* tp[4] = {p00, p00 + dx * kC, p10, p10 + dx * kC};
-            float4 a[4], b[4];
+            float a[4][8];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              a[t] = ld_f4(tp[t]);
-              b[t] = ld_f4(tp[t] + 4);
-            }
+            for (int t = 0; t < 4; ++t) ld8(tp[t], a[t]);
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              v[0] = fmaf(a[t].x, wt[t], v[0]); v[1] = fmaf(a[t].y, wt[t], v[1]);
-              v[2] = fmaf(a[t].z, wt[t], v[2]); v[3] = fmaf(a[t].w, wt[t], v[3]);
-              v[4] = fmaf(b[t].x, wt[t], v[4]); v[5] = fmaf(b[t].y, wt[t], v[5]);
-              v[6] = fmaf(b[t].z, wt[t], v[6]); v[7] = fmaf(b[t].w, wt[t], v[7]);
-            }
+            for (int t = 0; t < 4; ++t)
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = fmaf(a[t][i], wt[t], v[i]);
           }
           if (l >= halo && l < halo + own_n) {
-            float4* dst = reinterpret_cast<float4*>(wf_chain + ((size_t)t_oct * p.npos + (size_t)(pos0 + l - halo)) * 8);
-            __stcg(dst, make_float4(v[0], v[1], v[2], v[3]));
-            __stcg(dst + 1, make_float4(v[4], v[5], v[6], v[7]));
+            st8_cg(wf_chain + ((size_t)t_oct * p.npos + (size_t)(pos0 + l - halo)) * 8, v);
           }
           uint4 hi, lo;
           tc::split8(v, &hi, &lo);
@@ -389,27 +398,25 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_wide_kernel(const WideParams 
       // what is added to the accumulators (image half of conv0 + bias0, or bias1), loaded one tile ahead; the raw
       // output goes back into the tile's first accumulator columns (tcgen05.st) and is read again behind the chain
       // barrier, so that nothing per tile stays in registers across it
-      auto load_add = [&](int t, float4* i0, float4* i1) {
-        *i0 = *i1 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (layer == 0) {
-          if (own_pix[t] >= 0) {
-            const float4* icp = reinterpret_cast<const float4*>(   // [n][D][octet][pixel][8] (launch_image_conv, oct_major)
-                p.imgconv + ((((size_t)chain * p.D + step) * 4 + oct_e) * pixels + own_pix[t]) * 8);
-            *i0 = __ldg(icp);
-            *i1 = __ldg(icp + 1);
-          }
+      auto load_add = [&](int t, float* nx) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) nx[k] = 0.f;
+        if (layer == 0) {   // [n][D][octet][pixel][8] (launch_image_conv, oct_major)
+          if (own_pix[t] >= 0) ld8_nc(p.imgconv + ((((size_t)chain * p.D + step) * 4 + oct_e) * pixels + own_pix[t]) * 8, nx);
         } else {
-          *i0 = *reinterpret_cast<const float4*>(&s_bias[0][oct_e * 8]);
-          *i1 = *reinterpret_cast<const float4*>(&s_bias[0][oct_e * 8 + 4]);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) nx[k] = s_bias[0][oct_e * 8 + k];
         }
       };
-      float4 n0, n1;
-      load_add(0, &n0, &n1);
+      float nx[8];
+      load_add(0, nx);
 #pragma unroll
       for (int t = 0; t < MT; ++t) {
         if (t < nmy) {
-          const float add[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
-          if (t + 1 < MT) load_add(t + 1, &n0, &n1);
+          float add[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) add[k] = nx[k];
+          if (t + 1 < MT) load_add(t + 1 < MT ? t + 1 : 0, nx);
           float y[8], c[8];
           tc::mbar_wait(&s_bar[t], conv_phase);
           tc::fence_after_sync();
@@ -425,9 +432,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_wide_kernel(const WideParams 
             }
           }
           if (own_bnd[t]) {
-            float4* dst = reinterpret_cast<float4*>(y_layer + (size_t)(pos0 + t * MTILE + wq * 32 + lane) * kC + oct_e * 8);
-            __stcg(dst, make_float4(y[0], y[1], y[2], y[3]));
-            __stcg(dst + 1, make_float4(y[4], y[5], y[6], y[7]));
+            st8_cg(y_layer + (size_t)(pos0 + t * MTILE + wq * 32 + lane) * kC + oct_e * 8, y);
           }
         }
       }
@@ -458,17 +463,14 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_wide_kernel(const WideParams 
       WIDE_MARK(3 + 3 * layer);
       // the neighbours' boundary rows this thread normalises (two tasks at most: 2 halo * 4 <= 2 * NT): in flight under
       // the coefficients and the own rows
-      float4 hy[2][2];
+      float hy[2][8];
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int h = (tid + i * NT) >> 2;
         const int q = pos0 + (h < halo ? h : h + own_n) - halo;   // the output position the halo position mirrors
-        hy[i][0] = hy[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (h < 2 * halo && q >= 0 && q < npos_img && q % PW < p.cols) {
-          const float4* src = reinterpret_cast<const float4*>(y_layer + (size_t)q * kC + t_oct * 8);
-          hy[i][0] = __ldcg(src);
-          hy[i][1] = __ldcg(src + 1);
-        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) hy[i][k] = 0.f;
+        if (h < 2 * halo && q >= 0 && q < npos_img && q % PW < p.cols) ld8_cg(y_layer + (size_t)q * kC + t_oct * 8, hy[i]);
       }
       // ---- GroupNorm coefficients: warp g adds the chain's slots of group g in one fixed order ----
       if (warp < kGroups) {
@@ -545,7 +547,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_wide_kernel(const WideParams 
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = 0.f;
             if (q >= 0 && q < npos_img && q % PW < p.cols) {
-              const float yy[8] = {hy[i][0].x, hy[i][0].y, hy[i][0].z, hy[i][0].w, hy[i][1].x, hy[i][1].y, hy[i][1].z, hy[i][1].w};
+              const float* yy = hy[i];
               float xprev[8];
               if (layer == 1) unsplit8(*ph, *plo, xprev);
 #pragma unroll
@@ -571,39 +573,31 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_wide_kernel(const WideParams 
       float* dst_h = p.vol + ((size_t)chain * p.D + step) * pixels * kC + oct_e * 8;
       const float4 b0 = *reinterpret_cast<const float4*>(&s_bias[1][oct_e * 8]);
       const float4 b1 = *reinterpret_cast<const float4*>(&s_bias[1][oct_e * 8 + 4]);
-      auto load_wf = [&](int t, float4* w0, float4* w1) {
-        *w0 = *w1 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (own_pix[t] >= 0) {
-          const float4* wp = reinterpret_cast<const float4*>(wf_chain + ((size_t)oct_e * p.npos + (size_t)(pos0 + t * MTILE + wq * 32 + lane)) * 8);
-          *w0 = __ldcg(wp);
-          *w1 = __ldcg(wp + 1);
-        }
+      auto load_wf = [&](int t, float* w) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) w[k] = 0.f;
+        if (own_pix[t] >= 0) ld8_cg(wf_chain + ((size_t)oct_e * p.npos + (size_t)(pos0 + t * MTILE + wq * 32 + lane)) * 8, w);
       };
-      float4 n0[2], n1[2];   // two tiles ahead
-      load_wf(0, &n0[0], &n1[0]);
-      if (MT > 1) load_wf(MT > 1 ? 1 : 0, &n0[1], &n1[1]);
+      float nw[2][8];   // two tiles ahead
+      load_wf(0, nw[0]);
+      if (MT > 1) load_wf(MT > 1 ? 1 : 0, nw[1]);
 #pragma unroll
       for (int t = 0; t < MT; ++t) {
         if (t < nmy) {
-          const float4 w0 = n0[t & 1], w1 = n1[t & 1];
-          if (t + 2 < MT) load_wf(t + 2 < MT ? t + 2 : 0, &n0[t & 1], &n1[t & 1]);
+          float w[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) w[k] = nw[t & 1][k];
+          if (t + 2 < MT) load_wf(t + 2 < MT ? t + 2 : 0, nw[t & 1]);
           tc::mbar_wait(&s_bar[t], conv_phase);
           tc::fence_after_sync();
           float v[8], c[8];
           tmem_ld8x2(tmem_my + (uint32_t)(t * 64), tmem_my + (uint32_t)(t * 64) + 32u, v, c);
           if (own_pix[t] >= 0) {
-            float4 r0, r1;
-            r0.x = w0.x + ((v[0] + c[0]) + b0.x);
-            r0.y = w0.y + ((v[1] + c[1]) + b0.y);
-            r0.z = w0.z + ((v[2] + c[2]) + b0.z);
-            r0.w = w0.w + ((v[3] + c[3]) + b0.w);
-            r1.x = w1.x + ((v[4] + c[4]) + b1.x);
-            r1.y = w1.y + ((v[5] + c[5]) + b1.y);
-            r1.z = w1.z + ((v[6] + c[6]) + b1.z);
-            r1.w = w1.w + ((v[7] + c[7]) + b1.w);
-            float4* dst = reinterpret_cast<float4*>(dst_h + (size_t)own_pix[t] * kC);
-            dst[0] = r0;
-            dst[1] = r1;
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float r[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] = w[k] + ((v[k] + c[k]) + bb[k]);
+            st8(dst_h + (size_t)own_pix[t] * kC, r);
           }
         }
       }
