@@ -88,6 +88,30 @@ __device__ __forceinline__ void stg_hint(void* ptr, const uint4& v, uint64_t pol
                : "memory");
 }
 
+// 256-bit global accesses (sm_100: LDG / STG .256): a thread's 8 channels of one position in ONE instruction -- the
+// L1 processes a warp instruction once per 128-byte line it touches, so two 16-byte halves cost twice the wavefronts.
+// ld8: weak load that may be served by L1 (never the non-coherent path); _cg: L2 only; _nc: read-only data.
+#define B200MVS_LD8(name, op)                                                                                        \
+  __device__ __forceinline__ void name(const float* p, float* v) {                                                  \
+    asm volatile(op " {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"                                                       \
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])    \
+                 : "l"(p)                                                                                            \
+                 : "memory");                                                                                        \
+  }
+B200MVS_LD8(ld8, "ld.global.v8.f32")
+B200MVS_LD8(ld8_cg, "ld.global.cg.v8.f32")
+B200MVS_LD8(ld8_nc, "ld.global.nc.v8.f32")
+#undef B200MVS_LD8
+#define B200MVS_ST8(name, op)                                                                                        \
+  __device__ __forceinline__ void name(float* p, const float* v) {                                                  \
+    asm volatile(op " [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), \
+                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])                                                          \
+                 : "memory");                                                                                        \
+  }
+B200MVS_ST8(st8, "st.global.v8.f32")
+B200MVS_ST8(st8_cg, "st.global.cg.v8.f32")
+#undef B200MVS_ST8
+
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 

@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
       //     last read by the MMAs of the output slice four back, whose completion this thread observed in its epilogue
       //   issue the global loads of input slice it + 1
       //   epilogue of output slice it - 3
-      float4 ya[MAX_TASKS], yb[MAX_TASKS];
+      float y8[MAX_TASKS][8];
       bool loaded_valid = false;
       auto issue_loads = [&](int slice) {
         const int din = d0 - 1 + slice;
@@ -227,10 +227,7 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
           const float* src = in_n + (size_t)din * slice_elems;
 #pragma unroll
           for (int k = 0; k < MAX_TASKS; ++k) {
-            if (t_real[k]) {
-              ya[k] = __ldg(reinterpret_cast<const float4*>(src + t_off[k]));
-              yb[k] = __ldg(reinterpret_cast<const float4*>(src + t_off[k] + 4));
-            }
+            if (t_real[k]) ld8_nc(src + t_off[k], y8[k]);   // one 256-bit load per (position, octet)
           }
         }
       };
@@ -246,8 +243,8 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] = 0.f;
               if (t_real[k] && loaded_valid) {
-                v[0] = ya[k].x; v[1] = ya[k].y; v[2] = ya[k].z; v[3] = ya[k].w;
-                v[4] = yb[k].x; v[5] = yb[k].y; v[6] = yb[k].z; v[7] = yb[k].w;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = y8[k][e];
                 if (p.mode >= FEAT_GN) {
 #pragma unroll
                   for (int e = 0; e < 8; ++e) v[e] = lrelu(fmaf(v[e], s_a[8 * t_oct + e], s_b[8 * t_oct + e]));
@@ -284,9 +281,8 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
             float* dst = out_n + (size_t)(d0 + qe) * slice_elems + e_off;
 #pragma unroll
             for (int k = 0; k < 16; ++k) v[k] = (v[k] + c[k]) + s_bias[chalf * 16 + k];
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4)
-              *reinterpret_cast<float4*>(dst + 4 * k4) = make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
+            st8(dst, v);
+            st8(dst + 8, v + 8);
             float fs[2] = {0.f, 0.f}, fq[2] = {0.f, 0.f};
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
