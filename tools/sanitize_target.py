@@ -11,6 +11,10 @@ with torch.no_grad():
     cases = ((512, 640, 2, 6), (64, 80, 1, 8), (68, 90, 1, 5))
     if os.environ.get("CASES") == "big":
         cases = cases[:1]
+    if os.environ.get("WIDE"):
+        # the wide sweep (sweep_wide.cu) forced onto a multi-CTA shape: 2 chains x 11 CTAs, 3 dependent steps
+        net.set_option("sweep", 1)
+        cases = ((512, 640, 2, 4),)
     for rows, cols, views, hyps in cases:
         inp = synthetic.to_device(synthetic.make_inputs(rows, cols, views, 1), "cuda")
         out = net(*inp, hyps, True, [True] * 5)
