@@ -442,6 +442,34 @@ __global__ void __launch_bounds__(256) upsample_mask_kernel(const uint8_t* __res
   }
 }
 
+// Exact 2x upsampling (H = 2h, W = 2w, every level of an even-sized pyramid).  With scale 1/2 the source coordinate of
+// output x is x/2 - 1/4: the four taps carry the weights {3/4, 1/4} x {3/4, 1/4} (all exact in float32), so for 0/1
+// inputs the interpolated value exceeds 1/2 exactly when the NEAREST input pixel is set (9/16 alone, at most 7/16
+// without it; at the border the clamped coordinate puts weight 1 on it).  The bilinear-then-threshold of
+// multi_view_stereonet.py:389-396 is therefore a 2x2 replication -- bit-identical to upsample_mask_kernel (tested) --
+// and the kernel is a byte expander at HBM speed: one thread reads 8 input bytes and writes 16 bytes to each of the
+// two output rows (the general kernel issues four byte loads per output pixel: 0.6 TB/s).
+__global__ void __launch_bounds__(256) upsample_mask2x_kernel(const uint8_t* __restrict__ in, int h, int w,
+                                                              uint8_t* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long plane = blockIdx.y;
+  const int w8 = w >> 3;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= h * w8) return;
+  const int xv = i % w8, y = i / w8;
+  const uint2 s = __ldg(reinterpret_cast<const uint2*>(in + (size_t)plane * h * w + (size_t)y * w) + xv);
+  uint4 o;
+  o.x = __byte_perm(s.x, 0, 0x1100);
+  o.y = __byte_perm(s.x, 0, 0x3322);
+  o.z = __byte_perm(s.y, 0, 0x1100);
+  o.w = __byte_perm(s.y, 0, 0x3322);
+  const int W = 2 * w;
+  uint8_t* dst = out + (size_t)plane * 4 * h * w + (size_t)(2 * y) * W + (size_t)xv * 16;
+  __stcs(reinterpret_cast<uint4*>(dst), o);        // written once, read by nobody on the device at the finest level
+  __stcs(reinterpret_cast<uint4*>(dst + W), o);
+}
+
 // The same upsampling written as a bit volume: out (planes, H, ceil(W / 8)), bit 7 of a byte = its first pixel
 // (numpy.packbits(mask, axis=-1)).  One thread = one output byte.
 __global__ void __launch_bounds__(256) upsample_mask_packed_kernel(const uint8_t* __restrict__ in, int h, int w, int H,
@@ -613,13 +641,18 @@ int launch_upsample_mask(const uint8_t* in, long long n_planes, int h, int w, in
     }
     return 0;
   }
+  const bool exact2x = H == 2 * h && W == 2 * w && w % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(in) & 7) == 0;
   const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 3) == 0) && (((long long)H * W) % 4 == 0);
   const bool vec16 = (W % 16 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   for (long long p0 = 0; p0 < n_planes; p0 += 65535) {
     const int np = (int)((n_planes - p0) < 65535 ? (n_planes - p0) : 65535);
     const uint8_t* src = in + (size_t)p0 * h * w;
     uint8_t* dst = out + (size_t)p0 * H * W;
-    if (vec16) {
+    if (exact2x) {
+      dim3 grid(cdiv(h * (w / 8), 256), np);
+      launch_pdl(upsample_mask2x_kernel, grid, dim3(256), (size_t)0, stream, src, h, w, dst);
+    } else if (vec16) {
       dim3 grid(cdiv(H * (W / 16), 256), np);
       launch_pdl(upsample_mask_kernel<16>, grid, dim3(256), (size_t)0, stream, src, h, w, H, W, dst);
     } else if (vec) {

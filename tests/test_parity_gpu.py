@@ -177,6 +177,26 @@ def test_lazy_and_packed_mask_volumes(net):
         np.testing.assert_array_equal(bits, want)
 
 
+@pytest.mark.parametrize("h,w,H,W", [(32, 40, 64, 80), (8, 16, 16, 32), (64, 80, 128, 160), (9, 13, 17, 25), (32, 40, 63, 80),
+                                     (6, 12, 12, 24)])
+def test_mask_upsampling_against_interpolate(h, w, H, W):
+    """MaskUpsampler (multi_view_stereonet.py:389-396: float -> bilinear -> > 0.5) on random 0/1 volumes against
+    torch's own interpolate: the exact-2x sizes take the byte-replication kernel (upsample_mask2x_kernel: for 0/1
+    inputs the thresholded bilinear value IS the nearest input pixel), the others the general kernel."""
+    from multi_view_stereonet_b200.multi_view_stereonet import LazyMaskPyramid
+    g = torch.Generator().manual_seed(h * 1000 + W)
+    for density in (0.5, 0.1, 0.9):
+        m = (torch.rand(3, 5, h, w, generator=g) < density).to(torch.uint8).cuda()
+        pyr = LazyMaskPyramid(m, [(H, W)] * 4 + [(h, w)])
+        got = pyr._upsample(m, 3, False)
+        val = torch.nn.functional.interpolate(m.float().cpu(), size=(H, W), mode="bilinear", align_corners=False)
+        diff = got.bool().cpu() != (val > 0.5)
+        if H == 2 * h and W == 2 * w:
+            assert int(diff.sum()) == 0, (h, w, H, W, density)      # dyadic weights: no rounding anywhere
+        else:   # general sizes: only values that sit on the threshold to float32 rounding may differ
+            assert float((val[diff] - 0.5).abs().max()) <= 1e-6 if bool(diff.any()) else True, (h, w, H, W, density)
+
+
 def test_weights_follow_in_place_updates(gta_state):
     """The native weight copy follows in-place parameter updates no module hook sees: a submodule's
     load_state_dict, torch.nn.init, an optimizer step."""
