@@ -171,9 +171,9 @@ __global__ void __launch_bounds__(NT, 1) conv5x5s2_c32_tc_kernel(const float* __
     if (oxl < A_TW && ox < Wo && oy < Ho) {
       float* o = out + (((size_t)img * Ho + oy) * Wo + ox) * kC + half * 16;
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        *reinterpret_cast<float4*>(o + 4 * q) = make_float4(v[4 * q] + c[4 * q], v[4 * q + 1] + c[4 * q + 1],
-                                                            v[4 * q + 2] + c[4 * q + 2], v[4 * q + 3] + c[4 * q + 3]);
+      for (int k = 0; k < 16; ++k) v[k] += c[k];
+      st8(o, v);   // 256-bit stores: a thread's 64 bytes in two instructions (half the L1 wavefronts of four float4)
+      st8(o + 8, v + 8);
     }
   }
   tc::fence_before_sync();
@@ -324,9 +324,9 @@ __global__ void __launch_bounds__(NT, MINB) conv5x5s2_c3_tc_kernel(const float* 
       if (ox < Wo && oy < Ho) {
         float* o = out + (((size_t)img * Ho + oy) * Wo + ox) * kC + half * 16;
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<float4*>(o + 4 * q) = make_float4(v[4 * q] + c[4 * q], v[4 * q + 1] + c[4 * q + 1],
-                                                              v[4 * q + 2] + c[4 * q + 2], v[4 * q + 3] + c[4 * q + 3]);
+        for (int k = 0; k < 16; ++k) v[k] += c[k];
+        st8(o, v);
+        st8(o + 8, v + 8);
       }
     }
   }

@@ -368,10 +368,8 @@ __global__ void __launch_bounds__(NT, MINB) conv3x3_tc_kernel(const ConvParams p
           *reinterpret_cast<uint4*>(oh) = pack8(r16);
           *reinterpret_cast<uint4*>(oh + 8) = pack8(r16 + 8);
         } else {
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<float4*>(o + half * 16 + 4 * q) =
-                make_float4(r16[4 * q], r16[4 * q + 1], r16[4 * q + 2], r16[4 * q + 3]);
+          st8(o + half * 16, r16);       // 256-bit stores
+          st8(o + half * 16 + 8, r16 + 8);
         }
       }
     }
