@@ -167,7 +167,7 @@ struct Workspace {
   float* imgconv = nullptr;
   float* rec_plan = nullptr;   // gather plan of the persistent sweep, [n][D][recurrence_plan_stride][4]
   int* rec_flags = nullptr;    // [n][17] progress / out-of-window flags of the persistent sweep
-  WideScratch wide{nullptr, nullptr, nullptr, nullptr};   // scratch of the wide sweep (sweep_wide.cu)
+  WideScratch wide;   // scratch of the wide sweep (sweep_wide.cu)
   float *vol = nullptr, *wf = nullptr, *wimg = nullptr, *sy0 = nullptr, *sx0 = nullptr, *sy1 = nullptr;
   // cost volume
   float *cost = nullptr, *cvfA = nullptr, *cost1 = nullptr;
@@ -255,6 +255,7 @@ struct b200mvs_net {
   bool left_late = true;          // left feature network waits for the right one (side stream)
   bool conv0_precompute = true;   // refiner conv0 = precomputed guide part + idepth part (tail.cu)
   int rec_debug = 0;
+  unsigned* wide_abort_host = nullptr;   // pinned: the wide sweep's watchdog flag of the last forward that used it
   int sweep_mode = 0;             // option "sweep": 0 = cluster kernel where the image fits one cluster, else the wide
                                   // kernel; 1 = wide kernel wherever it is supported; 2 = step by step (a launch per layer)
   // Side stream for the work that does not depend on the comparison views (left feature network) or that
@@ -480,6 +481,15 @@ int build_weights(b200mvs_net* net, const StateDict& sd) {
     }
   }
   return 0;
+}
+
+// The wide sweep's watchdog (sweep_wide.cu: chain_wait): non-zero once a forward's chain barrier has timed out.
+int check_sweep_watchdog(b200mvs_net* net) {
+  if (net->wide_abort_host == nullptr || *net->wide_abort_host == 0) return 0;
+  *net->wide_abort_host = 0;
+  set_error("depth sweep: a chain barrier of the wide kernel timed out (its CTAs were not all making progress -- e.g. two "
+            "such forwards running concurrently on one GPU); the results of that forward are invalid");
+  return B200MVS_ECUDA;
 }
 
 struct Levels {
@@ -893,6 +903,7 @@ int forward_impl(b200mvs_net* net, Lane& lane, bool sweep_on_own_stream, const b
   };
   RC(validate_call(s, left_pyr, K_pyr, Ts, right_l0, right_l4));
   B200MVS_CUDA_OK(cudaSetDevice(net->device));
+  RC(check_sweep_watchdog(net));   // (of an earlier asynchronous forward)
   RC(ensure_workspace(net, s));
   Workspace& ws = net->cur->ws;
   const Levels L = levels_of(s);
@@ -1070,6 +1081,11 @@ int forward_impl(b200mvs_net* net, Lane& lane, bool sweep_on_own_stream, const b
     ra.debug = net->rec_debug;
     if (wide_sweep) {
       probe_before(TAG_RECURRENCE, stream);
+      if (net->wide_abort_host == nullptr) {
+        B200MVS_CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&net->wide_abort_host), sizeof(unsigned), cudaHostAllocDefault));
+        *net->wide_abort_host = 0;
+      }
+      ws.wide.abort_host = net->wide_abort_host;
       RC(launch_sweep_wide(ra, ws.wide, stream));
       probe_after(TAG_RECURRENCE, stream);
     } else if (sweep_on_own_stream) {
@@ -1394,6 +1410,7 @@ B200MVS_API void b200mvs_destroy(b200mvs_net* net) {
   if (net->copy_stream != nullptr) cudaStreamDestroy(net->copy_stream);
   if (net->host_stream != nullptr) cudaStreamDestroy(net->host_stream);
   if (net->pinned_small != nullptr) cudaFreeHost(net->pinned_small);
+  if (net->wide_abort_host != nullptr) cudaFreeHost(net->wide_abort_host);
   delete net;
 }
 
@@ -1822,6 +1839,8 @@ B200MVS_API int b200mvs_forward_host(b200mvs_net* net, const b200mvs_shape* shap
     if (e != cudaSuccess) {
       set_error(std::string("b200mvs_forward_host: ") + cudaGetErrorString(e));
       rc = B200MVS_ECUDA;
+    } else {
+      rc = check_sweep_watchdog(net);
     }
   } else {
     cudaStreamSynchronize(cs);

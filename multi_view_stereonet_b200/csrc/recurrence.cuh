@@ -48,10 +48,11 @@ int launch_recurrence(const RecurrenceArgs& a, cudaStream_t stream);
 // the chain's CTAs exchange statistics and boundary rows through L2 behind a counter barrier.  Uses the same
 // weights, image half and gather plan as launch_recurrence.
 struct WideScratch {
-  float* wf;       // sizes from sweep_wide_scratch
-  float* y;
-  float* part;     // float2 pairs
-  unsigned* ctr;
+  float* wf = nullptr;       // sizes from sweep_wide_scratch
+  float* y = nullptr;
+  float* part = nullptr;     // float2 pairs
+  unsigned* ctr = nullptr;   // chain counters + the watchdog's abort flag
+  unsigned* abort_host = nullptr;   // pinned host word that receives the abort flag behind the sweep (optional)
 };
 bool sweep_wide_supported(int rows, int cols);
 void sweep_wide_scratch(int rows, int cols, int n, size_t* wf_floats, size_t* y_floats, size_t* part_float2,

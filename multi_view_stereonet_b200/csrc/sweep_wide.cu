@@ -72,17 +72,39 @@ struct WideParams {
   float* ybuf;           // [n][2][npos][32] raw layer outputs next to the CTA boundaries
   float2* part;          // [n][2][T_max][4] GroupNorm partials per CTA
   unsigned* ctr;         // [n] arrivals at the chain barrier (zeroed before the launch)
+  unsigned* abort_flag;  // raised by a CTA whose chain barrier did not complete within kSpinLimit cycles
   int part_stride;       // T_max
   int npos;              // tiles * 128
   int chain0;            // first chain of this launch
   int D, rows, cols, tiles, T;
   long long* prof;       // optional [16] phase cycle totals of CTA (0, 0)
+  int debug;             // 32: CTA 0 of chain 0 skips its first arrival (watchdog test: the chain's barrier times out)
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+// The chain barrier's wait (one thread per CTA).  A spin barrier is only safe while every CTA of the chain is resident;
+// the cooperative launch guarantees that, but a wait that can never end would hang the GPU instead of reporting an
+// error, so it carries a watchdog: after kSpinLimit cycles (~1 s) the CTA raises the launch's abort flag, every CTA
+// that sees the flag stops waiting, the kernel ends (with garbage) and the host reports the failure (api.cu).
+constexpr long long kSpinLimit = 2000000000ll;
+__device__ __forceinline__ bool chain_wait(const unsigned* ctr, unsigned target, unsigned* abort_flag) {
+  unsigned it = 0;
+  long long t0 = 0;
+  while (ld_acquire_u32(ctr) < target) {
+    if ((++it & 1023u) == 0) {
+      if (it == 1024u) t0 = clock64();
+      if (*reinterpret_cast<volatile unsigned*>(abort_flag) != 0) return false;
+      if (clock64() - t0 > kSpinLimit) {
+        atomicExch(abort_flag, 1u);
+        return false;
+      }
+    }
+  }
+  return true;
 }
 // arrival at a chain counter: one release reduction (everything this thread wrote, and what the block barrier in front
 // of it made it observe, is ordered before the increment)
@@ -252,6 +274,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_wide_kernel(const WideParams 
   unsigned* const ctr = p.ctr + chain;
   unsigned sync_k = 0;
   const unsigned T = (unsigned)p.T;
+  bool alive = true;   // (thread 0) no chain barrier has timed out
 
   // This thread's accumulator slices: tile t, lane quarter wq, ONE channel octet (= one GroupNorm group).
   const int wq = warp & 3, oct_e = warp >> 2;
@@ -318,10 +341,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_wide_kernel(const WideParams 
     // ================= W: warp the previous hypothesis into the conv0 operand =================
     if (step >= 2) {   // every CTA of the chain has published hypothesis step - 1
       ++sync_k;
-      if (tid == 0) {
-        const unsigned target = T * sync_k;
-        while (ld_acquire_u32(ctr) < target) {}
-      }
+      if (tid == 0 && alive) alive = chain_wait(ctr, T * sync_k, p.abort_flag);
       sync_workers();
     }
     WIDE_MARK(0);
@@ -432,9 +452,8 @@ __global__ void __launch_bounds__(NT_ALL, 1) sweep_wide_kernel(const WideParams 
           const float2 u0 = s_loc[g][0], u1 = s_loc[g][1], u2 = s_loc[g][2], u3 = s_loc[g][3];
           __stcg(slot + g, make_float2((u0.x + u1.x) + (u2.x + u3.x), (u0.y + u1.y) + (u2.y + u3.y)));
         }
-        red_release_add(ctr);
-        const unsigned target = T * sync_k;
-        while (ld_acquire_u32(ctr) < target) {}
+        if (!((p.debug & 32) && cta == 0 && chain == 0 && sync_k == 1)) red_release_add(ctr);
+        if (alive) alive = chain_wait(ctr, T * sync_k, p.abort_flag);
       }
       sync_workers();
       WIDE_MARK(3 + 3 * layer);
@@ -667,7 +686,7 @@ void sweep_wide_scratch(int rows, int cols, int n, size_t* wf_floats, size_t* y_
   *wf_floats = (size_t)n * npos * kC;
   *y_floats = (size_t)n * 2 * npos * kC;
   *part_float2 = (size_t)n * 2 * tiles * kGroups;
-  *counters = (size_t)n;
+  *counters = (size_t)n + 1;   // + the watchdog's abort flag
 }
 
 int launch_sweep_wide(const RecurrenceArgs& a, const WideScratch& s, cudaStream_t stream) {
@@ -681,7 +700,7 @@ int launch_sweep_wide(const RecurrenceArgs& a, const WideScratch& s, cudaStream_
   }
   const WideLayout L = make_wide_layout(a.cols, pl.mt);
   const int tiles = cdiv(a.rows * L.PW, MTILE);
-  B200MVS_CUDA_OK(cudaMemsetAsync(s.ctr, 0, (size_t)a.n * sizeof(unsigned), stream));
+  B200MVS_CUDA_OK(cudaMemsetAsync(s.ctr, 0, ((size_t)a.n + 1) * sizeof(unsigned), stream));
   WideParams p;
   p.vol_in = a.vol;
   p.vol = a.vol;
@@ -699,6 +718,7 @@ int launch_sweep_wide(const RecurrenceArgs& a, const WideScratch& s, cudaStream_
   p.ybuf = s.y;
   p.part = reinterpret_cast<float2*>(s.part);
   p.ctr = s.ctr;
+  p.abort_flag = s.ctr + a.n;
   p.part_stride = tiles;
   p.npos = tiles * MTILE;
   p.D = a.D;
@@ -707,6 +727,7 @@ int launch_sweep_wide(const RecurrenceArgs& a, const WideScratch& s, cudaStream_
   p.tiles = tiles;
   p.T = pl.T;
   p.prof = a.prof;
+  p.debug = a.debug;
   for (int c0 = 0; c0 < a.n; c0 += pl.chains_per_launch) {
     const int chains = a.n - c0 < pl.chains_per_launch ? a.n - c0 : pl.chains_per_launch;
     p.chain0 = c0;
@@ -721,6 +742,9 @@ int launch_sweep_wide(const RecurrenceArgs& a, const WideScratch& s, cudaStream_
     if (rc != 0) return rc;
     p.prof = nullptr;
   }
+  // the watchdog's verdict travels to the host behind the sweep; the caller looks at it after its next synchronise
+  if (s.abort_host != nullptr)
+    B200MVS_CUDA_OK(cudaMemcpyAsync(s.abort_host, p.abort_flag, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
   return 0;
 }
 

@@ -281,6 +281,24 @@ def test_wide_sweep_vs_oracle(rows, cols, views, hyps, batch, net, gta_state):
         assert rep[f"v{v}/right_feature_volume"] <= 1e-3
 
 
+def test_wide_sweep_watchdog_reports_a_stuck_barrier(gta_state):
+    """The wide sweep's chain barriers spin; a wait that cannot complete must end in an error, not in a hung GPU.
+    Debug bit 32 makes one CTA skip an arrival: after ~1 s the watchdog raises the abort flag, the kernel ends, and the
+    host entry reports it; the next forward (bit cleared) is fine again."""
+    from tests._gpu_util import make_net
+    net = make_net(gta_state)
+    inputs = synthetic.make_inputs(512, 640, 1, 1, smooth=True)
+    with torch.no_grad():
+        good = net(*synthetic.to_device(inputs, "cuda"), 4, True, [True] * 5)["left_idepthmap_pyr"][0].cpu()
+        net.set_option("sweep", 1)
+        net.set_option("recurrence_debug", 32)
+        with pytest.raises(RuntimeError, match="timed out"):
+            net(*inputs, 4, True, [True] * 5)          # CPU tensors: b200mvs_forward_host synchronises and checks
+        net.set_option("recurrence_debug", 0)
+        again = net(*inputs, 4, True, [True] * 5)["left_idepthmap_pyr"][0]
+    assert rel_linf(again, good) <= REL_LINF_TOL / 2
+
+
 def test_flag_variants(net, gta_state):
     """do_cost_volume_filter=False and partially disabled refiners, including the
     reference's double baseline division when do_refiners[4] is False."""
