@@ -675,8 +675,10 @@ int launch_mt(const WideParams& p, int chains, size_t smem, cudaStream_t stream)
 }  // namespace
 
 bool sweep_wide_supported(int rows, int cols) {
+  int sms = 0;
+  if (current_device_sm_count(&sms) != 0 || sms < 1) return false;   // (one chain must fit the device it will run on)
   WidePlan pl;
-  return plan_wide(rows, cols, 1, 148, &pl);
+  return plan_wide(rows, cols, 1, sms, &pl);
 }
 
 void sweep_wide_scratch(int rows, int cols, int n, size_t* wf_floats, size_t* y_floats, size_t* part_float2,
