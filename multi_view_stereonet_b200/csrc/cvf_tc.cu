@@ -4,15 +4,22 @@
 // A CTA owns RT output rows of a column strip of width cw (RT * (cw+2) <= 128 positions = one UMMA M-tile; images
 // wider than 48 pixels are cut into equal strips whose halo columns come from the neighbouring strip) of a chunk of
 // depth slices of one volume and streams through depth: every input slice tile ((RT+2) rows, previous layer's GroupNorm + LeakyReLU
-// applied, split into hi/lo fp16 planes) is staged ONCE into a 4-slot shared-memory ring and used by the three
-// output slices that touch it.  Output slice q = 27 taps x 2 k-steps x 2 MMAs reading ring slots q, q+1, q+2 with
-// the shifted-window descriptors of conv_tc.cu; accumulators are double-buffered in TMEM.
-// Warp-specialised: eight worker warps stage slices and drain accumulators, a ninth warp only issues MMAs.  One
-// slice's 108 MMAs take ~4.9 k cycles of the tensor pipe and nearly as long to ISSUE (tools/mma_bench.cu: 45 cycles
-// per MMA at N = 64 / 32); with the issue loop on a worker warp every iteration paid issue time plus staging plus
-// epilogue (~9 k cycles, round 1), now the tensor pipe runs back to back and the workers hide under it.  The roles
-// meet only at mbarriers: full[slot] (workers -> issuer), acc_full[buf] (tcgen05.commit -> workers), acc_empty[buf]
-// (workers -> issuer).
+// applied, split into hi/lo fp16 planes) is staged ONCE into a 4-slot shared-memory ring and read by ONE batch of MMAs.
+//
+// Sliding accumulator window: input slice i contributes to output slices i - 1, i, i + 1 through the taps kz = 2, 1, 0.
+// The accumulators of consecutive output slices sit in consecutive 32-column slots of tensor memory (a ring of 16), and
+// the weights of the three kz taps of one in-plane tap are stacked along N (96 rows, kz = 2 first), so one N = 96 MMA
+// per (in-plane tap, k-step, split-precision product) adds a slice's contribution to all three outputs at once:
+// 9 x 2 x 3 = 54 MMAs per slice instead of 108 (N = 64 / 32) per output slice, and the 4 KB A operand is fetched once
+// for three outputs.  The MMA rate is set by the operand bytes read from shared memory, (A + B) / 128 per clock
+// (tools/mma_bench.cu: N = 32 43 cycles, 64 55, 96 60, 128 69); a batch is 3.25 k cycles against 4.87 k before.  The
+// output slice a batch starts takes its first product as an MMA of its own with accumulate = 0; windows that wrap around
+// the ring (2 batches of 16) and the ends of a segment split into N = 64 + 32 (general path of the issuer).  An output
+// slice is complete after the batch of the input slice behind it: one tcgen05.commit per batch.
+// Warp-specialised: sixteen worker warps stage slices and drain accumulators (8 channels of one position per thread), a
+// seventeenth warp only issues MMAs.  The roles meet only at mbarriers: full[slot] (workers -> issuer), acc_full[slot]
+// (tcgen05.commit -> workers), acc_empty[slot] (workers -> issuer).
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
@@ -23,12 +30,18 @@
 namespace b200mvs {
 namespace {
 
-constexpr int NW = 256;            // worker threads (8 warps): staging + epilogue
+constexpr int NW = 512;            // worker threads (16 warps): staging + epilogue
 constexpr int NT = NW + 32;        // + the MMA-issuing warp
-constexpr int MAX_TASKS = 4;
+constexpr int MAX_TASKS = 2;
 constexpr int W_BLOCKS = 27 * 2;
 constexpr int W_BYTES = W_BLOCKS * 2048;
 constexpr int RING = 4;
+constexpr int ACC = 16;            // accumulator slots in tensor memory (32 columns each, a ring over the output slices)
+// The workers drain output slice it - LAG in the iteration that stages input slice it.  3, not more: staging reuses the
+// ring slot of input slice it - 4, whose batch must be through -- the epilogue of iteration it - 1 waited for the commit
+// behind batch it - 2 (LAG = 4 would leave iteration 4 of a segment without that knowledge).
+constexpr int LAG = 3;
+constexpr uint32_t TMEM_COLS = 32u * ACC;
 
 struct Geo {
   int PW, RT, NP, np_pad;
@@ -62,6 +75,8 @@ struct CvfParams {
   int dbg;     // timing ablations (wrong results): 1 no MMAs, 2 no operand staging stores, 4 no output stores, 8 no input loads
 };
 
+__device__ __forceinline__ uint32_t idesc_n(uint32_t n) { return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
+
 __device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(NW) : "memory"); }
 
 // Work decomposition.  A column = all D output slices of one (volume n, row tile, column strip); the n * row_tiles *
@@ -74,7 +89,7 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ float s_a[kC], s_b[kC], s_bias[kC];
   __shared__ double s_stats[2 * kGroups];
-  __shared__ __align__(8) uint64_t s_full[RING], s_acc_full[2], s_acc_empty[2], s_wbar;
+  __shared__ __align__(8) uint64_t s_full[RING], s_acc_full[ACC], s_acc_empty[ACC], s_wbar;
   __shared__ uint32_t s_tmem;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -95,10 +110,10 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
   uint8_t* s_w = smem;
   uint8_t* s_ring = smem + W_BYTES;
 
-  if (warp == 0) tc::tmem_alloc(&s_tmem, 128u);
+  if (warp == 0) tc::tmem_alloc(&s_tmem, TMEM_COLS);
   if (tid == 32) {
     for (int i = 0; i < RING; ++i) tc::mbar_init(&s_full[i], NW / 32);   // one arrival per worker warp
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < ACC; ++i) {
       tc::mbar_init(&s_acc_full[i], 1);
       tc::mbar_init(&s_acc_empty[i], NW / 32);
     }
@@ -119,25 +134,47 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
   const size_t slice_elems = (size_t)p.h * p.w * kC;
 
   if (warp == NW / 32) {
-    // ================= MMA issuer: output slice q of a segment once its input slices q .. q+2 are staged and its
-    //                   accumulator is free
+    // ================= MMA issuer: the batch of input slice i (its contributions to output slices i - 2, i - 1, i)
+    //                   once the slice is staged and the accumulator slot of the output it starts is drained
     if (tc::elect_one()) {
       const uint64_t da0 = tc::umma_desc(tc::smem_u32(s_ring), g.plane_bytes, 128u);
-      const uint64_t db0 = tc::umma_desc(tc::smem_u32(s_w), 1024u, 128u);
+      const uint64_t db0 = tc::umma_desc(tc::smem_u32(s_w), 96u * 16u, 128u);
       tc::mbar_wait(&s_wbar, 0u);   // the bulk-copied weights have landed
       uint32_t sc = 0, oc = 0;      // staged slices / output slices of all earlier segments
+#ifdef CVF_PROF
+      long long pf_full = 0, pf_empty = 0, pf_issue = 0, pf_n = 0, pf_t0 = clock64();
+#endif
       for (long long u = u_begin; u < u_end;) {
         const int d0 = (int)(u % p.D);
         const int dcount = (int)((long long)(p.D - d0) < u_end - u ? (long long)(p.D - d0) : u_end - u);
-        for (int q = 0; q < dcount; ++q) {
-          const uint32_t S = sc + (uint32_t)q + 2u, O = oc + (uint32_t)q;
+        for (int i = 0; i <= dcount + 1; ++i) {
+          const uint32_t S = sc + (uint32_t)i;
+          const bool fresh = i < dcount;   // output slice i receives its first contribution (kz = 0) from this slice
+#ifdef CVF_PROF
+          const long long pa = clock64();
+#endif
           tc::mbar_wait(&s_full[S & (RING - 1)], (S / RING) & 1u);
-          if (O >= 2) tc::mbar_wait(&s_acc_empty[O & 1], ((O >> 1) - 1u) & 1u);
+#ifdef CVF_PROF
+          const long long pb = clock64();
+#endif
+          if (fresh) {
+            const uint32_t O = oc + (uint32_t)i;
+            if (O >= ACC) tc::mbar_wait(&s_acc_empty[O & (ACC - 1)], ((O / ACC) - 1u) & 1u);
+          }
+#ifdef CVF_PROF
+          const long long pc = clock64();
+#endif
           tc::fence_after_sync();
-          const uint32_t acc = tmem_base + (O & 1u) * 64u;
-#pragma unroll
-          for (int kz = 0; kz < ((P.dbg & 1) ? 0 : 3); ++kz) {
-            const uint64_t da_slot = da0 + (uint64_t)(((sc + (uint32_t)(q + kz)) & (RING - 1)) * slot_u16);
+          // Window entry j = 0, 1, 2 is output slice i - 2 + j (weights kz = 2 - j) in accumulator slot (oc + i - 2 + j)
+          // mod ACC; all three split-precision products (A_hi W_hi, A_lo W_hi, A_hi W_lo) add into the same columns.
+          const uint32_t slot0 = (oc + (uint32_t)i - 2u) & (ACC - 1);
+          const uint64_t da_slot = da0 + (uint64_t)((S & (RING - 1)) * slot_u16);
+          if (P.dbg & 1) {
+            // timing ablation: no MMAs
+          } else if (i >= 2 && i < dcount && slot0 <= ACC - 3) {
+            // Inside a segment, window in consecutive slots: one N = 96 MMA per product.  Output slice i starts in
+            // this batch: the very first product goes in as N = 64 (accumulate) + N = 32 (overwrite).
+            const uint32_t dx = tmem_base + 32u * slot0;
 #pragma unroll
             for (int t2 = 0; t2 < 9; ++t2) {
               const uint32_t pos = (uint32_t)((t2 / 3) * PW + (t2 % 3));
@@ -145,29 +182,104 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
               for (int ks = 0; ks < 2; ++ks) {
                 const uint64_t a_hi = da_slot + (uint64_t)(2 * ks * plane_u16 + pos);
                 const uint64_t a_lo = a_hi + (uint64_t)(4 * plane_u16);
-                const uint64_t b = db0 + (uint64_t)((((kz * 9 + t2) * 2) + ks) * 128);
-                tc::mma_f16(acc, a_hi, b, tc::idesc_f16(64), (kz | t2 | ks) != 0 ? 1u : 0u);
-                tc::mma_f16(acc, a_lo, b, tc::idesc_f16(32), 1u);
+                const uint64_t b_hi = db0 + (uint64_t)((t2 * 2 + ks) * 384);   // [W_hi | W_lo] x 2 k-octets x 96 rows
+                const uint64_t b_lo = b_hi + 192u;
+                if ((t2 | ks) == 0) {
+                  tc::mma_f16(dx, a_hi, b_hi, tc::idesc_f16(64), 1u);
+                  tc::mma_f16(dx + 64u, a_hi, b_hi + 64u, tc::idesc_f16(32), 0u);
+                } else {
+                  tc::mma_f16(dx, a_hi, b_hi, tc::idesc_f16(96), 1u);
+                }
+                tc::mma_f16(dx, a_lo, b_hi, tc::idesc_f16(96), 1u);
+                tc::mma_f16(dx, a_hi, b_lo, tc::idesc_f16(96), 1u);
+              }
+            }
+          } else {
+            // Segment ends (entries outside the segment are skipped) and windows that wrap around the ring: entries in
+            // consecutive slots share an MMA (N = 32 per entry), the entry a batch starts is on its own in the first product.
+            const int jlo = i >= 2 ? 0 : 2 - i;
+            const int jhi = dcount + 1 - i < 2 ? dcount + 1 - i : 2;
+            uint32_t e_col[3], e_idesc[2][3];   // per window entry: accumulator column, descriptor of the run it starts
+            bool e_start[2][3];                 // [1]: in the first product of a batch that starts an output slice
+            {
+              bool val[3], brk[2][3];
+#pragma unroll
+              for (int j = 0; j < 3; ++j) {
+                const uint32_t slot = (slot0 + (uint32_t)j) & (ACC - 1);
+                val[j] = j >= jlo && j <= jhi;
+                e_col[j] = tmem_base + 32u * slot;
+                brk[0][j] = j == 0 || !val[j - (j > 0)] || slot == 0u;
+                brk[1][j] = brk[0][j] || (fresh && j == 2);
+              }
+#pragma unroll
+              for (int f = 0; f < 2; ++f) {
+                const uint32_t len2 = 1u;
+                const uint32_t len1 = 1u + ((val[2] && !brk[f][2]) ? len2 : 0u);
+                const uint32_t len0 = 1u + ((val[1] && !brk[f][1]) ? len1 : 0u);
+                e_start[f][0] = val[0];
+                e_start[f][1] = val[1] && brk[f][1];
+                e_start[f][2] = val[2] && brk[f][2];
+                e_idesc[f][0] = idesc_n(32u * len0);
+                e_idesc[f][1] = idesc_n(32u * len1);
+                e_idesc[f][2] = idesc_n(32u * len2);
+              }
+            }
+            const uint32_t acc_last = fresh ? 0u : 1u;   // accumulate flag of entry 2's own run in the first product
+#pragma unroll
+            for (int t2 = 0; t2 < 9; ++t2) {
+              const uint32_t pos = (uint32_t)((t2 / 3) * PW + (t2 % 3));
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                const uint64_t a_hi = da_slot + (uint64_t)(2 * ks * plane_u16 + pos);
+                const uint64_t a_lo = a_hi + (uint64_t)(4 * plane_u16);
+                const uint64_t b_hi = db0 + (uint64_t)((t2 * 2 + ks) * 384);
+                const uint64_t b_lo = b_hi + 192u;
+                const int f = (t2 | ks) == 0 ? 1 : 0;
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                  if (e_start[f][j])
+                    tc::mma_f16(e_col[j], a_hi, b_hi + 32u * j, e_idesc[f][j], (f == 1 && j == 2) ? acc_last : 1u);
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                  if (e_start[0][j]) tc::mma_f16(e_col[j], a_lo, b_hi + 32u * j, e_idesc[0][j], 1u);
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                  if (e_start[0][j]) tc::mma_f16(e_col[j], a_hi, b_lo + 32u * j, e_idesc[0][j], 1u);
               }
             }
           }
-          tc::mma_commit(&s_acc_full[O & 1]);   // implies tcgen05.fence::before_thread_sync
+          // output slice i - 2 is complete (implies tcgen05.fence::before_thread_sync)
+          if (i >= 2) tc::mma_commit(&s_acc_full[(oc + (uint32_t)i - 2u) & (ACC - 1)]);
+#ifdef CVF_PROF
+          pf_full += pb - pa;
+          pf_empty += pc - pb;
+          pf_issue += clock64() - pc;
+          ++pf_n;
+#endif
         }
         sc += (uint32_t)dcount + 2u;
         oc += (uint32_t)dcount;
         u += dcount;
       }
+#ifdef CVF_PROF
+      if (blockIdx.x == 0 || blockIdx.x == 77)
+        printf("cvf issuer cta %d: %lld batches, per batch: wait full %lld, wait acc_empty %lld, issue %lld, total %lld\n",
+               (int)blockIdx.x, pf_n, pf_full / pf_n, pf_empty / pf_n, pf_issue / pf_n, (clock64() - pf_t0) / pf_n);
+#endif
     }
     __syncwarp();
   } else {
     // ================= workers: staging + epilogue
     const int t_oct = tid & 3;
-    const int wq = warp & 3, chalf = warp >> 2;
+    const int wq = warp & 3, cq = warp >> 2;   // TMEM lane quarter, GroupNorm group (8 output channels)
     const int jl = wq * 32 + lane;
     const int e_oy = jl / PW, e_ox = jl % PW;
-    const uint32_t tmem_my = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(chalf * 16);
+    const uint32_t tmem_my = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(cq * 8);
     uint32_t sc = 0, oc = 0;
     int cur_n = -1;
+#ifdef CVF_PROF
+    long long pw_stage = 0, pw_loads = 0, pw_wait = 0, pw_epi = 0, pw_n = 0, pw_t0 = clock64();
+#endif
     for (long long u = u_begin; u < u_end;) {
       const int col = (int)(u / p.D), d0 = (int)(u % p.D);
       const int dcount = (int)((long long)(p.D - d0) < u_end - u ? (long long)(p.D - d0) : u_end - u);
@@ -204,14 +316,14 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
         t_real[k] = t_in[k] && iy < RT + 2 && gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;
         t_off[k] = t_real[k] ? ((size_t)gy * p.w + gx) * kC + 8 * t_oct : 0;
       }
-      // epilogue slice of this thread: one output position, 16 channels
+      // epilogue slice of this thread: one output position, 8 channels (one GroupNorm group)
       const bool e_real = e_oy < RT && e_ox < P.cw && (x0 + e_ox) < p.w && (y0 + e_oy) < p.h;
-      const size_t e_off = e_real ? ((size_t)(y0 + e_oy) * p.w + x0 + e_ox) * kC + chalf * 16 : 0;
+      const size_t e_off = e_real ? ((size_t)(y0 + e_oy) * p.w + x0 + e_ox) * kC + cq * 8 : 0;
       const float* in_n = p.in + (size_t)n * p.D * slice_elems;
       float* out_n = p.out + (size_t)n * p.D * slice_elems;
       // statistics: float32 within one slice (8 values per group), float64 across slices -- the result must not
       // depend on how many slices a segment happens to hold
-      double gs[2] = {0.0, 0.0}, gq[2] = {0.0, 0.0};
+      double gs = 0.0, gq = 0.0;
 
       // Software pipeline over the segment's depth range.  Iteration `it`:
       //   transform + stage input slice it (its global loads were issued one iteration earlier) -> next ring slot,
@@ -232,7 +344,10 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
         }
       };
       issue_loads(0);
-      for (int it = 0; it <= dcount + 2; ++it) {
+      for (int it = 0; it <= dcount + LAG - 1; ++it) {
+#ifdef CVF_PROF
+        const long long wa = clock64();
+#endif
         if (it <= dcount + 1) {
           const uint32_t S = sc + (uint32_t)it;
           uint8_t* slot = s_ring + (size_t)(S & (RING - 1)) * g.slot_bytes;
@@ -263,55 +378,61 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
           if (lane == 0) tc::mbar_arrive(&s_full[S & (RING - 1)]);
         }
 
+#ifdef CVF_PROF
+        const long long wb = clock64();
+#endif
         issue_loads(it + 1);
+#ifdef CVF_PROF
+        const long long wc = clock64();
+        long long wd = wc;
+#endif
 
-        const int qe = it - 3;
+        const int qe = it - LAG;
         if (qe >= 0 && qe < dcount) {
           const uint32_t O = oc + (uint32_t)qe;
-          tc::mbar_wait_warp(&s_acc_full[O & 1], (O >> 1) & 1u);
+          tc::mbar_wait_warp(&s_acc_full[O & (ACC - 1)], (O / ACC) & 1u);
+#ifdef CVF_PROF
+          wd = clock64();
+#endif
           tc::fence_after_sync();
-          float v[16], c[16];
-          const uint32_t acc = tmem_my + (O & 1u) * 64u;
-          tc::tmem_ld16(acc, v);
-          tc::tmem_ld16(acc + 32u, c);
+          float v[8];
+          tc::tmem_ld8(tmem_my + (O & (ACC - 1)) * 32u, v);
           tc::fence_before_sync();
           __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&s_acc_empty[O & 1]);   // the accumulator may be overwritten
+          if (lane == 0) tc::mbar_arrive(&s_acc_empty[O & (ACC - 1)]);   // the accumulator may be overwritten
           if (e_real && !(P.dbg & 4)) {
             float* dst = out_n + (size_t)(d0 + qe) * slice_elems + e_off;
 #pragma unroll
-            for (int k = 0; k < 16; ++k) v[k] = (v[k] + c[k]) + s_bias[chalf * 16 + k];
+            for (int k = 0; k < 8; ++k) v[k] += s_bias[cq * 8 + k];
             st8(dst, v);
-            st8(dst + 8, v + 8);
-            float fs[2] = {0.f, 0.f}, fq[2] = {0.f, 0.f};
+            float fs = 0.f, fq = 0.f;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-              fs[0] += v[k];
-              fq[0] += v[k] * v[k];
-              fs[1] += v[8 + k];
-              fq[1] += v[8 + k] * v[8 + k];
+              fs += v[k];
+              fq += v[k] * v[k];
             }
-            gs[0] += (double)fs[0];
-            gq[0] += (double)fq[0];
-            gs[1] += (double)fs[1];
-            gq[1] += (double)fq[1];
+            gs += (double)fs;
+            gq += (double)fq;
           }
         }
+#ifdef CVF_PROF
+        pw_stage += wb - wa;
+        pw_loads += wc - wb;
+        pw_wait += wd - wc;
+        pw_epi += clock64() - wd;
+        ++pw_n;
+#endif
       }
       // ---- GroupNorm statistics of what this segment stored (volume n) ----
       if (p.out_stats != nullptr) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-          gs[0] += __shfl_xor_sync(0xffffffffu, gs[0], o);
-          gq[0] += __shfl_xor_sync(0xffffffffu, gq[0], o);
-          gs[1] += __shfl_xor_sync(0xffffffffu, gs[1], o);
-          gq[1] += __shfl_xor_sync(0xffffffffu, gq[1], o);
+          gs += __shfl_xor_sync(0xffffffffu, gs, o);
+          gq += __shfl_xor_sync(0xffffffffu, gq, o);
         }
         if (lane == 0) {
-          atomicAdd(&s_stats[(2 * chalf) * 2 + 0], gs[0]);
-          atomicAdd(&s_stats[(2 * chalf) * 2 + 1], gq[0]);
-          atomicAdd(&s_stats[(2 * chalf + 1) * 2 + 0], gs[1]);
-          atomicAdd(&s_stats[(2 * chalf + 1) * 2 + 1], gq[1]);
+          atomicAdd(&s_stats[cq * 2 + 0], gs);
+          atomicAdd(&s_stats[cq * 2 + 1], gq);
         }
         worker_barrier();
         if (tid < 2 * kGroups) {
@@ -327,10 +448,16 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
       oc += (uint32_t)dcount;
       u += dcount;
     }
+#ifdef CVF_PROF
+    if ((blockIdx.x == 0 || blockIdx.x == 77) && (tid == 0 || tid == 511))
+      printf("cvf worker cta %d tid %d: %lld iterations, per iteration: stage %lld, issue loads %lld, wait acc_full %lld, "
+             "epilogue %lld, total %lld\n", (int)blockIdx.x, tid, pw_n, pw_stage / pw_n, pw_loads / pw_n, pw_wait / pw_n,
+             pw_epi / pw_n, (clock64() - pw_t0) / pw_n);
+#endif
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem_base, 128u);
+  if (warp == 0) tc::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 }  // namespace
@@ -338,10 +465,19 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
 void pack_cvf_tc_weights(const float* w_oidhw, std::vector<uint8_t>* out) {
   out->assign(W_BYTES, 0);
   __half* h = reinterpret_cast<__half*>(out->data());
+  // per (in-plane tap t2, k-step ks) one 6 KB block: [W_hi, W_lo][k octet (2)][row (96)][8 fp16], row = 32 j + output
+  // channel with j = 2 - kz -- the window of output slices (i - 2, i - 1, i) an input slice i contributes to
   for (int tap = 0; tap < 27; ++tap)
     for (int nn = 0; nn < 32; ++nn)
-      for (int c = 0; c < 32; ++c)
-        tc::put_split_weight(h, tap * 2 + c / 16, c % 16, nn, w_oidhw[((size_t)nn * 32 + c) * 27 + tap]);
+      for (int c = 0; c < 32; ++c) {
+        const int kz = tap / 9, t2 = tap % 9, ks = c / 16, k = c % 16;
+        const float w = w_oidhw[((size_t)nn * 32 + c) * 27 + tap];
+        const __half hi = __float2half_rn(w);
+        const __half lo = __float2half_rn(w - __half2float(hi));
+        const size_t e = (size_t)(t2 * 2 + ks) * 3072 + (size_t)(k / 8) * 768 + (size_t)((2 - kz) * 32 + nn) * 8 + (size_t)(k % 8);
+        h[e] = hi;
+        h[e + 1536] = lo;
+      }
 }
 
 bool cvf_tc_supported(int h, int w) {

@@ -18,7 +18,7 @@ void set_pdl_enabled(bool) {}
 // PATTERN: 0 = same A every MMA; 1 = nine taps (ky*PW + kx) of a PW=42 plane, two K-steps, as the conv kernels issue
 // them; 2 = split-precision pairs (N=64 on A_hi, N=32 on A_lo) over the nine taps x two K-steps.
 template <int N, int PATTERN, int COUNT, int BASE, bool INTERLEAVED>
-__global__ void __launch_bounds__(128, 1) bench_kernel(long long* out, int plane_bytes) {
+__global__ void __launch_bounds__(128, 1) bench_kernel(long long* out, int plane_bytes, int d_off) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t s_tmem;
@@ -53,7 +53,14 @@ __global__ void __launch_bounds__(128, 1) bench_kernel(long long* out, int plane
             const uint64_t a = da0 + (uint64_t)(BASE + 2u * ks * plane_u16 + pos);
             const uint64_t b = db0 + (uint64_t)(((tap * 2 + ks) % 18) * 128);
             if (PATTERN == 1) {
-              tc::mma_f16(tmem, a, b, tc::idesc_f16(N), i ? 1u : 0u);
+              tc::mma_f16(tmem + d_off, a, b, tc::idesc_f16(N), i ? 1u : 0u);
+            } else if (PATTERN == 3) {
+              // sliding-window Conv3d batch (cvf_tc.cu): A_hi W_hi, A_lo W_hi into X, A_hi W_lo into Y = X + 256 columns,
+              // weight blocks of 96 rows (LBO 1536)
+              const uint64_t b3 = tc::umma_desc(tc::smem_u32(smem + 64 * 1024), 1536u, 128u) + (uint64_t)((tap * 2 + ks) * 384);
+              tc::mma_f16(tmem + d_off, a, b3, tc::idesc_f16(N), i ? 1u : 0u);
+              tc::mma_f16(tmem + d_off, a + 4u * plane_u16, b3, tc::idesc_f16(N), 1u);
+              tc::mma_f16(tmem + 256 + d_off, a, b3 + 192u, tc::idesc_f16(N), i ? 1u : 0u);
             } else {
               tc::mma_f16(tmem, a, b, tc::idesc_f16(64), i ? 1u : 0u);
               tc::mma_f16(tmem, a + 4u * plane_u16, b, tc::idesc_f16(32), 1u);
@@ -172,15 +179,16 @@ void run_m(long long* d) {
   cudaFree(rows);
 }
 
+int g_grid = 1;
 template <int N, int PATTERN, int COUNT, int BASE, bool INTERLEAVED>
-void run(const char* name, long long* d) {
+void run(const char* name, long long* d, int d_off = 0) {
   auto k = bench_kernel<N, PATTERN, COUNT, BASE, INTERLEAVED>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  k<<<1, 128, 200 * 1024>>>(d, 218 * 16);
+  k<<<g_grid, 128, 200 * 1024>>>(d, 218 * 16, d_off);
   cudaError_t e = cudaDeviceSynchronize();
   long long h[10];
   cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
-  const int mmas = COUNT * (PATTERN == 2 ? 2 : 1);
+  const int mmas = COUNT * (PATTERN == 2 ? 2 : PATTERN == 3 ? 3 : 1);
   printf("%-44s issue %5lld  total %6lld cycles = %6.1f / MMA  (%s)\n", name, h[8], h[9], (double)h[9] / mmas,
          cudaGetErrorString(e));
 }
@@ -203,6 +211,28 @@ int main() {
   run<16, 0, 36, 0, false>("N=16 same A aligned", d);
   run<32, 1, 18, 0, false>("N=32 conv taps x2 ksteps (18)", d);
   run<64, 1, 18, 0, false>("N=64 conv taps x2 ksteps (18)", d);
+  run<96, 1, 18, 0, false>("N=96 conv taps x2 ksteps (18)", d);
+  run<128, 1, 18, 0, false>("N=128 conv taps x2 ksteps (18)", d);
+  run<192, 1, 18, 0, false>("N=192 conv taps x2 ksteps (18)", d);
+  run<256, 1, 18, 0, false>("N=256 conv taps x2 ksteps (18)", d);
+  run<96, 1, 54, 0, false>("N=96 conv taps x2 ksteps (54)", d);
+  run<96, 1, 54, 0, false>("N=96 conv taps (54), D at column 32", d, 32);
+  run<96, 1, 54, 0, false>("N=96 conv taps (54), D at column 64", d, 64);
+  run<96, 1, 54, 0, false>("N=96 conv taps (54), D at column 96", d, 96);
+  run<96, 1, 54, 0, false>("N=96 conv taps (54), D at column 128", d, 128);
+  run<96, 3, 18, 0, false>("sliding batch N=96 x3 (54), D at 0", d, 0);
+  run<96, 3, 18, 0, false>("sliding batch N=96 x3 (54), D at 32", d, 32);
+  run<96, 3, 18, 0, false>("sliding batch N=96 x3 (54), D at 64", d, 64);
+  run<96, 3, 18, 0, false>("sliding batch N=96 x3 (54), D at 128", d, 128);
+  run<64, 3, 18, 0, false>("sliding batch N=64 x3 (54), D at 32", d, 32);
+  run<128, 3, 18, 0, false>("sliding batch N=128 x3 (54), D at 0", d, 0);
+  run<128, 3, 18, 0, false>("sliding batch N=128 x3 (54), D at 32", d, 32);
+  g_grid = 148;
+  run<96, 3, 18, 0, false>("148 CTAs: sliding batch N=96 x3 (54)", d, 32);
+  run<64, 3, 18, 0, false>("148 CTAs: sliding batch N=64 x3 (54)", d, 32);
+  run<32, 2, 54, 0, false>("148 CTAs: split pairs N=64+N=32 (108)", d);
+  run<256, 0, 36, 0, false>("148 CTAs: N=256 same A", d);
+  g_grid = 1;
   run<32, 2, 18, 0, false>("split pairs N=64+N=32 (36), one conv", d);
   run<32, 2, 54, 0, false>("split pairs N=64+N=32 (108), conv3d slice", d);
   run<32, 0, 36, 0, true>("N=32 interleaved K chunks aligned", d);

@@ -44,6 +44,15 @@ mac, byt, _ = bench.algorithmic_work(rows, cols, views, hyps)
 print(f"{rows}x{cols} V={views} D={hyps} B={batch}: event mean {sum(ms) / steps:.3f} ms (min {min(ms):.3f}), "
       f"wall/step {1e3 * wall / steps:.3f} ms, {batch / (sum(ms) / steps) * 1e3:.1f} depthmaps/s, "
       f"launches {net.last_launch_count()}, mem {torch.cuda.max_memory_allocated() / 2**30:.2f} GiB torch", flush=True)
+if os.environ.get("PROBE"):
+    # event pairs around every launch of one kernel class (b200mvs_probe_select), e.g. PROBE=cvf_conv32
+    net.probe_select(os.environ["PROBE"])
+    with torch.no_grad():
+        net(*inp, *flags)
+    torch.cuda.synchronize()
+    total_ms, launches = net.probe_read()
+    net.probe_select("none")
+    print(f"probe {os.environ['PROBE']}: {launches} launches, {1e3 * total_ms / max(1, launches):.1f} us each", flush=True)
 if os.environ.get("SWEEP_PROF"):
     # per-phase cycle totals of CTA (0, 0) of the wide sweep (sweep_wide.cu) or rank 0 of the cluster kernel
     net.set_option("recurrence_profile", 1)
