@@ -35,6 +35,7 @@ import torch  # noqa: E402
 ROWS, COLS, VIEWS, HYPS = 512, 640, 1, 64       # BASELINE cfg2 / cfg4 per-item shape
 METRIC = "depthmaps/sec at 512x640, 2-view, 64 hyp"
 UNIT = "depthmaps/s"
+E2E_BLOCKS = 5    # the end-to-end leg times this many blocks of K steps and reports the median block
 
 
 _REAL_STDOUT = None
@@ -409,11 +410,17 @@ def run_ours(args, rank, world, local_rank):
         for _ in range(max(args.warmup, 20)):
             net(*host_inputs, *flags)
         barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            net(*host_inputs, *flags)          # synchronous: returns after the D2H copy
-        torch.cuda.synchronize(dev)
-        e2e_s = time.perf_counter() - t0
+        # A block of K steps is ~30 ms of wall clock at this workload: one host hiccup on a fresh box moves it by 10-20 %
+        # (a 565 next to 650-670 depthmaps/s in otherwise identical runs).  The block is therefore timed E2E_BLOCKS
+        # times back to back and the MEDIAN block is reported; every block is listed in the JSON line.
+        e2e_blocks_s = []
+        for _ in range(E2E_BLOCKS):
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                net(*host_inputs, *flags)          # synchronous: returns after the D2H copy
+            torch.cuda.synchronize(dev)
+            e2e_blocks_s.append(time.perf_counter() - t0)
+        e2e_s = sorted(e2e_blocks_s)[len(e2e_blocks_s) // 2]
     h2d, d2h = net.last_h2d_bytes, net.last_d2h_bytes
     # the same call with EVERYTHING the module returns downloaded (raw priors and the five dense mask volumes as well,
     # +28 MB at this workload): reported next to `e2e` as `e2e_all_outputs` (rank 0's own time, not part of `value`)
@@ -494,6 +501,8 @@ def run_ours(args, rank, world, local_rank):
             "clocks": sampler.summary(mark0, max(mark1, mark0 + 1)),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": worst_e2e_ms / e2e_steps,
+                    "estimator": f"median of {E2E_BLOCKS} back-to-back blocks of {e2e_steps} steps (wall clock), max over ranks",
+                    "blocks_ms_per_step_rank0": [round(1e3 * b / e2e_steps, 4) for b in e2e_blocks_s],
                     "what": "MultiViewStereoNet.forward on pinned CPU tensors -> b200mvs_forward_host: H2D of the "
                             "image pyramids/K/T, full path incl. mask volumes on device, D2H of the 5-level idepth "
                             "pyramid"},

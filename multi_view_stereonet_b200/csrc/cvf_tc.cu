@@ -37,10 +37,9 @@ constexpr int W_BLOCKS = 27 * 2;
 constexpr int W_BYTES = W_BLOCKS * 2048;
 constexpr int RING = 4;
 constexpr int ACC = 16;            // accumulator slots in tensor memory (32 columns each, a ring over the output slices)
-// The workers drain output slice it - LAG in the iteration that stages input slice it.  3, not more: staging reuses the
-// ring slot of input slice it - 4, whose batch must be through -- the epilogue of iteration it - 1 waited for the commit
-// behind batch it - 2 (LAG = 4 would leave iteration 4 of a segment without that knowledge).
-constexpr int LAG = 3;
+// The workers drain output slice it - LAG in the iteration that stages input slice it: the batch that completes it
+// (input slice it - LAG + 2) was issued two iterations earlier, so neither role waits for the other in steady state.
+constexpr int LAG = 4;
 constexpr uint32_t TMEM_COLS = 32u * ACC;
 
 struct Geo {
@@ -89,11 +88,15 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ float s_a[kC], s_b[kC], s_bias[kC];
   __shared__ double s_stats[2 * kGroups];
-  __shared__ __align__(8) uint64_t s_full[RING], s_acc_full[ACC], s_acc_empty[ACC], s_wbar;
+  __shared__ __align__(8) uint64_t s_full[RING], s_free[RING], s_acc_full[ACC], s_acc_empty[ACC], s_wbar;
   __shared__ uint32_t s_tmem;
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = tc::uniform_warp_index();
+#ifdef CVF_PROF
+  unsigned long long pk_t0, pk_t1, pk_t2;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pk_t0));
+#endif
   const Geo g = make_geo(P.cw);
   const int PW = g.PW, RT = g.RT, NP = g.NP;
   const int cols_per_n = P.row_tiles * P.col_tiles;
@@ -112,7 +115,10 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
 
   if (warp == 0) tc::tmem_alloc(&s_tmem, TMEM_COLS);
   if (tid == 32) {
-    for (int i = 0; i < RING; ++i) tc::mbar_init(&s_full[i], NW / 32);   // one arrival per worker warp
+    for (int i = 0; i < RING; ++i) {
+      tc::mbar_init(&s_full[i], NW / 32);   // one arrival per worker warp
+      tc::mbar_init(&s_free[i], 1);         // tcgen05.commit behind the batch that read the slot
+    }
     for (int i = 0; i < ACC; ++i) {
       tc::mbar_init(&s_acc_full[i], 1);
       tc::mbar_init(&s_acc_empty[i], NW / 32);
@@ -129,6 +135,9 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
   pdl_launch_dependents();   // after the TMEM allocation (see common.cuh)
   // (no ring initialisation: every position an MMA reads, [0, NP), is written by the staging of its slice)
   pdl_wait();
+#ifdef CVF_PROF
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pk_t1));
+#endif
   const uint32_t tmem_base = s_tmem;
   const uint32_t plane_u16 = g.plane_bytes >> 4, slot_u16 = g.slot_bytes >> 4;
   const size_t slice_elems = (size_t)p.h * p.w * kC;
@@ -250,6 +259,7 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
           }
           // output slice i - 2 is complete (implies tcgen05.fence::before_thread_sync)
           if (i >= 2) tc::mma_commit(&s_acc_full[(oc + (uint32_t)i - 2u) & (ACC - 1)]);
+          tc::mma_commit(&s_free[S & (RING - 1)]);   // the ring slot may be overwritten
 #ifdef CVF_PROF
           pf_full += pb - pa;
           pf_empty += pc - pb;
@@ -327,9 +337,9 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
 
       // Software pipeline over the segment's depth range.  Iteration `it`:
       //   transform + stage input slice it (its global loads were issued one iteration earlier) -> next ring slot,
-      //     last read by the MMAs of the output slice four back, whose completion this thread observed in its epilogue
+      //     once the batch of the slice four back has released it (free[slot])
       //   issue the global loads of input slice it + 1
-      //   epilogue of output slice it - 3
+      //   epilogue of output slice it - LAG
       float y8[MAX_TASKS][8];
       bool loaded_valid = false;
       auto issue_loads = [&](int slice) {
@@ -351,6 +361,7 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
         if (it <= dcount + 1) {
           const uint32_t S = sc + (uint32_t)it;
           uint8_t* slot = s_ring + (size_t)(S & (RING - 1)) * g.slot_bytes;
+          if (S >= RING) tc::mbar_wait_warp(&s_free[S & (RING - 1)], ((S / RING) - 1u) & 1u);
 #pragma unroll
           for (int k = 0; k < MAX_TASKS; ++k) {
             if (t_in[k]) {
@@ -457,6 +468,12 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
   }
   tc::fence_before_sync();
   __syncthreads();
+#ifdef CVF_PROF
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pk_t2));
+  if (tid == 0 && blockIdx.x % 21 == 0)
+    printf("cvf cta %d: entry %llu ns, after pdl_wait +%llu, exit +%llu, units %lld\n", (int)blockIdx.x, pk_t0 % 100000000ull,
+           pk_t1 - pk_t0, pk_t2 - pk_t0, u_end - u_begin);
+#endif
   if (warp == 0) tc::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
