@@ -91,6 +91,27 @@ def test_batch8_matches_single_items(net, gta_state):
         assert int((out8["left_idepthmap_mask_pyr"][lvl][5].cpu() != ref["left_idepthmap_mask_pyr"][lvl][0]).sum()) == 0
 
 
+def test_cost_filter_decompositions_agree(net):
+    """The Conv3d filter (cvf_tc.cu) cuts its work differently at batch 1 (every (row tile, strip) column in 13 depth
+    chunks of 5 slices: accumulator windows never wrap around the tensor-memory ring) and at batch 8 (equal ranges of 39
+    output slices that cross column boundaries: several segments per CTA, wrapped windows, the N = 64 + 32 path).  Every
+    output slice adds its products in the same order either way, so the filtered cost volumes agree to the float64
+    GroupNorm statistics' summation order."""
+    batch = synthetic.make_inputs(512, 640, 1, 8)
+    net.keep_stages(True)
+    try:
+        with torch.no_grad():
+            net(*synthetic.to_device(batch, "cuda"), 64, True, [True] * 5)
+            cost8 = net.get_stage("cost_filtered", torch.float32).view(8, 64, 32, 40).clone()
+            for i in (0, 6):
+                one = synthetic.make_inputs(512, 640, 1, 1, first_item=i)
+                net(*synthetic.to_device(one, "cuda"), 64, True, [True] * 5)
+                cost1 = net.get_stage("cost_filtered", torch.float32).view(64, 32, 40)
+                assert rel_linf(cost8[i].cpu(), cost1.cpu()) <= 1e-5, i
+    finally:
+        net.keep_stages(False)
+
+
 def test_many_chains_take_the_wide_sweep(net):
     """From the third round of clusters on (more than 14 (image group, view) chains on B200) the automatic rule hands
     the depth sweep to the wide kernel (one co-resident grid for all chains).  Batch 8 with two views = 16 chains:
