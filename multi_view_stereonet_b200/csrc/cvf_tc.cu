@@ -13,9 +13,9 @@
 // 9 x 2 x 3 = 54 MMAs per slice instead of 108 (N = 64 / 32) per output slice, and the 4 KB A operand is fetched once
 // for three outputs.  The MMA rate is set by the operand bytes read from shared memory, (A + B) / 128 per clock
 // (tools/mma_bench.cu: N = 32 43 cycles, 64 55, 96 60, 128 69); a batch is 3.25 k cycles against 4.87 k before.  The
-// output slice a batch starts takes its first product as an MMA of its own with accumulate = 0; windows that wrap around
-// the ring (2 batches of 16) and the ends of a segment split into N = 64 + 32 (general path of the issuer).  An output
-// slice is complete after the batch of the input slice behind it: one tcgen05.commit per batch.
+// output slice a batch starts takes its first product as an MMA of its own with accumulate = 0; a window that wraps around
+// the ring (2 batches of 16) is two runs (N = 64 + 32), at the ends of a segment the entries outside it are left out
+// (N = 32 / 64).  An output slice is complete after the batch of the input slice behind it: one tcgen05.commit per batch.
 // Warp-specialised: sixteen worker warps stage slices and drain accumulators (8 channels of one position per thread), a
 // seventeenth warp only issues MMAs.  The roles meet only at mbarriers: full[slot] (workers -> issuer), acc_full[slot]
 // (tcgen05.commit -> workers), acc_empty[slot] (workers -> issuer).
@@ -178,82 +178,66 @@ __global__ void __launch_bounds__(NT, 1) cvf_tc_kernel(const CvfParams P) {
           // mod ACC; all three split-precision products (A_hi W_hi, A_lo W_hi, A_hi W_lo) add into the same columns.
           const uint32_t slot0 = (oc + (uint32_t)i - 2u) & (ACC - 1);
           const uint64_t da_slot = da0 + (uint64_t)((S & (RING - 1)) * slot_u16);
-          if (P.dbg & 1) {
-            // timing ablation: no MMAs
-          } else if (i >= 2 && i < dcount && slot0 <= ACC - 3) {
-            // Inside a segment, window in consecutive slots: one N = 96 MMA per product.  Output slice i starts in
-            // this batch: the very first product goes in as N = 64 (accumulate) + N = 32 (overwrite).
-            const uint32_t dx = tmem_base + 32u * slot0;
-#pragma unroll
-            for (int t2 = 0; t2 < 9; ++t2) {
-              const uint32_t pos = (uint32_t)((t2 / 3) * PW + (t2 % 3));
-#pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
-                const uint64_t a_hi = da_slot + (uint64_t)(2 * ks * plane_u16 + pos);
-                const uint64_t a_lo = a_hi + (uint64_t)(4 * plane_u16);
-                const uint64_t b_hi = db0 + (uint64_t)((t2 * 2 + ks) * 384);   // [W_hi | W_lo] x 2 k-octets x 96 rows
-                const uint64_t b_lo = b_hi + 192u;
-                if ((t2 | ks) == 0) {
-                  tc::mma_f16(dx, a_hi, b_hi, tc::idesc_f16(64), 1u);
-                  tc::mma_f16(dx + 64u, a_hi, b_hi + 64u, tc::idesc_f16(32), 0u);
-                } else {
-                  tc::mma_f16(dx, a_hi, b_hi, tc::idesc_f16(96), 1u);
-                }
-                tc::mma_f16(dx, a_lo, b_hi, tc::idesc_f16(96), 1u);
-                tc::mma_f16(dx, a_hi, b_lo, tc::idesc_f16(96), 1u);
-              }
-            }
-          } else {
-            // Segment ends (entries outside the segment are skipped) and windows that wrap around the ring: entries in
-            // consecutive slots share an MMA (N = 32 per entry), the entry a batch starts is on its own in the first product.
+          if (!(P.dbg & 1)) {   // (bit 0: timing ablation without MMAs)
+            // Entries inside the segment: jlo .. jhi.  Run A = those up to the end of the ring, run B = the rest of a
+            // window that wraps around it (slot 0 on); one MMA per run and product, N = 32 per entry.  The single
+            // issuing thread needs ~6 cycles per uniform-datapath instruction, predicated off or not, so the two cases
+            // are separate unrolled loops without predicates.
             const int jlo = i >= 2 ? 0 : 2 - i;
             const int jhi = dcount + 1 - i < 2 ? dcount + 1 - i : 2;
-            uint32_t e_col[3], e_idesc[2][3];   // per window entry: accumulator column, descriptor of the run it starts
-            bool e_start[2][3];                 // [1]: in the first product of a batch that starts an output slice
-            {
-              bool val[3], brk[2][3];
+            const uint32_t slotA = (slot0 + (uint32_t)jlo) & (ACC - 1);
+            int lenA = jhi - jlo + 1;
+            if ((int)(ACC - slotA) < lenA) lenA = (int)(ACC - slotA);
+            const int lenB = jhi - jlo + 1 - lenA;
+            const uint32_t dA = tmem_base + 32u * slotA, dB = tmem_base;
+            const uint64_t bA = (uint64_t)(32 * jlo), bB = (uint64_t)(32 * (jlo + lenA));   // 32 weight rows per entry
+            const uint32_t iA = idesc_n(32u * (uint32_t)lenA), iB = idesc_n(32u * (uint32_t)(lenB > 0 ? lenB : 1));
+            // First product (A_hi W_hi of tap 0, k-step 0).  A batch that starts an output slice (entry 2) overwrites
+            // that entry and accumulates into the others: one N = 32 MMA per entry, once per batch.
+            if (fresh) {
 #pragma unroll
-              for (int j = 0; j < 3; ++j) {
-                const uint32_t slot = (slot0 + (uint32_t)j) & (ACC - 1);
-                val[j] = j >= jlo && j <= jhi;
-                e_col[j] = tmem_base + 32u * slot;
-                brk[0][j] = j == 0 || !val[j - (j > 0)] || slot == 0u;
-                brk[1][j] = brk[0][j] || (fresh && j == 2);
-              }
-#pragma unroll
-              for (int f = 0; f < 2; ++f) {
-                const uint32_t len2 = 1u;
-                const uint32_t len1 = 1u + ((val[2] && !brk[f][2]) ? len2 : 0u);
-                const uint32_t len0 = 1u + ((val[1] && !brk[f][1]) ? len1 : 0u);
-                e_start[f][0] = val[0];
-                e_start[f][1] = val[1] && brk[f][1];
-                e_start[f][2] = val[2] && brk[f][2];
-                e_idesc[f][0] = idesc_n(32u * len0);
-                e_idesc[f][1] = idesc_n(32u * len1);
-                e_idesc[f][2] = idesc_n(32u * len2);
-              }
+              for (int j = 0; j < 3; ++j)
+                if (j >= jlo)
+                  tc::mma_f16(tmem_base + 32u * ((slot0 + (uint32_t)j) & (ACC - 1)), da_slot, db0 + (uint64_t)(32 * j),
+                              tc::idesc_f16(32), j == 2 ? 0u : 1u);
+            } else {
+              tc::mma_f16(dA, da_slot, db0 + bA, iA, 1u);
+              if (lenB > 0) tc::mma_f16(dB, da_slot, db0 + bB, iB, 1u);
             }
-            const uint32_t acc_last = fresh ? 0u : 1u;   // accumulate flag of entry 2's own run in the first product
+            if (lenB == 0) {
 #pragma unroll
-            for (int t2 = 0; t2 < 9; ++t2) {
-              const uint32_t pos = (uint32_t)((t2 / 3) * PW + (t2 % 3));
+              for (int t2 = 0; t2 < 9; ++t2) {
+                const uint32_t pos = (uint32_t)((t2 / 3) * PW + (t2 % 3));
 #pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
-                const uint64_t a_hi = da_slot + (uint64_t)(2 * ks * plane_u16 + pos);
-                const uint64_t a_lo = a_hi + (uint64_t)(4 * plane_u16);
-                const uint64_t b_hi = db0 + (uint64_t)((t2 * 2 + ks) * 384);
-                const uint64_t b_lo = b_hi + 192u;
-                const int f = (t2 | ks) == 0 ? 1 : 0;
+                for (int ks = 0; ks < 2; ++ks) {
+                  const uint64_t a_hi = da_slot + (uint64_t)(2 * ks * plane_u16 + pos);
+                  const uint64_t a_lo = a_hi + (uint64_t)(4 * plane_u16);
+                  const uint64_t b_hi = db0 + (uint64_t)((t2 * 2 + ks) * 384) + bA;   // [W_hi | W_lo] x 2 k-octets x 96 rows
+                  const uint64_t b_lo = b_hi + 192u;
+                  if ((t2 | ks) != 0) tc::mma_f16(dA, a_hi, b_hi, iA, 1u);
+                  tc::mma_f16(dA, a_lo, b_hi, iA, 1u);
+                  tc::mma_f16(dA, a_hi, b_lo, iA, 1u);
+                }
+              }
+            } else {
 #pragma unroll
-                for (int j = 0; j < 3; ++j)
-                  if (e_start[f][j])
-                    tc::mma_f16(e_col[j], a_hi, b_hi + 32u * j, e_idesc[f][j], (f == 1 && j == 2) ? acc_last : 1u);
+              for (int t2 = 0; t2 < 9; ++t2) {
+                const uint32_t pos = (uint32_t)((t2 / 3) * PW + (t2 % 3));
 #pragma unroll
-                for (int j = 0; j < 3; ++j)
-                  if (e_start[0][j]) tc::mma_f16(e_col[j], a_lo, b_hi + 32u * j, e_idesc[0][j], 1u);
-#pragma unroll
-                for (int j = 0; j < 3; ++j)
-                  if (e_start[0][j]) tc::mma_f16(e_col[j], a_hi, b_lo + 32u * j, e_idesc[0][j], 1u);
+                for (int ks = 0; ks < 2; ++ks) {
+                  const uint64_t a_hi = da_slot + (uint64_t)(2 * ks * plane_u16 + pos);
+                  const uint64_t a_lo = a_hi + (uint64_t)(4 * plane_u16);
+                  const uint64_t b_hi = db0 + (uint64_t)((t2 * 2 + ks) * 384);
+                  const uint64_t b_lo = b_hi + 192u;
+                  if ((t2 | ks) != 0) {
+                    tc::mma_f16(dA, a_hi, b_hi + bA, iA, 1u);
+                    tc::mma_f16(dB, a_hi, b_hi + bB, iB, 1u);
+                  }
+                  tc::mma_f16(dA, a_lo, b_hi + bA, iA, 1u);
+                  tc::mma_f16(dB, a_lo, b_hi + bB, iB, 1u);
+                  tc::mma_f16(dA, a_hi, b_lo + bA, iA, 1u);
+                  tc::mma_f16(dB, a_hi, b_lo + bB, iB, 1u);
+                }
               }
             }
           }
